@@ -1,0 +1,339 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+R is not available in this image, so the reference-facing layer is restated in
+Python with the reference's own names, argument meaning and return lists
+(INTEGRATION.md shows the R shim that binds the same C ABI):
+
+    GAPIT.kinship.VanRaden(snps, hasInbred)   -> GAPIT_kinship_VanRaden
+    emma.eigen.L.wo.Z(K) / emma.eigen.R.wo.Z  -> emma_eigen_L_wo_Z / emma_eigen_R_wo_Z
+    GAPIT.emma.REMLE(y, X, K, ...)            -> GAPIT_emma_REMLE
+    GAPIT.EMMAxP3D(ys, xs, K, Z, X0, ...)     -> GAPIT_EMMAxP3D
+
+All arithmetic happens in libgapitcuda.so; this module only marshals buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib
+from ._lib import GapitCudaError, check  # noqa: F401
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Context:
+    """One GPU (gapit_ctx).  One per process under torchrun, one per R session."""
+
+    def __init__(self, device=0, slices=None):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.gapit_ctx_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = int(device)
+        if slices:
+            check(self.lib.gapit_set_slices(self.h, int(slices)))
+
+    def set_slices(self, slices):
+        check(self.lib.gapit_set_slices(self.h, int(slices)))
+
+    def stats(self):
+        s = _lib.Stats()
+        check(self.lib.gapit_ctx_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gapit_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+class Genotypes:
+    """Device-resident dosage matrix (gapit_geno): int8, marker-major, plus column statistics."""
+
+    def __init__(self, snps, ctx=None, impute=None, marker_major=False):
+        """snps: n x m array (taxa x markers, the reference's orientation), or with
+        ``marker_major=True`` an (m, n) C-contiguous array (= R's column-major memory)."""
+        self.ctx = ctx or default_context()
+        lib = self.ctx.lib
+        a = np.asarray(snps)
+        if not marker_major:
+            # n x m: column-major memory is what the C ABI wants (element (i,k) at i + k*ld)
+            a = a.T  # (m, n) view
+        if a.dtype == np.int8 or a.dtype == np.uint8:
+            dtype = _lib.GAPIT_I8
+        elif a.dtype == np.int32:
+            dtype = _lib.GAPIT_I32
+        else:
+            a = a.astype(np.float64, copy=False)
+            dtype = _lib.GAPIT_F64
+        a = np.ascontiguousarray(a)  # (m, n) row-major == n x m column-major, ld = n
+        m, n = a.shape
+        h = C.c_void_p()
+        check(lib.gapit_geno_pack(self.ctx.h, _ptr(a), dtype, n, m, n, _lib.IMPUTE[impute], C.byref(h)))
+        self.h = h
+        self.n, self.m = int(n), int(m)
+
+    def colsums(self):
+        cs = np.empty(self.m, dtype=np.int32)
+        cq = np.empty(self.m, dtype=np.int32)
+        check(self.ctx.lib.gapit_geno_colsums(self.h, _ptr(cs), _ptr(cq)))
+        return cs, cq
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gapit_geno_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EigenSystem:
+    """Eigen-system of K resident on the device, eigenvectors sliced for the int8 rotation."""
+
+    def __init__(self, values, vectors, ctx=None):
+        self.ctx = ctx or default_context()
+        self.values = np.ascontiguousarray(values, dtype=np.float64)
+        v = np.asfortranarray(vectors, dtype=np.float64)
+        n = self.values.shape[0]
+        assert v.shape == (n, n)
+        h = C.c_void_p()
+        check(self.ctx.lib.gapit_eigsys_upload(self.ctx.h, _ptr(v), _ptr(self.values), n, C.byref(h)))
+        self.h = h
+        self.n = n
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.gapit_eigsys_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _as_geno(snps, ctx, impute=None):
+    if isinstance(snps, Genotypes):
+        return snps, False
+    return Genotypes(snps, ctx=ctx, impute=impute), True
+
+
+# ---------------------------------------------------------------------------
+# GAPIT.kinship.VanRaden(snps, hasInbred=TRUE)      GAPIT.kinship.VanRaden.R:1-37
+# ---------------------------------------------------------------------------
+def GAPIT_kinship_VanRaden(snps, hasInbred=True, ctx=None, return_gram=False, verbose=True):
+    """n x m dosages (array or Genotypes) -> n x n kinship (bare fp64 matrix, like the reference).
+
+    The reference's five progress prints are kept (user-visible behaviour)."""
+    ctx = ctx or default_context()
+    say = print if verbose else (lambda *_: None)
+    say("Calculating kinship with VanRaden method...")
+    g, owned = _as_geno(snps, ctx)
+    n = g.n
+    K = np.empty((n, n), dtype=np.float64, order="F")
+    G = np.empty((n, n), dtype=np.int32) if return_gram else None
+    say("substracting P...")
+    say("Getting X'X...")
+    check(ctx.lib.gapit_vanraden(ctx.h, g.h, _ptr(K), _ptr(G)))
+    say("Adjusting...")
+    if owned:
+        g.close()
+    say("Calculating kinship with VanRaden method: done")
+    return (K, G) if return_gram else K
+
+
+# ---------------------------------------------------------------------------
+# emma.eigen.L.wo.Z / emma.eigen.R.wo.Z             emma.txt:58-61, 82-89
+# ---------------------------------------------------------------------------
+def emma_eigen_L_wo_Z(K, ctx=None):
+    ctx = ctx or default_context()
+    K = np.asfortranarray(K, dtype=np.float64)
+    n = K.shape[0]
+    values = np.empty(n)
+    vectors = np.empty((n, n), order="F")
+    check(ctx.lib.gapit_eigh(ctx.h, _ptr(K), n, _ptr(values), _ptr(vectors)))
+    return {"values": values, "vectors": vectors}
+
+
+def emma_eigen_R_wo_Z(K, X, ctx=None):
+    ctx = ctx or default_context()
+    K = np.asfortranarray(K, dtype=np.float64)
+    X = np.asfortranarray(X, dtype=np.float64)
+    n, q = X.shape
+    values = np.empty(n - q)
+    vectors = np.empty((n, n - q), order="F")
+    check(ctx.lib.gapit_eigen_R(ctx.h, _ptr(K), _ptr(X), n, q, _ptr(values), _ptr(vectors)))
+    return {"values": values, "vectors": vectors}
+
+
+# ---------------------------------------------------------------------------
+# GAPIT.emma.REMLE(y, X, K, Z=NULL, ngrids, llim, ulim, esp, eig.L, eig.R)
+#                                                    GAPIT.emma.REMLE.R:1-111
+# ---------------------------------------------------------------------------
+def GAPIT_emma_REMLE(y, X, K, Z=None, ngrids=100, llim=-10, ulim=10, esp=1e-10, eig_L=None, eig_R=None, ctx=None):
+    if Z is not None:
+        raise NotImplementedError("compressed MLM (non-NULL Z) keeps the reference's R body; see DESIGN.md")
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+    X = np.asfortranarray(X, dtype=np.float64)
+    n, q = X.shape
+    if np.linalg.det(X.T @ X) == 0:                      # GAPIT.emma.REMLE.R:15-18
+        return {"REML": 0.0, "delta": 0.0, "ve": 0.0, "vg": 0.0}
+    if eig_R is None:                                    # :22-24
+        eig_R = emma_eigen_R_wo_Z(K, X, ctx=ctx)
+    lam = np.ascontiguousarray(eig_R["values"], dtype=np.float64)
+    etas = np.ascontiguousarray(eig_R["vectors"].T @ y)  # :25 (n-q dot products; host)
+    out = _lib.RemlOut()
+    check(_lib.load().gapit_reml(_ptr(lam), _ptr(etas), lam.shape[0], int(ngrids), float(llim), float(ulim),
+                                 float(esp), C.byref(out)))
+    return {"REML": out.REML, "delta": out.delta, "ve": out.ve, "vg": out.vg}
+
+
+# ---------------------------------------------------------------------------
+# the marker scan proper
+# ---------------------------------------------------------------------------
+def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None):
+    """Scan all markers of ``geno`` for T traits.  Returns (dict of (T, m) arrays, list of per-trait base dicts)."""
+    ctx = ctx or geno.ctx
+    X0 = np.asfortranarray(X0, dtype=np.float64)
+    Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(geno.n, -1))
+    n, q0 = X0.shape
+    T = Y.shape[1]
+    m = geno.m
+    names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
+    arrs = {k: np.empty((T, m), dtype=np.float64) for k in names}
+    arrs["maf"] = np.empty(m, dtype=np.float64)
+    so = _lib.ScanOut(**{k: arrs[k].ctypes.data_as(C.POINTER(C.c_double)) for k in arrs})
+    base = (_lib.ScanBase * T)()
+    d = np.ascontiguousarray(delta, dtype=np.float64).reshape(-1) if delta is not None else None
+    v = np.ascontiguousarray(vg, dtype=np.float64).reshape(-1) if vg is not None else None
+    check(ctx.lib.gapit_p3d_scan_dev(ctx.h, geno.h, eigsys.h if eigsys is not None else None, _ptr(X0), q0, _ptr(Y), T,
+                                     _ptr(d), _ptr(v), 1 if glm else 0, C.byref(so), base))
+    bases = []
+    for t in range(T):
+        b = base[t]
+        bases.append({"logL0": b.logL0, "logLM_base": b.logLM_base, "rsquare_base": b.rsquare_base, "ves": b.ves,
+                      "reml": b.reml, "df": b.df, "beta0": np.array(b.beta0[:q0]), "singular_x0": bool(b.singular_x0)})
+    return arrs, bases
+
+
+def _timmer(Timmer, label):
+    """GAPIT.Timmer.R:8-17: append (label, now, elapsed since previous stamp)."""
+    now = time.time()
+    if Timmer is None:
+        return [(label, now, 0.0)]
+    return Timmer + [(label, now, now - Timmer[-1][1])]
+
+
+# ---------------------------------------------------------------------------
+# GAPIT.EMMAxP3D(ys, xs, K, Z, X0, CVI, ..., SNP.P3D, Timmer, Memory, optOnly, ...)
+#                                                    GAPIT.EMMAxP3D.R:1-1022
+# ---------------------------------------------------------------------------
+def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=None, GI=None, GP=None,
+                   fullGD=True, SNP_P3D=True, Timmer=None, Memory=None, optOnly=False, SNP_effect="Add",
+                   SNP_impute="Middle", ngrids=100, llim=-10, ulim=10, esp=1e-10, name_of_trait=None,
+                   Create_indicator=False, ctx=None, eig_L=None, reml=None):
+    """The accelerated branch of GAPIT.EMMAxP3D: Z NULL or square, SNP.P3D, fullGD, no indicators, !optOnly.
+
+    Returns the reference's named list (GAPIT.EMMAxP3D.R:1018-1020) as a dict; per-marker
+    entries are (m, 1) arrays like the reference's m x g matrices with g = 1.  ``eig_L`` /
+    ``reml`` may be injected (tests feed both sides identical spectra); they are otherwise
+    computed exactly where the reference computes them (:48, :58, :202).
+    Other argument combinations are the reference's other code paths and are not provided here.
+    """
+    ctx = ctx or default_context()
+    if Z is not None and Z.shape[0] != Z.shape[1]:
+        raise NotImplementedError("compressed MLM (rectangular Z) keeps the reference's R body")
+    if not SNP_P3D or not fullGD or Create_indicator or optOnly:
+        raise NotImplementedError("only the P3D / fullGD / additive scan is accelerated (SURVEY.md section 8b)")
+    Timmer = _timmer(Timmer, "P3D Start")
+    ys = np.asarray(ys, dtype=np.float64).reshape(-1)                     # :29
+    n = ys.shape[0]
+    if X0 is None:                                                        # :30
+        X0 = np.ones((n, 1))
+    X0 = np.asarray(X0, dtype=np.float64)
+    if K is not None and np.size(K) <= 1:                                 # :34
+        K = None
+    q0 = X0.shape[1]
+    geno, owned = _as_geno(xs, ctx, impute=SNP_impute)                    # :20-24 (NA -> impute value)
+    m = geno.m
+    glm = K is None
+    if not glm:
+        if eig_L is None:
+            eig_L = emma_eigen_L_wo_Z(K, ctx=ctx)                         # :48
+        Timmer = _timmer(Timmer, "eig.L")
+        if reml is None:
+            try:
+                eig_R = emma_eigen_R_wo_Z(K, X0, ctx=ctx)                 # :58
+            except GapitCudaError:
+                # :70-74 early return when eig.R fails
+                return {"ps": None, "REMLs": np.nan, "stats": None, "effect.est": None, "dfs": None, "maf": None,
+                        "nobs": None, "Timmer": Timmer, "Memory": Memory, "vgs": np.nan, "ves": np.nan,
+                        "BLUP": None, "BLUP_Plus_Mean": None, "PEV": None, "BLUE": None}
+            Timmer = _timmer(Timmer, "eig.R")
+            reml = GAPIT_emma_REMLE(ys, X0, K, None, ngrids, llim, ulim, esp, eig_R=eig_R, ctx=ctx)   # :202
+        Timmer = _timmer(Timmer, "REML")
+        es = EigenSystem(eig_L["values"], eig_L["vectors"], ctx=ctx)      # :224 folded into the kernel weights
+        Timmer = _timmer(Timmer, "U Matrix")
+        arrs, bases = p3d_scan(geno, X0, ys, eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]], ctx=ctx)
+        es.close()
+        vgs, ves, REMLs = reml["vg"], reml["ve"], reml["REML"]
+    else:
+        arrs, bases = p3d_scan(geno, X0, ys, glm=True, ctx=ctx)
+        vgs, ves, REMLs = 0.0, bases[0]["ves"], bases[0]["reml"]           # :868-872
+    Timmer = _timmer(Timmer, "Screening SNPs")
+    if bases[0]["singular_x0"]:                                           # :711
+        print("At least two of your covariates are linearly dependent. Please reconsider the covariates you are using for GWAS and GPS")
+    b = bases[0]
+    col = lambda a: a.reshape(m, 1)
+    stats = arrs["tvalue"][0]
+    normal = ~np.isnan(stats)
+    dfs = np.where(normal, b["df"], np.nan)
+    # :972 stderr = beta[ncol(CVI)+1] / t -- an index into the (q0+1)-vector of the full model that only
+    # lands on the marker effect when ncol(CVI) == q0; past the end R yields NA.
+    stderr = np.full(m, np.nan)
+    if CVI is not None:
+        idx = np.asarray(CVI).shape[1]                                    # 0-based position ncol(CVI)
+        if idx == q0:
+            stderr = arrs["effect"][0] / stats
+        # idx < q0 would need the per-marker covariate effects the scan does not return
+    rsq_base = np.where(normal, b["rsquare_base"], np.nan)
+    if owned:
+        geno.close()
+    Timmer = _timmer(Timmer, "GWAS done for this Trait")
+    return {
+        "ps": col(arrs["pvalue"][0]), "REMLs": -2.0 * REMLs, "stats": col(stats),
+        "effect.est": col(arrs["effect"][0]), "rsquare_base": col(rsq_base), "rsquare": col(arrs["rsquare"][0]),
+        "dfs": col(dfs), "df": col(dfs.copy()), "tvalue": col(stats.copy()), "stderr": col(stderr),
+        "maf": col(arrs["maf"]), "nobs": col(np.full(m, float(n))), "Timmer": Timmer, "Memory": Memory,
+        "vgs": vgs, "ves": ves,
+        # i = 0 BLUP/PEV/BLUE block (:779-861) is off the data-parallel path
+        "BLUP": None, "BLUP_Plus_Mean": None, "PEV": None, "BLUE": None,
+        "logLM": col(arrs["loglm"][0]), "effect.snp": col(arrs["effect"][0]), "effect.cv": b["beta0"],
+        "se": col(arrs["se"][0]), "delta": (None if glm else reml["delta"]),
+    }

@@ -1,0 +1,116 @@
+// Context, error channel and library-level glue of the C ABI (include/gapitcuda.h).
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "umma_i8.cuh"
+
+namespace gapit {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+// cuTensorMapEncodeTiled lives in libcuda; resolve it through the runtime so the
+// library links (and loads for the symbol checks) on a box without a driver.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tensor_map_u8(CUtensorMap* out, const void* base, uint64_t inner_bytes, uint64_t rows, uint64_t ld_bytes,
+                       uint32_t box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(GAPIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (ld_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 127) != 0 || box_rows > 256)
+    return fail(GAPIT_ERR_ARG, "make_tensor_map_u8: misaligned tensor");
+  cuuint64_t dims[2] = {inner_bytes, rows};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GAPIT_ERR_CUDA, "cuTensorMapEncodeTiled failed, CUresult " + std::to_string(int(r)));
+  return GAPIT_OK;
+}
+
+}  // namespace gapit
+
+using namespace gapit;
+
+extern "C" const char* gapit_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int gapit_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int gapit_ctx_create(int device, gapit_ctx** out) {
+  if (!out) return fail(GAPIT_ERR_ARG, "gapit_ctx_create: NULL out");
+  int ndev = gapit_device_count();
+  if (ndev <= 0) return fail(GAPIT_ERR_NO_DEVICE, "no CUDA device visible: libgapitcuda has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(GAPIT_ERR_ARG, "gapit_ctx_create: device index out of range");
+  cudaDeviceProp prop;
+  GAPIT_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(GAPIT_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                                         "; libgapitcuda is built for sm_100a only");
+  GAPIT_CUDA(cudaSetDevice(device));
+  gapit_ctx* ctx = new gapit_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e != cudaSuccess) {
+    gapit_ctx_destroy(ctx);
+    return fail(GAPIT_ERR_CUDA, std::string("gapit_ctx_create: ") + cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return GAPIT_OK;
+}
+
+extern "C" void gapit_ctx_destroy(gapit_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int gapit_ctx_stats(const gapit_ctx* ctx, gapit_stats* out) {
+  if (!ctx || !out) return fail(GAPIT_ERR_ARG, "gapit_ctx_stats: NULL argument");
+  *out = ctx->stats;
+  return GAPIT_OK;
+}
+
+extern "C" int gapit_set_slices(gapit_ctx* ctx, int slices) {
+  if (!ctx) return fail(GAPIT_ERR_ARG, "gapit_set_slices: NULL ctx");
+  if (slices == 0) slices = 6;
+  if (slices < 4 || slices > 8) return fail(GAPIT_ERR_ARG, "gapit_set_slices: slices must be 4..8");
+  ctx->slices = slices;
+  return GAPIT_OK;
+}

@@ -1,0 +1,61 @@
+// Shared host-side plumbing of libgapitcuda: error capture, the context and
+// genotype handles behind the C ABI (include/gapitcuda.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/gapitcuda.h"
+
+namespace gapit {
+
+void set_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+
+#define GAPIT_CUDA(call)                                                                          \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      return ::gapit::fail(GAPIT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) +  \
+                                               " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                             \
+  } while (0)
+
+#define GAPIT_CHECK(call)          \
+  do {                             \
+    int rc__ = (call);             \
+    if (rc__ != GAPIT_OK) return rc__; \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace gapit
+
+// Opaque handles of the C ABI.
+struct gapit_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  // timings of the last call, ms (CUDA events on `stream`)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  gapit_stats stats = {};
+  int slices = 6;  // int8 slices of V used by the rotation (Ozaki split)
+};
+
+struct gapit_geno {
+  gapit_ctx* ctx = nullptr;
+  int64_t n = 0;      // taxa
+  int64_t m = 0;      // markers
+  int64_t ldn = 0;    // bytes per marker row of the marker-major copy (multiple of 128)
+  int8_t* mk = nullptr;   // marker-major  [m][ldn]   : K-major operand of the rotation (contract over taxa)
+  int64_t n_rows_t = 0;   // rows of the taxa-major copy (n rounded up to 256)
+  int64_t ldm = 0;        // bytes per taxon row of the taxa-major copy (multiple of 128)
+  int8_t* tx = nullptr;   // taxa-major    [n_rows_t][ldm] : K-major operand of the kinship (contract over markers); built lazily
+  int32_t* colsum = nullptr;    // [m] sum_i x_ik
+  int32_t* colsumsq = nullptr;  // [m] sum_i x_ik^2
+};

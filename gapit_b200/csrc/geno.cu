@@ -1,0 +1,244 @@
+// Genotype ingestion: host matrix (R column-major n x m, f64 / i32 / i8) ->
+// device int8 marker-major [m][ldn] with per-marker sum and sum of squares,
+// plus the taxa-major transposed copy the kinship cross-product contracts over.
+// All three kernels are HBM-bound byte shuffles (128-bit loads, coalesced rows).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gapit {
+
+// ---- f64 / i32 -> int8 with validation ------------------------------------
+// src: chunk of `mc` markers, element (i,k) at src[i + k*ld]; dst row k at dst + k*ldn.
+template <typename T>
+__global__ void convert_kernel(const T* __restrict__ src, int64_t ld, int64_t n, int64_t mc, int8_t* __restrict__ dst,
+                               int64_t ldn, int impute, int* __restrict__ bad) {
+  const int64_t k = blockIdx.y;
+  if (k >= mc) return;
+  const T* s = src + k * ld;
+  int8_t* d = dst + k * ldn;
+  for (int64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    double v = static_cast<double>(s[i]);
+    int8_t o;
+    if (v != v) {  // NA
+      if (impute < 0) {
+        atomicOr(bad, 2);
+        o = 0;
+      } else {
+        o = static_cast<int8_t>(impute);
+      }
+    } else if (v == 0.0) {
+      o = 0;
+    } else if (v == 1.0) {
+      o = 1;
+    } else if (v == 2.0) {
+      o = 2;
+    } else {
+      atomicOr(bad, 1);
+      o = 0;
+    }
+    d[i] = o;
+  }
+}
+
+// ---- per-marker statistics: one warp per marker, 16-byte loads -------------
+__global__ void colstats_kernel(const int8_t* __restrict__ mk, int64_t ldn, int64_t n, int64_t m,
+                                int32_t* __restrict__ colsum, int32_t* __restrict__ colsumsq, int* __restrict__ bad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t k = warp; k < m; k += nwarps) {
+    const uint4* row = reinterpret_cast<const uint4*>(mk + k * ldn);
+    int s1 = 0, s2 = 0, flag = 0;
+    for (int64_t c = lane; c * 16 < n; c += 32) {
+      uint4 v = __ldg(row + c);
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // bytes are 0,1,2 (padding bytes beyond n are zero): sum and sum of squares by dp4a
+        s1 = __dp4a(static_cast<int>(w[j]), 0x01010101, s1);
+        s2 = __dp4a(static_cast<int>(w[j]), static_cast<int>(w[j]), s2);
+        flag |= (w[j] & 0xFCFCFCFCu) | ((w[j] >> 1) & w[j] & 0x01010101u);  // any byte > 2
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      flag |= __shfl_xor_sync(0xffffffffu, flag, o);
+    }
+    if (lane == 0) {
+      colsum[k] = s1;
+      colsumsq[k] = s2;
+      if (flag) atomicOr(bad, 1);
+    }
+  }
+}
+
+// ---- marker-major -> taxa-major byte transpose -----------------------------
+// 128 markers x 128 taxa per block; each thread owns a 4x4 byte block that is
+// transposed in registers (prmt), staged through shared memory and written
+// back as coalesced 128-byte rows.
+__global__ void __launch_bounds__(1024) transpose_kernel(const int8_t* __restrict__ mk, int64_t ldn, int64_t n,
+                                                         int64_t m, int8_t* __restrict__ tx, int64_t ldm,
+                                                         int64_t n_rows_t) {
+  __shared__ uint32_t tile[128][33];
+  const int txi = threadIdx.x;  // 0..31: taxa chunk (4 taxa)
+  const int tyi = threadIdx.y;  // 0..31: marker chunk (4 markers)
+  const int64_t k0 = int64_t(blockIdx.x) * 128;  // marker tile
+  const int64_t i0 = int64_t(blockIdx.y) * 128;  // taxa tile
+  uint32_t w[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int64_t k = k0 + tyi * 4 + r;
+    const int64_t i = i0 + txi * 4;
+    w[r] = (k < m && i < ldn) ? __ldg(reinterpret_cast<const uint32_t*>(mk + k * ldn + i)) : 0u;
+  }
+  // 4x4 byte transpose: o[c] = { w[0].c, w[1].c, w[2].c, w[3].c }
+  const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140);  // w0.b0 w1.b0 w0.b1 w1.b1
+  const uint32_t t1 = __byte_perm(w[0], w[1], 0x7362);  // w0.b2 w1.b2 w0.b3 w1.b3
+  const uint32_t t2 = __byte_perm(w[2], w[3], 0x5140);
+  const uint32_t t3 = __byte_perm(w[2], w[3], 0x7362);
+  uint32_t o[4];
+  o[0] = __byte_perm(t0, t2, 0x5410);
+  o[1] = __byte_perm(t0, t2, 0x7632);
+  o[2] = __byte_perm(t1, t3, 0x5410);
+  o[3] = __byte_perm(t1, t3, 0x7632);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) tile[txi * 4 + c][tyi] = o[c];
+  __syncthreads();
+  // row `txi + 32*j` of the tile = one taxon, 32 words = 128 markers
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int rrow = tyi + 32 * j;
+    const int64_t i = i0 + rrow;
+    if (i < n_rows_t) {
+      uint32_t v = (i < n) ? tile[rrow][txi] : 0u;
+      *reinterpret_cast<uint32_t*>(tx + i * ldm + k0 + txi * 4) = v;
+    }
+  }
+}
+
+static int run_colstats(gapit_geno* g) {
+  gapit_ctx* ctx = g->ctx;
+  int* bad = nullptr;
+  GAPIT_CUDA(cudaMalloc(&bad, sizeof(int)));
+  GAPIT_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+  const int threads = 256;
+  const int blocks = std::max<int64_t>(1, std::min<int64_t>((g->m * 32 + threads - 1) / threads, int64_t(ctx->sm_count) * 16));
+  colstats_kernel<<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, g->colsum, g->colsumsq, bad);
+  GAPIT_CUDA(cudaGetLastError());
+  int hbad = 0;
+  GAPIT_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(bad);
+  if (hbad) return fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}");
+  return GAPIT_OK;
+}
+
+int geno_build_taxa_major(gapit_geno* g) {
+  if (g->tx) return GAPIT_OK;
+  gapit_ctx* ctx = g->ctx;
+  g->n_rows_t = round_up(g->n, 256);
+  g->ldm = round_up(g->m, 128);
+  GAPIT_CUDA(cudaMalloc(&g->tx, size_t(g->n_rows_t) * g->ldm));
+  dim3 block(32, 32);
+  dim3 grid(static_cast<unsigned>(g->ldm / 128), static_cast<unsigned>(g->n_rows_t / 128));
+  transpose_kernel<<<grid, block, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, g->tx, g->ldm, g->n_rows_t);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
+}  // namespace gapit
+
+using namespace gapit;
+
+extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
+                               gapit_impute impute, gapit_geno** out) {
+  if (!ctx || !snps || !out || n <= 0 || m <= 0 || ld < n) return fail(GAPIT_ERR_ARG, "gapit_geno_pack: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  gapit_geno* g = new gapit_geno();
+  g->ctx = ctx;
+  g->n = n;
+  g->m = m;
+  g->ldn = round_up(n, 128);
+  auto cleanup = [&](int rc) {
+    gapit_geno_free(g);
+    return rc;
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&g->mk, size_t(m) * g->ldn)) != cudaSuccess ||
+      (e = cudaMalloc(&g->colsum, size_t(m) * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&g->colsumsq, size_t(m) * 4)) != cudaSuccess)
+    return cleanup(fail(GAPIT_ERR_CUDA, std::string("gapit_geno_pack: cudaMalloc: ") + cudaGetErrorString(e)));
+
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  int rc = GAPIT_OK;
+  if (dtype == GAPIT_I8) {
+    if (g->ldn != n) cudaMemsetAsync(g->mk, 0, size_t(m) * g->ldn, ctx->stream);
+    e = cudaMemcpy2DAsync(g->mk, g->ldn, snps, ld, n, m, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return cleanup(fail(GAPIT_ERR_CUDA, std::string("H2D genotype copy: ") + cudaGetErrorString(e)));
+  } else if (dtype == GAPIT_F64 || dtype == GAPIT_I32) {
+    const size_t esz = (dtype == GAPIT_F64) ? 8 : 4;
+    cudaMemsetAsync(g->mk, 0, size_t(m) * g->ldn, ctx->stream);
+    // stream the wide host matrix through a bounded device staging buffer
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(m, 65535), (int64_t(256) << 20) / int64_t(n * esz)));
+    void* stage = nullptr;
+    int* bad = nullptr;
+    if ((e = cudaMalloc(&stage, size_t(chunk) * n * esz)) != cudaSuccess || (e = cudaMalloc(&bad, 4)) != cudaSuccess)
+      return cleanup(fail(GAPIT_ERR_CUDA, std::string("staging cudaMalloc: ") + cudaGetErrorString(e)));
+    cudaMemsetAsync(bad, 0, 4, ctx->stream);
+    for (int64_t k0 = 0; k0 < m && e == cudaSuccess; k0 += chunk) {
+      const int64_t mc = std::min(chunk, m - k0);
+      const char* src = static_cast<const char*>(snps) + size_t(k0) * ld * esz;
+      e = cudaMemcpy2DAsync(stage, size_t(n) * esz, src, size_t(ld) * esz, size_t(n) * esz, mc, cudaMemcpyHostToDevice,
+                            ctx->stream);
+      if (e != cudaSuccess) break;
+      dim3 grid(static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64)), static_cast<unsigned>(mc));
+      if (dtype == GAPIT_F64)
+        convert_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double*>(stage), n, n, mc,
+                                                              g->mk + k0 * g->ldn, g->ldn, int(impute), bad);
+      else
+        convert_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const int32_t*>(stage), n, n, mc,
+                                                               g->mk + k0 * g->ldn, g->ldn, int(impute), bad);
+      e = cudaGetLastError();
+    }
+    int hbad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(stage);
+    cudaFree(bad);
+    if (e != cudaSuccess) return cleanup(fail(GAPIT_ERR_CUDA, std::string("genotype conversion: ") + cudaGetErrorString(e)));
+    if (hbad & 2) return cleanup(fail(GAPIT_ERR_DATA, "genotype matrix holds NA and no impute rule was given"));
+    if (hbad & 1) return cleanup(fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}"));
+  } else {
+    return cleanup(fail(GAPIT_ERR_ARG, "gapit_geno_pack: unknown dtype"));
+  }
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  rc = run_colstats(g);
+  if (rc != GAPIT_OK) return cleanup(rc);
+  *out = g;
+  return GAPIT_OK;
+}
+
+extern "C" void gapit_geno_free(gapit_geno* g) {
+  if (!g) return;
+  if (g->ctx) cudaSetDevice(g->ctx->device);
+  cudaFree(g->mk);
+  cudaFree(g->tx);
+  cudaFree(g->colsum);
+  cudaFree(g->colsumsq);
+  delete g;
+}
+
+extern "C" int64_t gapit_geno_n(const gapit_geno* g) { return g ? g->n : 0; }
+extern "C" int64_t gapit_geno_m(const gapit_geno* g) { return g ? g->m : 0; }
+
+extern "C" int gapit_geno_colsums(const gapit_geno* g, int32_t* colsum_out, int32_t* colsumsq_out) {
+  if (!g) return fail(GAPIT_ERR_ARG, "gapit_geno_colsums: NULL handle");
+  GAPIT_CUDA(cudaSetDevice(g->ctx->device));
+  if (colsum_out) GAPIT_CUDA(cudaMemcpy(colsum_out, g->colsum, size_t(g->m) * 4, cudaMemcpyDeviceToHost));
+  if (colsumsq_out) GAPIT_CUDA(cudaMemcpy(colsumsq_out, g->colsumsq, size_t(g->m) * 4, cudaMemcpyDeviceToHost));
+  return GAPIT_OK;
+}

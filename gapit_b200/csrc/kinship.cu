@@ -1,0 +1,249 @@
+// VanRaden kinship (GAPIT.kinship.VanRaden.R:11-32), B200-native.
+//
+//   K1  gram_i8_umma      G += T T'   int8 x int8 -> int32 on tcgen05 (kind::i8), lower-triangular
+//                         256 x 256 tiles, split along the marker axis; partial tiles are added with
+//                         integer RED (exact, order-independent => bit-identical for any split / GPU count)
+//   K2a colsum_reduce     sum c, sum c^2, #columns with c == 2n          (int64, exact)
+//   K2b gram_mirror       fill the strictly-upper tiles from the lower ones
+//   K2c gram_rowsum       s_i = sum_j G_ij                                (int64, exact)
+//   K2d vanraden_epilogue K_ij = 2 (n^2 G'_ij - n (s'_i + s'_j) + sum c^2) / D   (one fp64 division per element)
+//
+// Algebra.  With c_k = sum_i x_ik, the reference's Z[k,i] = x_ik - 2 p_k = x_ik - c_k/n (:20-25) gives
+//   (Z'Z)_ij = G_ij - (s_i + s_j)/n + sum_k c_k^2 / n^2,  s_i = sum_k c_k x_ik = sum_j G_ij,
+//   adj = 2 sum p(1-p) = D / (2 n^2),  D = sum_k c_k (2n - c_k)   (:31)
+// over the columns the reference keeps (:11-13).  Dropped columns: c_k = 0 contributes nothing anywhere;
+// c_k = 2n (all dosages 2) contributes exactly 4 to every G_ij, 4n to every s_i, 4n^2 to sum c^2 and 0 to D,
+// so the epilogue subtracts n2 = #(c_k == 2n) of those instead of re-packing the matrix.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "umma_i8.cuh"
+
+namespace gapit {
+
+int geno_build_taxa_major(gapit_geno* g);
+
+// ------------------------------------------------------------------ K1 pieces
+struct GramSched {
+  struct Params {
+    int tiles_side;  // number of 256-row blocks
+    int ntri;        // tiles_side (tiles_side + 1) / 2
+    int ksplit;      // splits of the marker axis
+    int kblocks;     // marker axis in units of kBlockK
+  };
+  static constexpr uint64_t kHintA = ptx::kEvictNormal;
+  static constexpr uint64_t kHintB = ptx::kEvictNormal;
+  Params p;
+  int next_job, stride;
+  __device__ GramSched(const Params& pp, int block, int nblocks) : p(pp), next_job(block), stride(nblocks) {}
+  __device__ bool next(Job& j) {
+    if (next_job >= p.ntri * p.ksplit) return false;
+    // split-major order: CTAs running together share one marker window (L2 reuse of the row panels)
+    const int ks = next_job / p.ntri;
+    const int t = next_job - ks * p.ntri;
+    int I = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f);
+    while ((I + 1) * (I + 2) / 2 <= t) ++I;
+    while (I * (I + 1) / 2 > t) --I;
+    const int J = t - I * (I + 1) / 2;
+    j.a_row0 = I * 256;
+    j.b_row0 = J * 256;
+    j.kb_begin = static_cast<int>((static_cast<long long>(ks) * p.kblocks) / p.ksplit);
+    j.kb_end = static_cast<int>((static_cast<long long>(ks + 1) * p.kblocks) / p.ksplit);
+    j.tag0 = I;
+    j.tag1 = J;
+    j.group_first = j.group_last = true;
+    next_job += stride;
+    return true;
+  }
+};
+
+struct GramEpi {
+  struct Params {
+    int32_t* G;   // [ldg][ldg] row-major, zero-initialised
+    int64_t ldg;
+  };
+  Params p;
+  __device__ explicit GramEpi(const Params& pp) : p(pp) {}
+  __device__ void run(const Job& job, uint32_t taddr, int sub, int row) {
+    int32_t* dst = p.G + (int64_t(job.a_row0) + sub * 128 + row) * p.ldg + job.b_row0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 16) {
+      uint32_t r[16];
+      ptx::tmem_ld_x16(taddr + c0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int v = static_cast<int>(r[i]);
+        if (v != 0) atomicAdd(dst + c0 + i, v);
+      }
+    }
+  }
+};
+
+using GramCfg = UmmaCfg<2, 256, 3>;
+
+// ------------------------------------------------------------------ K2 pieces
+__global__ void colsum_reduce_kernel(const int32_t* __restrict__ colsum, int64_t m, int64_t two_n,
+                                     unsigned long long* __restrict__ sums /* [3] */) {
+  long long s1 = 0, s2 = 0, n2 = 0;
+  for (int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; k < m; k += int64_t(gridDim.x) * blockDim.x) {
+    const long long c = colsum[k];
+    s1 += c;
+    s2 += c * c;
+    n2 += (c == two_n);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&sums[0], static_cast<unsigned long long>(s1));
+    atomicAdd(&sums[1], static_cast<unsigned long long>(s2));
+    atomicAdd(&sums[2], static_cast<unsigned long long>(n2));
+  }
+}
+
+// upper tile (I < J in 256-blocks) <- transpose of lower tile; 32x32 sub-tiles through shared memory
+__global__ void gram_mirror_kernel(int32_t* __restrict__ G, int64_t ldg) {
+  __shared__ int32_t t[32][33];
+  const int64_t bi = blockIdx.y, bj = blockIdx.x;  // 32-blocks: source (bi rows, bj cols), bi >= bj region
+  if ((bj >> 3) >= (bi >> 3)) return;              // only strictly-lower 256-tiles are sources
+  const int x = threadIdx.x, y0 = threadIdx.y;
+  for (int y = y0; y < 32; y += 8) t[y][x] = G[(bi * 32 + y) * ldg + bj * 32 + x];
+  __syncthreads();
+  for (int y = y0; y < 32; y += 8) G[(bj * 32 + y) * ldg + bi * 32 + x] = t[x][y];
+}
+
+__global__ void gram_rowsum_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n, long long* __restrict__ s) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const int32_t* g = G + row * ldg;
+  long long acc = 0;
+  for (int64_t j = lane; j < n; j += 32) acc += g[j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) s[row] = acc;
+}
+
+// K (column-major n x n) from the mirrored G; exact int64 numerator, one fp64 division.
+__global__ void vanraden_epilogue_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n,
+                                         const long long* __restrict__ s, const unsigned long long* __restrict__ sums,
+                                         double* __restrict__ K) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long sum_c = static_cast<long long>(sums[0]);
+  const long long sum_c2 = static_cast<long long>(sums[1]);
+  const long long n2 = static_cast<long long>(sums[2]);
+  const long long nn = n;
+  // remove the all-2 columns (GAPIT.kinship.VanRaden.R:11-13)
+  const long long c2 = sum_c2 - n2 * 4 * nn * nn;
+  const long long c1 = sum_c - n2 * 2 * nn;
+  const long long D = 2 * nn * c1 - c2;
+  const long long si = s[i] - 4 * n2 * nn;
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+    const long long g = static_cast<long long>(G[j * ldg + i]) - 4 * n2;  // symmetric: read along the row
+    const long long sj = s[j] - 4 * n2 * nn;
+    const long long num = nn * nn * g - nn * (si + sj) + c2;
+    K[i + j * n] = 2.0 * static_cast<double>(num) / static_cast<double>(D);
+  }
+}
+
+static int choose_ksplit(int ntri, int kblocks, int sms) {
+  // enough jobs for >= ~6 waves, each job keeping >= 32 k-blocks of work
+  int ks = 1;
+  while (ntri * ks < 6 * sms && kblocks / (ks + 1) >= 32) ++ks;
+  return ks;
+}
+
+static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ldg) {
+  GAPIT_CHECK(geno_build_taxa_major(g));
+  CUtensorMap map;
+  GAPIT_CHECK(make_tensor_map_u8(&map, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
+                                 static_cast<uint64_t>(g->ldm), 256));
+  GramSched::Params sp;
+  sp.tiles_side = static_cast<int>(ldg / 256);
+  sp.ntri = sp.tiles_side * (sp.tiles_side + 1) / 2;
+  sp.kblocks = static_cast<int>(g->ldm / kBlockK);
+  sp.ksplit = choose_ksplit(sp.ntri, sp.kblocks, ctx->sm_count);
+  GramEpi::Params ep{G_dev, ldg};
+  auto kern = umma_i8_kernel<2, 256, 3, GramSched, GramEpi, 0, 0>;
+  GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
+  const int grid = std::min(ctx->sm_count, sp.ntri * sp.ksplit);
+  kern<<<grid, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream>>>(map, map, sp, ep);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
+}  // namespace gapit
+
+using namespace gapit;
+
+extern "C" int64_t gapit_gram_ld(int64_t n) { return round_up(n, 256); }
+
+extern "C" int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t* sums_dev) {
+  if (!ctx || !g || !G_dev || !sums_dev) return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram: NULL argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int64_t ldg = gapit_gram_ld(g->n);
+  GAPIT_CUDA(cudaMemsetAsync(G_dev, 0, size_t(ldg) * ldg * 4, ctx->stream));
+  GAPIT_CUDA(cudaMemsetAsync(sums_dev, 0, 3 * 8, ctx->stream));
+  colsum_reduce_kernel<<<std::min<int64_t>(1024, (g->m + 255) / 256), 256, 0, ctx->stream>>>(
+      g->colsum, g->m, 2 * g->n, reinterpret_cast<unsigned long long*>(sums_dev));
+  GAPIT_CUDA(cudaGetLastError());
+  GAPIT_CHECK(launch_gram(ctx, g, G_dev, ldg));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GAPIT_OK;
+}
+
+extern "C" int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, const int64_t* sums_dev,
+                                     double* K_dev_out, double* K_host_out, int32_t* G_host_out) {
+  if (!ctx || !G_dev || !sums_dev || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_vanraden_finish: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int64_t ldg = gapit_gram_ld(n);
+  long long* s = nullptr;
+  double* K_dev = K_dev_out;
+  GAPIT_CUDA(cudaMalloc(&s, size_t(n) * 8));
+  if (!K_dev) GAPIT_CUDA(cudaMalloc(&K_dev, size_t(n) * n * 8));
+  {
+    dim3 grid(static_cast<unsigned>(ldg / 32), static_cast<unsigned>(ldg / 32));
+    gram_mirror_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg);
+    gram_rowsum_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(G_dev, ldg, n, s);
+    dim3 g2(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(std::min<int64_t>(n, 65535)));
+    vanraden_epilogue_kernel<<<g2, 256, 0, ctx->stream>>>(G_dev, ldg, n, s,
+                                                           reinterpret_cast<const unsigned long long*>(sums_dev), K_dev);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && K_host_out)
+    e = cudaMemcpyAsync(K_host_out, K_dev, size_t(n) * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && G_host_out)
+    e = cudaMemcpy2DAsync(G_host_out, size_t(n) * 4, G_dev, size_t(ldg) * 4, size_t(n) * 4, n, cudaMemcpyDeviceToHost,
+                          ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(s);
+  if (!K_dev_out) cudaFree(K_dev);
+  if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("gapit_vanraden_finish: ") + cudaGetErrorString(e));
+  return GAPIT_OK;
+}
+
+extern "C" int gapit_vanraden(gapit_ctx* ctx, gapit_geno* g, double* K_out, int32_t* G_out) {
+  if (!ctx || !g || !K_out) return fail(GAPIT_ERR_ARG, "gapit_vanraden: NULL argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int64_t ldg = gapit_gram_ld(g->n);
+  int32_t* G_dev = nullptr;
+  int64_t* sums = nullptr;
+  GAPIT_CUDA(cudaMalloc(&G_dev, size_t(ldg) * ldg * 4));
+  cudaError_t e = cudaMalloc(&sums, 3 * 8);
+  if (e != cudaSuccess) {
+    cudaFree(G_dev);
+    return fail(GAPIT_ERR_CUDA, "gapit_vanraden: cudaMalloc");
+  }
+  int rc = gapit_vanraden_gram(ctx, g, G_dev, sums);
+  if (rc == GAPIT_OK) rc = gapit_vanraden_finish(ctx, g->n, G_dev, sums, nullptr, K_out, G_out);
+  cudaFree(G_dev);
+  cudaFree(sums);
+  return rc;
+}

@@ -1,0 +1,780 @@
+// EMMAx / P3D marker scan (GAPIT.EMMAxP3D.R:397-979), B200-native.
+//
+// The reference rotates one marker at a time by U = V diag((lambda+delta)^-1/2) (two n x n GEMVs per
+// marker, :634 and :957).  Here the rotation is batched into a GEMM  W = V' X  and never written to HBM:
+//
+//   K3a slice_v          V (fp64) -> S int8 digit planes per eigenvector (balanced base-256 digits of
+//                        V_jk / 2^e_k; "Ozaki split").  The genotype operand is exactly int8, so
+//                        D_s[k,i] = sum_j digit_s(V_jk) x_ji are exact int32 and
+//                        W_ki = c_k sum_s 256^s D_s[k,i] reproduces the fp64 product to ~2^-(8S-2)
+//                        relative to max_j |V_jk|, deterministically (integer sums are order-free).
+//   K3  rotate_reduce    tcgen05 kind::i8, M = markers (TMEM lanes), N = (k, slice) columns.  Each epilogue
+//                        thread owns one marker: it rebuilds W_ki from the S int32 slices and accumulates
+//                        xx = sum_k w_k W_ki^2,  xa_j = sum_k w_k A_kj W_ki,  xy = sum_k w_k b_k W_ki
+//                        (w = 1/(lambda+delta), A = V'X0, b = V'y: the dot products of :653-655,:682)
+//                        in registers while sweeping k, in a fixed order => bit-identical rows for
+//                        identical genotype columns wherever they sit.
+//   K3g glm_reduce       K = NULL branch (:759-763): same three reductions straight from the int8
+//                        genotypes (U = I); HBM-bound streaming kernel.
+//   K4  finalize         per marker: Schur complement of [X0t xst]'[X0t xst] (:736-748), beta (:772),
+//                        t (:936-937), p = 2 pt(|t|, df) (:939), logLM and R^2 (:955-967).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+#include "umma_i8.cuh"
+
+namespace gapit {
+
+// geometry of the sliced eigenvector operand for S slices
+struct SliceGeom {
+  int S, BN, KPB;
+};
+static SliceGeom slice_geom(int S) {
+  switch (S) {
+    case 4: return {4, 256, 64};
+    case 5: return {5, 240, 48};
+    case 6: return {6, 240, 40};
+    case 7: return {7, 224, 32};
+    default: return {8, 256, 32};
+  }
+}
+
+}  // namespace gapit
+
+struct gapit_eigsys {
+  gapit_ctx* ctx = nullptr;
+  int64_t n = 0;
+  int S = 0, BN = 0, KPB = 0;
+  int64_t ldn = 0;    // bytes per row of Vs
+  int64_t nkq = 0;    // number of BN-row tiles of Vs
+  int8_t* Vs = nullptr;      // [(nkq*BN)][ldn] row (k*S + s) = digit plane s of eigenvector k
+  double* V = nullptr;       // n x n column-major
+  double* scale = nullptr;   // [nkq*KPB] c_k = 2^(e_k - (8S-2)), 0 beyond n
+  std::vector<double> values;  // host, descending
+  std::vector<double> h_scale;
+};
+
+namespace gapit {
+
+// ------------------------------------------------------------------ K3a
+// one block per eigenvector k: exponent from max |V_jk|, then S balanced base-256 digits per element
+__global__ void slice_v_kernel(const double* __restrict__ V, int64_t n, int S, int8_t* __restrict__ Vs, int64_t ldn,
+                               double* __restrict__ scale) {
+  const int64_t k = blockIdx.x;
+  const double* v = V + k * n;
+  __shared__ double red[32];
+  double mx = 0.0;
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) mx = fmax(mx, fabs(v[j]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0) red[0] = mx;
+  }
+  __syncthreads();
+  mx = red[0];
+  int e = 0;
+  if (mx > 0.0) {
+    frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)  =>  |v| * 2^-e < 1
+  }
+  const int B = 8 * S - 2;
+  const double up = ldexp(1.0, B - e);
+  if (threadIdx.x == 0) scale[k] = ldexp(1.0, e - B);
+  for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
+    long long q = __double2ll_rn(v[j] * up);  // |q| <= 2^(8S-2)
+    for (int s = 0; s < S; ++s) {
+      const long long d = ((q + 128) & 255) - 128;  // balanced digit in [-128, 127]
+      Vs[(k * S + s) * ldn + j] = static_cast<int8_t>(d);
+      q = (q - d) >> 8;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ projections V'R
+// out[c*n + k] = sum_j V[j + k n] R[j + c n]; one warp per k, fixed summation order
+template <int NC>
+__global__ void vt_project_kernel(const double* __restrict__ V, int64_t n, const double* __restrict__ R, int nc,
+                                  int c0, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (k >= n) return;
+  const double* v = V + k * n;
+  double acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
+  for (int64_t j = lane; j < n; j += 32) {
+    const double vj = v[j];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+      if (c0 + c < nc) acc[c] = fma(vj, __ldg(R + (c0 + c) * n + j), acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    double a = acc[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0 && c0 + c < nc) out[(c0 + c) * n + k] = a;
+  }
+}
+
+// ------------------------------------------------------------------ K3 pieces
+struct ScanSched {
+  struct Params {
+    int mtiles;   // 256-marker tiles
+    int gsplit;   // splits of the eigen index (partial sums per split)
+    int nkq;      // BN-row tiles of the sliced eigenvectors
+    int kblocks;  // taxa axis in units of kBlockK
+    int bn;
+  };
+  static constexpr uint64_t kHintA = ptx::kEvictLast;    // marker tile: re-read for every eigen tile
+  static constexpr uint64_t kHintB = ptx::kEvictNormal;  // eigen tiles: streamed, shared by concurrent CTAs
+  Params p;
+  int gid, stride, kq, kq_begin, kq_end, mt, ks;
+  __device__ ScanSched(const Params& pp, int block, int nblocks)
+      : p(pp), gid(block - nblocks), stride(nblocks), kq(0), kq_begin(0), kq_end(0), mt(0), ks(0) {}
+  __device__ bool next(Job& j) {
+    if (kq >= kq_end) {
+      gid += stride;
+      if (gid >= p.mtiles * p.gsplit) return false;
+      mt = gid / p.gsplit;
+      ks = gid - mt * p.gsplit;
+      kq_begin = (ks * p.nkq) / p.gsplit;
+      kq_end = ((ks + 1) * p.nkq) / p.gsplit;
+      kq = kq_begin;
+    }
+    j.a_row0 = mt * 256;
+    j.b_row0 = kq * p.bn;
+    j.kb_begin = 0;
+    j.kb_end = p.kblocks;
+    j.tag0 = kq;
+    j.tag1 = ks;
+    j.group_first = (kq == kq_begin);
+    j.group_last = (kq == kq_end - 1);
+    ++kq;
+    return true;
+  }
+};
+
+template <int S, int BN, int Q>
+struct ScanEpi {
+  static constexpr int KPB = BN / S;
+  static constexpr int GC = (S == 4 || S == 8) ? 8 : (S == 5 ? 40 : (S == 6 ? 24 : 56));  // lcm(S, 8)
+  static constexpr int KG = GC / S;
+  static_assert(BN % GC == 0, "accumulator columns must split into whole digit groups");
+  struct Params {
+    const double* gconst;  // [(nkq*KPB)][Q+2]: w c^2 | w c A_j ... | w c b
+    double* part;          // [gsplit][Q+2][m_ld]
+    int64_t m_ld;
+    int64_t m;
+  };
+  Params p;
+  double acc[Q + 2];
+  __device__ explicit ScanEpi(const Params& pp) : p(pp) {
+#pragma unroll
+    for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
+  }
+  __device__ void run(const Job& job, uint32_t taddr, int sub, int row) {
+    if (job.group_first) {
+#pragma unroll
+      for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
+    }
+    const double* gc = p.gconst + int64_t(job.tag0) * KPB * (Q + 2);
+#pragma unroll 1
+    for (int g = 0; g < BN / GC; ++g) {
+      uint32_t r[GC];
+#pragma unroll
+      for (int j = 0; j < GC / 8; ++j) ptx::tmem_ld_x8(taddr + g * GC + j * 8, *reinterpret_cast<uint32_t(*)[8]>(&r[j * 8]));
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk) {
+        double u = static_cast<double>(static_cast<int>(r[kk * S + S - 1]));
+#pragma unroll
+        for (int s = S - 2; s >= 0; --s) u = fma(u, 256.0, static_cast<double>(static_cast<int>(r[kk * S + s])));
+        const double* c = gc + (g * KG + kk) * (Q + 2);
+        acc[0] = fma(__ldg(c) * u, u, acc[0]);
+#pragma unroll
+        for (int i = 1; i < Q + 2; ++i) acc[i] = fma(__ldg(c + i), u, acc[i]);
+      }
+    }
+    if (job.group_last) {
+      const int64_t mrk = int64_t(job.a_row0) + sub * 128 + row;
+      if (mrk < p.m_ld) {
+        double* dst = p.part + int64_t(job.tag1) * (Q + 2) * p.m_ld + mrk;
+#pragma unroll
+        for (int i = 0; i < Q + 2; ++i) dst[i * p.m_ld] = acc[i];
+      }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ K3g
+// GLM: xx = sum x^2, xa_j = sum X0_ij x_i, xy = sum y_i x_i ; one warp per marker, fixed order
+template <int Q>
+__global__ void glm_reduce_kernel(const int8_t* __restrict__ mk, int64_t ldn, int64_t n, int64_t m,
+                                  const double* __restrict__ R /* [Q+1][n]: X0 columns then y */,
+                                  double* __restrict__ part, int64_t m_ld) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t k = warp; k < m; k += nwarps) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(mk + k * ldn);
+    double acc[Q + 2];
+#pragma unroll
+    for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
+    for (int64_t c = lane; c * 4 < n; c += 32) {
+      const uint32_t w = __ldg(row + c);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int64_t i = c * 4 + b;
+        const double x = static_cast<double>((w >> (8 * b)) & 0xff);
+        if (i < n && x != 0.0) {
+          acc[0] = fma(x, x, acc[0]);
+#pragma unroll
+          for (int j = 0; j < Q + 1; ++j) acc[1 + j] = fma(x, __ldg(R + j * n + i), acc[1 + j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < Q + 2; ++i) {
+      double a = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) part[i * m_ld + k] = a;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ K4
+struct FinalizeConsts {
+  double iXX[GAPIT_MAX_Q0 * GAPIT_MAX_Q0];  // (X0t'X0t)^-1, row-major q0 x q0
+  double beta0[GAPIT_MAX_Q0];
+  double var_scale;   // vg (MLM) or ves (GLM)
+  double rss0;        // reduced-model weighted RSS
+  double sumlog;      // sum log(lambda + delta)   (0 for GLM)
+  double logL0;
+  double n;
+  double df;
+  double lbeta;       // log Beta(df/2, 1/2)
+  int q0;
+  int qpad;    // covariate width the reduction kernels were instantiated for (>= q0)
+  int gsplit;  // partial sums per marker (splits of the eigen index)
+};
+
+// continued fraction of the incomplete beta function (modified Lentz)
+__device__ double betacf(double a, double b, double x) {
+  const double FPMIN = 1e-300, EPS = 2.5e-16;
+  const double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < FPMIN) d = FPMIN;
+  d = 1.0 / d;
+  double h = d;
+  for (int mm = 1; mm <= 2000; ++mm) {
+    const double m2 = 2.0 * mm;
+    double aa = mm * (b - mm) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c;
+    if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d;
+    h *= d * c;
+    aa = -(a + mm) * (qab + mm) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c;
+    if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < EPS) break;
+  }
+  return h;
+}
+
+// 2 * pt(|t|, df, lower.tail = FALSE) = I_{df/(df+t^2)}(df/2, 1/2)
+__device__ double two_sided_t_pvalue(double t, double df, double lbeta) {
+  if (t != t) return t;
+  const double t2 = t * t;
+  if (isinf(t2)) return 0.0;
+  const double a = 0.5 * df, b = 0.5;
+  const double x = df / (df + t2);
+  const double y = t2 / (df + t2);
+  const double ln_x = -log1p(t2 / df);
+  const double ln_y = log(y);
+  if (x < (a + 1.0) / (a + b + 2.0)) {
+    return exp(a * ln_x + b * ln_y - lbeta - log(a)) * betacf(a, b, x);
+  }
+  if (y <= 0.0) return 1.0;
+  return 1.0 - exp(b * ln_y + a * ln_x - lbeta - log(b)) * betacf(b, a, y);
+}
+
+__global__ void finalize_kernel(const double* __restrict__ part, int64_t m_ld, int64_t m, const int32_t* __restrict__ colsum,
+                                const int32_t* __restrict__ colsumsq, FinalizeConsts fc, double* __restrict__ effect,
+                                double* __restrict__ tvalue, double* __restrict__ se, double* __restrict__ pvalue,
+                                double* __restrict__ rsquare, double* __restrict__ loglm, double* __restrict__ maf) {
+  const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (k >= m) return;
+  const int q0 = fc.q0;
+  const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+  const long long ss = colsum[k], sq = colsumsq[k];
+  const double half_freq = 0.5 * static_cast<double>(ss) / fc.n;
+  if (maf) maf[k] = fmin(half_freq, 1.0 - half_freq);
+  // constant marker (min == max  <=>  n sum x^2 == (sum x)^2): GAPIT.EMMAxP3D.R:499-511
+  if (static_cast<long long>(fc.n) * sq == ss * ss) {
+    effect[k] = NaN; tvalue[k] = NaN; se[k] = NaN; pvalue[k] = 1.0; rsquare[k] = NaN; loglm[k] = NaN;
+    return;
+  }
+  double xx = 0.0, xy = 0.0, xa[GAPIT_MAX_Q0];
+  for (int j = 0; j < q0; ++j) xa[j] = 0.0;
+  for (int g = 0; g < fc.gsplit; ++g) {  // fixed order: deterministic for any grid
+    const double* pp = part + int64_t(g) * (fc.qpad + 2) * m_ld + k;
+    xx += pp[0];
+    for (int j = 0; j < q0; ++j) xa[j] += pp[(1 + j) * m_ld];
+    xy += pp[int64_t(fc.qpad + 1) * m_ld];
+  }
+  // Schur complement of the bordered normal equations (:736-748)
+  double quad = 0.0, num = xy;
+  for (int i = 0; i < q0; ++i) {
+    double ti = 0.0;
+    for (int j = 0; j < q0; ++j) ti = fma(fc.iXX[i * q0 + j], xa[j], ti);
+    quad = fma(xa[i], ti, quad);
+    num = fma(-xa[i], fc.beta0[i], num);
+  }
+  const double B22 = xx - quad;
+  const double beta = num / B22;                      // :772 last element
+  const double sdev = sqrt(fc.var_scale / B22);       // sqrt(iXX[q1,q1] * vg|ve)
+  const double t = beta / sdev;                       // :936-937
+  double p = two_sided_t_pvalue(t, fc.df, fc.lbeta);  // :939
+  if (p != p) p = 1.0;                                // :940
+  const double rss = fc.rss0 - num * beta;            // ||U'(y - X beta)||^2 (:957) via the Schur update
+  const double ll = 0.5 * (-fc.n * log((2.0 * 3.14159265358979323846 / fc.n) * rss) - fc.sumlog - fc.n);  // :958
+  effect[k] = beta;
+  tvalue[k] = t;
+  se[k] = sdev;
+  pvalue[k] = p;
+  loglm[k] = ll;
+  rsquare[k] = 1.0 - exp(-(2.0 / fc.n) * (ll - fc.logL0));  // :967
+}
+
+}  // namespace gapit
+
+// =============================================================================== host side
+namespace gapit {
+
+// inverse of a small symmetric matrix; falls back to the Moore-Penrose inverse (MASS::ginv's role at
+// GAPIT.EMMAxP3D.R:708-712) when it is numerically singular.  A: q x q row-major.
+static void sym_inverse(int q, const double* A, double* inv, int* singular) {
+  std::vector<double> L(q * q, 0.0);
+  bool ok = true;
+  double dmax = 0.0, dmin = INFINITY;
+  for (int i = 0; i < q && ok; ++i) {
+    for (int j = 0; j <= i; ++j) {
+      double s = A[i * q + j];
+      for (int k = 0; k < j; ++k) s -= L[i * q + k] * L[j * q + k];
+      if (i == j) {
+        if (!(s > 0.0)) { ok = false; break; }
+        L[i * q + i] = std::sqrt(s);
+        dmax = std::max(dmax, L[i * q + i]);
+        dmin = std::min(dmin, L[i * q + i]);
+      } else {
+        L[i * q + j] = s / L[j * q + j];
+      }
+    }
+  }
+  if (ok && dmin / dmax < 1e-8) ok = false;  // cond(A) ~ (dmax/dmin)^2 beyond what solve() accepts
+  if (ok) {
+    // inv = L^-T L^-1
+    std::vector<double> Li(q * q, 0.0);
+    for (int i = 0; i < q; ++i) {
+      Li[i * q + i] = 1.0 / L[i * q + i];
+      for (int j = 0; j < i; ++j) {
+        double s = 0.0;
+        for (int k = j; k < i; ++k) s -= L[i * q + k] * Li[k * q + j];
+        Li[i * q + j] = s / L[i * q + i];
+      }
+    }
+    for (int i = 0; i < q; ++i)
+      for (int j = 0; j < q; ++j) {
+        double s = 0.0;
+        for (int k = std::max(i, j); k < q; ++k) s += Li[k * q + i] * Li[k * q + j];
+        inv[i * q + j] = s;
+      }
+    *singular = 0;
+    return;
+  }
+  // Jacobi eigen-decomposition, then pseudo-inverse with MASS::ginv's tolerance sqrt(eps) * max
+  *singular = 1;
+  std::vector<double> M(A, A + q * q), E(q * q, 0.0);
+  for (int i = 0; i < q; ++i) E[i * q + i] = 1.0;
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < q; ++i)
+      for (int j = i + 1; j < q; ++j) off += M[i * q + j] * M[i * q + j];
+    if (off < 1e-300) break;
+    for (int p = 0; p < q; ++p)
+      for (int r = p + 1; r < q; ++r) {
+        if (std::fabs(M[p * q + r]) < 1e-300) continue;
+        const double theta = (M[r * q + r] - M[p * q + p]) / (2.0 * M[p * q + r]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < q; ++k) {
+          const double a = M[k * q + p], b = M[k * q + r];
+          M[k * q + p] = c * a - s * b;
+          M[k * q + r] = s * a + c * b;
+        }
+        for (int k = 0; k < q; ++k) {
+          const double a = M[p * q + k], b = M[r * q + k];
+          M[p * q + k] = c * a - s * b;
+          M[r * q + k] = s * a + c * b;
+        }
+        for (int k = 0; k < q; ++k) {
+          const double a = E[k * q + p], b = E[k * q + r];
+          E[k * q + p] = c * a - s * b;
+          E[k * q + r] = s * a + c * b;
+        }
+      }
+  }
+  double emax = 0.0;
+  for (int i = 0; i < q; ++i) emax = std::max(emax, std::fabs(M[i * q + i]));
+  const double tol = std::sqrt(2.220446049250313e-16) * emax;
+  for (int i = 0; i < q; ++i)
+    for (int j = 0; j < q; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < q; ++k)
+        if (M[k * q + k] > tol) s += E[i * q + k] * E[j * q + k] / M[k * q + k];
+      inv[i * q + j] = s;
+    }
+}
+
+static int pad_q(int q0) {
+  if (q0 <= 1) return 1;
+  if (q0 <= 2) return 2;
+  if (q0 <= 4) return 4;
+  if (q0 <= 8) return 8;
+  return 16;
+}
+
+template <int S, int BN, int Q>
+static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* gconst_dev, double* part_dev,
+                          int64_t m_ld, int gsplit) {
+  using Cfg = UmmaCfg<2, BN, 3>;
+  using Epi = ScanEpi<S, BN, Q>;
+  CUtensorMap map_a, map_b;
+  GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
+                                 static_cast<uint64_t>(g->ldn), 256));
+  GAPIT_CHECK(make_tensor_map_u8(&map_b, e->Vs, static_cast<uint64_t>(e->ldn), static_cast<uint64_t>(e->nkq * BN),
+                                 static_cast<uint64_t>(e->ldn), BN));
+  ScanSched::Params sp;
+  sp.mtiles = static_cast<int>(m_ld / 256);
+  sp.gsplit = gsplit;
+  sp.nkq = static_cast<int>(e->nkq);
+  sp.kblocks = static_cast<int>(g->ldn / kBlockK);
+  sp.bn = BN;
+  typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m};
+  auto kern = umma_i8_kernel<2, BN, 3, ScanSched, Epi, 1, 1>;
+  GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const int grid = std::min(ctx->sm_count, sp.mtiles * sp.gsplit);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(map_a, map_b, sp, ep);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
+template <int S, int BN>
+static int launch_scan_S(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int Q, const double* gconst_dev,
+                         double* part_dev, int64_t m_ld, int gsplit) {
+  switch (Q) {
+    case 1: return launch_scan_SQ<S, BN, 1>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    case 2: return launch_scan_SQ<S, BN, 2>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    case 4: return launch_scan_SQ<S, BN, 4>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    case 8: return launch_scan_SQ<S, BN, 8>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    default: return launch_scan_SQ<S, BN, 16>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+  }
+}
+
+static int launch_scan(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int Q, const double* gconst_dev, double* part_dev,
+                       int64_t m_ld, int gsplit) {
+  switch (e->S) {
+    case 4: return launch_scan_S<4, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    case 5: return launch_scan_S<5, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    case 6: return launch_scan_S<6, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    case 7: return launch_scan_S<7, 224>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    default: return launch_scan_S<8, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+  }
+}
+
+static int launch_glm(gapit_ctx* ctx, gapit_geno* g, int Q, const double* R_dev, double* part_dev, int64_t m_ld) {
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->m * 32 + threads - 1) / threads, int64_t(ctx->sm_count) * 8)));
+  switch (Q) {
+    case 1: glm_reduce_kernel<1><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
+    case 2: glm_reduce_kernel<2><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
+    case 4: glm_reduce_kernel<4><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
+    case 8: glm_reduce_kernel<8><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
+    default: glm_reduce_kernel<16><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
+  }
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
+// eigen-index splits: keep the marker tiles of the CTAs that run together (148/g tiles of 256 x ldn bytes)
+// inside ~48 MB of L2.  Depends on n only, so results do not change with the marker shard or SM count.
+static int choose_gsplit(int64_t ldn, int64_t nkq) {
+  const double bytes = 148.0 * 256.0 * static_cast<double>(ldn);
+  int g = static_cast<int>(std::ceil(bytes / 48.0e6));
+  g = std::max(1, g);
+  return static_cast<int>(std::min<int64_t>(g, nkq));
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <class T> T* as() { return static_cast<T*>(p); }
+};
+
+static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
+                     const double* delta, const double* vg, int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
+  if (!ctx || !g || !X0 || !Y || !out || T < 1) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL argument");
+  if (q0 < 1 || q0 > GAPIT_MAX_Q0) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: q0 must be 1.." + std::to_string(GAPIT_MAX_Q0));
+  if (!glm && (!e || !delta || !vg)) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: MLM needs an eigen-system, delta and vg");
+  const int64_t n = g->n, m = g->m;
+  if (!glm && e->n != n) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: eigen-system and genotypes disagree on n");
+  if (n - q0 - 1 < 1) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: no residual degrees of freedom");
+  if (!out->effect || !out->tvalue || !out->se || !out->pvalue || !out->rsquare || !out->loglm)
+    return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: output arrays effect/tvalue/se/pvalue/rsquare/loglm are required");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int Q = pad_q(q0);
+  const int64_t m_ld = round_up(m, 256);
+  const int gsplit = glm ? 1 : choose_gsplit(g->ldn, e->nkq);
+  const int nc = q0 + T;
+
+  DevBuf dR, dProj, dGc, dPart, dOut, dRg;
+  GAPIT_CUDA(dR.alloc(size_t(n) * nc * 8));
+  GAPIT_CUDA(dPart.alloc(size_t(gsplit) * (Q + 2) * m_ld * 8));
+  GAPIT_CUDA(dOut.alloc(size_t(7) * m * 8));
+  GAPIT_CUDA(cudaMemcpyAsync(dR.p, X0, size_t(n) * q0 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  GAPIT_CUDA(cudaMemcpyAsync(dR.as<double>() + size_t(n) * q0, Y, size_t(n) * T * 8, cudaMemcpyHostToDevice, ctx->stream));
+
+  std::vector<double> proj;  // [(q0+T)][n]: rotated covariates then rotated phenotypes (or the raw ones for GLM)
+  proj.resize(size_t(nc) * n);
+  if (!glm) {
+    GAPIT_CUDA(dProj.alloc(size_t(n) * nc * 8));
+    const unsigned blocks = static_cast<unsigned>((n * 32 + 255) / 256);
+    for (int c0 = 0; c0 < nc; c0 += 8) {
+      vt_project_kernel<8><<<blocks, 256, 0, ctx->stream>>>(e->V, n, dR.as<double>(), nc, c0, dProj.as<double>());
+    }
+    GAPIT_CUDA(cudaGetLastError());
+    GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj.p, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int64_t nk = e->nkq * e->KPB;
+    GAPIT_CUDA(dGc.alloc(size_t(nk) * (Q + 2) * 8));
+  } else {
+    std::copy(X0, X0 + size_t(n) * q0, proj.begin());
+    std::copy(Y, Y + size_t(n) * T, proj.begin() + size_t(n) * q0);
+    GAPIT_CUDA(dRg.alloc(size_t(Q + 1) * n * 8));
+  }
+
+  float kernel_ms = 0.f, post_ms = 0.f;
+  std::vector<double> w(n), gconst;
+  for (int t = 0; t < T; ++t) {
+    const double* yt = proj.data() + size_t(q0 + t) * n;
+    double sumlog = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+      if (glm) {
+        w[k] = 1.0;
+      } else {
+        const double ld = e->values[k] + delta[t];
+        w[k] = 1.0 / ld;
+        sumlog += std::log(ld);
+      }
+    }
+    // ---- i = 0 of the reference loop: the marker-free model (:617-620,:646,:678,:707-714,:772)
+    FinalizeConsts fc;
+    std::fill(fc.iXX, fc.iXX + GAPIT_MAX_Q0 * GAPIT_MAX_Q0, 0.0);
+    std::fill(fc.beta0, fc.beta0 + GAPIT_MAX_Q0, 0.0);
+    std::vector<double> XX(q0 * q0, 0.0), XY(q0, 0.0), inv(q0 * q0, 0.0);
+    for (int i = 0; i < q0; ++i) {
+      const double* xi = proj.data() + size_t(i) * n;
+      for (int j = 0; j <= i; ++j) {
+        const double* xj = proj.data() + size_t(j) * n;
+        double s = 0.0;
+        for (int64_t k = 0; k < n; ++k) s += w[k] * xi[k] * xj[k];
+        XX[i * q0 + j] = XX[j * q0 + i] = s;
+      }
+      double s = 0.0;
+      for (int64_t k = 0; k < n; ++k) s += w[k] * xi[k] * yt[k];
+      XY[i] = s;
+    }
+    int singular = 0;
+    sym_inverse(q0, XX.data(), inv.data(), &singular);
+    for (int i = 0; i < q0; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < q0; ++j) {
+        fc.iXX[i * q0 + j] = inv[i * q0 + j];
+        s += inv[i * q0 + j] * XY[j];
+      }
+      fc.beta0[i] = s;
+    }
+    double rss0 = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+      double r = yt[k];
+      for (int j = 0; j < q0; ++j) r -= fc.beta0[j] * proj[size_t(j) * n + k];
+      rss0 += w[k] * r * r;
+    }
+    // intercept-only OLS likelihood on the raw phenotype (:536-553)
+    const double* yraw = Y + size_t(t) * n;
+    double ybar = 0.0;
+    for (int64_t k = 0; k < n; ++k) ybar += yraw[k];
+    ybar /= static_cast<double>(n);
+    double ss0 = 0.0;
+    for (int64_t k = 0; k < n; ++k) ss0 += (yraw[k] - ybar) * (yraw[k] - ybar);
+    const double dn = static_cast<double>(n);
+    const double two_pi = 2.0 * 3.14159265358979323846;
+    fc.logL0 = 0.5 * (-dn * std::log((two_pi / dn) * ss0) - dn);
+    fc.rss0 = rss0;
+    fc.sumlog = sumlog;
+    fc.n = dn;
+    fc.df = static_cast<double>(n - q0 - 1);
+    fc.lbeta = std::lgamma(0.5 * fc.df) + std::lgamma(0.5) - std::lgamma(0.5 * fc.df + 0.5);
+    fc.q0 = q0;
+    fc.qpad = Q;
+    fc.gsplit = gsplit;
+    const double ves_glm = rss0 / static_cast<double>(n - q0);
+    fc.var_scale = glm ? ves_glm : vg[t];
+    if (base_out) {
+      gapit_scan_base& b = base_out[t];
+      b.logL0 = fc.logL0;
+      b.logLM_base = 0.5 * (-dn * std::log((two_pi / dn) * rss0) - sumlog - dn);
+      b.rsquare_base = 1.0 - std::exp(-(2.0 / dn) * (b.logLM_base - fc.logL0));
+      b.ves = glm ? ves_glm : delta[t] * vg[t];
+      b.reml = glm ? (-0.5 * (dn - q0) * std::log(ves_glm) - 0.5 * dn - 0.5 * (dn - q0) * std::log(two_pi)) : 0.0;
+      b.df = fc.df;
+      std::fill(b.beta0, b.beta0 + GAPIT_MAX_Q0, 0.0);
+      for (int j = 0; j < q0; ++j) b.beta0[j] = fc.beta0[j];
+      b.singular_x0 = singular;
+    }
+
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    if (!glm) {
+      const int64_t nk = e->nkq * e->KPB;
+      gconst.assign(size_t(nk) * (Q + 2), 0.0);
+      for (int64_t k = 0; k < n; ++k) {
+        const double c = e->h_scale[k];
+        double* gk = gconst.data() + size_t(k) * (Q + 2);
+        gk[0] = w[k] * c * c;
+        for (int j = 0; j < q0; ++j) gk[1 + j] = w[k] * c * proj[size_t(j) * n + k];
+        gk[Q + 1] = w[k] * c * yt[k];
+      }
+      GAPIT_CUDA(cudaMemcpyAsync(dGc.p, gconst.data(), gconst.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+      cudaEventRecord(ctx->ev0, ctx->stream);
+      GAPIT_CHECK(launch_scan(ctx, g, e, Q, dGc.as<double>(), dPart.as<double>(), m_ld, gsplit));
+    } else {
+      // R for the GLM kernel: Q covariate columns (zero-padded) then y
+      GAPIT_CUDA(cudaMemsetAsync(dRg.p, 0, size_t(Q + 1) * n * 8, ctx->stream));
+      GAPIT_CUDA(cudaMemcpyAsync(dRg.p, dR.p, size_t(n) * q0 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      GAPIT_CUDA(cudaMemcpyAsync(dRg.as<double>() + size_t(Q) * n, dR.as<double>() + size_t(q0 + t) * n, size_t(n) * 8,
+                                 cudaMemcpyDeviceToDevice, ctx->stream));
+      cudaEventRecord(ctx->ev0, ctx->stream);
+      GAPIT_CHECK(launch_glm(ctx, g, Q, dRg.as<double>(), dPart.as<double>(), m_ld));
+    }
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    double* o = dOut.as<double>();
+    finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, ctx->stream>>>(
+        dPart.as<double>(), m_ld, m, g->colsum, g->colsumsq, fc, o, o + m, o + 2 * m, o + 3 * m, o + 4 * m, o + 5 * m,
+        o + 6 * m);
+    GAPIT_CUDA(cudaGetLastError());
+    cudaEvent_t ev2;
+    GAPIT_CUDA(cudaEventCreate(&ev2));
+    cudaEventRecord(ev2, ctx->stream);
+    double* dsts[7] = {out->effect, out->tvalue, out->se, out->pvalue, out->rsquare, out->loglm, out->maf};
+    for (int a = 0; a < 7; ++a) {
+      if (!dsts[a]) continue;
+      if (a == 6 && t > 0) continue;
+      double* dst = dsts[a] + (a == 6 ? 0 : size_t(t) * m);
+      GAPIT_CUDA(cudaMemcpyAsync(dst, o + size_t(a) * m, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    kernel_ms += ms;
+    cudaEventElapsedTime(&ms, ctx->ev1, ev2);
+    post_ms += ms;
+    cudaEventDestroy(ev2);
+  }
+  ctx->stats = gapit_stats{};
+  ctx->stats.kernel_ms = kernel_ms;
+  ctx->stats.post_ms = post_ms;
+  return GAPIT_OK;
+}
+
+}  // namespace gapit
+
+using namespace gapit;
+
+extern "C" int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const double* values, int64_t n,
+                                   gapit_eigsys** out) {
+  if (!ctx || !vectors || !values || !out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_eigsys_upload: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  gapit_eigsys* e = new gapit_eigsys();
+  e->ctx = ctx;
+  e->n = n;
+  const SliceGeom sg = slice_geom(ctx->slices);
+  e->S = sg.S;
+  e->BN = sg.BN;
+  e->KPB = sg.KPB;
+  e->ldn = round_up(n, 128);
+  e->nkq = (n + e->KPB - 1) / e->KPB;
+  e->values.assign(values, values + n);
+  const int64_t nk = e->nkq * e->KPB;
+  cudaError_t err = cudaMalloc(&e->V, size_t(n) * n * 8);
+  if (err == cudaSuccess) err = cudaMalloc(&e->Vs, size_t(e->nkq) * e->BN * e->ldn);
+  if (err == cudaSuccess) err = cudaMalloc(&e->scale, size_t(nk) * 8);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(e->V, vectors, size_t(n) * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (err == cudaSuccess) err = cudaMemsetAsync(e->Vs, 0, size_t(e->nkq) * e->BN * e->ldn, ctx->stream);
+  if (err == cudaSuccess) err = cudaMemsetAsync(e->scale, 0, size_t(nk) * 8, ctx->stream);
+  if (err == cudaSuccess) {
+    slice_v_kernel<<<static_cast<unsigned>(n), 256, 0, ctx->stream>>>(e->V, n, e->S, e->Vs, e->ldn, e->scale);
+    err = cudaGetLastError();
+  }
+  e->h_scale.assign(size_t(nk), 0.0);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(e->h_scale.data(), e->scale, size_t(nk) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+  if (err != cudaSuccess) {
+    gapit_eigsys_free(e);
+    return fail(GAPIT_ERR_CUDA, std::string("gapit_eigsys_upload: ") + cudaGetErrorString(err));
+  }
+  *out = e;
+  return GAPIT_OK;
+}
+
+extern "C" void gapit_eigsys_free(gapit_eigsys* e) {
+  if (!e) return;
+  if (e->ctx) cudaSetDevice(e->ctx->device);
+  cudaFree(e->V);
+  cudaFree(e->Vs);
+  cudaFree(e->scale);
+  delete e;
+}
+
+extern "C" int gapit_p3d_scan_dev(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y,
+                                  int T, const double* delta, const double* vg, int glm, gapit_scan_out* out,
+                                  gapit_scan_base* base_out) {
+  return scan_impl(ctx, g, e, X0, q0, Y, T, delta, vg, glm, out, base_out);
+}
+
+extern "C" int gapit_p3d_scan(gapit_ctx* ctx, gapit_geno* g, const double* vectors, const double* values, const double* X0,
+                              int q0, const double* Y, int T, const double* delta, const double* vg, int glm,
+                              gapit_scan_out* out, gapit_scan_base* base_out) {
+  if (glm) return scan_impl(ctx, g, nullptr, X0, q0, Y, T, delta, vg, 1, out, base_out);
+  if (!g) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL genotype handle");
+  gapit_eigsys* e = nullptr;
+  GAPIT_CHECK(gapit_eigsys_upload(ctx, vectors, values, g->n, &e));
+  const int rc = scan_impl(ctx, g, e, X0, q0, Y, T, delta, vg, 0, out, base_out);
+  gapit_eigsys_free(e);
+  return rc;
+}

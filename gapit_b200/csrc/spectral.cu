@@ -1,0 +1,229 @@
+// Spectral pieces of the P3D path (emma.txt:58-61 and :82-89).  The O(n^3) work is cuSOLVER's
+// syevd (a library call, timed separately from the hot-path roofline); this file only forms
+// S (K+I) S without the reference's two n^3 GEMMs and puts the spectrum in R's order.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace gapit {
+
+static int ensure_solver(gapit_ctx* ctx) {
+  if (ctx->solver) return GAPIT_OK;
+  if (cusolverDnCreate(&ctx->solver) != CUSOLVER_STATUS_SUCCESS) return fail(GAPIT_ERR_CUDA, "cusolverDnCreate failed");
+  if (cusolverDnSetStream(ctx->solver, ctx->stream) != CUSOLVER_STATUS_SUCCESS)
+    return fail(GAPIT_ERR_CUDA, "cusolverDnSetStream failed");
+  return GAPIT_OK;
+}
+
+// out[c*n + k] = sum_j A[j + k n] R[j + c n]   (A symmetric => (A R)[k][c]); one warp per k
+__global__ void sym_times_cols_kernel(const double* __restrict__ A, int64_t n, const double* __restrict__ R, int nc,
+                                      double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t k = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (k >= n) return;
+  const double* a = A + k * n;
+  for (int c = 0; c < nc; ++c) {
+    double acc = 0.0;
+    for (int64_t j = lane; j < n; j += 32) acc = fma(a[j], __ldg(R + c * n + j), acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[c * n + k] = acc;
+  }
+}
+
+// A = S M S with M = K + I, S = I - X (X'X)^-1 X', expanded as a rank-2q correction:
+//   A_ij = M_ij - sum_l ( Y1_il B_jl + B_il Y1_jl - Y2_il Y1_jl ),  B = M X, Y1 = X (X'X)^-1, Y2 = Y1 (X'B)
+// only the lower triangle (i >= j) is needed by syevd; the full matrix is written anyway.
+__global__ void form_sks_kernel(const double* __restrict__ K, int64_t n, const double* __restrict__ Y1,
+                                const double* __restrict__ B, const double* __restrict__ Y2, int q,
+                                double* __restrict__ A) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+    double v = K[i + j * n] + (i == j ? 1.0 : 0.0);
+    for (int l = 0; l < q; ++l) {
+      const double y1i = Y1[l * n + i], y1j = Y1[l * n + j];
+      v -= y1i * B[l * n + j] + B[l * n + i] * y1j - Y2[l * n + i] * y1j;
+    }
+    A[i + j * n] = v;
+  }
+}
+
+// column c of dst <- column (n-1-c) of src, for c < ncols
+__global__ void reverse_cols_kernel(const double* __restrict__ src, int64_t n, int64_t ncols, double* __restrict__ dst) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int64_t c = blockIdx.y; c < ncols; c += gridDim.y) dst[i + c * n] = src[i + (n - 1 - c) * n];
+}
+
+// in-place syevd on a device matrix; eigenvalues (ascending) into w_dev
+static int syevd_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* w_dev) {
+  GAPIT_CHECK(ensure_solver(ctx));
+  if (n > 46000) return fail(GAPIT_ERR_ARG, "eigh: n above the 32-bit cuSOLVER workspace limit");
+  int lwork = 0;
+  if (cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, int(n), A_dev, int(n),
+                                  w_dev, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    return fail(GAPIT_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed");
+  double* work = nullptr;
+  int* info = nullptr;
+  GAPIT_CUDA(cudaMalloc(&work, size_t(lwork) * 8));
+  cudaError_t e = cudaMalloc(&info, 4);
+  if (e != cudaSuccess) {
+    cudaFree(work);
+    return fail(GAPIT_ERR_CUDA, "eigh: cudaMalloc");
+  }
+  cusolverStatus_t st = cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, int(n), A_dev,
+                                         int(n), w_dev, work, lwork, info);
+  int hinfo = -1;
+  e = cudaMemcpyAsync(&hinfo, info, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(work);
+  cudaFree(info);
+  if (st != CUSOLVER_STATUS_SUCCESS) return fail(GAPIT_ERR_CUDA, "cusolverDnDsyevd failed, status " + std::to_string(int(st)));
+  if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("eigh: ") + cudaGetErrorString(e));
+  if (hinfo != 0) return fail(GAPIT_ERR_NUMERIC, "syevd did not converge, info " + std::to_string(hinfo));
+  return GAPIT_OK;
+}
+
+// shared tail: A_dev holds eigenvectors (ascending); emit the first `keep` in descending order
+static int emit_desc(gapit_ctx* ctx, double* A_dev, double* w_dev, int64_t n, int64_t keep, double shift,
+                     double* values_out, double* vectors_out) {
+  double* rev = nullptr;
+  GAPIT_CUDA(cudaMalloc(&rev, size_t(n) * keep * 8));
+  dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(std::min<int64_t>(keep, 65535)));
+  reverse_cols_kernel<<<grid, 256, 0, ctx->stream>>>(A_dev, n, keep, rev);
+  std::vector<double> w(n);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(w.data(), w_dev, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(vectors_out, rev, size_t(n) * keep * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(rev);
+  if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("eigh output: ") + cudaGetErrorString(e));
+  for (int64_t c = 0; c < keep; ++c) values_out[c] = w[n - 1 - c] + shift;
+  return GAPIT_OK;
+}
+
+}  // namespace gapit
+
+using namespace gapit;
+
+extern "C" int gapit_eigh(gapit_ctx* ctx, const double* A, int64_t n, double* values_out, double* vectors_out) {
+  if (!ctx || !A || !values_out || !vectors_out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_eigh: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  double *A_dev = nullptr, *w_dev = nullptr;
+  GAPIT_CUDA(cudaMalloc(&A_dev, size_t(n) * n * 8));
+  cudaError_t e = cudaMalloc(&w_dev, size_t(n) * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(A_dev, A, size_t(n) * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  int rc = (e == cudaSuccess) ? GAPIT_OK : fail(GAPIT_ERR_CUDA, std::string("gapit_eigh: ") + cudaGetErrorString(e));
+  if (rc == GAPIT_OK) rc = syevd_dev(ctx, A_dev, n, w_dev);
+  if (rc == GAPIT_OK) rc = emit_desc(ctx, A_dev, w_dev, n, n, 0.0, values_out, vectors_out);
+  cudaFree(A_dev);
+  cudaFree(w_dev);
+  return rc;
+}
+
+extern "C" int gapit_eigen_R(gapit_ctx* ctx, const double* K, const double* X, int64_t n, int64_t q, double* values_out,
+                             double* vectors_out) {
+  if (!ctx || !K || !X || !values_out || !vectors_out || n <= 0 || q < 1 || q >= n || q > GAPIT_MAX_Q0)
+    return fail(GAPIT_ERR_ARG, "gapit_eigen_R: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  double *K_dev = nullptr, *A_dev = nullptr, *w_dev = nullptr, *small = nullptr;
+  auto freeall = [&] {
+    cudaFree(K_dev);
+    cudaFree(A_dev);
+    cudaFree(w_dev);
+    cudaFree(small);
+  };
+  cudaError_t e = cudaMalloc(&K_dev, size_t(n) * n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&A_dev, size_t(n) * n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&w_dev, size_t(n) * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&small, size_t(n) * q * 8 * 4);  // X | B | Y1 | Y2
+  if (e == cudaSuccess) e = cudaMemcpyAsync(K_dev, K, size_t(n) * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  double* X_dev = small;
+  double* B_dev = small + size_t(n) * q;
+  double* Y1_dev = small + size_t(n) * q * 2;
+  double* Y2_dev = small + size_t(n) * q * 3;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(X_dev, X, size_t(n) * q * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    freeall();
+    return fail(GAPIT_ERR_CUDA, std::string("gapit_eigen_R: ") + cudaGetErrorString(e));
+  }
+  // B = (K + I) X
+  sym_times_cols_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(K_dev, n, X_dev, int(q), B_dev);
+  std::vector<double> B(size_t(n) * q);
+  e = cudaMemcpyAsync(B.data(), B_dev, size_t(n) * q * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    freeall();
+    return fail(GAPIT_ERR_CUDA, std::string("gapit_eigen_R: ") + cudaGetErrorString(e));
+  }
+  for (size_t i = 0; i < B.size(); ++i) B[i] += X[i];
+  // small host algebra: iXX = (X'X)^-1 (Gauss-Jordan with partial pivoting, as solve() would), C = X'B
+  std::vector<double> XX(q * q), iXX(q * q, 0.0), C(q * q), Y1(size_t(n) * q), Y2(size_t(n) * q);
+  for (int64_t a = 0; a < q; ++a)
+    for (int64_t b = 0; b < q; ++b) {
+      double s = 0.0, c = 0.0;
+      for (int64_t i = 0; i < n; ++i) {
+        s += X[a * n + i] * X[b * n + i];
+        c += X[a * n + i] * B[b * n + i];
+      }
+      XX[a * q + b] = s;
+      C[a * q + b] = c;
+    }
+  {
+    std::vector<double> aug(q * 2 * q, 0.0);
+    for (int64_t a = 0; a < q; ++a) {
+      for (int64_t b = 0; b < q; ++b) aug[a * 2 * q + b] = XX[a * q + b];
+      aug[a * 2 * q + q + a] = 1.0;
+    }
+    for (int64_t c = 0; c < q; ++c) {
+      int64_t piv = c;
+      for (int64_t r = c + 1; r < q; ++r)
+        if (std::fabs(aug[r * 2 * q + c]) > std::fabs(aug[piv * 2 * q + c])) piv = r;
+      if (std::fabs(aug[piv * 2 * q + c]) < 1e-300) {
+        freeall();
+        return fail(GAPIT_ERR_NUMERIC, "gapit_eigen_R: X'X is singular");
+      }
+      if (piv != c)
+        for (int64_t b = 0; b < 2 * q; ++b) std::swap(aug[c * 2 * q + b], aug[piv * 2 * q + b]);
+      const double d = aug[c * 2 * q + c];
+      for (int64_t b = 0; b < 2 * q; ++b) aug[c * 2 * q + b] /= d;
+      for (int64_t r = 0; r < q; ++r) {
+        if (r == c) continue;
+        const double f = aug[r * 2 * q + c];
+        if (f != 0.0)
+          for (int64_t b = 0; b < 2 * q; ++b) aug[r * 2 * q + b] -= f * aug[c * 2 * q + b];
+      }
+    }
+    for (int64_t a = 0; a < q; ++a)
+      for (int64_t b = 0; b < q; ++b) iXX[a * q + b] = aug[a * 2 * q + q + b];
+  }
+  for (int64_t l = 0; l < q; ++l)
+    for (int64_t i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int64_t a = 0; a < q; ++a) s += X[a * n + i] * iXX[a * q + l];
+      Y1[l * n + i] = s;
+    }
+  for (int64_t l = 0; l < q; ++l)
+    for (int64_t i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int64_t a = 0; a < q; ++a) s += Y1[a * n + i] * C[a * q + l];
+      Y2[l * n + i] = s;
+    }
+  e = cudaMemcpyAsync(B_dev, B.data(), size_t(n) * q * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(Y1_dev, Y1.data(), size_t(n) * q * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(Y2_dev, Y2.data(), size_t(n) * q * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(std::min<int64_t>(n, 65535)));
+    form_sks_kernel<<<grid, 256, 0, ctx->stream>>>(K_dev, n, Y1_dev, B_dev, Y2_dev, int(q), A_dev);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // host vectors B/Y1/Y2 must outlive the copies
+  int rc = (e == cudaSuccess) ? GAPIT_OK : fail(GAPIT_ERR_CUDA, std::string("gapit_eigen_R: ") + cudaGetErrorString(e));
+  if (rc == GAPIT_OK) rc = syevd_dev(ctx, A_dev, n, w_dev);
+  if (rc == GAPIT_OK) rc = emit_desc(ctx, A_dev, w_dev, n, n - q, -1.0, values_out, vectors_out);
+  freeall();
+  return rc;
+}

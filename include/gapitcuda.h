@@ -1,0 +1,162 @@
+/* libgapitcuda.so -- C ABI of the B200-native GAPIT hot path.
+ *
+ * The reference (Zhiwu-Zhang-Lab/GAPIT, "2016.03.01") has no FFI layer: the
+ * boundary of its hot path is two R closures.  Each entry point below names
+ * the reference lines it replaces; INTEGRATION.md shows the `.Call` shim and
+ * the replacement R bodies that bind them.
+ *
+ *   GAPIT.kinship.VanRaden(snps)            GAPIT.kinship.VanRaden.R:1-37   -> gapit_vanraden
+ *   emma.eigen.L.wo.Z / emma.eigen.R.wo.Z   emma.txt:58-61, 82-89           -> gapit_eigh, gapit_eigen_R
+ *   GAPIT.emma.REMLE (Z = NULL)             GAPIT.emma.REMLE.R:21-54,96-110 -> gapit_reml
+ *   GAPIT.EMMAxP3D marker loop              GAPIT.EMMAxP3D.R:397-979        -> gapit_p3d_scan
+ *
+ * Conventions: plain pointers and sizes only.  Host buffers are caller-owned,
+ * read-only unless named *_out; device memory lives behind opaque handles.
+ * Every call is synchronous on return, returns GAPIT_OK (0) or a negative
+ * status, and never throws or longjmps; gapit_last_error() gives the message
+ * of the last failure on the calling thread.  A context is not re-entrant.
+ * There is no CPU fallback: without a CUDA device every compute call fails
+ * with GAPIT_ERR_NO_DEVICE.
+ */
+#ifndef GAPITCUDA_H
+#define GAPITCUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAPIT_OK 0
+#define GAPIT_ERR_ARG (-1)       /* bad argument (shape, NULL, unsupported q0 ...) */
+#define GAPIT_ERR_CUDA (-2)      /* CUDA / cuSOLVER runtime failure */
+#define GAPIT_ERR_NO_DEVICE (-3) /* no usable sm_100 device */
+#define GAPIT_ERR_DATA (-4)      /* genotype value outside {0,1,2} (or NA without an impute rule) */
+#define GAPIT_ERR_NUMERIC (-5)   /* eigen solver did not converge, REML bracket failure ... */
+
+#define GAPIT_MAX_Q0 16 /* covariate columns incl. intercept the scan kernels are instantiated for */
+
+typedef struct gapit_ctx gapit_ctx;
+typedef struct gapit_geno gapit_geno;
+
+/* element type of a host genotype matrix */
+typedef enum { GAPIT_F64 = 0, GAPIT_I32 = 1, GAPIT_I8 = 2 } gapit_dtype;
+/* NA rule for GAPIT_F64 input (GAPIT.EMMAxP3D.R:20-24, SNP.impute): NaN -> value; NONE rejects NaN */
+typedef enum { GAPIT_IMPUTE_NONE = -1, GAPIT_IMPUTE_MINOR = 0, GAPIT_IMPUTE_MIDDLE = 1, GAPIT_IMPUTE_MAJOR = 2 } gapit_impute;
+
+/* wall/device timings of the last call on a context, milliseconds (CUDA events) */
+typedef struct {
+  double h2d_ms;    /* host->device copies */
+  double pack_ms;   /* dtype conversion, column statistics, transposition */
+  double kernel_ms; /* the hot kernel(s): cross-product or rotation+reduction */
+  double post_ms;   /* epilogue kernels after the hot kernel */
+  double d2h_ms;    /* device->host copies */
+  double total_ms;
+} gapit_stats;
+
+const char* gapit_last_error(void);
+int gapit_device_count(void);
+
+/* One context = one GPU (one process per GPU under torchrun / one R session). */
+int gapit_ctx_create(int device, gapit_ctx** out);
+void gapit_ctx_destroy(gapit_ctx* ctx);
+int gapit_ctx_stats(const gapit_ctx* ctx, gapit_stats* out);
+
+/* Genotypes: host matrix `snps`, n taxa x m markers, element (i,k) at
+ * snps[i + k*ld] (R's column-major layout, ld >= n), values 0/1/2.  Stored on
+ * the device as int8, marker-major, with per-marker sum and sum of squares.
+ * Replaces the `as.matrix(thisGD)` / `xs` arguments of GAPIT.Genotype.R:431 and
+ * GAPIT.Main.R:427. */
+int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
+                    gapit_impute impute, gapit_geno** out);
+void gapit_geno_free(gapit_geno* g);
+int64_t gapit_geno_n(const gapit_geno* g);
+int64_t gapit_geno_m(const gapit_geno* g);
+/* per-marker allele-count sums (host out, length m) */
+int gapit_geno_colsums(const gapit_geno* g, int32_t* colsum_out, int32_t* colsumsq_out);
+
+/* ---- VanRaden kinship (GAPIT.kinship.VanRaden.R:11-32) -------------------
+ * K_out: n x n fp64 column-major (symmetric).  G_out (optional, may be NULL):
+ * n x n int32 row-major raw cross-product sum_k x_ik x_jk over ALL markers of
+ * `g` (the exact integer the epilogue starts from). */
+int gapit_vanraden(gapit_ctx* ctx, gapit_geno* g, double* K_out, int32_t* G_out);
+
+/* Sharded form (markers split across processes): each rank computes its
+ * partial cross-product into a caller-owned DEVICE buffer G_dev
+ * (gapit_gram_ld(n)^2 int32, zeroed by the call) and 3 int64 partial scalars
+ * {sum c, sum c^2, #all-2 columns} into sums_dev (device); the caller sums both
+ * across ranks (ncclAllReduce, integer => bit-identical for any rank count)
+ * and any rank finishes. */
+int64_t gapit_gram_ld(int64_t n);
+int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t* sums_dev);
+int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, const int64_t* sums_dev, double* K_dev_out,
+                          double* K_host_out, int32_t* G_host_out);
+
+/* ---- spectral pieces (emma.txt:58-61, 82-89) ------------------------------
+ * gapit_eigh: eigen(A, symmetric=TRUE): values descending, vectors n x n
+ * column-major in matching order (cuSOLVER syevd; timed separately). */
+int gapit_eigh(gapit_ctx* ctx, const double* A, int64_t n, double* values_out, double* vectors_out);
+/* gapit_eigen_R: eigen(S (K+I) S) with S = I - X (X'X)^-1 X'; returns the first
+ * n-q values minus 1 and the first n-q vectors (n x (n-q) column-major). */
+int gapit_eigen_R(gapit_ctx* ctx, const double* K, const double* X, int64_t n, int64_t q, double* values_out,
+                  double* vectors_out);
+
+/* ---- REML variance components (GAPIT.emma.REMLE.R:21-54, 96-110) ----------
+ * lambda: n-q eigenvalues from gapit_eigen_R; etas = vectors' y.  Host code. */
+typedef struct {
+  double REML, delta, ve, vg;
+} gapit_reml_out;
+int gapit_reml(const double* lambda, const double* etas, int64_t nq, int ngrids, double llim, double ulim,
+               double esp, gapit_reml_out* out);
+
+/* ---- P3D / EMMAx marker scan (GAPIT.EMMAxP3D.R:397-979) -------------------
+ * Inputs: eigen-system of K (vectors n x n column-major, values), covariates
+ * X0 (n x q0 column-major, intercept included by the caller as GAPIT.Main.R:319
+ * does), phenotypes Y (n x T column-major) with per-trait delta and vg from
+ * gapit_reml.  glm != 0 runs the K = NULL branch (:759-763, :865-870, :937,
+ * :961-964): vectors/values/delta/vg are ignored.
+ * Outputs are caller-allocated SoA arrays of m*T doubles (trait-major blocks of
+ * m), NULL to skip one.  Rows of constant markers follow :499-511 (p = 1,
+ * everything else NaN). */
+typedef struct {
+  double* effect;   /* beta of the marker                   effect.est  :938 */
+  double* tvalue;   /* beta / sqrt(iXX_ss * vg|ve)          stats       :936-937 */
+  double* se;       /* sqrt(iXX_ss * vg|ve)  (clean SE; the reference's `stderr` quirk :972 is rebuilt in the shim) */
+  double* pvalue;   /* 2 pt(|t|, n-q0-1, lower=FALSE)       ps          :939-940 */
+  double* rsquare;  /* 1 - exp(-(2/n)(logLM - logL0))       rsquare     :967 */
+  double* loglm;    /* full-model log-likelihood            logLM       :958-963 */
+  double* maf;      /* min(ss/2n, 1 - ss/2n), length m      maf         :486 */
+} gapit_scan_out;
+
+/* per-trait scalars of the marker-free model (i = 0 of the loop) */
+typedef struct {
+  double logL0;         /* :551-553 */
+  double logLM_base;    /* :918-925 */
+  double rsquare_base;  /* :926 */
+  double ves;           /* GLM residual variance :868 (MLM: delta*vg passthrough) */
+  double reml;          /* GLM: :870 ; MLM: unused (comes from gapit_reml) */
+  double df;            /* n - q0 - 1 :586 */
+  double beta0[GAPIT_MAX_Q0]; /* effect.cv :913 */
+  int singular_x0;      /* 1 if X0'X0 needed the pseudo-inverse (:708-712) */
+} gapit_scan_base;
+
+int gapit_p3d_scan(gapit_ctx* ctx, gapit_geno* g, const double* vectors, const double* values, const double* X0,
+                   int q0, const double* Y, int T, const double* delta, const double* vg, int glm,
+                   gapit_scan_out* out, gapit_scan_base* base_out /* T entries */);
+
+/* Device-resident form for repeated scans / benchmarking: upload the
+ * eigen-system once (slices V for the int8 rotation), then scan. */
+typedef struct gapit_eigsys gapit_eigsys;
+int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const double* values, int64_t n, gapit_eigsys** out);
+void gapit_eigsys_free(gapit_eigsys* e);
+int gapit_p3d_scan_dev(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
+                       const double* delta, const double* vg, int glm, gapit_scan_out* out,
+                       gapit_scan_base* base_out);
+
+/* tuning knobs (0 = default): number of int8 slices of V (4..8) */
+int gapit_set_slices(gapit_ctx* ctx, int slices);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAPITCUDA_H */

@@ -1,0 +1,374 @@
+"""CPU restatement (numpy, fp64) of GAPIT's data-parallel hot path.
+
+TEST INFRASTRUCTURE ONLY -- the parity oracle.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs may import this module; the product path
+(``gapit_b200`` -> ``libgapitcuda.so``) never does.
+
+PARITY UNPINNED: the reference (/root/reference, GAPIT "2016.03.01") ships no
+tests, golden vectors or example data and R is not
+installed in this image, so the restatement below cannot be checked against
+the reference's own output.  It is pinned instead by independent derivations
+(``oracle/crosscheck.py``: exact-rational kinship, dense Cholesky GLS,
+mpmath tails) and hand-computable cases in ``tests/``.
+
+Every function cites the reference lines it follows.  The operation order of
+the reference is kept where it matters numerically; R base calls are replaced
+by their numpy/scipy stand-ins (``eigen`` -> ``numpy.linalg.eigh`` re-sorted
+descending, ``solve`` -> ``numpy.linalg.solve``/``inv``, ``MASS::ginv`` ->
+``numpy.linalg.pinv``, ``uniroot``/``pt`` -> ``oracle.rmath``).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import rmath
+
+
+# --------------------------------------------------------------------------
+# GAPIT.kinship.VanRaden  (GAPIT.kinship.VanRaden.R:1-37)
+# --------------------------------------------------------------------------
+def kinship_vanraden(snps: np.ndarray) -> np.ndarray:
+    """n x m dosage matrix (0/1/2) -> n x n VanRaden kinship.
+
+    Follows GAPIT.kinship.VanRaden.R line by line:
+      :11-13  drop columns whose allele frequency is >=1 or <=0
+      :20-22  p = colSums/(2n); P = 2(p-.5); snps-1
+      :25     Z = t(snps) - P           (m x n, Z[k,i] = x_ik - 2 p_k)
+      :28     K = crossprod(Z, Z)       (dgemm)
+      :31-32  K / (2 sum p(1-p))
+    ``hasInbred`` is accepted and ignored by the reference (:2).
+    """
+    snps = np.asarray(snps, dtype=np.float64)
+    fa = snps.sum(axis=0) / (2.0 * snps.shape[0])
+    index_non = (fa >= 1.0) | (fa <= 0.0)
+    snps = snps[:, ~index_non]
+    n_ind = snps.shape[0]
+    p = snps.sum(axis=0) / (2.0 * n_ind)
+    P = 2.0 * (p - 0.5)
+    snps = snps - 1.0
+    Z = snps.T - P[:, None]
+    K = Z.T @ Z
+    adj = 2.0 * np.sum(p * (1.0 - p))
+    return K / adj
+
+
+# --------------------------------------------------------------------------
+# EMMA pieces on the path  (emma.txt)
+# --------------------------------------------------------------------------
+def _eigh_desc(A):
+    """R's eigen(A, symmetric=TRUE): eigenvalues in decreasing order."""
+    w, v = np.linalg.eigh(A)
+    return w[::-1].copy(), v[:, ::-1].copy()
+
+
+def emma_eigen_L_wo_Z(K):
+    """emma.txt:58-61."""
+    values, vectors = _eigh_desc(np.asarray(K, dtype=np.float64))
+    return {"values": values, "vectors": vectors}
+
+
+def emma_eigen_R_wo_Z(K, X):
+    """emma.txt:82-89: eigen(S (K+I) S), keep the first n-q, values minus 1."""
+    K = np.asarray(K, dtype=np.float64)
+    X = np.asarray(X, dtype=np.float64)
+    n, q = X.shape
+    S = np.eye(n) - X @ np.linalg.solve(X.T @ X, X.T)
+    values, vectors = _eigh_desc(S @ (K + np.eye(n)) @ S)
+    return {"values": values[: n - q] - 1.0, "vectors": vectors[:, : n - q]}
+
+
+def emma_delta_REML_LL_wo_Z(logdelta, lam, etas):
+    """emma.txt:145-149."""
+    nq = etas.shape[0]
+    delta = math.exp(logdelta)
+    return 0.5 * (nq * (math.log(nq / (2 * math.pi)) - 1 - math.log(np.sum(etas * etas / (lam + delta))))
+                  - np.sum(np.log(lam + delta)))
+
+
+def emma_delta_REML_dLL_wo_Z(logdelta, lam, etas):
+    """emma.txt:158-164 (note: no leading delta factor, unlike the grid dLL)."""
+    nq = etas.shape[0]
+    delta = math.exp(logdelta)
+    etasq = etas * etas
+    ldelta = lam + delta
+    return 0.5 * (nq * np.sum(etasq / (ldelta * ldelta)) / np.sum(etasq / ldelta) - np.sum(1.0 / ldelta))
+
+
+def replace_nan(LL):
+    """GAPIT.replaceNaN.R:9-12: NaN log-likelihoods become the worst finite one."""
+    LL = np.array(LL, dtype=np.float64)
+    index = np.isnan(LL)
+    if LL.size > 0 and (~index).any():
+        LL[index] = LL[~index].min()
+    return LL
+
+
+def emma_REMLE(y, X, K, ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10, eig_R=None):
+    """GAPIT.emma.REMLE.R:1-111, Z = NULL branch (:21-54, :96-110)."""
+    y = np.asarray(y, dtype=np.float64).reshape(-1)
+    X = np.asarray(X, dtype=np.float64)
+    n = y.shape[0]
+    q = X.shape[1]
+    if np.linalg.det(X.T @ X) == 0:                       # :15-18
+        return {"REML": 0.0, "delta": 0.0, "ve": 0.0, "vg": 0.0}
+    if eig_R is None:                                     # :22-24
+        eig_R = emma_eigen_R_wo_Z(K, X)
+    lam = eig_R["values"]
+    etas = eig_R["vectors"].T @ y                         # :25
+    logdelta = np.arange(ngrids + 1) / ngrids * (ulim - llim) + llim   # :27
+    m = logdelta.shape[0]
+    delta = np.exp(logdelta)
+    Lambdas = lam[:, None] + delta[None, :]               # :30
+    Etasq = (etas * etas)[:, None]                        # :31
+    with np.errstate(divide="ignore", invalid="ignore"):
+        dLL = 0.5 * delta * ((n - q) * np.sum(Etasq / (Lambdas * Lambdas), axis=0)
+                             / np.sum(Etasq / Lambdas, axis=0) - np.sum(1.0 / Lambdas, axis=0))  # :33
+    optlogdelta = []
+    optLL = []
+    if dLL[0] < esp:                                      # :37
+        optlogdelta.append(llim)
+        optLL.append(emma_delta_REML_LL_wo_Z(llim, lam, etas))
+    if dLL[m - 2] > 0 - esp:                              # :41  (sic: dLL[m-1], 1-based)
+        optlogdelta.append(ulim)
+        optLL.append(emma_delta_REML_LL_wo_Z(ulim, lam, etas))
+    for i in range(m - 1):                                # :46-54
+        if dLL[i] * dLL[i + 1] < 0 and dLL[i] > 0 and dLL[i + 1] < 0:
+            root = rmath.uniroot(lambda ld: emma_delta_REML_dLL_wo_Z(ld, lam, etas),
+                                 float(logdelta[i]), float(logdelta[i + 1]))
+            optlogdelta.append(root)
+            optLL.append(emma_delta_REML_LL_wo_Z(root, lam, etas))
+    optLL_arr = np.array(optLL, dtype=np.float64)
+    # :96 which.max ignores NaN (R: which.max drops NA/NaN)
+    maxdelta = math.exp(optlogdelta[int(np.nanargmax(optLL_arr))])
+    optLL_arr = replace_nan(optLL_arr)                    # :99
+    maxLL = float(optLL_arr.max())                        # :101
+    maxva = float(np.sum(etas * etas / (lam + maxdelta)) / (n - q))    # :103
+    maxve = maxva * maxdelta                              # :108
+    return {"REML": maxLL, "delta": maxdelta, "ve": maxve, "vg": maxva}
+
+
+# --------------------------------------------------------------------------
+# GAPIT.EMMAxP3D  (GAPIT.EMMAxP3D.R), Z = NULL / SNP.P3D / fullGD / no indicator
+# --------------------------------------------------------------------------
+def _solve_or_ginv(A):
+    """try(solve(A)) with the MASS::ginv fallback (GAPIT.EMMAxP3D.R:708-712)."""
+    try:
+        inv = np.linalg.inv(A)
+        if not np.all(np.isfinite(inv)) or np.linalg.cond(A) > 1.0 / np.finfo(float).eps:
+            raise np.linalg.LinAlgError
+        return inv, False
+    except np.linalg.LinAlgError:
+        return np.linalg.pinv(A), True
+
+
+@dataclass
+class P3DResult:
+    ps: np.ndarray
+    stats: np.ndarray
+    effect_est: np.ndarray
+    rsquare_base: np.ndarray
+    rsquare: np.ndarray
+    dfs: np.ndarray
+    df: np.ndarray
+    tvalue: np.ndarray
+    stderr: np.ndarray
+    maf: np.ndarray
+    nobs: np.ndarray
+    REMLs: float
+    vgs: float
+    ves: float
+    delta: float
+    logLM: np.ndarray
+    logLM_Base: float
+    logL0: float
+    effect_cv: np.ndarray
+    se_clean: np.ndarray = field(default=None)
+    singular_X0: bool = False
+
+    def as_dict(self):
+        return dict(self.__dict__)
+
+
+def emmax_p3d(ys, xs, K=None, X0=None, ncol_CVI=None,
+              ngrids=100, llim=-10.0, ulim=10.0, esp=1e-10,
+              eig_L=None, reml=None, progress=None) -> P3DResult:
+    """The per-marker scan of GAPIT.EMMAxP3D.R:397-979 with its prologue.
+
+    ys : n phenotypes (one trait; the reference reshapes it to 1 x n at :29)
+    xs : n x m dosages, no NA (the reference imputes before the loop, :20-24)
+    K  : n x n kinship, or None / 1x1 for the GLM branch (:34)
+    X0 : n x q0 covariates including the intercept (default matrix(1,n,1), :30)
+    ncol_CVI : ncol(CVI) as seen by :972 (``stderr = beta[ncol(CVI)+1]/t``);
+               None reproduces the no-covariate call where that index runs past
+               ``beta`` and R yields NA.
+    eig_L / reml : optionally inject (values, vectors) and {delta, vg, ve, REML}
+               so the tight parity tests feed both sides identical spectra.
+
+    The loop keeps the reference's per-marker structure (two n x n products
+    per marker, :634 and :957) -- it doubles as the CPU baseline.
+    """
+    ys = np.asarray(ys, dtype=np.float64).reshape(-1)
+    xs = np.asarray(xs)
+    n = ys.shape[0]
+    if X0 is None:                                        # :30
+        X0 = np.ones((n, 1))
+    X0 = np.asarray(X0, dtype=np.float64)
+    if K is not None and np.size(K) <= 1:                 # :34
+        K = None
+    q0 = X0.shape[1]                                      # :40-41
+    q1 = q0 + 1
+    m = xs.shape[1]
+
+    X = X0
+    if K is not None:
+        K = np.asarray(K, dtype=np.float64)
+        if eig_L is None:
+            eig_L = emma_eigen_L_wo_Z(K)                  # :48
+        if reml is None:
+            # :58 computes eig.R, :202 passes it into the eig.L formal so REMLE
+            # recomputes it (GAPIT.emma.REMLE.R:2-3,22-24) -- same numbers.
+            reml = emma_REMLE(ys, X, K, ngrids=ngrids, llim=llim, ulim=ulim, esp=esp)
+        vgs, ves, REMLs, delta = reml["vg"], reml["ve"], reml["REML"], reml["delta"]
+        lam = np.asarray(eig_L["values"], dtype=np.float64)
+        U = np.asarray(eig_L["vectors"], dtype=np.float64) * np.sqrt(1.0 / (lam + delta))[None, :]   # :224
+        eig_full_plus_delta = lam + delta                 # :227
+    else:
+        vgs = ves = REMLs = delta = None
+        U = None
+
+    ps = np.full(m, np.nan)
+    stats = np.full(m, np.nan)
+    effect_est = np.full(m, np.nan)
+    rsquare_base = np.full(m, np.nan)
+    rsquare = np.full(m, np.nan)
+    dfs = np.full(m, np.nan)
+    df = np.full(m, np.nan)
+    tvalue = np.full(m, np.nan)
+    stderr = np.full(m, np.nan)
+    se_clean = np.full(m, np.nan)
+    maf = np.full(m, np.nan)
+    nobs = np.full(m, np.nan)
+    logLM_all = np.full(m, np.nan)
+
+    # ---- i = 0: the model without a marker (:404-408, :529-561, :617-620,
+    #      :646, :678-679, :707-714, :772, :865-870, :912-928)
+    yv = ys
+    X_int = np.ones((n, 1))                               # :536
+    beta_int = np.linalg.solve(X_int.T @ X_int, X_int.T @ yv)   # :537-539
+    res_int = yv - X_int @ beta_int
+    logL0 = 0.5 * ((-n) * math.log(((2 * math.pi) / n) * float(res_int @ res_int)) - n)   # :551-553
+
+    singular = False
+    if K is not None:
+        yt = U.T @ yv                                     # :617
+        X0t = U.T @ X0                                    # :619
+        X0X0 = X0t.T @ X0t                                # :646
+        X0Y = X0t.T @ yt                                  # :678
+        iX0X0, singular = _solve_or_ginv(X0X0)            # :708-712
+        iXX = iX0X0
+        XY = X0Y
+    else:
+        yt = yv                                           # :640
+        X0t = X0                                          # :641
+        X0X0 = X0t.T @ X0t
+        iXX, singular = _solve_or_ginv(X.T @ X)           # :760-761
+        XY = X.T @ yv                                     # :762
+        X0Y = XY
+        iX0X0 = iXX
+    beta = iXX.T @ XY                                     # :772
+    if K is None:                                         # :865-870
+        YY = float(yt @ yt)
+        ves = (YY - float(beta @ XY)) / (n - q0)
+        REMLs = -0.5 * (n - q0) * math.log(ves) - 0.5 * n - 0.5 * (n - q0) * math.log(2 * math.pi)
+        vgs = 0.0
+    beta_cv = beta.copy()                                 # :913
+    X_beta = X @ beta                                     # :914
+    if K is not None:                                     # :916-921
+        r0 = U.T @ (yv - X_beta)
+        logLM_Base = 0.5 * (-n * math.log(((2 * math.pi) / n) * float(r0 @ r0))
+                            - float(np.sum(np.log(eig_full_plus_delta))) - n)
+    else:                                                 # :922-925
+        r0 = yv - X_beta
+        logLM_Base = 0.5 * (-n * math.log(((2 * math.pi) / n) * float(r0 @ r0)) - n)
+    rsquare_base_init = 1 - math.exp(-(2.0 / n) * (logLM_Base - logL0))   # :926
+
+    # ---- i = 1..m
+    x_prev = None
+    for i in range(m):
+        if progress is not None and (i + 1) % 1000 == 0:
+            progress(i + 1)                               # :402
+        xv = np.asarray(xs[:, i], dtype=np.float64)       # :477
+        ns = n
+        ss = float(xv.sum())                              # :484
+        maf[i] = min(0.5 * ss / ns, 1 - 0.5 * ss / ns)    # :486
+        nobs[i] = ns                                      # :487
+        if xv.min() == xv.max():                          # :499-511
+            ps[i] = 1.0
+            x_prev = xv
+            continue
+        if x_prev is not None and i > 0 and np.array_equal(x_prev, xv):   # :512-527
+            for arr in (dfs, stats, effect_est, ps, rsquare, rsquare_base, df, tvalue, stderr, se_clean, logLM_all):
+                arr[i] = arr[i - 1]
+            x_prev = xv
+            continue
+        dfs[i] = n - q1                                   # :586
+        Xfull = np.column_stack([X0, xv])                 # :588
+        if K is not None:
+            xst = U.T @ xv                                # :634  (n x n GEMV #1)
+            X0Xst = X0t.T @ xst                           # :653
+            XstX0 = X0Xst[None, :]                        # :654
+            xstxst = float(xst @ xst)                     # :655
+            xsY = float(xst @ yt)                         # :682
+            XY = np.concatenate([X0Y, [xsY]])             # :683
+            B22 = xstxst - float(XstX0 @ iX0X0 @ X0Xst)   # :736
+            invB22 = 1.0 / B22                            # :737
+            B21 = XstX0 @ iX0X0.T                         # :739 tcrossprod(XstX0, iX0X0)
+            NeginvB22B21 = (-invB22) * B21                # :740
+            B11 = iX0X0 + invB22 * (B21.T @ B21)          # :742
+            iXX = np.empty((q1, q1))
+            iXX[:q0, :q0] = B11                           # :745
+            iXX[q0, q0] = 1.0 / B22                       # :746
+            iXX[q0, :q0] = NeginvB22B21                   # :747
+            iXX[:q0, q0] = NeginvB22B21                   # :748
+        else:
+            iXX, _ = _solve_or_ginv(Xfull.T @ Xfull)      # :760-761
+            XY = Xfull.T @ yv                             # :762
+        beta = iXX.T @ XY                                 # :772
+        if K is not None:
+            stats[i] = beta[q1 - 1] / math.sqrt(iXX[q1 - 1, q1 - 1] * vgs)   # :936
+            se_clean[i] = math.sqrt(iXX[q1 - 1, q1 - 1] * vgs)
+        else:
+            stats[i] = beta[q1 - 1] / math.sqrt(iXX[q1 - 1, q1 - 1] * ves)   # :937
+            se_clean[i] = math.sqrt(iXX[q1 - 1, q1 - 1] * ves)
+        effect_est[i] = beta[q1 - 1]                      # :938
+        p = float(rmath.pt_upper_two_sided(abs(stats[i]), dfs[i]))   # :939
+        ps[i] = 1.0 if math.isnan(p) else p               # :940
+        X_beta = Xfull @ beta                             # :955
+        if K is not None:
+            r = U.T @ (yv - X_beta)                       # :957  (n x n GEMV #2)
+            logLM = 0.5 * (-n * math.log(((2 * math.pi) / n) * float(r @ r))
+                           - float(np.sum(np.log(eig_full_plus_delta))) - n)   # :958-959
+        else:
+            r = yv - X_beta                               # :962
+            logLM = 0.5 * (-n * math.log(((2 * math.pi) / n) * float(r @ r)) - n)   # :963
+        logLM_all[i] = logLM
+        rsquare_base[i] = rsquare_base_init               # :966
+        rsquare[i] = 1 - math.exp(-(2.0 / n) * (logLM - logL0))   # :967
+        df[i] = dfs[i]                                    # :970
+        tvalue[i] = stats[i]                              # :971
+        # :972  stderr = beta[ncol(CVI)+1] / t  (1-based index into beta)
+        if ncol_CVI is not None and ncol_CVI + 1 <= beta.shape[0]:
+            stderr[i] = beta[ncol_CVI] / stats[i]
+        else:
+            stderr[i] = np.nan
+        x_prev = xv                                       # :977
+
+    return P3DResult(ps=ps, stats=stats, effect_est=effect_est, rsquare_base=rsquare_base,
+                     rsquare=rsquare, dfs=dfs, df=df, tvalue=tvalue, stderr=stderr, maf=maf,
+                     nobs=nobs, REMLs=-2.0 * REMLs, vgs=vgs, ves=ves, delta=delta,
+                     logLM=logLM_all, logLM_Base=logLM_Base, logL0=logL0, effect_cv=beta_cv,
+                     se_clean=se_clean, singular_X0=singular)
