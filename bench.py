@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""Benchmark of the GAPIT hot path on B200: SNPs tested/sec (MLM P3D) and kinship TOPS.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (libgapitcuda)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle restatement)
+
+Workload (BASELINE.json configs[1]): 5,000 taxa x 500,000 SNPs per GPU, one trait,
+intercept-only covariates, VanRaden kinship + MLM/P3D scan (GLM scan reported beside it).
+A "step" is one P3D scan of every marker resident on the GPU.  Under torchrun each rank
+holds its own 500,000-marker shard (weak scaling); the kinship partial cross-products are
+summed with one NCCL all-reduce, the eigen-system is broadcast once, the scan needs no
+collective and rank 0 gathers the p-values.
+One JSON line is printed by rank 0 (see the task contract for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SNPs tested/sec (MLM P3D)"
+UNIT = "SNPs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--n", type=int, default=5000, help="taxa (default: BASELINE configs[1])")
+    ap.add_argument("--m", type=int, default=500000, help="markers per GPU")
+    ap.add_argument("--slices", type=int, default=6)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="markers of the CPU baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_scan_sample(n, ns, seed, eig_L, reml, G=None, Y=None, X0=None):
+    """Time the oracle's per-marker loop (two n x n GEMVs per marker, GAPIT.EMMAxP3D.R:634,957)
+    on `ns` markers.  Returns SNPs/s."""
+    from oracle import gapit_oracle as go
+    t0 = time.perf_counter()
+    go.emmax_p3d(Y, G[:ns].T, K=np.zeros((2, 2)), X0=X0, eig_L=eig_L, reml=reml)
+    dt = time.perf_counter() - t0
+    return ns / dt, dt
+
+
+def run_reference(args):
+    """CPU reference arm: the oracle restatement (R is not installable here) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gapit_b200 import synth
+    from oracle import gapit_oracle as go
+    n = args.n
+    m_kin = min(args.m, 20000)          # markers used to build a realistic K on the CPU
+    G = synth.make_genotypes(n, m_kin, seed=synth.BASE_SEED + 1, threads=os.cpu_count() or 8)
+    Y = synth.make_phenotypes(G)[:, 0]
+    X0 = np.ones((n, 1))
+    K = go.kinship_vanraden(G.T)
+    eig_L = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    # bounded sample per step: ~2-4 s of GEMVs
+    ns = args.cpu_sample or max(8, min(m_kin, int(6.0e9 / (n * n * 8.0))))
+    for _ in range(args.warmup):
+        cpu_scan_sample(n, max(2, ns // 8), 0, eig_L, reml, G, Y, X0)
+    t = []
+    for _ in range(args.steps):
+        v, dt = cpu_scan_sample(n, ns, 0, eig_L, reml, G, Y, X0)
+        t.append(dt)
+    dt = float(np.mean(t))
+    value = ns / dt
+    cores = cpu_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"MLM P3D scan, {n} taxa x {args.m} SNPs per GPU, 1 trait, q0=1",
+                       "sample": f"{ns} markers per step, per-marker loop with two n x n GEMVs"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{ns} of {args.m} markers per step (cost is exactly linear in markers); "
+                                       f"numpy/OpenBLAS oracle restatement of GAPIT.EMMAxP3D.R:397-979, K from {m_kin} markers"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import gapit_b200 as gb
+    from gapit_b200 import synth, _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, m = args.n, args.m
+    S = args.slices
+    pk = peaks()
+
+    # ---------------- synthetic inputs (host, pinned) ----------------
+    G_np = synth.make_genotypes(n, m, seed=synth.BASE_SEED + 1 + 1000 * rank, threads=min(32, os.cpu_count() or 8))
+    G_pin = torch.empty((m, n), dtype=torch.int8).pin_memory()
+    G_pin.numpy()[:] = G_np
+    del G_np
+    G_host = G_pin.numpy()
+    Y = synth.make_phenotypes(G_host[:4096] if m > 4096 else G_host)   # QTN drawn from the first markers
+    if world > 1:   # every rank must scan the same phenotype
+        yt = torch.from_numpy(Y).to(dev)
+        dist.broadcast(yt, 0)
+        Y = yt.cpu().numpy()
+    X0 = np.ones((n, 1))
+
+    ctx = gb.Context(local, slices=S)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    lib = ctx.lib
+    geno = gb.Genotypes(G_host, ctx=ctx, marker_major=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        kms = []
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+            kms.append(ctx.stats()["kernel_ms"])
+        e1.record(stream)
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, float(np.mean(kms))
+
+    # ---------------- kinship: gram (+ all-reduce) + epilogue ----------------
+    ldg = lib.gapit_gram_ld(n)
+    G_t = torch.empty((ldg, ldg), dtype=torch.int32, device=dev)
+    sums_t = torch.empty(3, dtype=torch.int64, device=dev)
+    K_dev = torch.empty((n, n), dtype=torch.float64, device=dev)
+
+    def kinship_step():
+        _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_t.data_ptr(), sums_t.data_ptr()))
+        if world > 1:
+            dist.all_reduce(G_t)
+            dist.all_reduce(sums_t)
+        st = ctx.stats()
+        _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_t.data_ptr(), sums_t.data_ptr(), K_dev.data_ptr(), None, None))
+        ctx._last_gram_ms = st["kernel_ms"]
+
+    kin_ms, _ = timed(kinship_step, args.steps, args.warmup)
+    gram_ms = ctx._last_gram_ms
+    m_total = m * world
+    kin_ops = float(n) * (n + 1) * m_total            # one multiply + one add per lower-triangle pair per marker
+    kin_tops = kin_ops / (kin_ms * 1e-3) / 1e12
+    gram_tops_local = float(n) * (n + 1) * m / (gram_ms * 1e-3) / 1e12
+
+    # ---------------- spectra + REML (rank 0; one-off per trait set; timed separately) ----------------
+    setup = {}
+    vec_t = torch.empty((n, n), dtype=torch.float64, device=dev)
+    val_t = torch.empty(n, dtype=torch.float64, device=dev)
+    dv_t = torch.empty(2, dtype=torch.float64, device=dev)
+    if rank == 0:
+        K_host = np.asfortranarray(K_dev.cpu().numpy())   # symmetric, so the row/column-major view is immaterial
+        t0 = time.perf_counter()
+        eL = gb.emma_eigen_L_wo_Z(K_host, ctx=ctx)
+        setup["eigh_L_ms"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        eR = gb.emma_eigen_R_wo_Z(K_host, X0, ctx=ctx)
+        setup["eigen_R_ms"] = (time.perf_counter() - t0) * 1e3
+        t0 = time.perf_counter()
+        reml = gb.GAPIT_emma_REMLE(Y[:, 0], X0, K_host, eig_R=eR, ctx=ctx)
+        setup["reml_ms"] = (time.perf_counter() - t0) * 1e3
+        del eR
+        vec_t.copy_(torch.from_numpy(np.ascontiguousarray(eL["vectors"].T)))   # row r of vec_t = eigenvector r
+        val_t.copy_(torch.from_numpy(eL["values"]))
+        dv_t.copy_(torch.tensor([reml["delta"], reml["vg"]], dtype=torch.float64))
+    if world > 1:
+        dist.broadcast(vec_t, 0)
+        dist.broadcast(val_t, 0)
+        dist.broadcast(dv_t, 0)
+    vectors = np.asfortranarray(vec_t.cpu().numpy().T)
+    values = val_t.cpu().numpy()
+    delta, vg = [float(x) for x in dv_t.cpu().numpy()]
+    del vec_t
+    t0 = time.perf_counter()
+    es = gb.EigenSystem(values, vectors, ctx=ctx)
+    setup["eigsys_upload_slice_ms"] = (time.perf_counter() - t0) * 1e3
+
+    # ---------------- the timed hot path: MLM P3D scan ----------------
+    gather_buf = [torch.empty(m, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    last = {}
+
+    def scan_step():
+        arrs, bases = gb.p3d_scan(geno, X0, Y[:, :1], eigsys=es, delta=[delta], vg=[vg], ctx=ctx)
+        last["arrs"] = arrs
+        if world > 1:
+            p = torch.from_numpy(arrs["pvalue"][0]).to(dev)
+            dist.gather(p, gather_buf, dst=0)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    scan_ms, scan_kernel_ms = timed(scan_step, args.steps, args.warmup)
+    clocks = sampler.stop()
+    value = m_total / (scan_ms * 1e-3)
+
+    # GLM scan (K = NULL branch), HBM-bound
+    def glm_step():
+        gb.p3d_scan(geno, X0, Y[:, :1], glm=True, ctx=ctx)
+
+    glm_ms, glm_kernel_ms = timed(glm_step, max(2, args.steps), args.warmup)
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            g2 = gb.Genotypes(G_host, ctx=ctx, marker_major=True)          # H2D of the step's genotypes (pinned)
+            arrs, _ = gb.p3d_scan(g2, X0, Y[:, :1], eigsys=es, delta=[delta], vg=[vg], ctx=ctx)   # D2H of the results
+            g2.close()
+            last["e2e_min_p"] = float(np.nanmin(arrs["pvalue"]))
+        e2e_ms, _ = timed(e2e_step, args.steps, 1)
+        e2e = {"value": m_total / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(n) * int(m) + 8 * n * 2, "d2h_bytes_per_step": 7 * 8 * int(m),
+               "note": "host int8 dosages (pinned) -> gapit_geno_pack -> gapit_p3d_scan_dev -> host result arrays; "
+                       "eigen-system resident (one-off per trait set, see setup_ms)"}
+
+    # ---------------- CPU baseline beside it (rank 0, N=1) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = args.cpu_sample or max(8, min(m, int(1.6e10 / (n * n * 8.0))))
+        eig_L = {"values": values, "vectors": vectors}
+        reml_d = {"delta": delta, "vg": vg, "ve": delta * vg, "REML": 0.0}
+        v, dt = cpu_scan_sample(n, ns, 0, eig_L, reml_d, G_host, Y[:, 0], X0)
+        cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+               "sample": f"first {ns} of {m} markers ({dt:.1f} s); oracle restatement of GAPIT.EMMAxP3D.R:397-979 "
+                         f"(two n x n GEMVs per marker) on numpy/OpenBLAS, eigen-system and delta injected"}
+
+    # ---------------- roofline of the dominant kernel (rotate_reduce) ----------------
+    int8_ops = 2.0 * n * n * m * S                     # int8-native: S digit planes of V
+    fp64_flops = 2.0 * n * n * m                       # algorithmic fp64 flops of the rotation
+    achieved = int8_ops / (scan_kernel_ms * 1e-3) / 1e12
+    int8_peak = 2.0 * pk["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": "umma_i8_kernel<ScanSched,ScanEpi> (rotate_reduce)",
+                "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s", "frac": achieved / int8_peak,
+                "traffic": None,
+                "peak_note": f"int8 dense = 2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({pk['source']}); "
+                             f"kind::i8 issues at twice the bf16 rate on sm_100",
+                "kernel_ms": scan_kernel_ms, "slices": S,
+                "fp64_equivalent_tflops": fp64_flops / (scan_kernel_ms * 1e-3) / 1e12}
+    glm_bytes = float(n) * m
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": scan_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int8 x int8 -> int32 rotation (6 digit planes of fp64 V), fp64 epilogue",
+        "data": "synthetic",
+        "config": {"workload": f"MLM P3D scan, {n} taxa x {m} SNPs per GPU ({m_total} total), 1 trait, q0=1 "
+                               f"(BASELINE configs[1] per GPU)", "kinship": "VanRaden", "slices": S,
+                   "l2": "inputs larger than L2 (genotypes 2.5 GB per GPU)", "parallelism": f"marker-shard x{world}"},
+        "kinship": {"tops": kin_tops, "ms": kin_ms, "gram_kernel_ms": gram_ms, "gram_kernel_tops_per_gpu": gram_tops_local,
+                    "ops": "n(n+1)m integer multiply-adds counted once per lower-triangle pair",
+                    "frac_of_int8_peak": 2.0 * gram_tops_local / int8_peak,
+                    "includes": "gram + NCCL all-reduce (N>1) + fp64 epilogue"},
+        "glm": {"snps_per_s": m_total / (glm_ms * 1e-3), "ms": glm_ms, "kernel_ms": glm_kernel_ms,
+                "hbm_gbs": glm_bytes / (glm_kernel_ms * 1e-3) / 1e9,
+                "frac_of_hbm_peak": glm_bytes / (glm_kernel_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+        "setup_ms": setup,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": e2e,
+        "gpu_launches": args.steps * 3,
+        "gpu_launches_note": "per scan step: vt_project + umma_i8 rotate_reduce + finalize",
+        "clocks": clocks,
+        "reml": {"delta": delta, "vg": vg},
+        "min_p": float(np.nanmin(last["arrs"]["pvalue"])),
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    es.close()
+    geno.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -52,6 +52,7 @@ SIGNATURES = {
     "gapit_ctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "gapit_ctx_destroy": (None, [_P]),
     "gapit_ctx_stats": (C.c_int, [_P, C.POINTER(Stats)]),
+    "gapit_ctx_set_stream": (C.c_int, [_P, _P]),
     "gapit_geno_pack": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _I64, C.c_int, C.POINTER(_P)]),
     "gapit_geno_free": (None, [_P]),
     "gapit_geno_n": (_I64, [_P]),

@@ -38,6 +38,10 @@ class Context:
         if slices:
             check(self.lib.gapit_set_slices(self.h, int(slices)))
 
+    def set_stream(self, cuda_stream):
+        """Run on a caller-owned stream (e.g. ``torch.cuda.current_stream().cuda_stream``); None restores."""
+        check(self.lib.gapit_ctx_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
     def set_slices(self, slices):
         check(self.lib.gapit_set_slices(self.h, int(slices)))
 

@@ -80,7 +80,8 @@ extern "C" int gapit_ctx_create(int device, gapit_ctx** out) {
   gapit_ctx* ctx = new gapit_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+  ctx->stream = ctx->own_stream;
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
   if (e != cudaSuccess) {
@@ -97,13 +98,20 @@ extern "C" void gapit_ctx_destroy(gapit_ctx* ctx) {
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
 extern "C" int gapit_ctx_stats(const gapit_ctx* ctx, gapit_stats* out) {
   if (!ctx || !out) return fail(GAPIT_ERR_ARG, "gapit_ctx_stats: NULL argument");
   *out = ctx->stats;
+  return GAPIT_OK;
+}
+
+extern "C" int gapit_ctx_set_stream(gapit_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return fail(GAPIT_ERR_ARG, "gapit_ctx_set_stream: NULL ctx");
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  if (ctx->solver) cusolverDnSetStream(ctx->solver, ctx->stream);
   return GAPIT_OK;
 }
 

@@ -40,6 +40,7 @@ struct gapit_ctx {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
   cusolverDnHandle_t solver = nullptr;
   // timings of the last call, ms (CUDA events on `stream`)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;

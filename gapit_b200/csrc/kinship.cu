@@ -194,8 +194,21 @@ extern "C" int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev
   colsum_reduce_kernel<<<std::min<int64_t>(1024, (g->m + 255) / 256), 256, 0, ctx->stream>>>(
       g->colsum, g->m, 2 * g->n, reinterpret_cast<unsigned long long*>(sums_dev));
   GAPIT_CUDA(cudaGetLastError());
+  cudaEvent_t evt;
+  GAPIT_CUDA(cudaEventCreate(&evt));
+  cudaEventRecord(evt, ctx->stream);
+  GAPIT_CHECK(geno_build_taxa_major(g));  // no-op when the taxa-major copy already exists
+  cudaEventRecord(ctx->ev0, ctx->stream);
   GAPIT_CHECK(launch_gram(ctx, g, G_dev, ldg));
+  cudaEventRecord(ctx->ev1, ctx->stream);
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  ctx->stats = gapit_stats{};
+  cudaEventElapsedTime(&ms, evt, ctx->ev0);
+  ctx->stats.pack_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats.kernel_ms = ms;
+  cudaEventDestroy(evt);
   return GAPIT_OK;
 }
 

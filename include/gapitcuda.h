@@ -61,6 +61,9 @@ int gapit_device_count(void);
 int gapit_ctx_create(int device, gapit_ctx** out);
 void gapit_ctx_destroy(gapit_ctx* ctx);
 int gapit_ctx_stats(const gapit_ctx* ctx, gapit_stats* out);
+/* Run this context's work on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL restores the
+ * context's own stream), so a host framework can bracket calls with its own events. */
+int gapit_ctx_set_stream(gapit_ctx* ctx, void* cuda_stream);
 
 /* Genotypes: host matrix `snps`, n taxa x m markers, element (i,k) at
  * snps[i + k*ld] (R's column-major layout, ld >= n), values 0/1/2.  Stored on
