@@ -324,7 +324,7 @@ def emmax_p3d(ys, xs, K=None, X0=None, ncol_CVI=None,
             xstxst = float(xst @ xst)                     # :655
             xsY = float(xst @ yt)                         # :682
             XY = np.concatenate([X0Y, [xsY]])             # :683
-            B22 = xstxst - float(XstX0 @ iX0X0 @ X0Xst)   # :736
+            B22 = xstxst - float((XstX0 @ iX0X0 @ X0Xst)[0])   # :736
             invB22 = 1.0 / B22                            # :737
             B21 = XstX0 @ iX0X0.T                         # :739 tcrossprod(XstX0, iX0X0)
             NeginvB22B21 = (-invB22) * B21                # :740

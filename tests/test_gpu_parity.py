@@ -1,0 +1,374 @@
+"""GPU parity tests (-m gpu): libgapitcuda through its C ABI (ctypes) against the oracle.
+
+Tolerances are BASELINE.json's north_star: integer cross-products bit-exact, kinship 1e-12
+(max-abs relative to max|K|, against the exact-rational value), beta/SE 1e-8 relative,
+-log10(p) 1e-6 absolute, marker order identical.
+"""
+import numpy as np
+import pytest
+
+from gapit_b200 import synth
+from oracle import crosscheck as cc
+from oracle import gapit_oracle as go
+from conftest import c1_inputs
+
+pytestmark = pytest.mark.gpu
+
+BETA_RTOL = 1e-8
+SE_RTOL = 1e-8
+LOGP_ATOL = 1e-6
+K_RTOL = 1e-12
+
+
+def gb():
+    import gapit_b200
+    return gapit_b200
+
+
+def case(n, m, npc=0, seed=1, edge=True):
+    G = synth.make_genotypes(n, m, seed=seed, threads=4)
+    if edge and m > 25:
+        G[3, :] = 0
+        G[7, :] = 2
+        G[11, :] = 1
+        G[20, :] = G[19, :]
+    Y = synth.make_phenotypes(G, seed=seed)[:, 0]
+    X0 = synth.make_covariates(G, npc=npc)
+    return G, Y, X0
+
+
+def rel_err(got, ref, floor):
+    """max relative error over entries whose reference magnitude exceeds `floor` * max|ref|,
+    and max absolute error (relative to max|ref|) over the rest."""
+    ok = ~np.isnan(ref)
+    scale = np.nanmax(np.abs(ref))
+    big = ok & (np.abs(ref) > floor * scale)
+    small = ok & ~big
+    r = np.max(np.abs(got[big] - ref[big]) / np.abs(ref[big])) if big.any() else 0.0
+    a = np.max(np.abs(got[small] - ref[small])) / scale if small.any() else 0.0
+    return r, a
+
+
+def check_scan(res, ora, glm=False):
+    ps, stats = res["ps"][:, 0], res["stats"][:, 0]
+    assert np.array_equal(np.isnan(stats), np.isnan(ora.stats)), "NA rows differ"
+    const = np.isnan(ora.stats)
+    assert np.all(ps[const] == 1.0)
+    r, a = rel_err(res["effect.est"][:, 0], ora.effect_est, 1e-4)
+    assert r < BETA_RTOL and a < BETA_RTOL * 1e-4 * 10, (r, a)
+    r, a = rel_err(res["se"][:, 0], ora.se_clean, 0.0)
+    assert r < SE_RTOL, r
+    r, a = rel_err(stats, ora.stats, 1e-4)
+    assert r < BETA_RTOL and a < BETA_RTOL, (r, a)
+    with np.errstate(divide="ignore"):
+        dlp = np.abs(np.log10(ps) - np.log10(ora.ps))
+    dlp[(ps == 0) & (ora.ps == 0)] = 0.0
+    assert np.nanmax(dlp) < LOGP_ATOL, np.nanmax(dlp)
+    ok = ~const
+    assert np.max(np.abs(res["rsquare"][ok, 0] - ora.rsquare[ok])) < 1e-9
+    assert np.max(np.abs(res["logLM"][ok, 0] - ora.logLM[ok]) / np.abs(ora.logLM[ok])) < 1e-10
+    assert np.max(np.abs(res["rsquare_base"][ok, 0] - ora.rsquare_base[ok])) < 1e-10
+    assert np.array_equal(res["maf"][:, 0], ora.maf)
+    assert np.array_equal(res["nobs"][:, 0], ora.nobs)
+    assert np.array_equal(res["dfs"][ok, 0], ora.dfs[ok])
+
+
+# ------------------------------------------------------------------ genotype ingestion
+@pytest.mark.parametrize("n,m", [(5, 3), (127, 129), (281, 3093), (300, 1000)])
+def test_pack_and_column_stats(gpu_ctx, n, m):
+    G, _, _ = case(n, m, edge=False)
+    x = G.astype(np.int64)
+    for arr, mm in [(G, True), (G.T.astype(np.float64), False), (G.T.astype(np.int32), False),
+                    (np.asfortranarray(G.T), False)]:
+        g = gb().Genotypes(arr, ctx=gpu_ctx, marker_major=mm)
+        cs, cq = g.colsums()
+        assert (g.n, g.m) == (n, m)
+        assert np.array_equal(cs, x.sum(1)) and np.array_equal(cq, (x * x).sum(1))
+        g.close()
+
+
+def test_pack_rejects_bad_values_and_imputes_na(gpu_ctx):
+    G, _, _ = case(40, 60, edge=False)
+    bad = G.T.astype(np.float64)
+    bad[3, 5] = 3.0
+    with pytest.raises(gb().GapitCudaError):
+        gb().Genotypes(bad, ctx=gpu_ctx)
+    bad8 = G.copy()
+    bad8[5, 3] = 7
+    with pytest.raises(gb().GapitCudaError):
+        gb().Genotypes(bad8, ctx=gpu_ctx, marker_major=True)
+    na = G.T.astype(np.float64)
+    na[2, 4] = np.nan
+    with pytest.raises(gb().GapitCudaError):
+        gb().Genotypes(na, ctx=gpu_ctx)
+    for rule, val in [("Middle", 1), ("Major", 2), ("Minor", 0)]:      # GAPIT.EMMAxP3D.R:20-24
+        g = gb().Genotypes(na, ctx=gpu_ctx, impute=rule)
+        ref = G.T.astype(np.int64).copy()
+        ref[2, 4] = val
+        assert np.array_equal(g.colsums()[0], ref.sum(0))
+        g.close()
+
+
+# ------------------------------------------------------------------ kinship
+@pytest.mark.parametrize("n,m", [(4, 3), (37, 50), (281, 3093), (257, 1000), (600, 4097), (1030, 20000)])
+def test_vanraden_gram_bit_exact_and_kinship(gpu_ctx, n, m):
+    G, _, _ = case(n, m)
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    K, gram = gb().GAPIT_kinship_VanRaden(geno, ctx=gpu_ctx, return_gram=True, verbose=False)
+    x = G.astype(np.int64)
+    assert np.array_equal(gram, x.T @ x), "integer cross-product must be bit-exact"
+    K_ref = go.kinship_vanraden(G.T)
+    assert np.abs(K - K_ref).max() <= K_RTOL * np.abs(K_ref).max()
+    assert np.array_equal(K, K.T)
+    if n <= 300:
+        Kex = cc.kinship_exact(G.T)
+        assert np.abs(K - Kex).max() <= 4 * np.finfo(float).eps * np.abs(Kex).max()
+
+
+def test_vanraden_hand_case_and_degenerate(gpu_ctx):
+    snps = np.array([[0, 1, 2], [1, 1, 0], [2, 0, 0], [1, 2, 2]], dtype=float)
+    K = gb().GAPIT_kinship_VanRaden(snps, ctx=gpu_ctx, verbose=False)
+    p = snps.sum(0) / 8.0
+    Z = snps - 2 * p
+    assert np.allclose(K, Z @ Z.T / (2 * np.sum(p * (1 - p))), atol=1e-15)
+    # every column monomorphic: the reference divides 0 by 0 -> NaN matrix
+    mono = np.tile(np.array([[0.0, 2.0, 2.0]]), (6, 1))
+    Km = gb().GAPIT_kinship_VanRaden(mono, ctx=gpu_ctx, verbose=False)
+    assert np.all(np.isnan(Km)) and np.all(np.isnan(go.kinship_vanraden(mono)))
+
+
+def test_vanraden_sharded_partials_sum_exactly(gpu_ctx):
+    """Two marker shards on one GPU, partial integers added on the host = one-shot result (N-GPU path)."""
+    import ctypes as C
+    import torch
+    from gapit_b200 import _lib
+    G, _, _ = case(300, 5000)
+    lib = gpu_ctx.lib
+    n = 300
+    ldg = lib.gapit_gram_ld(n)
+    tot_G = torch.zeros((ldg, ldg), dtype=torch.int32, device="cuda")
+    tot_s = torch.zeros(3, dtype=torch.int64, device="cuda")
+    for lo, hi in [(0, 1777), (1777, 5000)]:
+        g = gb().Genotypes(G[lo:hi], ctx=gpu_ctx, marker_major=True)
+        Gp = torch.empty((ldg, ldg), dtype=torch.int32, device="cuda")
+        sp = torch.empty(3, dtype=torch.int64, device="cuda")
+        _lib.check(lib.gapit_vanraden_gram(gpu_ctx.h, g.h, Gp.data_ptr(), sp.data_ptr()))
+        tot_G += Gp
+        tot_s += sp
+        g.close()
+    K = np.empty((n, n), order="F")
+    _lib.check(lib.gapit_vanraden_finish(gpu_ctx.h, n, tot_G.data_ptr(), tot_s.data_ptr(), None,
+                                         K.ctypes.data_as(C.c_void_p), None))
+    K1 = gb().GAPIT_kinship_VanRaden(gb().Genotypes(G, ctx=gpu_ctx, marker_major=True), ctx=gpu_ctx, verbose=False)
+    assert np.array_equal(K, K1), "sharded and one-shot kinship must be bit-identical"
+
+
+def test_gram_checksums_at_scale(gpu_ctx):
+    """Size-independent identities at a size the oracle cannot reach quickly: sum_ij G_ij = sum_k c_k^2,
+    trace G = sum_k sum_i x_ik^2, and K 1 = 0."""
+    n, m = 3000, 200000
+    G = synth.make_genotypes(n, m, seed=77, threads=8)
+    g = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    K, gram = gb().GAPIT_kinship_VanRaden(g, ctx=gpu_ctx, return_gram=True, verbose=False)
+    cs, cq = g.colsums()
+    c = cs.astype(np.int64)
+    assert int(gram.astype(np.int64).sum()) == int((c * c).sum())
+    assert int(np.trace(gram.astype(np.int64))) == int(cq.astype(np.int64).sum())
+    assert np.array_equal(gram, gram.T)
+    assert np.abs(K.sum(1)).max() < 1e-9
+    sub = G[:, :64].astype(np.int64)
+    assert np.array_equal(gram[:64, :64], sub.T @ sub)
+    g.close()
+
+
+# ------------------------------------------------------------------ spectra + REML
+def test_eigh_eigenR_reml_match_oracle(gpu_ctx):
+    G, Y, X0 = case(220, 1500, npc=2)
+    K = go.kinship_vanraden(G.T)
+    eL = gb().emma_eigen_L_wo_Z(K, ctx=gpu_ctx)
+    eLo = go.emma_eigen_L_wo_Z(K)
+    assert np.abs(eL["values"] - eLo["values"]).max() < 1e-11
+    assert np.all(np.diff(eL["values"]) <= 1e-12)                      # R's decreasing order
+    rec = (eL["vectors"] * eL["values"]) @ eL["vectors"].T
+    assert np.abs(rec - K).max() < 1e-11
+    eR = gb().emma_eigen_R_wo_Z(K, X0, ctx=gpu_ctx)
+    eRo = go.emma_eigen_R_wo_Z(K, X0)
+    assert eR["values"].shape == (220 - 3,) and eR["vectors"].shape == (220, 217)
+    assert np.abs(eR["values"] - eRo["values"]).max() < 1e-11
+    assert np.abs(eR["vectors"].T @ X0).max() < 1e-9
+    r1 = gb().GAPIT_emma_REMLE(Y, X0, K, ctx=gpu_ctx)                     # own eig.R
+    r2 = go.emma_REMLE(Y, X0, K)
+    for k in ("REML", "delta", "ve", "vg"):
+        assert r1[k] == pytest.approx(r2[k], rel=1e-7), k
+
+
+# ------------------------------------------------------------------ the scan
+@pytest.mark.parametrize("n,m,npc", [(48, 160, 2), (281, 3093, 0), (200, 700, 3), (333, 900, 6), (150, 300, 12)])
+def test_mlm_scan_parity_injected_spectrum(gpu_ctx, n, m, npc):
+    G, Y, X0 = case(n, m, npc=npc)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    ora = go.emmax_p3d(Y, G.T, K, X0, ncol_CVI=X0.shape[1], eig_L=eL, reml=reml)
+    res = gb().GAPIT_EMMAxP3D(Y, G.T.astype(np.float64), K, X0=X0, CVI=np.zeros((n, X0.shape[1])), ctx=gpu_ctx,
+                              eig_L=eL, reml=reml)
+    check_scan(res, ora)
+    ok = ~np.isnan(ora.stats)
+    assert np.max(np.abs(res["stderr"][ok, 0] - ora.stderr[ok]) / np.abs(ora.stderr[ok])) < 1e-6
+    assert res["vgs"] == reml["vg"] and res["ves"] == reml["ve"] and res["REMLs"] == -2 * reml["REML"]
+    assert np.allclose(res["effect.cv"], ora.effect_cv, rtol=1e-9)
+    # duplicated adjacent marker: bit-identical row (the reference copies it, :512-527)
+    for key in ("ps", "stats", "effect.est", "rsquare"):
+        assert res[key][20, 0] == res[key][19, 0]
+    # without CVI the reference's stderr index runs past beta -> NA (:972)
+    res2 = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0, ctx=gpu_ctx, eig_L=eL, reml=reml)
+    assert np.all(np.isnan(res2["stderr"]))
+
+
+@pytest.mark.parametrize("slices", [5, 6, 7, 8])
+def test_mlm_scan_slice_counts(gpu_ctx, slices):
+    G, Y, X0 = case(260, 800, npc=1)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    ora = go.emmax_p3d(Y, G.T, K, X0, eig_L=eL, reml=reml)
+    gpu_ctx.set_slices(slices)
+    try:
+        res = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0, ctx=gpu_ctx, eig_L=eL, reml=reml)
+    finally:
+        gpu_ctx.set_slices(6)
+    r, a = rel_err(res["effect.est"][:, 0], ora.effect_est, 1e-3)
+    assert r < (1e-6 if slices == 5 else BETA_RTOL)
+    with np.errstate(divide="ignore"):
+        assert np.nanmax(np.abs(np.log10(res["ps"][:, 0]) - np.log10(ora.ps))) < LOGP_ATOL
+
+
+@pytest.mark.parametrize("n,m,npc", [(48, 160, 2), (281, 3093, 0), (300, 1000, 5)])
+def test_glm_scan_parity(gpu_ctx, n, m, npc):
+    G, Y, X0 = case(n, m, npc=npc)
+    ora = go.emmax_p3d(Y, G.T, None, X0, ncol_CVI=X0.shape[1])
+    res = gb().GAPIT_EMMAxP3D(Y, G.T, None, X0=X0, CVI=np.zeros((n, X0.shape[1])), ctx=gpu_ctx)
+    check_scan(res, ora, glm=True)
+    assert res["ves"] == pytest.approx(ora.ves, rel=1e-11)
+    assert res["REMLs"] == pytest.approx(ora.REMLs, rel=1e-11)
+    assert res["vgs"] == 0.0
+
+
+def test_end_to_end_own_spectrum_and_reml(gpu_ctx):
+    """Whole function on the GPU side (own eigen + own REML) against the whole oracle.  delta comes out of a
+    root finder with tolerance 1.2e-4 on both sides, so parity here is delta-agreement plus a looser scan bound."""
+    G, Y, X0 = case(281, 3093, npc=0)
+    K = gb().GAPIT_kinship_VanRaden(G.T, ctx=gpu_ctx, verbose=False)
+    res = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0, ctx=gpu_ctx)
+    ora = go.emmax_p3d(Y, G.T, go.kinship_vanraden(G.T), X0)
+    assert res["delta"] == pytest.approx(ora.delta, rel=1e-6)
+    assert res["vgs"] == pytest.approx(ora.vgs, rel=1e-6)
+    ok = ~np.isnan(ora.stats)
+    with np.errstate(divide="ignore"):
+        assert np.nanmax(np.abs(np.log10(res["ps"][:, 0]) - np.log10(ora.ps))) < 1e-4
+    r, a = rel_err(res["effect.est"][:, 0], ora.effect_est, 1e-3)
+    assert r < 1e-5
+    # output table order: sort by (P, marker index) as GAPIT.Perform.BH.FDR...R:46 does
+    assert np.array_equal(np.argsort(res["ps"][ok, 0], kind="stable")[:50], np.argsort(ora.ps[ok], kind="stable")[:50])
+
+
+def test_scan_golden_fixtures(gpu_ctx, tiny_golden, c1_golden):
+    g = tiny_golden
+    eL = {"values": g["eigL_values"], "vectors": g["eigL_vectors"]}
+    reml = {"delta": float(g["delta"]), "vg": float(g["vg"]), "ve": float(g["ve"]), "REML": float(g["REML"])}
+    res = gb().GAPIT_EMMAxP3D(g["Y"], g["G"].T, g["K"], X0=g["X0"], ctx=gpu_ctx, eig_L=eL, reml=reml)
+    ok = ~np.isnan(g["mlm_stats"])
+    assert np.allclose(res["effect.est"][ok, 0], g["mlm_effect"][ok], rtol=BETA_RTOL, atol=1e-12)
+    assert np.nanmax(np.abs(np.log10(res["ps"][:, 0]) - np.log10(g["mlm_ps"]))) < LOGP_ATOL
+    Kg, gram = gb().GAPIT_kinship_VanRaden(g["G"].T, ctx=gpu_ctx, return_gram=True, verbose=False)
+    assert np.array_equal(gram, g["gram"]) and np.abs(Kg - g["K"]).max() <= K_RTOL * np.abs(g["K"]).max()
+    # BASELINE configs[0] shape
+    c = c1_golden
+    G, Y, X0 = c1_inputs(c)
+    Kc, gramc = gb().GAPIT_kinship_VanRaden(G.T, ctx=gpu_ctx, return_gram=True, verbose=False)
+    assert np.array_equal(np.diag(gramc), c["gram_diag"]) and np.array_equal(gramc[0], c["gram_row0"])
+    assert int(gramc.astype(np.int64).sum()) == int(c["gram_checksum"][0])
+    assert np.allclose(np.diag(Kc), c["K_diag"], rtol=1e-12) and np.allclose(Kc[0], c["K_row0"], rtol=1e-9, atol=1e-13)
+    glm = gb().GAPIT_EMMAxP3D(Y, G.T, None, X0=X0, ctx=gpu_ctx)
+    with np.errstate(divide="ignore"):
+        assert np.nanmax(np.abs(np.log10(glm["ps"][:, 0]) - np.log10(c["glm_ps"]))) < LOGP_ATOL
+    mlm = gb().GAPIT_EMMAxP3D(Y, G.T, Kc, X0=X0, ctx=gpu_ctx)
+    assert mlm["delta"] == pytest.approx(float(c["delta"]), rel=1e-6)
+    with np.errstate(divide="ignore"):
+        assert np.nanmax(np.abs(np.log10(mlm["ps"][:, 0]) - np.log10(c["mlm_ps"]))) < 1e-4
+
+
+def test_scan_properties_at_scale(gpu_ctx):
+    """n large enough for several eigen-index splits and marker tiles: duplicate columns give bit-identical rows
+    wherever they sit, 0<->2 recoding flips the sign of beta only, a sub-range scan equals the same rows of the
+    full scan (marker-shard independence), spot rows match the dense GLS solve."""
+    n, m = 1500, 6000
+    G = synth.make_genotypes(n, m, seed=5, threads=8)
+    G[4999] = G[17]
+    G[300] = G[17]
+    Y = synth.make_phenotypes(G, seed=5)[:, 0]
+    X0 = synth.make_covariates(G, npc=2)
+    K = gb().GAPIT_kinship_VanRaden(G.T, ctx=gpu_ctx, verbose=False)
+    eL = gb().emma_eigen_L_wo_Z(K, ctx=gpu_ctx)
+    reml = gb().GAPIT_emma_REMLE(Y, X0, K, ctx=gpu_ctx)
+    run = lambda snps: gb().GAPIT_EMMAxP3D(Y, snps, K, X0=X0, ctx=gpu_ctx, eig_L=eL, reml=reml)
+    full = run(gb().Genotypes(G, ctx=gpu_ctx, marker_major=True))
+    for key in ("ps", "stats", "effect.est", "rsquare", "logLM"):
+        assert full[key][4999, 0] == full[key][17, 0] == full[key][300, 0]
+    part = run(gb().Genotypes(G[2000:4500], ctx=gpu_ctx, marker_major=True))
+    for key in ("ps", "stats", "effect.est"):
+        assert np.array_equal(part[key][:, 0], full[key][2000:4500, 0], equal_nan=True)
+    flip = run(gb().Genotypes((2 - G).astype(np.int8), ctx=gpu_ctx, marker_major=True))
+    ok = ~np.isnan(full["stats"][:, 0])
+    assert np.allclose(flip["effect.est"][ok, 0], -full["effect.est"][ok, 0], rtol=1e-7, atol=1e-10)
+    assert np.allclose(flip["ps"][ok, 0], full["ps"][ok, 0], rtol=1e-6)
+    for i in (0, 17, 1234, 5999):
+        if np.isnan(full["stats"][i, 0]):
+            continue
+        d = cc.gls_dense(Y, X0, G[i].astype(float), K, reml["delta"], reml["vg"])
+        assert full["effect.est"][i, 0] == pytest.approx(d["beta"][-1], rel=1e-7, abs=1e-10)
+        assert full["stats"][i, 0] == pytest.approx(d["t"], rel=1e-7, abs=1e-10)
+
+
+def test_multi_trait_matches_single_trait_calls(gpu_ctx):
+    G, _, X0 = case(150, 400, npc=1)
+    Yt = synth.make_phenotypes(G, ntraits=3, seed=8)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    remls = [go.emma_REMLE(Yt[:, t], X0, K) for t in range(3)]
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    arrs, bases = gb().p3d_scan(geno, X0, Yt, eigsys=es, delta=[r["delta"] for r in remls], vg=[r["vg"] for r in remls],
+                                ctx=gpu_ctx)
+    for t in range(3):
+        one, b1 = gb().p3d_scan(geno, X0, Yt[:, t], eigsys=es, delta=[remls[t]["delta"]], vg=[remls[t]["vg"]], ctx=gpu_ctx)
+        assert np.array_equal(arrs["pvalue"][t], one["pvalue"][0], equal_nan=True)
+        ora = go.emmax_p3d(Yt[:, t], G.T, K, X0, eig_L=eL, reml=remls[t])
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(arrs["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
+        assert bases[t]["rsquare_base"] == pytest.approx(ora.rsquare_base[~np.isnan(ora.rsquare_base)][0], abs=1e-10)
+
+
+def test_singular_covariates_fall_back_to_pseudo_inverse(gpu_ctx, capsys):
+    G, Y, X0 = case(120, 200, npc=1)
+    X0d = np.column_stack([X0, X0[:, 1] * 2.0])          # linearly dependent covariates (:708-712)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    res = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0d, ctx=gpu_ctx, eig_L=eL, reml=reml)
+    assert "linearly dependent" in capsys.readouterr().out
+    ref = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0, ctx=gpu_ctx, eig_L=eL, reml=reml)
+    ok = ~np.isnan(ref["stats"][:, 0])
+    # the marker effect is estimable either way
+    assert np.allclose(res["effect.est"][ok, 0], ref["effect.est"][ok, 0], rtol=1e-6, atol=1e-9)
+
+
+def test_bad_arguments_are_errors_not_crashes(gpu_ctx):
+    G, Y, X0 = case(60, 80)
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    with pytest.raises(gb().GapitCudaError):
+        gb().p3d_scan(geno, np.ones((60, 17)), Y, glm=True, ctx=gpu_ctx)        # q0 > GAPIT_MAX_Q0
+    with pytest.raises(gb().GapitCudaError):
+        gb().p3d_scan(geno, X0, Y, glm=False, ctx=gpu_ctx)                      # MLM without an eigen-system
+    with pytest.raises(NotImplementedError):
+        gb().GAPIT_EMMAxP3D(Y, G.T, None, X0=X0, ctx=gpu_ctx, SNP_P3D=False)

