@@ -71,6 +71,8 @@ SIGNATURES = {
     "gapit_eigsys_free": (None, [_P]),
     "gapit_p3d_scan_dev": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
                                      C.POINTER(ScanOut), C.POINTER(ScanBase)]),
+    "gapit_p3d_scan_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _I64, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, _P,
+                                      C.c_int, C.POINTER(ScanOut), C.POINTER(ScanBase)]),
     "gapit_set_slices": (C.c_int, [_P, C.c_int]),
 }
 

@@ -221,8 +221,17 @@ def GAPIT_emma_REMLE(y, X, K, Z=None, ngrids=100, llim=-10, ulim=10, esp=1e-10, 
 # ---------------------------------------------------------------------------
 # the marker scan proper
 # ---------------------------------------------------------------------------
-def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None):
-    """Scan all markers of ``geno`` for T traits.  Returns (dict of (T, m) arrays, list of per-trait base dicts)."""
+def _host_array(shape, pinned):
+    if pinned:
+        import torch
+        return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    return np.empty(shape, dtype=np.float64)
+
+
+def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None, pinned=False):
+    """Scan all markers of ``geno`` for T traits.  Returns (dict of (T, m) arrays, list of per-trait base dicts).
+    ``pinned=True`` puts the result arrays in page-locked host memory (needs torch) so the D2H copy runs at
+    full PCIe rate."""
     ctx = ctx or geno.ctx
     X0 = np.asfortranarray(X0, dtype=np.float64)
     Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(geno.n, -1))
@@ -230,8 +239,8 @@ def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None)
     T = Y.shape[1]
     m = geno.m
     names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
-    arrs = {k: np.empty((T, m), dtype=np.float64) for k in names}
-    arrs["maf"] = np.empty(m, dtype=np.float64)
+    arrs = {k: _host_array((T, m), pinned) for k in names}
+    arrs["maf"] = _host_array((m,), pinned)
     so = _lib.ScanOut(**{k: arrs[k].ctypes.data_as(C.POINTER(C.c_double)) for k in arrs})
     base = (_lib.ScanBase * T)()
     d = np.ascontiguousarray(delta, dtype=np.float64).reshape(-1) if delta is not None else None
@@ -243,6 +252,47 @@ def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None)
         b = base[t]
         bases.append({"logL0": b.logL0, "logLM_base": b.logLM_base, "rsquare_base": b.rsquare_base, "ves": b.ves,
                       "reml": b.reml, "df": b.df, "beta0": np.array(b.beta0[:q0]), "singular_x0": bool(b.singular_x0)})
+    return arrs, bases
+
+
+def _host_geno(snps, marker_major):
+    """-> (array (m, n) C-contiguous, dtype code) exactly as the C ABI wants it (ld = n)."""
+    a = np.asarray(snps)
+    if not marker_major:
+        a = a.T
+    if a.dtype == np.int8 or a.dtype == np.uint8:
+        dtype = _lib.GAPIT_I8
+    elif a.dtype == np.int32:
+        dtype = _lib.GAPIT_I32
+    else:
+        a = a.astype(np.float64, copy=False)
+        dtype = _lib.GAPIT_F64
+    return np.ascontiguousarray(a), dtype
+
+
+def p3d_scan_host(snps, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None, impute=None, marker_major=False,
+                  pinned=False):
+    """Streaming scan straight from a host genotype matrix (H2D overlapped with the scan).  Same returns as
+    :func:`p3d_scan`."""
+    ctx = ctx or default_context()
+    a, dtype = _host_geno(snps, marker_major)
+    m, n = a.shape
+    X0 = np.asfortranarray(X0, dtype=np.float64)
+    Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n, -1))
+    q0, T = X0.shape[1], Y.shape[1]
+    names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
+    arrs = {k: _host_array((T, m), pinned) for k in names}
+    arrs["maf"] = _host_array((m,), pinned)
+    so = _lib.ScanOut(**{k: arrs[k].ctypes.data_as(C.POINTER(C.c_double)) for k in arrs})
+    base = (_lib.ScanBase * T)()
+    d = np.ascontiguousarray(delta, dtype=np.float64).reshape(-1) if delta is not None else None
+    v = np.ascontiguousarray(vg, dtype=np.float64).reshape(-1) if vg is not None else None
+    check(ctx.lib.gapit_p3d_scan_host(ctx.h, _ptr(a), dtype, n, m, n, _lib.IMPUTE[impute],
+                                      eigsys.h if eigsys is not None else None, _ptr(X0), q0, _ptr(Y), T, _ptr(d), _ptr(v),
+                                      1 if glm else 0, C.byref(so), base))
+    bases = [{"logL0": b.logL0, "logLM_base": b.logLM_base, "rsquare_base": b.rsquare_base, "ves": b.ves,
+              "reml": b.reml, "df": b.df, "beta0": np.array(b.beta0[:q0]), "singular_x0": bool(b.singular_x0)}
+             for b in base]
     return arrs, bases
 
 
@@ -284,8 +334,15 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
     if K is not None and np.size(K) <= 1:                                 # :34
         K = None
     q0 = X0.shape[1]
-    geno, owned = _as_geno(xs, ctx, impute=SNP_impute)                    # :20-24 (NA -> impute value)
-    m = geno.m
+    # :20-24 (NA -> SNP.impute value).  A host matrix is streamed (upload overlapped with the scan); an
+    # already-resident Genotypes handle is scanned in place.
+    resident = isinstance(xs, Genotypes)
+    m = xs.m if resident else np.asarray(xs).shape[1]
+
+    def run_scan(**kw):
+        if resident:
+            return p3d_scan(xs, X0, ys, ctx=ctx, **kw)
+        return p3d_scan_host(xs, X0, ys, ctx=ctx, impute=SNP_impute, **kw)
     glm = K is None
     if not glm:
         if eig_L is None:
@@ -304,11 +361,11 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
         Timmer = _timmer(Timmer, "REML")
         es = EigenSystem(eig_L["values"], eig_L["vectors"], ctx=ctx)      # :224 folded into the kernel weights
         Timmer = _timmer(Timmer, "U Matrix")
-        arrs, bases = p3d_scan(geno, X0, ys, eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]], ctx=ctx)
+        arrs, bases = run_scan(eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]])
         es.close()
         vgs, ves, REMLs = reml["vg"], reml["ve"], reml["REML"]
     else:
-        arrs, bases = p3d_scan(geno, X0, ys, glm=True, ctx=ctx)
+        arrs, bases = run_scan(glm=True)
         vgs, ves, REMLs = 0.0, bases[0]["ves"], bases[0]["reml"]           # :868-872
     Timmer = _timmer(Timmer, "Screening SNPs")
     if bases[0]["singular_x0"]:                                           # :711
@@ -327,8 +384,6 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
             stderr = arrs["effect"][0] / stats
         # idx < q0 would need the per-marker covariate effects the scan does not return
     rsq_base = np.where(normal, b["rsquare_base"], np.nan)
-    if owned:
-        geno.close()
     Timmer = _timmer(Timmer, "GWAS done for this Trait")
     return {
         "ps": col(arrs["pvalue"][0]), "REMLs": -2.0 * REMLs, "stats": col(stats),

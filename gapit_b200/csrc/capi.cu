@@ -51,6 +51,25 @@ int make_tensor_map_u8(CUtensorMap* out, const void* base, uint64_t inner_bytes,
   return GAPIT_OK;
 }
 
+int ctx_ws(gapit_ctx* ctx, int slot, size_t bytes, void** out) {
+  if (slot < 0 || slot >= gapit_ctx::kWsSlots) return fail(GAPIT_ERR_ARG, "ctx_ws: bad slot");
+  if (bytes == 0) bytes = 16;
+  if (ctx->ws_cap[slot] < bytes) {
+    if (ctx->ws_ptr[slot]) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFree(ctx->ws_ptr[slot]);
+      ctx->ws_ptr[slot] = nullptr;
+      ctx->ws_cap[slot] = 0;
+    }
+    const size_t cap = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&ctx->ws_ptr[slot], cap);
+    if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("workspace cudaMalloc: ") + cudaGetErrorString(e));
+    ctx->ws_cap[slot] = cap;
+  }
+  *out = ctx->ws_ptr[slot];
+  return GAPIT_OK;
+}
+
 }  // namespace gapit
 
 using namespace gapit;
@@ -84,6 +103,13 @@ extern "C" int gapit_ctx_create(int device, gapit_ctx** out) {
   ctx->stream = ctx->own_stream;
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev2);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev3);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     gapit_ctx_destroy(ctx);
     return fail(GAPIT_ERR_CUDA, std::string("gapit_ctx_create: ") + cudaGetErrorString(e));
@@ -98,6 +124,15 @@ extern "C" void gapit_ctx_destroy(gapit_ctx* ctx) {
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev2) cudaEventDestroy(ctx->ev2);
+  if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
+    if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
+  }
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  for (int i = 0; i < gapit_ctx::kWsSlots; ++i)
+    if (ctx->ws_ptr[i]) cudaFree(ctx->ws_ptr[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }

@@ -46,7 +46,28 @@ struct gapit_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   gapit_stats stats = {};
   int slices = 6;  // int8 slices of V used by the rotation (Ozaki split)
+  // grow-only device workspaces reused across calls (no cudaMalloc/cudaFree on the hot path)
+  static constexpr int kWsSlots = 24;
+  void* ws_ptr[kWsSlots] = {};
+  size_t ws_cap[kWsSlots] = {};
+  cudaStream_t copy_stream = nullptr;   // H2D of the next genotype chunk while the current one is scanned
+  cudaEvent_t ev2 = nullptr, ev3 = nullptr;
+  cudaEvent_t ev_ready[2] = {}, ev_free[2] = {};
 };
+
+namespace gapit {
+enum WsSlot { WS_R = 0, WS_PROJ, WS_GCONST, WS_PART, WS_OUT, WS_RG, WS_RS, WS_RSCALE, WS_BAD, WS_CHUNK0, WS_CHUNK1,
+              WS_CS0, WS_CS1, WS_CQ0, WS_CQ1, WS_STAGE0, WS_STAGE1 };
+// device workspace of at least `bytes` in `slot` (contents are not preserved when it grows)
+int ctx_ws(gapit_ctx* ctx, int slot, size_t bytes, void** out);
+template <class T>
+inline int ctx_ws_t(gapit_ctx* ctx, int slot, size_t count, T** out) {
+  void* p = nullptr;
+  int rc = ctx_ws(ctx, slot, count * sizeof(T), &p);
+  *out = static_cast<T*>(p);
+  return rc;
+}
+}  // namespace gapit
 
 struct gapit_geno {
   gapit_ctx* ctx = nullptr;

@@ -120,19 +120,37 @@ __global__ void __launch_bounds__(1024) transpose_kernel(const int8_t* __restric
   }
 }
 
+// asynchronous pieces shared with the streaming scan (scan.cu)
+int launch_colstats(gapit_ctx* ctx, cudaStream_t st, const int8_t* mk, int64_t ldn, int64_t n, int64_t m, int32_t* colsum,
+                    int32_t* colsumsq, int* bad_dev) {
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((m * 32 + threads - 1) / threads, int64_t(ctx->sm_count) * 16)));
+  colstats_kernel<<<blocks, threads, 0, st>>>(mk, ldn, n, m, colsum, colsumsq, bad_dev);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
+// stage: `mc` markers of n elements (dense, ld = n) already on the device
+int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
+                   int impute, int* bad_dev) {
+  dim3 grid(static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64)), static_cast<unsigned>(mc));
+  if (dtype == GAPIT_F64)
+    convert_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(stage), n, n, mc, dst, ldn, impute, bad_dev);
+  else
+    convert_kernel<int32_t><<<grid, 256, 0, st>>>(static_cast<const int32_t*>(stage), n, n, mc, dst, ldn, impute, bad_dev);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
 static int run_colstats(gapit_geno* g) {
   gapit_ctx* ctx = g->ctx;
   int* bad = nullptr;
-  GAPIT_CUDA(cudaMalloc(&bad, sizeof(int)));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_BAD, 4, &bad));
   GAPIT_CUDA(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
-  const int threads = 256;
-  const int blocks = std::max<int64_t>(1, std::min<int64_t>((g->m * 32 + threads - 1) / threads, int64_t(ctx->sm_count) * 16));
-  colstats_kernel<<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, g->colsum, g->colsumsq, bad);
-  GAPIT_CUDA(cudaGetLastError());
+  GAPIT_CHECK(launch_colstats(ctx, ctx->stream, g->mk, g->ldn, g->n, g->m, g->colsum, g->colsumsq, bad));
   int hbad = 0;
   GAPIT_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(bad);
   if (hbad) return fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}");
   return GAPIT_OK;
 }
@@ -177,7 +195,23 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
   int rc = GAPIT_OK;
   if (dtype == GAPIT_I8) {
     if (g->ldn != n) cudaMemsetAsync(g->mk, 0, size_t(m) * g->ldn, ctx->stream);
-    e = cudaMemcpy2DAsync(g->mk, g->ldn, snps, ld, n, m, cudaMemcpyHostToDevice, ctx->stream);
+    if (ld == n && g->ldn != n) {
+      // dense host rows: flat PCIe transfers through a staging buffer, re-pitched on the device
+      const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(256) << 20) / n));
+      void* stage = nullptr;
+      int rc2 = ctx_ws(ctx, WS_STAGE0, size_t(chunk) * n, &stage);
+      if (rc2 != GAPIT_OK) return cleanup(rc2);
+      e = cudaSuccess;
+      for (int64_t k0 = 0; k0 < m && e == cudaSuccess; k0 += chunk) {
+        const int64_t mc = std::min(chunk, m - k0);
+        e = cudaMemcpyAsync(stage, static_cast<const char*>(snps) + size_t(k0) * n, size_t(mc) * n, cudaMemcpyHostToDevice,
+                            ctx->stream);
+        if (e == cudaSuccess)
+          e = cudaMemcpy2DAsync(g->mk + k0 * g->ldn, g->ldn, stage, n, n, mc, cudaMemcpyDeviceToDevice, ctx->stream);
+      }
+    } else {
+      e = cudaMemcpy2DAsync(g->mk, g->ldn, snps, ld, n, m, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e != cudaSuccess) return cleanup(fail(GAPIT_ERR_CUDA, std::string("H2D genotype copy: ") + cudaGetErrorString(e)));
   } else if (dtype == GAPIT_F64 || dtype == GAPIT_I32) {
     const size_t esz = (dtype == GAPIT_F64) ? 8 : 4;

@@ -14,12 +14,13 @@
 //                        (w = 1/(lambda+delta), A = V'X0, b = V'y: the dot products of :653-655,:682)
 //                        in registers while sweeping k, in a fixed order => bit-identical rows for
 //                        identical genotype columns wherever they sit.
-//   K3g glm_reduce       K = NULL branch (:759-763): same three reductions straight from the int8
-//                        genotypes (U = I); HBM-bound streaming kernel.
+//   K3g glm_reduce       K = NULL branch (:759-763): the same UMMA main loop with the digit planes of [X0 | y]
+//                        as B operand (U = I); streams the genotypes once through TMA, HBM-bound.
 //   K4  finalize         per marker: Schur complement of [X0t xst]'[X0t xst] (:736-748), beta (:772),
 //                        t (:936-937), p = 2 pt(|t|, df) (:939), logLM and R^2 (:955-967).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -172,9 +173,14 @@ struct ScanEpi {
     double* part;          // [gsplit][Q+2][m_ld]
     int64_t m_ld;
     int64_t m;
+    int pair;  // 1: merge adjacent digit planes in int32 before converting (needs 65792 n < 2^31)
   };
   Params p;
   double acc[Q + 2];
+  // exact int32 -> fp64: the bits 0x43300000:(x ^ 0x80000000) are the double 2^52 + 2^31 + x
+  static __device__ __forceinline__ double i2d(int x) {
+    return __hiloint2double(0x43300000, x ^ static_cast<int>(0x80000000u)) - 4503601774854144.0;
+  }
   __device__ explicit ScanEpi(const Params& pp) : p(pp) {
 #pragma unroll
     for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
@@ -193,9 +199,26 @@ struct ScanEpi {
       ptx::tmem_ld_wait();
 #pragma unroll
       for (int kk = 0; kk < KG; ++kk) {
-        double u = static_cast<double>(static_cast<int>(r[kk * S + S - 1]));
+        // u = sum_s 256^s D_s.  Adjacent digit planes are first merged in int32 (exact while
+        // 257 * 256 * n < 2^31), halving the int -> fp64 conversions, which use the 2^52 magic
+        // constant (one LOP + one DADD) instead of the quarter-rate I2F.F64.
+        const int* d = reinterpret_cast<const int*>(&r[kk * S]);
+        double u;
+        if (p.pair) {
+          if (S & 1) {
+            u = i2d(d[S - 1]);
 #pragma unroll
-        for (int s = S - 2; s >= 0; --s) u = fma(u, 256.0, static_cast<double>(static_cast<int>(r[kk * S + s])));
+            for (int s = S - 3; s >= 0; s -= 2) u = fma(u, 65536.0, i2d(d[s + 1] * 256 + d[s]));
+          } else {
+            u = i2d(d[S - 1] * 256 + d[S - 2]);
+#pragma unroll
+            for (int s = S - 4; s >= 0; s -= 2) u = fma(u, 65536.0, i2d(d[s + 1] * 256 + d[s]));
+          }
+        } else {
+          u = i2d(d[S - 1]);
+#pragma unroll
+          for (int s = S - 2; s >= 0; --s) u = fma(u, 256.0, i2d(d[s]));
+        }
         const double* c = gc + (g * KG + kk) * (Q + 2);
         acc[0] = fma(__ldg(c) * u, u, acc[0]);
 #pragma unroll
@@ -214,41 +237,74 @@ struct ScanEpi {
 };
 
 // ------------------------------------------------------------------ K3g
-// GLM: xx = sum x^2, xa_j = sum X0_ij x_i, xy = sum y_i x_i ; one warp per marker, fixed order
-template <int Q>
-__global__ void glm_reduce_kernel(const int8_t* __restrict__ mk, int64_t ldn, int64_t n, int64_t m,
-                                  const double* __restrict__ R /* [Q+1][n]: X0 columns then y */,
-                                  double* __restrict__ part, int64_t m_ld) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (int64_t(gridDim.x) * blockDim.x) >> 5;
-  for (int64_t k = warp; k < m; k += nwarps) {
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(mk + k * ldn);
-    double acc[Q + 2];
+// GLM (K = NULL, U = I): xa_j = sum_i X0_ij x_i and xy = sum_i y_i x_i are the product of the marker tile
+// with R = [X0 | y] (n x (q0+1)), so the same int8 UMMA main loop is used with the digit planes of R as the
+// B operand (one BN-row tile, N = (q0+1) S columns).  The kernel then streams the genotypes exactly once
+// through TMA at HBM rate; xx = sum_i x_i^2 is the exact integer the pack stage already holds.
+struct GlmSched {
+  struct Params {
+    int mtiles;   // 256-marker tiles
+    int kblocks;  // taxa axis in units of kBlockK
+  };
+  static constexpr uint64_t kHintA = ptx::kEvictFirst;  // genotypes: read once
+  static constexpr uint64_t kHintB = ptx::kEvictLast;   // digit planes of R: re-read by every tile
+  Params p;
+  int tile, stride;
+  __device__ GlmSched(const Params& pp, int block, int nblocks) : p(pp), tile(block), stride(nblocks) {}
+  __device__ bool next(Job& j) {
+    if (tile >= p.mtiles) return false;
+    j.a_row0 = tile * 256;
+    j.b_row0 = 0;
+    j.kb_begin = 0;
+    j.kb_end = p.kblocks;
+    j.tag0 = j.tag1 = 0;
+    j.group_first = j.group_last = true;
+    tile += stride;
+    return true;
+  }
+};
+
+// exact int32 -> fp64: the bits 0x43300000:(x ^ 0x80000000) are the double 2^52 + 2^31 + x
+static __device__ __forceinline__ double int_to_double(int x) {
+  return __hiloint2double(0x43300000, x ^ static_cast<int>(0x80000000u)) - 4503601774854144.0;
+}
+
+template <int S, int BN>
+struct GlmEpi {
+  static constexpr int NCMAX = BN / S;
+  struct Params {
+    const double* scale;       // [nc] c_j = 2^(e_j - (8S-2)) of column j of R
+    const int32_t* colsumsq;   // [m]
+    double* part;              // [qpad+2][m_ld]
+    int64_t m_ld;
+    int64_t m;
+    int nc;                    // q0 + 1 columns of R in use
+    int qpad;
+  };
+  Params p;
+  __device__ explicit GlmEpi(const Params& pp) : p(pp) {}
+  __device__ void run(const Job& job, uint32_t taddr, int sub, int row) {
+    uint32_t r[BN];
 #pragma unroll
-    for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
-    for (int64_t c = lane; c * 4 < n; c += 32) {
-      const uint32_t w = __ldg(row + c);
+    for (int j = 0; j < BN / 8; ++j) ptx::tmem_ld_x8(taddr + j * 8, *reinterpret_cast<uint32_t(*)[8]>(&r[j * 8]));
+    ptx::tmem_ld_wait();
+    const int64_t mrk = int64_t(job.a_row0) + sub * 128 + row;
+    if (mrk >= p.m_ld) return;
+    p.part[mrk] = (mrk < p.m) ? static_cast<double>(p.colsumsq[mrk]) : 0.0;
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int64_t i = c * 4 + b;
-        const double x = static_cast<double>((w >> (8 * b)) & 0xff);
-        if (i < n && x != 0.0) {
-          acc[0] = fma(x, x, acc[0]);
+    for (int c = 0; c < NCMAX; ++c) {
+      if (c < p.nc) {
+        const int* d = reinterpret_cast<const int*>(&r[c * S]);
+        double u = int_to_double(d[S - 1]);
 #pragma unroll
-          for (int j = 0; j < Q + 1; ++j) acc[1 + j] = fma(x, __ldg(R + j * n + i), acc[1 + j]);
-        }
+        for (int s = S - 2; s >= 0; --s) u = fma(u, 256.0, int_to_double(d[s]));
+        // columns 0..q0-1 are covariates (slots 1..q0), column q0 is the phenotype (slot qpad+1)
+        const int slot = (c == p.nc - 1) ? (p.qpad + 1) : (1 + c);
+        p.part[int64_t(slot) * p.m_ld + mrk] = u * __ldg(p.scale + c);
       }
     }
-#pragma unroll
-    for (int i = 0; i < Q + 2; ++i) {
-      double a = acc[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) part[i * m_ld + k] = a;
-    }
   }
-}
+};
 
 // ------------------------------------------------------------------ K4
 struct FinalizeConsts {
@@ -475,7 +531,9 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   sp.nkq = static_cast<int>(e->nkq);
   sp.kblocks = static_cast<int>(g->ldn / kBlockK);
   sp.bn = BN;
-  typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m};
+  int pair = (65792ll * g->n < 2147483647ll) ? 1 : 0;
+  if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);  // A/B switch for profiling
+  typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair};
   auto kern = umma_i8_kernel<2, BN, 3, ScanSched, Epi, 1, 1>;
   GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int grid = std::min(ctx->sm_count, sp.mtiles * sp.gsplit);
@@ -507,18 +565,35 @@ static int launch_scan(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int Q, co
   }
 }
 
-static int launch_glm(gapit_ctx* ctx, gapit_geno* g, int Q, const double* R_dev, double* part_dev, int64_t m_ld) {
-  const int threads = 256;
-  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((g->m * 32 + threads - 1) / threads, int64_t(ctx->sm_count) * 8)));
-  switch (Q) {
-    case 1: glm_reduce_kernel<1><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
-    case 2: glm_reduce_kernel<2><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
-    case 4: glm_reduce_kernel<4><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
-    case 8: glm_reduce_kernel<8><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
-    default: glm_reduce_kernel<16><<<blocks, threads, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, R_dev, part_dev, m_ld); break;
-  }
+template <int BN>
+static int launch_glm_bn(gapit_ctx* ctx, gapit_geno* g, const int8_t* Rs_dev, int64_t rs_rows, const double* scale_dev,
+                         int nc, int Q, double* part_dev, int64_t m_ld) {
+  constexpr int S = 6;
+  using Cfg = UmmaCfg<2, BN, 4>;
+  using Epi = GlmEpi<S, BN>;
+  CUtensorMap map_a, map_b;
+  GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
+                                 static_cast<uint64_t>(g->ldn), 256));
+  GAPIT_CHECK(make_tensor_map_u8(&map_b, Rs_dev, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(rs_rows),
+                                 static_cast<uint64_t>(g->ldn), BN));
+  GlmSched::Params sp{static_cast<int>(m_ld / 256), static_cast<int>(g->ldn / kBlockK)};
+  typename Epi::Params ep{scale_dev, g->colsumsq, part_dev, m_ld, g->m, nc, Q};
+  auto kern = umma_i8_kernel<2, BN, 4, GlmSched, Epi, 1, 1>;
+  GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  const int grid = std::min(ctx->sm_count, sp.mtiles);
+  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(map_a, map_b, sp, ep);
   GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
+}
+
+// Rs_dev: digit planes of R = [X0 | y], rows (c*6 + s), `rs_rows` rows allocated (>= BN, zero beyond nc*6)
+static int launch_glm(gapit_ctx* ctx, gapit_geno* g, const int8_t* Rs_dev, int64_t rs_rows, const double* scale_dev,
+                      int nc, int Q, double* part_dev, int64_t m_ld) {
+  const int cols = nc * 6;
+  if (cols <= 16) return launch_glm_bn<16>(ctx, g, Rs_dev, rs_rows, scale_dev, nc, Q, part_dev, m_ld);
+  if (cols <= 32) return launch_glm_bn<32>(ctx, g, Rs_dev, rs_rows, scale_dev, nc, Q, part_dev, m_ld);
+  if (cols <= 64) return launch_glm_bn<64>(ctx, g, Rs_dev, rs_rows, scale_dev, nc, Q, part_dev, m_ld);
+  return launch_glm_bn<112>(ctx, g, Rs_dev, rs_rows, scale_dev, nc, Q, part_dev, m_ld);
 }
 
 // eigen-index splits: keep the marker tiles of the CTAs that run together (148/g tiles of 256 x ldn bytes)
@@ -530,57 +605,81 @@ static int choose_gsplit(int64_t ldn, int64_t nkq) {
   return static_cast<int>(std::min<int64_t>(g, nkq));
 }
 
-struct DevBuf {
-  void* p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
-  template <class T> T* as() { return static_cast<T*>(p); }
+int launch_colstats(gapit_ctx* ctx, cudaStream_t st, const int8_t* mk, int64_t ldn, int64_t n, int64_t m, int32_t* colsum,
+                    int32_t* colsumsq, int* bad_dev);
+int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
+                   int impute, int* bad_dev);
+
+// Everything about a scan that does not depend on the markers: the marker-free model of every trait
+// (i = 0 of the reference loop), the per-eigenvalue constants of the rotation epilogue (MLM) or the digit
+// planes of [X0 | y] (GLM), resident on the device.
+struct ScanPlan {
+  int64_t n = 0, ldn = 0;
+  int q0 = 0, Q = 0, T = 0, glm = 0, gsplit = 1;
+  gapit_eigsys* e = nullptr;
+  std::vector<FinalizeConsts> fc;   // per trait
+  double* gconst = nullptr;         // MLM: [T][nk][Q+2]
+  int64_t nk = 0;
+  int8_t* Rs = nullptr;             // GLM: [T][128][ldn] digit planes of [X0 | y_t]
+  double* Rscale = nullptr;         // GLM: [T][GAPIT_MAX_Q0+1]
 };
 
-static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
-                     const double* delta, const double* vg, int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
-  if (!ctx || !g || !X0 || !Y || !out || T < 1) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL argument");
+// one block of markers resident on the device
+struct MarkerView {
+  const int8_t* mk;
+  int64_t m;
+  const int32_t* colsum;
+  const int32_t* colsumsq;
+};
+
+static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e, const double* X0, int q0, const double* Y,
+                        int T, const double* delta, const double* vg, int glm, ScanPlan* plan, gapit_scan_base* base_out) {
+  if (!ctx || !X0 || !Y || T < 1) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL argument");
   if (q0 < 1 || q0 > GAPIT_MAX_Q0) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: q0 must be 1.." + std::to_string(GAPIT_MAX_Q0));
   if (!glm && (!e || !delta || !vg)) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: MLM needs an eigen-system, delta and vg");
-  const int64_t n = g->n, m = g->m;
   if (!glm && e->n != n) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: eigen-system and genotypes disagree on n");
   if (n - q0 - 1 < 1) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: no residual degrees of freedom");
-  if (!out->effect || !out->tvalue || !out->se || !out->pvalue || !out->rsquare || !out->loglm)
-    return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: output arrays effect/tvalue/se/pvalue/rsquare/loglm are required");
   GAPIT_CUDA(cudaSetDevice(ctx->device));
-  const int Q = pad_q(q0);
-  const int64_t m_ld = round_up(m, 256);
-  const int gsplit = glm ? 1 : choose_gsplit(g->ldn, e->nkq);
+  plan->n = n;
+  plan->ldn = ldn;
+  plan->q0 = q0;
+  plan->Q = pad_q(q0);
+  plan->T = T;
+  plan->glm = glm;
+  plan->e = e;
+  plan->gsplit = glm ? 1 : choose_gsplit(ldn, e->nkq);
+  plan->fc.resize(T);
+  const int Q = plan->Q;
   const int nc = q0 + T;
 
-  DevBuf dR, dProj, dGc, dPart, dOut, dRg;
-  GAPIT_CUDA(dR.alloc(size_t(n) * nc * 8));
-  GAPIT_CUDA(dPart.alloc(size_t(gsplit) * (Q + 2) * m_ld * 8));
-  GAPIT_CUDA(dOut.alloc(size_t(7) * m * 8));
-  GAPIT_CUDA(cudaMemcpyAsync(dR.p, X0, size_t(n) * q0 * 8, cudaMemcpyHostToDevice, ctx->stream));
-  GAPIT_CUDA(cudaMemcpyAsync(dR.as<double>() + size_t(n) * q0, Y, size_t(n) * T * 8, cudaMemcpyHostToDevice, ctx->stream));
+  double* dR = nullptr;
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n) * nc, &dR));
+  GAPIT_CUDA(cudaMemcpyAsync(dR, X0, size_t(n) * q0 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  GAPIT_CUDA(cudaMemcpyAsync(dR + size_t(n) * q0, Y, size_t(n) * T * 8, cudaMemcpyHostToDevice, ctx->stream));
 
-  std::vector<double> proj;  // [(q0+T)][n]: rotated covariates then rotated phenotypes (or the raw ones for GLM)
-  proj.resize(size_t(nc) * n);
+  std::vector<double> proj(size_t(nc) * n);  // [(q0+T)][n]: rotated covariates then rotated phenotypes (raw ones for GLM)
   if (!glm) {
-    GAPIT_CUDA(dProj.alloc(size_t(n) * nc * 8));
+    double* dProj = nullptr;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(n) * nc, &dProj));
     const unsigned blocks = static_cast<unsigned>((n * 32 + 255) / 256);
-    for (int c0 = 0; c0 < nc; c0 += 8) {
-      vt_project_kernel<8><<<blocks, 256, 0, ctx->stream>>>(e->V, n, dR.as<double>(), nc, c0, dProj.as<double>());
-    }
+    for (int c0 = 0; c0 < nc; c0 += 8) vt_project_kernel<8><<<blocks, 256, 0, ctx->stream>>>(e->V, n, dR, nc, c0, dProj);
     GAPIT_CUDA(cudaGetLastError());
-    GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj.p, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
     GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int64_t nk = e->nkq * e->KPB;
-    GAPIT_CUDA(dGc.alloc(size_t(nk) * (Q + 2) * 8));
+    plan->nk = e->nkq * e->KPB;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_GCONST, size_t(T) * plan->nk * (Q + 2), &plan->gconst));
   } else {
     std::copy(X0, X0 + size_t(n) * q0, proj.begin());
     std::copy(Y, Y + size_t(n) * T, proj.begin() + size_t(n) * q0);
-    GAPIT_CUDA(dRg.alloc(size_t(Q + 1) * n * 8));
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_RS, size_t(T) * 128 * ldn, &plan->Rs));
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_RSCALE, size_t(T) * (GAPIT_MAX_Q0 + 1), &plan->Rscale));
+    GAPIT_CUDA(cudaMemsetAsync(plan->Rs, 0, size_t(T) * 128 * ldn, ctx->stream));
   }
 
-  float kernel_ms = 0.f, post_ms = 0.f;
   std::vector<double> w(n), gconst;
+  if (!glm) gconst.assign(size_t(T) * plan->nk * (Q + 2), 0.0);
+  const double dn = static_cast<double>(n);
+  const double two_pi = 2.0 * 3.14159265358979323846;
   for (int t = 0; t < T; ++t) {
     const double* yt = proj.data() + size_t(q0 + t) * n;
     double sumlog = 0.0;
@@ -594,7 +693,7 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
       }
     }
     // ---- i = 0 of the reference loop: the marker-free model (:617-620,:646,:678,:707-714,:772)
-    FinalizeConsts fc;
+    FinalizeConsts& fc = plan->fc[t];
     std::fill(fc.iXX, fc.iXX + GAPIT_MAX_Q0 * GAPIT_MAX_Q0, 0.0);
     std::fill(fc.beta0, fc.beta0 + GAPIT_MAX_Q0, 0.0);
     std::vector<double> XX(q0 * q0, 0.0), XY(q0, 0.0), inv(q0 * q0, 0.0);
@@ -630,11 +729,9 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
     const double* yraw = Y + size_t(t) * n;
     double ybar = 0.0;
     for (int64_t k = 0; k < n; ++k) ybar += yraw[k];
-    ybar /= static_cast<double>(n);
+    ybar /= dn;
     double ss0 = 0.0;
     for (int64_t k = 0; k < n; ++k) ss0 += (yraw[k] - ybar) * (yraw[k] - ybar);
-    const double dn = static_cast<double>(n);
-    const double two_pi = 2.0 * 3.14159265358979323846;
     fc.logL0 = 0.5 * (-dn * std::log((two_pi / dn) * ss0) - dn);
     fc.rss0 = rss0;
     fc.sumlog = sumlog;
@@ -643,7 +740,7 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
     fc.lbeta = std::lgamma(0.5 * fc.df) + std::lgamma(0.5) - std::lgamma(0.5 * fc.df + 0.5);
     fc.q0 = q0;
     fc.qpad = Q;
-    fc.gsplit = gsplit;
+    fc.gsplit = plan->gsplit;
     const double ves_glm = rss0 / static_cast<double>(n - q0);
     fc.var_scale = glm ? ves_glm : vg[t];
     if (base_out) {
@@ -658,57 +755,188 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
       for (int j = 0; j < q0; ++j) b.beta0[j] = fc.beta0[j];
       b.singular_x0 = singular;
     }
-
-    cudaEventRecord(ctx->ev0, ctx->stream);
     if (!glm) {
-      const int64_t nk = e->nkq * e->KPB;
-      gconst.assign(size_t(nk) * (Q + 2), 0.0);
+      double* gt = gconst.data() + size_t(t) * plan->nk * (Q + 2);
       for (int64_t k = 0; k < n; ++k) {
         const double c = e->h_scale[k];
-        double* gk = gconst.data() + size_t(k) * (Q + 2);
+        double* gk = gt + size_t(k) * (Q + 2);
         gk[0] = w[k] * c * c;
         for (int j = 0; j < q0; ++j) gk[1 + j] = w[k] * c * proj[size_t(j) * n + k];
         gk[Q + 1] = w[k] * c * yt[k];
       }
-      GAPIT_CUDA(cudaMemcpyAsync(dGc.p, gconst.data(), gconst.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-      cudaEventRecord(ctx->ev0, ctx->stream);
-      GAPIT_CHECK(launch_scan(ctx, g, e, Q, dGc.as<double>(), dPart.as<double>(), m_ld, gsplit));
     } else {
-      // R for the GLM kernel: Q covariate columns (zero-padded) then y
-      GAPIT_CUDA(cudaMemsetAsync(dRg.p, 0, size_t(Q + 1) * n * 8, ctx->stream));
-      GAPIT_CUDA(cudaMemcpyAsync(dRg.p, dR.p, size_t(n) * q0 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-      GAPIT_CUDA(cudaMemcpyAsync(dRg.as<double>() + size_t(Q) * n, dR.as<double>() + size_t(q0 + t) * n, size_t(n) * 8,
-                                 cudaMemcpyDeviceToDevice, ctx->stream));
-      cudaEventRecord(ctx->ev0, ctx->stream);
-      GAPIT_CHECK(launch_glm(ctx, g, Q, dRg.as<double>(), dPart.as<double>(), m_ld));
+      // R_t = [X0 | y_t] (contiguous columns) -> 6 int8 digit planes per column, same split as the eigenvectors
+      double* dRg = nullptr;
+      GAPIT_CHECK(ctx_ws_t(ctx, WS_RG, size_t(GAPIT_MAX_Q0 + 1) * n, &dRg));
+      GAPIT_CUDA(cudaMemcpyAsync(dRg, dR, size_t(n) * q0 * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+      GAPIT_CUDA(cudaMemcpyAsync(dRg + size_t(q0) * n, dR + size_t(q0 + t) * n, size_t(n) * 8, cudaMemcpyDeviceToDevice,
+                                 ctx->stream));
+      slice_v_kernel<<<static_cast<unsigned>(q0 + 1), 256, 0, ctx->stream>>>(
+          dRg, n, 6, plan->Rs + size_t(t) * 128 * ldn, ldn, plan->Rscale + size_t(t) * (GAPIT_MAX_Q0 + 1));
+      GAPIT_CUDA(cudaGetLastError());
     }
+  }
+  if (!glm) {
+    GAPIT_CUDA(cudaMemcpyAsync(plan->gconst, gconst.data(), gconst.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));  // `gconst` (pageable) must outlive the copy
+  }
+  return GAPIT_OK;
+}
+
+// scan one block of markers for trait t; results to out_dev[a * out_ld + out_off + k], a = 0..6
+static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, int t, double* out_dev, int64_t out_ld,
+                    int64_t out_off, cudaEvent_t after_reduce = nullptr) {
+  const int Q = plan.Q;
+  const int64_t m_ld = round_up(v.m, 256);
+  double* part = nullptr;
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t(plan.gsplit) * (Q + 2) * m_ld, &part));
+  gapit_geno view;  // borrowed pointers only
+  view.ctx = ctx;
+  view.n = plan.n;
+  view.m = v.m;
+  view.ldn = plan.ldn;
+  view.mk = const_cast<int8_t*>(v.mk);
+  view.colsum = const_cast<int32_t*>(v.colsum);
+  view.colsumsq = const_cast<int32_t*>(v.colsumsq);
+  if (!plan.glm) {
+    GAPIT_CHECK(launch_scan(ctx, &view, plan.e, Q, plan.gconst + size_t(t) * plan.nk * (Q + 2), part, m_ld, plan.gsplit));
+  } else {
+    GAPIT_CHECK(launch_glm(ctx, &view, plan.Rs + size_t(t) * 128 * plan.ldn, 128,
+                           plan.Rscale + size_t(t) * (GAPIT_MAX_Q0 + 1), plan.q0 + 1, Q, part, m_ld));
+  }
+  if (after_reduce) cudaEventRecord(after_reduce, ctx->stream);
+  double* o = out_dev + out_off;
+  finalize_kernel<<<static_cast<unsigned>((v.m + 255) / 256), 256, 0, ctx->stream>>>(
+      part, m_ld, v.m, v.colsum, v.colsumsq, plan.fc[t], o, o + out_ld, o + 2 * out_ld, o + 3 * out_ld, o + 4 * out_ld,
+      o + 5 * out_ld, o + 6 * out_ld);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
+static int check_out(const gapit_scan_out* out) {
+  if (!out || !out->effect || !out->tvalue || !out->se || !out->pvalue || !out->rsquare || !out->loglm)
+    return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: output arrays effect/tvalue/se/pvalue/rsquare/loglm are required");
+  return GAPIT_OK;
+}
+
+// copy the 7 device result arrays of trait t (m values each, stride out_ld) to the caller's SoA arrays
+static int fetch_outputs(gapit_ctx* ctx, const double* out_dev, int64_t out_ld, int64_t m, int t, gapit_scan_out* out) {
+  double* dsts[7] = {out->effect, out->tvalue, out->se, out->pvalue, out->rsquare, out->loglm, out->maf};
+  for (int a = 0; a < 7; ++a) {
+    if (!dsts[a]) continue;
+    if (a == 6 && t > 0) continue;
+    double* dst = dsts[a] + (a == 6 ? 0 : size_t(t) * m);
+    GAPIT_CUDA(cudaMemcpyAsync(dst, out_dev + size_t(a) * out_ld, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  return GAPIT_OK;
+}
+
+static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
+                     const double* delta, const double* vg, int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
+  if (!g) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL genotype handle");
+  GAPIT_CHECK(check_out(out));
+  ScanPlan plan;
+  GAPIT_CHECK(scan_prepare(ctx, g->n, g->ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
+  const int64_t m = g->m;
+  double* o = nullptr;
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(7) * m, &o));
+  MarkerView v{g->mk, m, g->colsum, g->colsumsq};
+  float kernel_ms = 0.f, post_ms = 0.f, d2h_ms = 0.f;
+  for (int t = 0; t < T; ++t) {
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    GAPIT_CHECK(scan_run(ctx, plan, v, t, o, m, 0, ctx->ev3));
     cudaEventRecord(ctx->ev1, ctx->stream);
-    double* o = dOut.as<double>();
-    finalize_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, ctx->stream>>>(
-        dPart.as<double>(), m_ld, m, g->colsum, g->colsumsq, fc, o, o + m, o + 2 * m, o + 3 * m, o + 4 * m, o + 5 * m,
-        o + 6 * m);
-    GAPIT_CUDA(cudaGetLastError());
-    cudaEvent_t ev2;
-    GAPIT_CUDA(cudaEventCreate(&ev2));
-    cudaEventRecord(ev2, ctx->stream);
-    double* dsts[7] = {out->effect, out->tvalue, out->se, out->pvalue, out->rsquare, out->loglm, out->maf};
-    for (int a = 0; a < 7; ++a) {
-      if (!dsts[a]) continue;
-      if (a == 6 && t > 0) continue;
-      double* dst = dsts[a] + (a == 6 ? 0 : size_t(t) * m);
-      GAPIT_CUDA(cudaMemcpyAsync(dst, o + size_t(a) * m, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    GAPIT_CHECK(fetch_outputs(ctx, o, m, m, t, out));
+    cudaEventRecord(ctx->ev2, ctx->stream);
     GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev3);
     kernel_ms += ms;
-    cudaEventElapsedTime(&ms, ctx->ev1, ev2);
+    cudaEventElapsedTime(&ms, ctx->ev3, ctx->ev1);
     post_ms += ms;
-    cudaEventDestroy(ev2);
+    cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2);
+    d2h_ms += ms;
   }
   ctx->stats = gapit_stats{};
-  ctx->stats.kernel_ms = kernel_ms;
-  ctx->stats.post_ms = post_ms;
+  ctx->stats.kernel_ms = kernel_ms;   // rotate_reduce (MLM) or glm_reduce
+  ctx->stats.post_ms = post_ms;       // finalize
+  ctx->stats.d2h_ms = d2h_ms;
+  return GAPIT_OK;
+}
+
+// Streaming form: the host genotype matrix is uploaded in marker blocks on a copy stream while the previous
+// block is scanned, so a host-to-results call costs about max(H2D, scan) instead of their sum.
+static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
+                          gapit_impute impute, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
+                          const double* delta, const double* vg, int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
+  if (!snps || n <= 0 || m <= 0 || ld < n) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan_host: bad genotype argument");
+  GAPIT_CHECK(check_out(out));
+  const int64_t ldn = round_up(n, 128);
+  ScanPlan plan;
+  GAPIT_CHECK(scan_prepare(ctx, n, ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
+  const size_t esz = dtype == GAPIT_F64 ? 8 : (dtype == GAPIT_I32 ? 4 : 1);
+  // marker block: ~192 MB of int8 (multiple of 256 markers), at most 65535 for the convert grid
+  int64_t chunk = std::max<int64_t>(256, (int64_t(192) << 20) / ldn / 256 * 256);
+  if (const char* ev = getenv("GAPIT_STREAM_CHUNK")) chunk = std::max<int64_t>(256, atoll(ev) / 256 * 256);  // tests
+  if (dtype != GAPIT_I8) chunk = std::min<int64_t>(chunk, 65280);
+  chunk = std::min(chunk, round_up(m, 256));
+  int8_t* mk[2];
+  int32_t *cs[2], *cq[2];
+  void* stage[2] = {nullptr, nullptr};
+  int* bad = nullptr;
+  double* o = nullptr;
+  for (int b = 0; b < 2; ++b) {
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_CHUNK0 + b, size_t(chunk) * ldn, &mk[b]));
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_CS0 + b, size_t(chunk), &cs[b]));
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_CQ0 + b, size_t(chunk), &cq[b]));
+    if (dtype != GAPIT_I8 || (ld == n && ldn != n)) GAPIT_CHECK(ctx_ws(ctx, WS_STAGE0 + b, size_t(chunk) * n * esz, &stage[b]));
+    if (ldn != n) GAPIT_CUDA(cudaMemsetAsync(mk[b], 0, size_t(chunk) * ldn, ctx->stream));
+  }
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_BAD, 4, &bad));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(T) * 7 * m, &o));
+  GAPIT_CUDA(cudaMemsetAsync(bad, 0, 4, ctx->stream));
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  // the copy stream must not start before the workspaces are initialised
+  GAPIT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev0, 0));
+  const int64_t nchunks = (m + chunk - 1) / chunk;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int b = static_cast<int>(c & 1);
+    const int64_t k0 = c * chunk, mc = std::min(chunk, m - k0);
+    const char* src = static_cast<const char*>(snps) + size_t(k0) * ld * esz;
+    if (c >= 2) GAPIT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));   // buffer b scanned
+    if (dtype == GAPIT_I8 && stage[b]) {
+      // dense host rows: one flat PCIe transfer, then re-pitch on the device (a strided H2D of n-byte rows is ~2x slower)
+      GAPIT_CUDA(cudaMemcpyAsync(stage[b], src, size_t(mc) * n, cudaMemcpyHostToDevice, ctx->copy_stream));
+      GAPIT_CUDA(cudaMemcpy2DAsync(mk[b], ldn, stage[b], n, n, mc, cudaMemcpyDeviceToDevice, ctx->copy_stream));
+    } else if (dtype == GAPIT_I8) {
+      GAPIT_CUDA(cudaMemcpy2DAsync(mk[b], ldn, src, ld, n, mc, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+      GAPIT_CUDA(cudaMemcpy2DAsync(stage[b], size_t(n) * esz, src, size_t(ld) * esz, size_t(n) * esz, mc,
+                                   cudaMemcpyHostToDevice, ctx->copy_stream));
+      GAPIT_CHECK(launch_convert(ctx->copy_stream, dtype, stage[b], n, mc, mk[b], ldn, int(impute), bad));
+    }
+    GAPIT_CUDA(cudaEventRecord(ctx->ev_ready[b], ctx->copy_stream));
+    GAPIT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[b], 0));
+    GAPIT_CHECK(launch_colstats(ctx, ctx->stream, mk[b], ldn, n, mc, cs[b], cq[b], bad));
+    MarkerView v{mk[b], mc, cs[b], cq[b]};
+    for (int t = 0; t < T; ++t) GAPIT_CHECK(scan_run(ctx, plan, v, t, o + size_t(t) * 7 * m, m, k0));
+    GAPIT_CUDA(cudaEventRecord(ctx->ev_free[b], ctx->stream));
+  }
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  int hbad = 0;
+  GAPIT_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  for (int t = 0; t < T; ++t) GAPIT_CHECK(fetch_outputs(ctx, o + size_t(t) * 7 * m, m, m, t, out));
+  cudaEventRecord(ctx->ev2, ctx->stream);
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  if (hbad & 2) return fail(GAPIT_ERR_DATA, "genotype matrix holds NA and no impute rule was given");
+  if (hbad & 1) return fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}");
+  float ms = 0.f;
+  ctx->stats = gapit_stats{};
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats.kernel_ms = ms;   // upload + pack + scan, overlapped
+  cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2);
+  ctx->stats.d2h_ms = ms;
   return GAPIT_OK;
 }
 
@@ -765,6 +993,14 @@ extern "C" int gapit_p3d_scan_dev(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e
                                   int T, const double* delta, const double* vg, int glm, gapit_scan_out* out,
                                   gapit_scan_base* base_out) {
   return scan_impl(ctx, g, e, X0, q0, Y, T, delta, vg, glm, out, base_out);
+}
+
+extern "C" int gapit_p3d_scan_host(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
+                                   gapit_impute impute, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
+                                   const double* delta, const double* vg, int glm, gapit_scan_out* out,
+                                   gapit_scan_base* base_out) {
+  if (!ctx) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan_host: NULL ctx");
+  return scan_host_impl(ctx, snps, dtype, n, m, ld, impute, e, X0, q0, Y, T, delta, vg, glm, out, base_out);
 }
 
 extern "C" int gapit_p3d_scan(gapit_ctx* ctx, gapit_geno* g, const double* vectors, const double* values, const double* X0,

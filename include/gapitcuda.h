@@ -156,6 +156,14 @@ int gapit_p3d_scan_dev(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const dou
                        const double* delta, const double* vg, int glm, gapit_scan_out* out,
                        gapit_scan_base* base_out);
 
+/* Host-streaming form: the same scan straight from a host genotype matrix (layout as gapit_geno_pack).
+ * Marker blocks are uploaded on a copy stream while the previous block is scanned, so the call costs
+ * about max(H2D, scan).  e may be NULL when glm != 0. */
+int gapit_p3d_scan_host(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
+                        gapit_impute impute, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
+                        const double* delta, const double* vg, int glm, gapit_scan_out* out,
+                        gapit_scan_base* base_out);
+
 /* tuning knobs (0 = default): number of int8 slices of V (4..8) */
 int gapit_set_slices(gapit_ctx* ctx, int slices);
 

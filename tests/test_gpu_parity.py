@@ -372,3 +372,35 @@ def test_bad_arguments_are_errors_not_crashes(gpu_ctx):
         gb().p3d_scan(geno, X0, Y, glm=False, ctx=gpu_ctx)                      # MLM without an eigen-system
     with pytest.raises(NotImplementedError):
         gb().GAPIT_EMMAxP3D(Y, G.T, None, X0=X0, ctx=gpu_ctx, SNP_P3D=False)
+
+
+def test_streaming_scan_equals_resident_scan(gpu_ctx, monkeypatch):
+    """gapit_p3d_scan_host (chunked upload on a copy stream) must reproduce the resident scan bit for bit,
+    for every host dtype and with several chunks in flight."""
+    monkeypatch.setenv("GAPIT_STREAM_CHUNK", "512")
+    G, Y, X0 = case(200, 3000, npc=1)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    kw = dict(eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]], ctx=gpu_ctx)
+    ref, bref = gb().p3d_scan(geno, X0, Y, **kw)
+    for arr, mm in [(G, True), (G.T.astype(np.float64), False), (G.T.astype(np.int32), False)]:
+        got, bgot = gb().p3d_scan_host(arr, X0, Y, marker_major=mm, **kw)
+        for k in ref:
+            assert np.array_equal(got[k], ref[k], equal_nan=True), k
+        assert bgot[0]["rsquare_base"] == bref[0]["rsquare_base"]
+    gref, _ = gb().p3d_scan(geno, X0, Y, glm=True, ctx=gpu_ctx)
+    ggot, _ = gb().p3d_scan_host(G, X0, Y, glm=True, ctx=gpu_ctx, marker_major=True)
+    for k in gref:
+        assert np.array_equal(ggot[k], gref[k], equal_nan=True), k
+    bad = G.T.astype(np.float64)
+    bad[5, 2999] = 4.0
+    with pytest.raises(gb().GapitCudaError):
+        gb().p3d_scan_host(bad, X0, Y, **kw)
+    na = G.T.astype(np.float64)
+    na[5, 100] = np.nan
+    with pytest.raises(gb().GapitCudaError):
+        gb().p3d_scan_host(na, X0, Y, **kw)
+    gb().p3d_scan_host(na, X0, Y, impute="Middle", **kw)
