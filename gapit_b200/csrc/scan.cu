@@ -875,8 +875,8 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
   ScanPlan plan;
   GAPIT_CHECK(scan_prepare(ctx, n, ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
   const size_t esz = dtype == GAPIT_F64 ? 8 : (dtype == GAPIT_I32 ? 4 : 1);
-  // marker block: ~192 MB of int8 (multiple of 256 markers), at most 65535 for the convert grid
-  int64_t chunk = std::max<int64_t>(256, (int64_t(192) << 20) / ldn / 256 * 256);
+  // marker block: ~320 MB of int8 (multiple of 256 markers), at most 65535 for the convert grid
+  int64_t chunk = std::max<int64_t>(256, (int64_t(320) << 20) / ldn / 256 * 256);
   if (const char* ev = getenv("GAPIT_STREAM_CHUNK")) chunk = std::max<int64_t>(256, atoll(ev) / 256 * 256);  // tests
   if (dtype != GAPIT_I8) chunk = std::min<int64_t>(chunk, 65280);
   chunk = std::min(chunk, round_up(m, 256));

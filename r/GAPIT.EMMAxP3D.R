@@ -1,0 +1,66 @@
+# Replacement wrapper for GAPIT.EMMAxP3D (reference: GAPIT.EMMAxP3D.R:1-1022).
+# The signature is unchanged.  The call is accelerated when it is the plain P3D scan
+# (Z NULL or square, SNP.P3D, fullGD, no indicators, !optOnly -- SURVEY.md section 8b);
+# every other argument combination is forwarded to the reference's own body, which must
+# have been saved as GAPIT.EMMAxP3D.reference before sourcing this file:
+#     GAPIT.EMMAxP3D.reference <- GAPIT.EMMAxP3D ; source("r/GAPIT.EMMAxP3D.R")
+`GAPIT.EMMAxP3D` <-
+function(ys,xs,K=NULL,Z=NULL,X0=NULL,CVI=NULL,CV.Inheritance=NULL,GI=NULL,GP=NULL,
+		file.path=NULL,file.from=NULL,file.to=NULL,file.total=1, genoFormat="Hapmap", file.fragment=NULL,byFile=FALSE,fullGD=TRUE,SNP.fraction=1,
+    file.G=NULL,file.Ext.G=NULL,GTindex=NULL,file.GD=NULL, file.GM=NULL, file.Ext.GD=NULL,file.Ext.GM=NULL,
+    SNP.P3D=TRUE,Timmer,Memory,optOnly=TRUE,SNP.effect="Add",SNP.impute="Middle", SNP.permutation=FALSE,
+    ngrids=100,llim=-10,ulim=10,esp=1e-10,name.of.trait=NULL, Create.indicator = FALSE, Major.allele.zero = FALSE){
+squareZ = is.null(Z) || (ncol(Z) == nrow(Z))
+accelerated = squareZ && SNP.P3D && fullGD && !Create.indicator && !optOnly && !is.null(xs)
+if(!accelerated) return(GAPIT.EMMAxP3D.reference(ys=ys,xs=xs,K=K,Z=Z,X0=X0,CVI=CVI,CV.Inheritance=CV.Inheritance,GI=GI,GP=GP,
+    file.path=file.path,file.from=file.from,file.to=file.to,file.total=file.total,genoFormat=genoFormat,file.fragment=file.fragment,
+    byFile=byFile,fullGD=fullGD,SNP.fraction=SNP.fraction,file.G=file.G,file.Ext.G=file.Ext.G,GTindex=GTindex,file.GD=file.GD,
+    file.GM=file.GM,file.Ext.GD=file.Ext.GD,file.Ext.GM=file.Ext.GM,SNP.P3D=SNP.P3D,Timmer=Timmer,Memory=Memory,optOnly=optOnly,
+    SNP.effect=SNP.effect,SNP.impute=SNP.impute,SNP.permutation=SNP.permutation,ngrids=ngrids,llim=llim,ulim=ulim,esp=esp,
+    name.of.trait=name.of.trait,Create.indicator=Create.indicator,Major.allele.zero=Major.allele.zero))
+
+Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="P3D Start")
+Memory=GAPIT.Memory(Memory=Memory,Infor="P3D Start")
+if(is.null(dim(ys)) || ncol(ys) == 1)  ys <- matrix(ys, 1, length(ys))        # :29
+if(is.null(X0)) X0 <- matrix(1, ncol(ys), 1)                                  # :30
+if(!is.null(K)) {if(length(K)<= 1) K = NULL}                                  # :34
+n <- ncol(ys); q0 <- ncol(X0); q1 <- q0 + 1; m <- ncol(xs)
+y <- as.numeric(ys[1,])
+impute <- switch(SNP.impute, Minor=0L, Middle=1L, Major=2L, -1L)
+glm <- is.null(K)
+if(!glm){
+  eig.L <- .Call("gapit_R_eigen_L", K)                                        # :48
+  Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="eig.L"); Memory=GAPIT.Memory(Memory=Memory,Infor="eig.L")
+  eig.R <- try(.Call("gapit_R_eigen_R", K, X0), silent=TRUE)                  # :58
+  Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="eig.R"); Memory=GAPIT.Memory(Memory=Memory,Infor="eig.R")
+  if(inherits(eig.R, "try-error"))                                            # :70-74
+    return(list(ps = NULL, REMLs = NA, stats = NULL, effect.est = NULL, dfs = NULL,maf=NULL,nobs = NULL,Timmer=Timmer,Memory=Memory,
+        vgs = NA, ves = NA, BLUP = NULL, BLUP_Plus_Mean = NULL, PEV = NULL, BLUE=NULL))
+  etas <- crossprod(eig.R$vectors, y)                                         # GAPIT.emma.REMLE.R:25
+  r <- .Call("gapit_R_reml", eig.R$values, as.numeric(etas), as.integer(ngrids), llim, ulim, esp)   # :202
+  REMLs <- r[1]; REMLE_delta <- r[2]; ves <- r[3]; vgs <- r[4]
+  Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="REML"); Memory=GAPIT.Memory(Memory=Memory,Infor="REML")
+  rm(eig.R)
+  res <- .Call("gapit_R_p3d_scan", as.matrix(xs), eig.L$vectors, eig.L$values, X0, y, REMLE_delta, vgs, FALSE, impute)
+} else {
+  res <- .Call("gapit_R_p3d_scan", as.matrix(xs), NULL, NULL, X0, y, 0, 0, TRUE, impute)
+}
+Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="Screening SNPs"); Memory=GAPIT.Memory(Memory=Memory,Infor="Screening SNPs")
+base <- attr(res, "base")
+if(glm){ ves <- base[4]; REMLs <- base[5]; vgs <- 0 }                         # :868-872
+if(base[7] != 0) print("At least two of your covariates are linearly dependent. Please reconsider the covariates you are using for GWAS and GPS")   # :711
+beta.cv <- base[8:(7+q0)]
+col <- function(v) matrix(v, m, 1)
+stats <- res[,2]; normal <- !is.na(stats)
+dfs <- ifelse(normal, n - q1, NA)                                             # :586
+# :972  stderr = beta[ncol(CVI)+1]/t : lands on the marker effect only when ncol(CVI) == q0, past the end it is NA
+stderr <- rep(NA_real_, m)
+if(!is.null(CVI) && !is.null(ncol(CVI)) && ncol(CVI) == q0) stderr <- res[,1]/stats
+Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="GWAS done for this Trait"); Memory=GAPIT.Memory(Memory=Memory,Infor="GWAS done for this Trait")
+# the i = 0 BLUP/PEV/BLUE block (:779-861) is not on the data-parallel path; call the reference with optOnly=TRUE if needed
+return(list(ps = col(res[,4]), REMLs = -2*REMLs, stats = col(stats), effect.est = col(res[,1]),
+    rsquare_base = col(ifelse(normal, base[3], NA)), rsquare = col(res[,5]), dfs = col(dfs), df = col(dfs),
+    tvalue = col(stats), stderr = col(stderr), maf=col(res[,7]), nobs = col(rep(n, m)), Timmer=Timmer, Memory=Memory,
+    vgs = vgs, ves = ves, BLUP = NULL, BLUP_Plus_Mean = NULL, PEV = NULL, BLUE=NULL,
+    logLM = res[m,6], effect.snp=col(res[,1]), effect.cv=beta.cv))
+}

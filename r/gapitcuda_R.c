@@ -1,0 +1,148 @@
+/* .Call shim between R and libgapitcuda.so  (the only file that includes R headers).
+ *
+ * NOT BUILDABLE IN THE DEVELOPMENT IMAGE: R is not installed there (no Rinternals.h).  It is kept small
+ * and mirrors, call for call, the ctypes binding in gapit_b200/_lib.py + gapit_b200/api.py, which is what
+ * the test-suite drives.  Build on a machine with R:
+ *     R CMD SHLIB gapitcuda_R.c -I../include -L../gapit_b200 -lgapitcuda -o gapitcuda_R.so
+ *
+ * Conventions: arguments are read-only SEXPs owned by R; results are freshly
+ * allocated, PROTECTed R objects; Rf_error() is raised only after every CUDA resource of the call has
+ * been released (the C ABI returns status codes, it never longjmps); everything runs on R's main thread.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <string.h>
+
+#include "gapitcuda.h"
+
+static gapit_ctx* g_ctx = NULL;
+
+static gapit_ctx* ctx(void) {
+  if (!g_ctx && gapit_ctx_create(0, &g_ctx) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  return g_ctx;
+}
+
+static gapit_dtype sexp_dtype(SEXP x) {
+  if (TYPEOF(x) == REALSXP) return GAPIT_F64;
+  if (TYPEOF(x) == INTSXP) return GAPIT_I32;
+  Rf_error("gapitcuda: genotype matrix must be numeric or integer");
+  return GAPIT_F64;
+}
+
+static const void* sexp_data(SEXP x) { return TYPEOF(x) == REALSXP ? (const void*)REAL(x) : (const void*)INTEGER(x); }
+
+/* GAPIT.kinship.VanRaden(snps): n x m matrix -> n x n double matrix (GAPIT.kinship.VanRaden.R:1-37) */
+SEXP gapit_R_vanraden(SEXP snps) {
+  SEXP dim = Rf_getAttrib(snps, R_DimSymbol);
+  const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
+  gapit_geno* g = NULL;
+  /* the reference does not impute here: NA propagates to a NaN matrix, so NA is an error for us */
+  int rc = gapit_geno_pack(ctx(), sexp_data(snps), sexp_dtype(snps), n, m, n, GAPIT_IMPUTE_NONE, &g);
+  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  SEXP K = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
+  rc = gapit_vanraden(ctx(), g, REAL(K), NULL);
+  gapit_geno_free(g);
+  if (rc != GAPIT_OK) {
+    UNPROTECT(1);
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  }
+  UNPROTECT(1);
+  return K;
+}
+
+/* eigen(K, symmetric=TRUE) in R's order: list(values, vectors)   (emma.txt:58-61) */
+SEXP gapit_R_eigen_L(SEXP K) {
+  const int64_t n = INTEGER(Rf_getAttrib(K, R_DimSymbol))[0];
+  SEXP values = PROTECT(Rf_allocVector(REALSXP, n));
+  SEXP vectors = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
+  int rc = gapit_eigh(ctx(), REAL(K), n, REAL(values), REAL(vectors));
+  if (rc != GAPIT_OK) {
+    UNPROTECT(2);
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, values);
+  SET_VECTOR_ELT(out, 1, vectors);
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("values"));
+  SET_STRING_ELT(nm, 1, Rf_mkChar("vectors"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(4);
+  return out;
+}
+
+/* emma.eigen.R.wo.Z(K, X): list(values (n-q), vectors n x (n-q))   (emma.txt:82-89) */
+SEXP gapit_R_eigen_R(SEXP K, SEXP X) {
+  SEXP dim = Rf_getAttrib(X, R_DimSymbol);
+  const int64_t n = INTEGER(dim)[0], q = INTEGER(dim)[1];
+  SEXP values = PROTECT(Rf_allocVector(REALSXP, n - q));
+  SEXP vectors = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)(n - q)));
+  int rc = gapit_eigen_R(ctx(), REAL(K), REAL(X), n, q, REAL(values), REAL(vectors));
+  if (rc != GAPIT_OK) {
+    UNPROTECT(2);
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, values);
+  SET_VECTOR_ELT(out, 1, vectors);
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("values"));
+  SET_STRING_ELT(nm, 1, Rf_mkChar("vectors"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  UNPROTECT(4);
+  return out;
+}
+
+/* REML on the spectrum: c(REML, delta, ve, vg)   (GAPIT.emma.REMLE.R:27-54, 96-108) */
+SEXP gapit_R_reml(SEXP lambda, SEXP etas, SEXP ngrids, SEXP llim, SEXP ulim, SEXP esp) {
+  gapit_reml_out r;
+  int rc = gapit_reml(REAL(lambda), REAL(etas), XLENGTH(lambda), Rf_asInteger(ngrids), Rf_asReal(llim), Rf_asReal(ulim),
+                      Rf_asReal(esp), &r);
+  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 4));
+  REAL(out)[0] = r.REML;
+  REAL(out)[1] = r.delta;
+  REAL(out)[2] = r.ve;
+  REAL(out)[3] = r.vg;
+  UNPROTECT(1);
+  return out;
+}
+
+/* The marker loop of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:397-979), one trait.
+ * xs n x m (numeric/integer), vectors/values = eig.L (ignored when glm), X0 n x q0, y length n.
+ * impute: -1 none, 0 Minor, 1 Middle, 2 Major.  Returns an m x 7 matrix
+ * (effect, t, se, p, rsquare, logLM, maf) with attribute "base" =
+ * c(logL0, logLM_base, rsquare_base, ves, reml, df, singular_x0, beta0[1..q0]). */
+SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP delta, SEXP vg, SEXP glm, SEXP impute) {
+  SEXP dim = Rf_getAttrib(xs, R_DimSymbol);
+  const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
+  const int q0 = INTEGER(Rf_getAttrib(X0, R_DimSymbol))[1];
+  const int is_glm = Rf_asLogical(glm);
+  gapit_eigsys* e = NULL;
+  if (!is_glm && gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e) != GAPIT_OK)
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  SEXP res = PROTECT(Rf_allocMatrix(REALSXP, (int)m, 7));
+  double* r = REAL(res);
+  gapit_scan_out out = {r, r + m, r + 2 * m, r + 3 * m, r + 4 * m, r + 5 * m, r + 6 * m};
+  gapit_scan_base base;
+  double d = is_glm ? 0.0 : Rf_asReal(delta), v = is_glm ? 0.0 : Rf_asReal(vg);
+  int rc = gapit_p3d_scan_host(ctx(), sexp_data(xs), sexp_dtype(xs), n, m, n, (gapit_impute)Rf_asInteger(impute), e,
+                               REAL(X0), q0, REAL(y), 1, &d, &v, is_glm, &out, &base);
+  gapit_eigsys_free(e);
+  if (rc != GAPIT_OK) {
+    UNPROTECT(1);
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  }
+  SEXP b = PROTECT(Rf_allocVector(REALSXP, 7 + q0));
+  REAL(b)[0] = base.logL0;
+  REAL(b)[1] = base.logLM_base;
+  REAL(b)[2] = base.rsquare_base;
+  REAL(b)[3] = base.ves;
+  REAL(b)[4] = base.reml;
+  REAL(b)[5] = base.df;
+  REAL(b)[6] = (double)base.singular_x0;
+  memcpy(REAL(b) + 7, base.beta0, sizeof(double) * q0);
+  Rf_setAttrib(res, Rf_install("base"), b);
+  UNPROTECT(2);
+  return res;
+}
