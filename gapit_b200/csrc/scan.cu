@@ -132,19 +132,23 @@ struct ScanSched {
     int nkq;      // BN-row tiles of the sliced eigenvectors
     int kblocks;  // taxa axis in units of kBlockK
     int bn;
+    int nchunk;   // trait chunks: every chunk repeats the rotation of the tile with its own epilogue constants
   };
   static constexpr uint64_t kHintA = ptx::kEvictLast;    // marker tile: re-read for every eigen tile
   static constexpr uint64_t kHintB = ptx::kEvictNormal;  // eigen tiles: streamed, shared by concurrent CTAs
   Params p;
-  int gid, stride, kq, kq_begin, kq_end, mt, ks;
+  int gid, stride, kq, kq_begin, kq_end, mt, ks, tc;
   __device__ ScanSched(const Params& pp, int block, int nblocks)
-      : p(pp), gid(block - nblocks), stride(nblocks), kq(0), kq_begin(0), kq_end(0), mt(0), ks(0) {}
+      : p(pp), gid(block - nblocks), stride(nblocks), kq(0), kq_begin(0), kq_end(0), mt(0), ks(0), tc(0) {}
   __device__ bool next(Job& j) {
     if (kq >= kq_end) {
       gid += stride;
-      if (gid >= p.mtiles * p.gsplit) return false;
-      mt = gid / p.gsplit;
-      ks = gid - mt * p.gsplit;
+      if (gid >= p.mtiles * p.gsplit * p.nchunk) return false;
+      // split-minor, then trait chunk, then marker tile: CTAs running together share the marker tile
+      const int mc = gid / p.gsplit;
+      ks = gid - mc * p.gsplit;
+      mt = mc / p.nchunk;
+      tc = mc - mt * p.nchunk;
       kq_begin = (ks * p.nkq) / p.gsplit;
       kq_end = ((ks + 1) * p.nkq) / p.gsplit;
       kq = kq_begin;
@@ -155,6 +159,7 @@ struct ScanSched {
     j.kb_end = p.kblocks;
     j.tag0 = kq;
     j.tag1 = ks;
+    j.tag2 = tc;
     j.group_first = (kq == kq_begin);
     j.group_last = (kq == kq_end - 1);
     ++kq;
@@ -162,35 +167,44 @@ struct ScanSched {
   }
 };
 
-template <int S, int BN, int Q>
+template <int S, int BN, int Q, int TC>
 struct ScanEpi {
   static constexpr int KPB = BN / S;
   static constexpr int GC = (S == 4 || S == 8) ? 8 : (S == 5 ? 40 : (S == 6 ? 24 : 56));  // lcm(S, 8)
   static constexpr int KG = GC / S;
   static_assert(BN % GC == 0, "accumulator columns must split into whole digit groups");
   struct Params {
-    const double* gconst;  // [(nkq*KPB)][Q+2]: w c^2 | w c A_j ... | w c b
-    double* part;          // [gsplit][Q+2][m_ld]
+    const double* gconst;  // [T][(nkq*KPB)][Q+2]: w c^2 | w c A_j ... | w c b   (per trait)
+    double* part;          // [T][gsplit][Q+2][m_ld]
     int64_t m_ld;
     int64_t m;
-    int pair;  // 1: merge adjacent digit planes in int32 before converting (needs 65792 n < 2^31)
+    int pair;              // 1: merge adjacent digit planes in int32 before converting (needs 65792 n < 2^31)
+    int T;                 // traits; chunk c of a job covers traits [c*TC, min(T, (c+1)*TC))
+    int64_t gc_tstride;    // doubles between the constants of consecutive traits
+    int64_t part_tstride;  // doubles between the partial sums of consecutive traits
   };
   Params p;
-  double acc[Q + 2];
+  double acc[TC][Q + 2];
   // exact int32 -> fp64: the bits 0x43300000:(x ^ 0x80000000) are the double 2^52 + 2^31 + x
   static __device__ __forceinline__ double i2d(int x) {
     return __hiloint2double(0x43300000, x ^ static_cast<int>(0x80000000u)) - 4503601774854144.0;
   }
   __device__ explicit ScanEpi(const Params& pp) : p(pp) {
 #pragma unroll
-    for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
+    for (int t = 0; t < TC; ++t)
+#pragma unroll
+      for (int i = 0; i < Q + 2; ++i) acc[t][i] = 0.0;
   }
   __device__ void run(const Job& job, uint32_t taddr, int sub, int row) {
     if (job.group_first) {
 #pragma unroll
-      for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
+      for (int t = 0; t < TC; ++t)
+#pragma unroll
+        for (int i = 0; i < Q + 2; ++i) acc[t][i] = 0.0;
     }
-    const double* gc = p.gconst + int64_t(job.tag0) * KPB * (Q + 2);
+    const int t0 = job.tag2 * TC;
+    const int ntr = min(TC, p.T - t0);
+    const double* gc = p.gconst + int64_t(t0) * p.gc_tstride + int64_t(job.tag0) * KPB * (Q + 2);
 #pragma unroll 1
     for (int g = 0; g < BN / GC; ++g) {
       uint32_t r[GC];
@@ -220,17 +234,28 @@ struct ScanEpi {
           for (int s = S - 2; s >= 0; --s) u = fma(u, 256.0, i2d(d[s]));
         }
         const double* c = gc + (g * KG + kk) * (Q + 2);
-        acc[0] = fma(__ldg(c) * u, u, acc[0]);
 #pragma unroll
-        for (int i = 1; i < Q + 2; ++i) acc[i] = fma(__ldg(c + i), u, acc[i]);
+        for (int t = 0; t < TC; ++t) {
+          if (TC == 1 || t < ntr) {
+            const double* ct = c + int64_t(t) * p.gc_tstride;
+            acc[t][0] = fma(__ldg(ct) * u, u, acc[t][0]);
+#pragma unroll
+            for (int i = 1; i < Q + 2; ++i) acc[t][i] = fma(__ldg(ct + i), u, acc[t][i]);
+          }
+        }
       }
     }
     if (job.group_last) {
       const int64_t mrk = int64_t(job.a_row0) + sub * 128 + row;
       if (mrk < p.m_ld) {
-        double* dst = p.part + int64_t(job.tag1) * (Q + 2) * p.m_ld + mrk;
 #pragma unroll
-        for (int i = 0; i < Q + 2; ++i) dst[i * p.m_ld] = acc[i];
+        for (int t = 0; t < TC; ++t) {
+          if (TC == 1 || t < ntr) {
+            double* dst = p.part + int64_t(t0 + t) * p.part_tstride + int64_t(job.tag1) * (Q + 2) * p.m_ld + mrk;
+#pragma unroll
+            for (int i = 0; i < Q + 2; ++i) dst[i * p.m_ld] = acc[t][i];
+          }
+        }
       }
     }
   }
@@ -257,7 +282,7 @@ struct GlmSched {
     j.b_row0 = 0;
     j.kb_begin = 0;
     j.kb_end = p.kblocks;
-    j.tag0 = j.tag1 = 0;
+    j.tag0 = j.tag1 = j.tag2 = 0;
     j.group_first = j.group_last = true;
     tile += stride;
     return true;
@@ -515,11 +540,12 @@ static int pad_q(int q0) {
   return 16;
 }
 
-template <int S, int BN, int Q>
+// one launch scans traits [0, T): gconst_dev/part_dev are the arrays of trait 0, strides in doubles
+template <int S, int BN, int Q, int TC>
 static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* gconst_dev, double* part_dev,
-                          int64_t m_ld, int gsplit) {
+                          int64_t m_ld, int gsplit, int T, int64_t gc_tstride, int64_t part_tstride) {
   using Cfg = UmmaCfg<2, BN, 3>;
-  using Epi = ScanEpi<S, BN, Q>;
+  using Epi = ScanEpi<S, BN, Q, TC>;
   CUtensorMap map_a, map_b;
   GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
                                  static_cast<uint64_t>(g->ldn), 256));
@@ -531,37 +557,48 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   sp.nkq = static_cast<int>(e->nkq);
   sp.kblocks = static_cast<int>(g->ldn / kBlockK);
   sp.bn = BN;
+  sp.nchunk = (T + TC - 1) / TC;
   int pair = (65792ll * g->n < 2147483647ll) ? 1 : 0;
   if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);  // A/B switch for profiling
-  typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair};
+  typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair, T, gc_tstride, part_tstride};
   auto kern = umma_i8_kernel<2, BN, 3, ScanSched, Epi, 1, 1>;
   GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  const int grid = std::min(ctx->sm_count, sp.mtiles * sp.gsplit);
+  const int grid = std::min(ctx->sm_count, sp.mtiles * sp.gsplit * sp.nchunk);
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(map_a, map_b, sp, ep);
   GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
 }
 
+#define GAPIT_SCAN_ARGS ctx, g, e, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride
 template <int S, int BN>
 static int launch_scan_S(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int Q, const double* gconst_dev,
-                         double* part_dev, int64_t m_ld, int gsplit) {
+                         double* part_dev, int64_t m_ld, int gsplit, int T, int64_t gc_tstride, int64_t part_tstride) {
+  if (T > 1) {  // trait-chunked epilogue: TC traits share one rotation pass (TC * (Q+2) register accumulators)
+    switch (Q) {
+      case 1: return launch_scan_SQ<S, BN, 1, 16>(GAPIT_SCAN_ARGS);
+      case 2: return launch_scan_SQ<S, BN, 2, 12>(GAPIT_SCAN_ARGS);
+      case 4: return launch_scan_SQ<S, BN, 4, 8>(GAPIT_SCAN_ARGS);
+      case 8: return launch_scan_SQ<S, BN, 8, 4>(GAPIT_SCAN_ARGS);
+      default: return launch_scan_SQ<S, BN, 16, 2>(GAPIT_SCAN_ARGS);
+    }
+  }
   switch (Q) {
-    case 1: return launch_scan_SQ<S, BN, 1>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
-    case 2: return launch_scan_SQ<S, BN, 2>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
-    case 4: return launch_scan_SQ<S, BN, 4>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
-    case 8: return launch_scan_SQ<S, BN, 8>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
-    default: return launch_scan_SQ<S, BN, 16>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    case 1: return launch_scan_SQ<S, BN, 1, 1>(GAPIT_SCAN_ARGS);
+    case 2: return launch_scan_SQ<S, BN, 2, 1>(GAPIT_SCAN_ARGS);
+    case 4: return launch_scan_SQ<S, BN, 4, 1>(GAPIT_SCAN_ARGS);
+    case 8: return launch_scan_SQ<S, BN, 8, 1>(GAPIT_SCAN_ARGS);
+    default: return launch_scan_SQ<S, BN, 16, 1>(GAPIT_SCAN_ARGS);
   }
 }
 
 static int launch_scan(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int Q, const double* gconst_dev, double* part_dev,
-                       int64_t m_ld, int gsplit) {
+                       int64_t m_ld, int gsplit, int T, int64_t gc_tstride, int64_t part_tstride) {
   switch (e->S) {
-    case 4: return launch_scan_S<4, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
-    case 5: return launch_scan_S<5, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
-    case 6: return launch_scan_S<6, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
-    case 7: return launch_scan_S<7, 224>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
-    default: return launch_scan_S<8, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    case 4: return launch_scan_S<4, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
+    case 5: return launch_scan_S<5, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
+    case 6: return launch_scan_S<6, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
+    case 7: return launch_scan_S<7, 224>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
+    default: return launch_scan_S<8, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
   }
 }
 
@@ -783,13 +820,15 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
   return GAPIT_OK;
 }
 
-// scan one block of markers for trait t; results to out_dev[a * out_ld + out_off + k], a = 0..6
-static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, int t, double* out_dev, int64_t out_ld,
-                    int64_t out_off, cudaEvent_t after_reduce = nullptr) {
+// scan one block of markers for every trait of the plan; results of trait t go to
+// out_dev[t * out_tstride + a * out_ld + out_off + k], a = 0..6
+static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, double* out_dev, int64_t out_tstride,
+                    int64_t out_ld, int64_t out_off, cudaEvent_t after_reduce = nullptr) {
   const int Q = plan.Q;
   const int64_t m_ld = round_up(v.m, 256);
+  const int64_t part_tstride = int64_t(plan.gsplit) * (Q + 2) * m_ld;
   double* part = nullptr;
-  GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t(plan.gsplit) * (Q + 2) * m_ld, &part));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t(plan.T) * part_tstride, &part));
   gapit_geno view;  // borrowed pointers only
   view.ctx = ctx;
   view.n = plan.n;
@@ -799,16 +838,21 @@ static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, i
   view.colsum = const_cast<int32_t*>(v.colsum);
   view.colsumsq = const_cast<int32_t*>(v.colsumsq);
   if (!plan.glm) {
-    GAPIT_CHECK(launch_scan(ctx, &view, plan.e, Q, plan.gconst + size_t(t) * plan.nk * (Q + 2), part, m_ld, plan.gsplit));
+    // one launch for all traits: the rotation of a marker tile is shared by a chunk of traits
+    GAPIT_CHECK(launch_scan(ctx, &view, plan.e, Q, plan.gconst, part, m_ld, plan.gsplit, plan.T,
+                            plan.nk * (Q + 2), part_tstride));
   } else {
-    GAPIT_CHECK(launch_glm(ctx, &view, plan.Rs + size_t(t) * 128 * plan.ldn, 128,
-                           plan.Rscale + size_t(t) * (GAPIT_MAX_Q0 + 1), plan.q0 + 1, Q, part, m_ld));
+    for (int t = 0; t < plan.T; ++t)
+      GAPIT_CHECK(launch_glm(ctx, &view, plan.Rs + size_t(t) * 128 * plan.ldn, 128,
+                             plan.Rscale + size_t(t) * (GAPIT_MAX_Q0 + 1), plan.q0 + 1, Q, part + t * part_tstride, m_ld));
   }
   if (after_reduce) cudaEventRecord(after_reduce, ctx->stream);
-  double* o = out_dev + out_off;
-  finalize_kernel<<<static_cast<unsigned>((v.m + 255) / 256), 256, 0, ctx->stream>>>(
-      part, m_ld, v.m, v.colsum, v.colsumsq, plan.fc[t], o, o + out_ld, o + 2 * out_ld, o + 3 * out_ld, o + 4 * out_ld,
-      o + 5 * out_ld, o + 6 * out_ld);
+  for (int t = 0; t < plan.T; ++t) {
+    double* o = out_dev + t * out_tstride + out_off;
+    finalize_kernel<<<static_cast<unsigned>((v.m + 255) / 256), 256, 0, ctx->stream>>>(
+        part + t * part_tstride, m_ld, v.m, v.colsum, v.colsumsq, plan.fc[t], o, o + out_ld, o + 2 * out_ld,
+        o + 3 * out_ld, o + 4 * out_ld, o + 5 * out_ld, o + 6 * out_ld);
+  }
   GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
 }
@@ -839,28 +883,22 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
   GAPIT_CHECK(scan_prepare(ctx, g->n, g->ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
   const int64_t m = g->m;
   double* o = nullptr;
-  GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(7) * m, &o));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(T) * 7 * m, &o));
   MarkerView v{g->mk, m, g->colsum, g->colsumsq};
-  float kernel_ms = 0.f, post_ms = 0.f, d2h_ms = 0.f;
-  for (int t = 0; t < T; ++t) {
-    cudaEventRecord(ctx->ev0, ctx->stream);
-    GAPIT_CHECK(scan_run(ctx, plan, v, t, o, m, 0, ctx->ev3));
-    cudaEventRecord(ctx->ev1, ctx->stream);
-    GAPIT_CHECK(fetch_outputs(ctx, o, m, m, t, out));
-    cudaEventRecord(ctx->ev2, ctx->stream);
-    GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev3);
-    kernel_ms += ms;
-    cudaEventElapsedTime(&ms, ctx->ev3, ctx->ev1);
-    post_ms += ms;
-    cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2);
-    d2h_ms += ms;
-  }
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  GAPIT_CHECK(scan_run(ctx, plan, v, o, 7 * m, m, 0, ctx->ev3));
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  for (int t = 0; t < T; ++t) GAPIT_CHECK(fetch_outputs(ctx, o + size_t(t) * 7 * m, m, m, t, out));
+  cudaEventRecord(ctx->ev2, ctx->stream);
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
   ctx->stats = gapit_stats{};
-  ctx->stats.kernel_ms = kernel_ms;   // rotate_reduce (MLM) or glm_reduce
-  ctx->stats.post_ms = post_ms;       // finalize
-  ctx->stats.d2h_ms = d2h_ms;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev3);
+  ctx->stats.kernel_ms = ms;   // rotate_reduce (MLM, all traits) or glm_reduce
+  cudaEventElapsedTime(&ms, ctx->ev3, ctx->ev1);
+  ctx->stats.post_ms = ms;     // finalize
+  cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2);
+  ctx->stats.d2h_ms = ms;
   return GAPIT_OK;
 }
 
@@ -919,7 +957,7 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
     GAPIT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[b], 0));
     GAPIT_CHECK(launch_colstats(ctx, ctx->stream, mk[b], ldn, n, mc, cs[b], cq[b], bad));
     MarkerView v{mk[b], mc, cs[b], cq[b]};
-    for (int t = 0; t < T; ++t) GAPIT_CHECK(scan_run(ctx, plan, v, t, o + size_t(t) * 7 * m, m, k0));
+    GAPIT_CHECK(scan_run(ctx, plan, v, o, 7 * m, m, k0));
     GAPIT_CUDA(cudaEventRecord(ctx->ev_free[b], ctx->stream));
   }
   cudaEventRecord(ctx->ev1, ctx->stream);

@@ -34,6 +34,7 @@ struct Job {
   int kb_end;
   int tag0;  // scheduler payload for the epilogue
   int tag1;
+  int tag2;
   bool group_first;  // first / last job of a run whose epilogue state is carried in registers
   bool group_last;
 };

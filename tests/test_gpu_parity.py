@@ -404,3 +404,30 @@ def test_streaming_scan_equals_resident_scan(gpu_ctx, monkeypatch):
     with pytest.raises(gb().GapitCudaError):
         gb().p3d_scan_host(na, X0, Y, **kw)
     gb().p3d_scan_host(na, X0, Y, impute="Middle", **kw)
+
+
+@pytest.mark.parametrize("npc,T", [(0, 18), (1, 14), (3, 9)])
+def test_multi_trait_chunked_epilogue(gpu_ctx, npc, T):
+    """BASELINE configs[4] shape in miniature: many traits share one eigendecomposition and one rotation pass per
+    chunk of traits; every trait must match the oracle and the single-trait launch."""
+    G, _, X0 = case(130, 520, npc=npc, seed=21)
+    Yt = synth.make_phenotypes(G, ntraits=T, seed=21)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    eR = go.emma_eigen_R_wo_Z(K, X0)
+    remls = [go.emma_REMLE(Yt[:, t], X0, K, eig_R=eR) for t in range(T)]
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    arrs, bases = gb().p3d_scan(geno, X0, Yt, eigsys=es, delta=[r["delta"] for r in remls], vg=[r["vg"] for r in remls],
+                                ctx=gpu_ctx)
+    host, _ = gb().p3d_scan_host(G, X0, Yt, eigsys=es, delta=[r["delta"] for r in remls], vg=[r["vg"] for r in remls],
+                                 ctx=gpu_ctx, marker_major=True)
+    for t in (0, 1, T // 2, T - 1):
+        ora = go.emmax_p3d(Yt[:, t], G.T, K, X0, eig_L=eL, reml=remls[t])
+        ok = ~np.isnan(ora.stats)
+        r, a = rel_err(arrs["effect"][t], ora.effect_est, 1e-4)
+        assert r < BETA_RTOL, (t, r)
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(arrs["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
+        assert np.max(np.abs(arrs["rsquare"][t][ok] - ora.rsquare[ok])) < 1e-9
+        assert np.array_equal(host["pvalue"][t], arrs["pvalue"][t], equal_nan=True)
