@@ -153,6 +153,11 @@ def run_reference(args):
         return
     from gapit_b200 import synth
     from oracle import gapit_oracle as go
+    try:   # torchrun exports OMP_NUM_THREADS=1; the CPU reference is entitled to every host core
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:
+        pass
     n = args.n
     m_kin = min(args.m, 20000)          # markers used to build a realistic K on the CPU
     G = synth.make_genotypes(n, m_kin, seed=synth.BASE_SEED + 1, threads=os.cpu_count() or 8)

@@ -73,6 +73,7 @@ SIGNATURES = {
                                      C.POINTER(ScanOut), C.POINTER(ScanBase)]),
     "gapit_p3d_scan_host": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _I64, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, _P,
                                       C.c_int, C.POINTER(ScanOut), C.POINTER(ScanBase)]),
+    "gapit_blup_pev": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_double, C.c_double, _P, _P, _P]),
     "gapit_set_slices": (C.c_int, [_P, C.c_int]),
 }
 

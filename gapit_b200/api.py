@@ -296,6 +296,19 @@ def p3d_scan_host(snps, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=
     return arrs, bases
 
 
+def blup_pev(eigsys, X0, y, delta, vg, ctx=None):
+    """i = 0 BLUP / PEV block of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:779-839) in the eigenbasis of K.
+    Returns (BLUP, PEV, beta0)."""
+    ctx = ctx or eigsys.ctx
+    X0 = np.asfortranarray(X0, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+    n, q0 = X0.shape
+    blup, pev, beta = np.empty(n), np.empty(n), np.empty(q0)
+    check(ctx.lib.gapit_blup_pev(ctx.h, eigsys.h, _ptr(X0), q0, _ptr(y), float(delta), float(vg), _ptr(blup), _ptr(pev),
+                                 _ptr(beta)))
+    return blup, pev, beta
+
+
 def _timmer(Timmer, label):
     """GAPIT.Timmer.R:8-17: append (label, now, elapsed since previous stamp)."""
     now = time.time()
@@ -361,12 +374,17 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
         Timmer = _timmer(Timmer, "REML")
         es = EigenSystem(eig_L["values"], eig_L["vectors"], ctx=ctx)      # :224 folded into the kernel weights
         Timmer = _timmer(Timmer, "U Matrix")
+        # i = 0: BLUP / PEV of the marker-free model (:779-839), then the marker loop
+        BLUP, PEV, beta0 = blup_pev(es, X0, ys, reml["delta"], reml["vg"], ctx=ctx)
+        Timmer = _timmer(Timmer, "PEV")
         arrs, bases = run_scan(eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]])
         es.close()
         vgs, ves, REMLs = reml["vg"], reml["ve"], reml["REML"]
     else:
         arrs, bases = run_scan(glm=True)
         vgs, ves, REMLs = 0.0, bases[0]["ves"], bases[0]["reml"]           # :868-872
+        BLUP, PEV = 0.0, ves                                              # :873-875
+        beta0 = bases[0]["beta0"]
     Timmer = _timmer(Timmer, "Screening SNPs")
     if bases[0]["singular_x0"]:                                           # :711
         print("At least two of your covariates are linearly dependent. Please reconsider the covariates you are using for GWAS and GPS")
@@ -384,6 +402,17 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
             stderr = arrs["effect"][0] / stats
         # idx < q0 would need the per-marker covariate effects the scan does not return
     rsq_base = np.where(normal, b["rsquare_base"], np.nan)
+    # :841-861 / :877-889  BLUE = XCV %*% beta.Inheritance with XCV = cbind(1, CVI[,-1]) (X itself for an intercept-only fit)
+    BLUE = None
+    if q0 == 1:
+        BLUE = (X0 @ beta0).reshape(n, 1)
+    elif CVI is not None:
+        XCV = np.column_stack([np.ones(n), np.asarray(CVI, dtype=np.float64)[:, 1:]])
+        b_inh = beta0
+        if CV_Inheritance is not None:
+            XCV, b_inh = XCV[:, : 1 + CV_Inheritance], beta0[: 1 + CV_Inheritance]
+        if XCV.shape[1] == b_inh.shape[0]:
+            BLUE = (XCV @ b_inh).reshape(n, 1)
     Timmer = _timmer(Timmer, "GWAS done for this Trait")
     return {
         "ps": col(arrs["pvalue"][0]), "REMLs": -2.0 * REMLs, "stats": col(stats),
@@ -391,8 +420,10 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
         "dfs": col(dfs), "df": col(dfs.copy()), "tvalue": col(stats.copy()), "stderr": col(stderr),
         "maf": col(arrs["maf"]), "nobs": col(np.full(m, float(n))), "Timmer": Timmer, "Memory": Memory,
         "vgs": vgs, "ves": ves,
-        # i = 0 BLUP/PEV/BLUE block (:779-861) is off the data-parallel path
-        "BLUP": None, "BLUP_Plus_Mean": None, "PEV": None, "BLUE": None,
+        # i = 0 block (:779-861): BLUP = K H^-1 (y - X beta), PEV = diag(C22), BLUE = XCV beta
+        "BLUP": BLUP if glm else BLUP.reshape(n, 1),
+        "BLUP_Plus_Mean": (np.nan if glm else (beta0[0] + BLUP).reshape(n, 1)),           # :818-819, :874
+        "PEV": PEV if glm else PEV.reshape(n, 1), "BLUE": BLUE,
         "logLM": col(arrs["loglm"][0]), "effect.snp": col(arrs["effect"][0]), "effect.cv": b["beta0"],
         "se": col(arrs["se"][0]), "delta": (None if glm else reml["delta"]),
     }

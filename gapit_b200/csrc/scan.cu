@@ -1052,3 +1052,123 @@ extern "C" int gapit_p3d_scan(gapit_ctx* ctx, gapit_geno* g, const double* vecto
   gapit_eigsys_free(e);
   return rc;
 }
+
+// =============================================================================== i = 0 BLUP / PEV block
+// GAPIT.EMMAxP3D.R:779-839 in the eigenbasis of K.  With H = K + delta I, r = y - X0 beta0 and
+// B = K H^-1 = V diag(lambda/(lambda+delta)) V':
+//   BLUP = K U U'(y - X beta)            = B r                                   (:788-803)
+//   C11  = vg solve(Xt'Xt)               = vg (X0' H^-1 X0)^-1                   (:824)
+//   C21  = -K Zt'Xt C11                  = -(B X0) C11                           (:827)
+//   term.1 = solve(I/ve + Kinv/vg)       = V diag(1/(1/ve + kappa_k/vg)) V'      (:828-835)
+//   term.2 = C21 Xt'Zt K                 = C21 (B X0)'                           (:837)
+//   PEV_i  = diag(term.1 - term.2)_i     = sum_k V_ik^2 g_k + (BX0)_i' C11 (BX0)_i   (:838-839)
+// kappa_k = 1/lambda_k when solve(K) succeeds; when K is numerically singular (the usual case: centring by 2p
+// makes K 1 = 0) the reference falls back to MASS::ginv(K), i.e. kappa_k = 0 for |lambda_k| <= sqrt(eps) max|lambda|.
+// The O(n^3) inversions of the reference become O(n^2 q) products with V.
+namespace gapit {
+
+// out[c*n + j] = sum_k V[j + k n] Z[c*n + k]   (V Z, coalesced along j); optional squaring of V
+template <bool SQUARE>
+__global__ void v_times_cols_kernel(const double* __restrict__ V, int64_t n, const double* __restrict__ Z, int nc,
+                                    double* __restrict__ out) {
+  const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  for (int c = 0; c < nc; ++c) {
+    double acc = 0.0;
+    for (int64_t k = 0; k < n; ++k) {
+      const double v = V[j + k * n];
+      acc = fma(SQUARE ? v * v : v, __ldg(Z + c * n + k), acc);
+    }
+    out[c * n + j] = acc;
+  }
+}
+
+}  // namespace gapit
+
+extern "C" int gapit_blup_pev(gapit_ctx* ctx, gapit_eigsys* e, const double* X0, int q0, const double* y, double delta,
+                              double vg, double* blup_out, double* pev_out, double* beta_out) {
+  if (!ctx || !e || !X0 || !y || !blup_out || !pev_out || q0 < 1 || q0 > GAPIT_MAX_Q0)
+    return fail(GAPIT_ERR_ARG, "gapit_blup_pev: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = e->n;
+  const double ve = delta * vg;
+  const int nc = q0 + 1;
+  // projections V'[X0 | y]
+  double *dR = nullptr, *dProj = nullptr;
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n) * (nc + 2), &dR));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(n) * (nc + 2), &dProj));
+  GAPIT_CUDA(cudaMemcpyAsync(dR, X0, size_t(n) * q0 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  GAPIT_CUDA(cudaMemcpyAsync(dR + size_t(n) * q0, y, size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned blocks = static_cast<unsigned>((n * 32 + 255) / 256);
+  for (int c0 = 0; c0 < nc; c0 += 8) vt_project_kernel<8><<<blocks, 256, 0, ctx->stream>>>(e->V, n, dR, nc, c0, dProj);
+  GAPIT_CUDA(cudaGetLastError());
+  std::vector<double> proj(size_t(n) * nc);
+  GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  // reduced model in the eigenbasis (same arithmetic as scan_prepare)
+  std::vector<double> w(n), XX(q0 * q0, 0.0), XY(q0, 0.0), inv(q0 * q0), beta(q0), C11(q0 * q0);
+  const double* yt = proj.data() + size_t(q0) * n;
+  for (int64_t k = 0; k < n; ++k) w[k] = 1.0 / (e->values[k] + delta);
+  for (int i = 0; i < q0; ++i) {
+    const double* xi = proj.data() + size_t(i) * n;
+    for (int j = 0; j <= i; ++j) {
+      const double* xj = proj.data() + size_t(j) * n;
+      double s = 0.0;
+      for (int64_t k = 0; k < n; ++k) s += w[k] * xi[k] * xj[k];
+      XX[i * q0 + j] = XX[j * q0 + i] = s;
+    }
+    double s = 0.0;
+    for (int64_t k = 0; k < n; ++k) s += w[k] * xi[k] * yt[k];
+    XY[i] = s;
+  }
+  int singular = 0;
+  sym_inverse(q0, XX.data(), inv.data(), &singular);
+  for (int i = 0; i < q0; ++i) {
+    double s = 0.0;
+    for (int j = 0; j < q0; ++j) {
+      s += inv[i * q0 + j] * XY[j];
+      C11[i * q0 + j] = vg * inv[i * q0 + j];
+    }
+    beta[i] = s;
+    if (beta_out) beta_out[i] = s;
+  }
+  // Z columns (eigenbasis): f o V'X0 (q0 columns), f o V'r, and the term.1 spectrum g
+  double lmax = 0.0, lmin = INFINITY;
+  for (int64_t k = 0; k < n; ++k) {
+    lmax = std::max(lmax, std::fabs(e->values[k]));
+    lmin = std::min(lmin, std::fabs(e->values[k]));
+  }
+  const bool use_ginv = !(lmin / lmax >= 2.220446049250313e-16);   // solve(K) refuses rcond < eps (:828-829)
+  const double tol = std::sqrt(2.220446049250313e-16) * lmax;       // MASS::ginv
+  std::vector<double> Z(size_t(n) * (nc + 1));
+  for (int64_t k = 0; k < n; ++k) {
+    const double lam = e->values[k];
+    const double f = lam * w[k];
+    double rk = yt[k];
+    for (int j = 0; j < q0; ++j) {
+      Z[size_t(j) * n + k] = f * proj[size_t(j) * n + k];
+      rk -= beta[j] * proj[size_t(j) * n + k];
+    }
+    Z[size_t(q0) * n + k] = f * rk;
+    const double kappa = use_ginv ? (std::fabs(lam) > tol ? 1.0 / lam : 0.0) : 1.0 / lam;
+    Z[size_t(q0 + 1) * n + k] = 1.0 / (1.0 / ve + kappa / vg);
+  }
+  double* dZ = dR;       // reuse
+  double* dOut = dProj;  // reuse
+  GAPIT_CUDA(cudaMemcpyAsync(dZ, Z.data(), Z.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned b2 = static_cast<unsigned>((n + 127) / 128);
+  v_times_cols_kernel<false><<<b2, 128, 0, ctx->stream>>>(e->V, n, dZ, nc, dOut);
+  v_times_cols_kernel<true><<<b2, 128, 0, ctx->stream>>>(e->V, n, dZ + size_t(nc) * n, 1, dOut + size_t(nc) * n);
+  GAPIT_CUDA(cudaGetLastError());
+  std::vector<double> O(size_t(n) * (nc + 1));
+  GAPIT_CUDA(cudaMemcpyAsync(O.data(), dOut, O.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int64_t i = 0; i < n; ++i) {
+    blup_out[i] = O[size_t(q0) * n + i];
+    double quad = 0.0;
+    for (int a = 0; a < q0; ++a)
+      for (int b = 0; b < q0; ++b) quad += O[size_t(a) * n + i] * C11[a * q0 + b] * O[size_t(b) * n + i];
+    pev_out[i] = O[size_t(q0 + 1) * n + i] + quad;
+  }
+  return GAPIT_OK;
+}

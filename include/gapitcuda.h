@@ -164,6 +164,13 @@ int gapit_p3d_scan_host(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int
                         const double* delta, const double* vg, int glm, gapit_scan_out* out,
                         gapit_scan_base* base_out);
 
+/* ---- i = 0 BLUP / PEV block (GAPIT.EMMAxP3D.R:779-839), evaluated in the eigenbasis of K -------------
+ * BLUP = K H^-1 (y - X0 beta0), PEV = diag(C22) of the mixed-model equations, beta0 = effect.cv; all length n
+ * (beta_out: q0, may be NULL).  ve = delta * vg.  The reference's solve(K) -> MASS::ginv(K) fallback is decided
+ * from the spectrum (|lambda|min / |lambda|max < DBL_EPSILON => pseudo-inverse with tolerance sqrt(eps)). */
+int gapit_blup_pev(gapit_ctx* ctx, gapit_eigsys* e, const double* X0, int q0, const double* y, double delta, double vg,
+                   double* blup_out, double* pev_out, double* beta_out);
+
 /* tuning knobs (0 = default): number of int8 slices of V (4..8) */
 int gapit_set_slices(gapit_ctx* ctx, int slices);
 

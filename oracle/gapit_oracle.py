@@ -372,3 +372,76 @@ def emmax_p3d(ys, xs, K=None, X0=None, ncol_CVI=None,
                      nobs=nobs, REMLs=-2.0 * REMLs, vgs=vgs, ves=ves, delta=delta,
                      logLM=logLM_all, logLM_Base=logLM_Base, logL0=logL0, effect_cv=beta_cv,
                      se_clean=se_clean, singular_X0=singular)
+
+
+# --------------------------------------------------------------------------
+# i = 0 BLUP / PEV / BLUE block  (GAPIT.EMMAxP3D.R:779-861), Z = NULL
+# --------------------------------------------------------------------------
+def _r_solve(A):
+    """R's solve(A): LAPACK dgesv, error when the reciprocal condition number (1-norm) is below
+    .Machine$double.eps ("system is computationally singular")."""
+    A = np.asarray(A, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        rcond = 1.0 / np.linalg.cond(A, 1)
+    if not np.isfinite(rcond) or rcond < np.finfo(float).eps:
+        raise np.linalg.LinAlgError("system is computationally singular")
+    return np.linalg.inv(A)
+
+
+def _mass_ginv(A):
+    """MASS::ginv(A): SVD pseudo-inverse with tol = sqrt(.Machine$double.eps)."""
+    return np.linalg.pinv(np.asarray(A, dtype=np.float64), rcond=math.sqrt(np.finfo(float).eps))
+
+
+def blup_pev(ys, X0, K, eig_L, reml, CVI=None, CV_Inheritance=None):
+    """Dense restatement of GAPIT.EMMAxP3D.R:779-861 (the reference's two n x n inversions kept)."""
+    ys = np.asarray(ys, dtype=np.float64).reshape(-1)
+    X0 = np.asarray(X0, dtype=np.float64)
+    K = np.asarray(K, dtype=np.float64)
+    n = ys.shape[0]
+    vgs, ves, delta = reml["vg"], reml["ve"], reml["delta"]
+    lam = np.asarray(eig_L["values"], dtype=np.float64)
+    U = np.asarray(eig_L["vectors"], dtype=np.float64) * np.sqrt(1.0 / (lam + delta))[None, :]   # :224
+    yt = U.T @ ys
+    Xt = U.T @ X0
+    iX0X0, _ = _solve_or_ginv(Xt.T @ Xt)
+    beta = iX0X0.T @ (Xt.T @ yt)                               # :772
+    XtimesBetaHat = X0 @ beta                                  # :788
+    YminusXtimesBetaHat = ys - XtimesBetaHat                   # :790
+    Dt = U.T @ YminusXtimesBetaHat                             # :792
+    Zt = U.T                                                   # :795
+    BLUP = K @ (Zt.T @ Dt)                                     # :803
+    BLUP_Plus_Mean = beta[0] + BLUP                            # :818-819
+    try:                                                       # :824-825
+        C11 = vgs * _r_solve(Xt.T @ Xt)
+    except np.linalg.LinAlgError:
+        C11 = vgs * _mass_ginv(Xt.T @ Xt)
+    C21 = -K @ (Zt.T @ Xt) @ C11                               # :827
+    # :828-829  Kinv = try(solve(K)); on error ginv(K).  R's solve() errors when LAPACK's 1-norm rcond estimate is
+    # below .Machine$double.eps -- a coin toss for a kinship that is singular by construction (centring by 2p gives
+    # K 1 = 0 exactly).  Both this oracle and the CUDA path decide from the spectrum instead:
+    # |lambda|min / |lambda|max < eps  =>  pseudo-inverse.  (Documented deviation; DESIGN.md section 7.)
+    alam = np.abs(lam)
+    used_ginv = not (alam.min() / alam.max() >= np.finfo(float).eps)
+    Kinv = _mass_ginv(K) if used_ginv else np.linalg.inv(K)
+    term0 = np.diag(np.full(n, 1.0 / ves))                     # :832
+    try:                                                       # :834-835
+        term1 = _r_solve(term0 + Kinv / vgs)
+    except np.linalg.LinAlgError:
+        term1 = _mass_ginv(term0 + Kinv / vgs)
+    term2 = C21 @ (Xt.T @ Zt) @ K                              # :837
+    C22 = term1 - term2                                        # :838
+    PEV = np.diag(C22).copy()                                  # :839
+    BLUE = None
+    if CVI is not None:                                        # :841-854
+        CVI = np.asarray(CVI, dtype=np.float64)
+        XCV = np.column_stack([np.ones(n), CVI[:, 1:]])
+        beta_inh = beta
+        if CV_Inheritance is not None:
+            XCV = XCV[:, : 1 + CV_Inheritance]
+            beta_inh = beta[: 1 + CV_Inheritance]
+        if beta.shape[0] == 1:
+            XCV = X0
+        BLUE = XCV @ beta_inh if XCV.shape[1] == beta_inh.shape[0] else None
+    return {"BLUP": BLUP, "BLUP_Plus_Mean": BLUP_Plus_Mean, "PEV": PEV, "BLUE": BLUE, "beta": beta,
+            "used_ginv_K": used_ginv}

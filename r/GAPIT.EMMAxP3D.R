@@ -41,13 +41,16 @@ if(!glm){
   REMLs <- r[1]; REMLE_delta <- r[2]; ves <- r[3]; vgs <- r[4]
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="REML"); Memory=GAPIT.Memory(Memory=Memory,Infor="REML")
   rm(eig.R)
+  bp <- .Call("gapit_R_blup_pev", eig.L$vectors, eig.L$values, X0, y, REMLE_delta, vgs)      # :779-839
+  BLUP <- bp[[1]]; PEV <- bp[[2]]; BLUP_Plus_Mean <- bp[[3]][1] + BLUP                        # :818-819
+  Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="PEV"); Memory=GAPIT.Memory(Memory=Memory,Infor="PEV")
   res <- .Call("gapit_R_p3d_scan", as.matrix(xs), eig.L$vectors, eig.L$values, X0, y, REMLE_delta, vgs, FALSE, impute)
 } else {
   res <- .Call("gapit_R_p3d_scan", as.matrix(xs), NULL, NULL, X0, y, 0, 0, TRUE, impute)
 }
 Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="Screening SNPs"); Memory=GAPIT.Memory(Memory=Memory,Infor="Screening SNPs")
 base <- attr(res, "base")
-if(glm){ ves <- base[4]; REMLs <- base[5]; vgs <- 0 }                         # :868-872
+if(glm){ ves <- base[4]; REMLs <- base[5]; vgs <- 0; BLUP <- 0; BLUP_Plus_Mean <- NaN; PEV <- ves }   # :868-875
 if(base[7] != 0) print("At least two of your covariates are linearly dependent. Please reconsider the covariates you are using for GWAS and GPS")   # :711
 beta.cv <- base[8:(7+q0)]
 col <- function(v) matrix(v, m, 1)
@@ -57,10 +60,16 @@ dfs <- ifelse(normal, n - q1, NA)                                             # 
 stderr <- rep(NA_real_, m)
 if(!is.null(CVI) && !is.null(ncol(CVI)) && ncol(CVI) == q0) stderr <- res[,1]/stats
 Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="GWAS done for this Trait"); Memory=GAPIT.Memory(Memory=Memory,Infor="GWAS done for this Trait")
-# the i = 0 BLUP/PEV/BLUE block (:779-861) is not on the data-parallel path; call the reference with optOnly=TRUE if needed
+# BLUE = XCV %*% beta.Inheritance (:841-861, :877-889)
+BLUE <- NA
+if(q0 == 1) { BLUE <- X0 %*% beta.cv } else if(!is.null(CVI)) {
+  XCV <- as.matrix(cbind(1, data.frame(CVI[,-1]))); beta.Inheritance <- beta.cv
+  if(!is.null(CV.Inheritance)){ XCV <- XCV[,1:(1+CV.Inheritance)]; beta.Inheritance <- beta.cv[1:(1+CV.Inheritance)] }
+  BLUE <- try(XCV %*% beta.Inheritance, silent=TRUE); if(inherits(BLUE, "try-error")) BLUE <- NA
+}
 return(list(ps = col(res[,4]), REMLs = -2*REMLs, stats = col(stats), effect.est = col(res[,1]),
     rsquare_base = col(ifelse(normal, base[3], NA)), rsquare = col(res[,5]), dfs = col(dfs), df = col(dfs),
     tvalue = col(stats), stderr = col(stderr), maf=col(res[,7]), nobs = col(rep(n, m)), Timmer=Timmer, Memory=Memory,
-    vgs = vgs, ves = ves, BLUP = NULL, BLUP_Plus_Mean = NULL, PEV = NULL, BLUE=NULL,
+    vgs = vgs, ves = ves, BLUP = BLUP, BLUP_Plus_Mean = BLUP_Plus_Mean, PEV = PEV, BLUE=BLUE,
     logLM = res[m,6], effect.snp=col(res[,1]), effect.cv=beta.cv))
 }

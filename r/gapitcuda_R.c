@@ -146,3 +146,27 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP 
   UNPROTECT(2);
   return res;
 }
+
+/* i = 0 block of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:779-839): list(BLUP, PEV, beta) */
+SEXP gapit_R_blup_pev(SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP delta, SEXP vg) {
+  SEXP dim = Rf_getAttrib(X0, R_DimSymbol);
+  const int64_t n = INTEGER(dim)[0];
+  const int q0 = INTEGER(dim)[1];
+  gapit_eigsys* e = NULL;
+  if (gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  SEXP blup = PROTECT(Rf_allocMatrix(REALSXP, (int)n, 1));
+  SEXP pev = PROTECT(Rf_allocMatrix(REALSXP, (int)n, 1));
+  SEXP beta = PROTECT(Rf_allocVector(REALSXP, q0));
+  int rc = gapit_blup_pev(ctx(), e, REAL(X0), q0, REAL(y), Rf_asReal(delta), Rf_asReal(vg), REAL(blup), REAL(pev), REAL(beta));
+  gapit_eigsys_free(e);
+  if (rc != GAPIT_OK) {
+    UNPROTECT(3);
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  SET_VECTOR_ELT(out, 0, blup);
+  SET_VECTOR_ELT(out, 1, pev);
+  SET_VECTOR_ELT(out, 2, beta);
+  UNPROTECT(4);
+  return out;
+}

@@ -431,3 +431,23 @@ def test_multi_trait_chunked_epilogue(gpu_ctx, npc, T):
             assert np.nanmax(np.abs(np.log10(arrs["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
         assert np.max(np.abs(arrs["rsquare"][t][ok] - ora.rsquare[ok])) < 1e-9
         assert np.array_equal(host["pvalue"][t], arrs["pvalue"][t], equal_nan=True)
+
+
+@pytest.mark.parametrize("npc,ridge", [(0, 0.0), (2, 0.0), (1, 0.05)])
+def test_blup_pev_block(gpu_ctx, npc, ridge):
+    """i = 0 block (GAPIT.EMMAxP3D.R:779-861): eigenbasis evaluation against the dense restatement with the
+    reference's two n x n inversions; singular K (ridge = 0: pseudo-inverse branch) and regular K."""
+    G, Y, X0 = case(160, 900, npc=npc, seed=31)
+    K = go.kinship_vanraden(G.T) + ridge * np.eye(160)
+    eL = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    ora = go.blup_pev(Y, X0, K, eL, reml, CVI=np.column_stack([np.zeros(160), X0[:, 1:]]))
+    assert ora["used_ginv_K"] == (ridge == 0.0)
+    res = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0, CVI=np.column_stack([np.zeros(160), X0[:, 1:]]), ctx=gpu_ctx,
+                              eig_L=eL, reml=reml)
+    assert np.max(np.abs(res["BLUP"][:, 0] - ora["BLUP"])) < 1e-9 * max(1.0, np.abs(ora["BLUP"]).max())
+    assert np.max(np.abs(res["PEV"][:, 0] - ora["PEV"])) < 1e-8 * np.abs(ora["PEV"]).max()
+    assert np.allclose(res["BLUP_Plus_Mean"][:, 0], ora["BLUP_Plus_Mean"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(res["BLUE"][:, 0], ora["BLUE"], rtol=1e-9, atol=1e-9)
+    glm = gb().GAPIT_EMMAxP3D(Y, G.T, None, X0=X0, ctx=gpu_ctx)
+    assert glm["BLUP"] == 0.0 and glm["PEV"] == glm["ves"] and np.isnan(glm["BLUP_Plus_Mean"])   # :872-875
