@@ -35,24 +35,46 @@ struct GramSched {
   };
   static constexpr uint64_t kHintA = ptx::kEvictNormal;
   static constexpr uint64_t kHintB = ptx::kEvictNormal;
+  static constexpr int kBand = 12;
   Params p;
   int next_job, stride;
   __device__ GramSched(const Params& pp, int block, int nblocks) : p(pp), next_job(block), stride(nblocks) {}
   __device__ bool next(Job& j) {
     if (next_job >= p.ntri * p.ksplit) return false;
-    // split-major order: CTAs running together share one marker window (L2 reuse of the row panels)
+    // split-major order: CTAs running together share one marker window (L2 reuse of the row panels).
+    // Inside a split the lower triangle is walked in bands of kBand block-rows, column by column, so the
+    // ~148 tiles in flight cover about kBand x kBand blocks: 2 kBand row panels in L2 feed kBand^2 tiles
+    // (a plain row-major walk would stream one private 256-row panel per tile from HBM).
     const int ks = next_job / p.ntri;
     const int t = next_job - ks * p.ntri;
-    int I = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f);
-    while ((I + 1) * (I + 2) / 2 <= t) ++I;
-    while (I * (I + 1) / 2 > t) --I;
-    const int J = t - I * (I + 1) / 2;
+    const int T = p.tiles_side;
+    int b = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f) / kBand;
+    while ((b + 1) * kBand < T && ((b + 1) * kBand) * ((b + 1) * kBand + 1) / 2 <= t) ++b;
+    while (b > 0 && (b * kBand) * (b * kBand + 1) / 2 > t) --b;
+    const int I0 = b * kBand;
+    const int rows = min(kBand, T - I0);
+    int o = t - I0 * (I0 + 1) / 2;
+    int I, J;
+    if (o < rows * (I0 + 1)) {  // columns 0..I0 hold `rows` tiles each
+      J = o / rows;
+      I = I0 + o - J * rows;
+    } else {                    // triangular tail: column I0 + c holds rows - c tiles
+      o -= rows * (I0 + 1);
+      int c = 1;
+      while (o >= rows - c) {
+        o -= rows - c;
+        ++c;
+      }
+      J = I0 + c;
+      I = J + o;
+    }
     j.a_row0 = I * 256;
     j.b_row0 = J * 256;
     j.kb_begin = static_cast<int>((static_cast<long long>(ks) * p.kblocks) / p.ksplit);
     j.kb_end = static_cast<int>((static_cast<long long>(ks + 1) * p.kblocks) / p.ksplit);
     j.tag0 = I;
     j.tag1 = J;
+    j.tag2 = ks;
     j.group_first = j.group_last = true;
     next_job += stride;
     return true;
