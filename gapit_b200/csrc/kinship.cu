@@ -28,46 +28,58 @@ int geno_build_taxa_major(gapit_geno* g);
 // ------------------------------------------------------------------ K1 pieces
 struct GramSched {
   struct Params {
-    int tiles_side;  // number of 256-row blocks
-    int ntri;        // tiles_side (tiles_side + 1) / 2
+    int tiles_side;  // T: number of 256-row blocks
+    int cl;          // CTAs per cluster: a cluster takes CL consecutive block-rows against one block-column
+    int ntri;        // jobs per marker split = sum over row groups R of min(CL (R+1), T)
     int ksplit;      // splits of the marker axis
     int kblocks;     // marker axis in units of kBlockK
   };
   static constexpr uint64_t kHintA = ptx::kEvictNormal;
   static constexpr uint64_t kHintB = ptx::kEvictNormal;
-  static constexpr int kBand = 12;
+  static constexpr int kBandRows = 12;  // block-rows per band
   Params p;
-  int next_job, stride;
-  __device__ GramSched(const Params& pp, int block, int nblocks) : p(pp), next_job(block), stride(nblocks) {}
+  int next_job, stride, crank;
+  __device__ GramSched(const Params& pp, int unit, int nunits, uint32_t cta_rank)
+      : p(pp), next_job(unit), stride(nunits), crank(static_cast<int>(cta_rank)) {}
   __device__ bool next(Job& j) {
     if (next_job >= p.ntri * p.ksplit) return false;
     // split-major order: CTAs running together share one marker window (L2 reuse of the row panels).
-    // Inside a split the lower triangle is walked in bands of kBand block-rows, column by column, so the
-    // ~148 tiles in flight cover about kBand x kBand blocks: 2 kBand row panels in L2 feed kBand^2 tiles
-    // (a plain row-major walk would stream one private 256-row panel per tile from HBM).
+    // Inside a split the lower triangle is walked in bands of kBandRows block-rows, column by column, so the
+    // ~148 tiles in flight cover about 12 x 12 blocks: 24 row panels in L2 feed 144 tiles (a plain row-major
+    // walk would stream one private 256-row panel per tile from HBM).  Row group R = CL block-rows
+    // [CL R, CL R + CL); it meets block-columns J < min(CL (R+1), T) (with CL = 2 the one tile above the
+    // diagonal per group is computed redundantly and later overwritten by the mirror pass).
     const int ks = next_job / p.ntri;
-    const int t = next_job - ks * p.ntri;
-    const int T = p.tiles_side;
-    int b = static_cast<int>((sqrtf(8.0f * static_cast<float>(t) + 1.0f) - 1.0f) * 0.5f) / kBand;
-    while ((b + 1) * kBand < T && ((b + 1) * kBand) * ((b + 1) * kBand + 1) / 2 <= t) ++b;
-    while (b > 0 && (b * kBand) * (b * kBand + 1) / 2 > t) --b;
-    const int I0 = b * kBand;
-    const int rows = min(kBand, T - I0);
-    int o = t - I0 * (I0 + 1) / 2;
-    int I, J;
-    if (o < rows * (I0 + 1)) {  // columns 0..I0 hold `rows` tiles each
-      J = o / rows;
-      I = I0 + o - J * rows;
-    } else {                    // triangular tail: column I0 + c holds rows - c tiles
-      o -= rows * (I0 + 1);
-      int c = 1;
-      while (o >= rows - c) {
-        o -= rows - c;
-        ++c;
-      }
-      J = I0 + c;
-      I = J + o;
+    int t = next_job - ks * p.ntri;
+    const int T = p.tiles_side, CL = p.cl;
+    const int TR = (T + CL - 1) / CL;
+    const int GB = kBandRows / CL;
+    int R0 = 0, rows = 0;
+    for (;;) {
+      rows = min(GB, TR - R0);
+      int cnt = 0;
+      for (int r = 0; r < rows; ++r) cnt += min(CL * (R0 + r + 1), T);
+      if (t < cnt) break;
+      t -= cnt;
+      R0 += rows;
     }
+    int R, J;
+    const int full_cols = min(CL * R0 + CL, T);   // columns met by every row group of the band
+    if (t < rows * full_cols) {
+      J = t / rows;
+      R = R0 + t - J * rows;
+    } else {                                      // tail: column J is met by row groups R >= J / CL
+      t -= rows * full_cols;
+      J = full_cols;
+      for (;;) {
+        const int c = R0 + rows - J / CL;
+        if (t < c) break;
+        t -= c;
+        ++J;
+      }
+      R = J / CL + t;
+    }
+    const int I = R * CL + crank;
     j.a_row0 = I * 256;
     j.b_row0 = J * 256;
     j.kb_begin = static_cast<int>((static_cast<long long>(ks) * p.kblocks) / p.ksplit);
@@ -184,20 +196,34 @@ static int choose_ksplit(int ntri, int kblocks, int sms) {
 
 static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ldg) {
   GAPIT_CHECK(geno_build_taxa_major(g));
-  CUtensorMap map;
-  GAPIT_CHECK(make_tensor_map_u8(&map, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
-                                 static_cast<uint64_t>(g->ldm), 256));
   GramSched::Params sp;
-  sp.tiles_side = static_cast<int>(ldg / 256);
-  sp.ntri = sp.tiles_side * (sp.tiles_side + 1) / 2;
+  sp.tiles_side = static_cast<int>((g->n + 255) / 256);
+  // clusters of two CTAs take two block-rows against one block-column and multicast that column's panel
+  int cl = (sp.tiles_side >= 2) ? 2 : 1;
+  if (const char* ev = getenv("GAPIT_CLUSTER")) cl = std::max(1, std::min(cl, atoi(ev)));  // A/B switch for profiling
+  if (int64_t(round_up(sp.tiles_side, cl)) * 256 > ldg) return fail(GAPIT_ERR_ARG, "launch_gram: Gram buffer too small");
+  const int TR = (sp.tiles_side + cl - 1) / cl;
+  sp.cl = cl;
+  sp.ntri = 0;
+  for (int R = 0; R < TR; ++R) sp.ntri += std::min(cl * (R + 1), sp.tiles_side);
   sp.kblocks = static_cast<int>(g->ldm / kBlockK);
-  sp.ksplit = choose_ksplit(sp.ntri, sp.kblocks, ctx->sm_count);
+  sp.ksplit = choose_ksplit(sp.ntri * cl, sp.kblocks, ctx->sm_count);
+  CUtensorMap map_a, map_b;
+  GAPIT_CHECK(make_tensor_map_u8(&map_a, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
+                                 static_cast<uint64_t>(g->ldm), 256));
+  GAPIT_CHECK(make_tensor_map_u8(&map_b, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
+                                 static_cast<uint64_t>(g->ldm), 256 / cl));
   GramEpi::Params ep{G_dev, ldg};
-  auto kern = umma_i8_kernel<2, 256, 3, GramSched, GramEpi, 0, 0>;
-  GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
-  const int grid = std::min(ctx->sm_count, sp.ntri * sp.ksplit);
-  kern<<<grid, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream>>>(map, map, sp, ep);
-  GAPIT_CUDA(cudaGetLastError());
+  const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
+  if (cl == 2) {
+    auto kern = umma_i8_kernel<2, 256, 3, 2, GramSched, GramEpi, 0, 0>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+  } else {
+    auto kern = umma_i8_kernel<2, 256, 3, 1, GramSched, GramEpi, 0, 0>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
+    GAPIT_CUDA(launch_umma(kern, nunits, 1, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+  }
   return GAPIT_OK;
 }
 
@@ -205,7 +231,7 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ld
 
 using namespace gapit;
 
-extern "C" int64_t gapit_gram_ld(int64_t n) { return round_up(n, 256); }
+extern "C" int64_t gapit_gram_ld(int64_t n) { return round_up(n, 512); }  // whole pairs of 256-row blocks
 
 extern "C" int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t* sums_dev) {
   if (!ctx || !g || !G_dev || !sums_dev) return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram: NULL argument");
@@ -241,8 +267,8 @@ extern "C" int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, 
   const int64_t ldg = gapit_gram_ld(n);
   long long* s = nullptr;
   double* K_dev = K_dev_out;
-  GAPIT_CUDA(cudaMalloc(&s, size_t(n) * 8));
-  if (!K_dev) GAPIT_CUDA(cudaMalloc(&K_dev, size_t(n) * n * 8));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n), &s));                       // arena: no leak on the error paths below
+  if (!K_dev) GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(n) * n, &K_dev));
   {
     dim3 grid(static_cast<unsigned>(ldg / 32), static_cast<unsigned>(ldg / 32));
     gram_mirror_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg);
@@ -258,8 +284,6 @@ extern "C" int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, 
     e = cudaMemcpy2DAsync(G_host_out, size_t(n) * 4, G_dev, size_t(ldg) * 4, size_t(n) * 4, n, cudaMemcpyDeviceToHost,
                           ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(s);
-  if (!K_dev_out) cudaFree(K_dev);
   if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("gapit_vanraden_finish: ") + cudaGetErrorString(e));
   return GAPIT_OK;
 }

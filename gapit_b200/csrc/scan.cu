@@ -127,7 +127,8 @@ __global__ void vt_project_kernel(const double* __restrict__ V, int64_t n, const
 // ------------------------------------------------------------------ K3 pieces
 struct ScanSched {
   struct Params {
-    int mtiles;   // 256-marker tiles
+    int mtiles;   // units of CL 256-marker tiles (a cluster of CL CTAs takes one unit: same eigen tiles, CL marker tiles)
+    int cl;       // CTAs per cluster (1 or 2)
     int gsplit;   // splits of the eigen index (partial sums per split)
     int nkq;      // BN-row tiles of the sliced eigenvectors
     int kblocks;  // taxa axis in units of kBlockK
@@ -137,9 +138,10 @@ struct ScanSched {
   static constexpr uint64_t kHintA = ptx::kEvictLast;    // marker tile: re-read for every eigen tile
   static constexpr uint64_t kHintB = ptx::kEvictNormal;  // eigen tiles: streamed, shared by concurrent CTAs
   Params p;
-  int gid, stride, kq, kq_begin, kq_end, mt, ks, tc;
-  __device__ ScanSched(const Params& pp, int block, int nblocks)
-      : p(pp), gid(block - nblocks), stride(nblocks), kq(0), kq_begin(0), kq_end(0), mt(0), ks(0), tc(0) {}
+  int gid, stride, kq, kq_begin, kq_end, mt, ks, tc, crank;
+  __device__ ScanSched(const Params& pp, int unit, int nunits, uint32_t cta_rank)
+      : p(pp), gid(unit - nunits), stride(nunits), kq(0), kq_begin(0), kq_end(0), mt(0), ks(0), tc(0),
+        crank(static_cast<int>(cta_rank)) {}
   __device__ bool next(Job& j) {
     if (kq >= kq_end) {
       gid += stride;
@@ -153,7 +155,7 @@ struct ScanSched {
       kq_end = ((ks + 1) * p.nkq) / p.gsplit;
       kq = kq_begin;
     }
-    j.a_row0 = mt * 256;
+    j.a_row0 = (mt * p.cl + crank) * 256;
     j.b_row0 = kq * p.bn;
     j.kb_begin = 0;
     j.kb_end = p.kblocks;
@@ -275,7 +277,7 @@ struct GlmSched {
   static constexpr uint64_t kHintB = ptx::kEvictLast;   // digit planes of R: re-read by every tile
   Params p;
   int tile, stride;
-  __device__ GlmSched(const Params& pp, int block, int nblocks) : p(pp), tile(block), stride(nblocks) {}
+  __device__ GlmSched(const Params& pp, int unit, int nunits, uint32_t) : p(pp), tile(unit), stride(nunits) {}
   __device__ bool next(Job& j) {
     if (tile >= p.mtiles) return false;
     j.a_row0 = tile * 256;
@@ -549,10 +551,14 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   CUtensorMap map_a, map_b;
   GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
                                  static_cast<uint64_t>(g->ldn), 256));
+  // clusters of two CTAs share (multicast) the eigen tile; a single marker tile cannot be paired
+  int cl = (m_ld / 256 >= 2) ? 2 : 1;
+  if (const char* ev = getenv("GAPIT_CLUSTER")) cl = std::max(1, std::min(cl, atoi(ev)));  // A/B switch for profiling
   GAPIT_CHECK(make_tensor_map_u8(&map_b, e->Vs, static_cast<uint64_t>(e->ldn), static_cast<uint64_t>(e->nkq * BN),
-                                 static_cast<uint64_t>(e->ldn), BN));
+                                 static_cast<uint64_t>(e->ldn), BN / cl));
   ScanSched::Params sp;
-  sp.mtiles = static_cast<int>(m_ld / 256);
+  sp.mtiles = static_cast<int>((m_ld / 256 + cl - 1) / cl);
+  sp.cl = cl;
   sp.gsplit = gsplit;
   sp.nkq = static_cast<int>(e->nkq);
   sp.kblocks = static_cast<int>(g->ldn / kBlockK);
@@ -561,11 +567,16 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   int pair = (65792ll * g->n < 2147483647ll) ? 1 : 0;
   if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);  // A/B switch for profiling
   typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair, T, gc_tstride, part_tstride};
-  auto kern = umma_i8_kernel<2, BN, 3, ScanSched, Epi, 1, 1>;
-  GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  const int grid = std::min(ctx->sm_count, sp.mtiles * sp.gsplit * sp.nchunk);
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(map_a, map_b, sp, ep);
-  GAPIT_CUDA(cudaGetLastError());
+  const int nunits = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit * sp.nchunk);
+  if (cl == 2) {
+    auto kern = umma_i8_kernel<2, BN, 3, 2, ScanSched, Epi, 1, 1>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+  } else {
+    auto kern = umma_i8_kernel<2, BN, 3, 1, ScanSched, Epi, 1, 1>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    GAPIT_CUDA(launch_umma(kern, nunits, 1, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+  }
   return GAPIT_OK;
 }
 
@@ -615,11 +626,10 @@ static int launch_glm_bn(gapit_ctx* ctx, gapit_geno* g, const int8_t* Rs_dev, in
                                  static_cast<uint64_t>(g->ldn), BN));
   GlmSched::Params sp{static_cast<int>(m_ld / 256), static_cast<int>(g->ldn / kBlockK)};
   typename Epi::Params ep{scale_dev, g->colsumsq, part_dev, m_ld, g->m, nc, Q};
-  auto kern = umma_i8_kernel<2, BN, 4, GlmSched, Epi, 1, 1>;
+  auto kern = umma_i8_kernel<2, BN, 4, 1, GlmSched, Epi, 1, 1>;
   GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int grid = std::min(ctx->sm_count, sp.mtiles);
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(map_a, map_b, sp, ep);
-  GAPIT_CUDA(cudaGetLastError());
+  GAPIT_CUDA(launch_umma(kern, grid, 1, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
   return GAPIT_OK;
 }
 

@@ -53,13 +53,26 @@ struct UmmaCfg {
   static constexpr int kThreads = 128 + MSUB * 128;
 };
 
-// Sched: struct with `Params`, ctor(Params, block, nblocks), bool next(Job&).
-// Epi  : struct with `Params`, ctor(Params), run(job, taddr, sub, row), finish().
-template <int MSUB, int BN, int STAGES, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
+// Sched: struct with `Params`, ctor(Params, unit, nunits, cta_rank), bool next(Job&).
+// Epi  : struct with `Params`, ctor(Params), run(job, taddr, sub, row).
+//
+// CL == 2 runs the kernel as thread-block clusters of two CTAs that work on the same B tile with different
+// A tiles: each CTA fetches half of the B box and TMA-multicasts it into both CTAs' shared memory, so the
+// L2 -> SM operand traffic of a pair drops from 2(A+B) to 2A+B bytes.  A ring slot is released when the UMMAs of
+// BOTH CTAs have consumed it (tcgen05.commit multicast onto both `empty` barriers, arrival count 2).
+// map_b must then be encoded with boxes of BN/CL rows.
+template <int MSUB, int BN, int STAGES, int CL, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
 __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
     umma_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const typename Sched::Params sp, const typename Epi::Params ep) {
   using Cfg = UmmaCfg<MSUB, BN, STAGES>;
+  static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
+  static_assert((BN / CL) % 8 == 0, "each CTA's share of the B box must keep the 8-row swizzle groups whole");
+  constexpr uint32_t kBShare = (BN / CL) * kBlockK;
+  constexpr uint16_t kClusterMask = (1u << CL) - 1u;
+  const uint32_t crank = (CL > 1) ? ptx::cluster_ctarank() : 0u;
+  const int unit = blockIdx.x / CL;
+  const int nunits = gridDim.x / CL;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -80,7 +93,7 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], 1);
+      ptx::mbar_init(&empty[i], CL);
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       ptx::mbar_init(&tfull[i], 1);
@@ -90,14 +103,15 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
   }
   if (warp == 2) ptx::tmem_alloc(tmem_ptr, kTmemCols);
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if (CL > 1) ptx::cluster_sync();  // peers' barriers must be initialised before any remote arrive / multicast
+  else __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      Sched sch(sp, blockIdx.x, gridDim.x);
+      Sched sch(sp, unit, nunits, crank);
       Job job;
       uint32_t st = 0, ph = 0;
       while (sch.next(job)) {
@@ -107,7 +121,11 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
           uint8_t* sb = sa + Cfg::kABytes;
           ptx::mbar_arrive_expect_tx(&full[st], Cfg::kStageBytes);
           ptx::tma_load_2d(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, Sched::kHintA);
-          ptx::tma_load_2d(&map_b, &full[st], sb, kb * kBlockK, job.b_row0, Sched::kHintB);
+          if (CL > 1)
+            ptx::tma_load_2d_multicast(&map_b, &full[st], sb + crank * kBShare, kb * kBlockK,
+                                       job.b_row0 + static_cast<int>(crank) * (BN / CL), kClusterMask, Sched::kHintB);
+          else
+            ptx::tma_load_2d(&map_b, &full[st], sb, kb * kBlockK, job.b_row0, Sched::kHintB);
           if (++st == STAGES) {
             st = 0;
             ph ^= 1;
@@ -118,7 +136,7 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------- UMMA issuer
     constexpr uint32_t idesc = ptx::idesc_i8(128, BN, A_SIGNED, B_SIGNED);
-    Sched sch(sp, blockIdx.x, gridDim.x);
+    Sched sch(sp, unit, nunits, crank);
     Job job;
     uint32_t st = 0, ph = 0, it = 0;
     while (sch.next(job)) {
@@ -142,7 +160,8 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
               ptx::umma_i8_ss(d_col, da, db, idesc, (kb > job.kb_begin || k > 0) ? 1u : 0u);
             }
           }
-          ptx::umma_commit(&empty[st]);
+          if (CL > 1) ptx::umma_commit_multicast(&empty[st], kClusterMask);
+          else ptx::umma_commit(&empty[st]);
           if (kb == job.kb_end - 1) ptx::umma_commit(&tfull[acc]);
         }
         __syncwarp();
@@ -159,7 +178,7 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = quarter * 32 + lane;
     Epi epi(ep);
-    Sched sch(sp, blockIdx.x, gridDim.x);
+    Sched sch(sp, unit, nunits, crank);
     Job job;
     uint32_t it = 0;
     while (sch.next(job)) {
@@ -176,7 +195,8 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
   }
 
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if (CL > 1) ptx::cluster_sync();  // no CTA may exit while its peer can still multicast into it or arrive on its barriers
+  else __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -184,5 +204,23 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
 // (box_rows x 128 bytes), 128-byte swizzle, out-of-bounds rows read as zero.
 int make_tensor_map_u8(CUtensorMap* out, const void* base, uint64_t inner_bytes, uint64_t rows, uint64_t ld_bytes,
                        uint32_t box_rows);
+
+// Launch helper: grid of `nunits * CL` CTAs as clusters of CL (CL == 1: a plain launch).
+template <class Kernel, class... Args>
+inline cudaError_t launch_umma(Kernel kern, int nunits, int cl, int threads, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(nunits * cl));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cl);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 
 }  // namespace gapit
