@@ -16,6 +16,7 @@
 // so the epilogue subtracts n2 = #(c_k == 2n) of those instead of re-packing the matrix.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -215,7 +216,14 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ld
                                  static_cast<uint64_t>(g->ldm), 256 / cl));
   GramEpi::Params ep{G_dev, ldg};
   const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
-  if (cl == 2) {
+  int pair = 1;  // cta_group::2 UMMA (one M=256 instruction per CTA pair) unless switched off for A/B profiling
+  if (const char* ev = getenv("GAPIT_PAIR")) pair = atoi(ev);
+  if (cl == 2 && pair) {
+    using PCfg = UmmaPairCfg<2, 256, 4>;
+    auto kern = umma_i8_pair_kernel<2, 256, 4, GramSched, GramEpi, 0, 0>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+  } else if (cl == 2) {
     auto kern = umma_i8_kernel<2, 256, 3, 2, GramSched, GramEpi, 0, 0>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
     GAPIT_CUDA(launch_umma(kern, nunits, 2, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));

@@ -568,7 +568,14 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);  // A/B switch for profiling
   typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair, T, gc_tstride, part_tstride};
   const int nunits = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit * sp.nchunk);
-  if (cl == 2) {
+  int pair_mma = 1;  // cta_group::2 UMMA (one M=256 instruction per CTA pair) unless switched off for A/B profiling
+  if (const char* ev = getenv("GAPIT_PAIR")) pair_mma = atoi(ev);
+  if (cl == 2 && pair_mma) {
+    using PCfg = UmmaPairCfg<2, BN, 4>;
+    auto kern = umma_i8_pair_kernel<2, BN, 4, ScanSched, Epi, 1, 1>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+  } else if (cl == 2) {
     auto kern = umma_i8_kernel<2, BN, 3, 2, ScanSched, Epi, 1, 1>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     GAPIT_CUDA(launch_umma(kern, nunits, 2, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));

@@ -200,6 +200,164 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
   if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Pair form (tcgen05 cta_group::2).  Two CTAs on the SM pair of one TPC run as a cluster and issue ONE UMMA of
+// M = 256 per 128-row sub-tile: each CTA stages its own 128 x MSUB rows of A and only HALF of the B rows
+// (BN/2) in shared memory; the tensor cores of both SMs read their own A and exchange the B halves over the
+// pair datapath.  Per SM this halves the shared-memory reads of B and the TMA fill of B, which is what bounds
+// the single-CTA form (operand reads 96 B/clk + TMA fill 64 B/clk against 128 B/clk of shared-memory bandwidth).
+//   producer (both CTAs): TMA with .cta_group::2, bytes complete on the LEADER's `full` barrier
+//   UMMA issuer (leader only): tcgen05.mma.cta_group::2; tcgen05.commit multicast frees the slot in both CTAs
+//                              and publishes the accumulator to both epilogues
+//   epilogue (both CTAs): each drains its own 128 x MSUB TMEM lanes, then arrives on the leader's `tempty`
+template <int MSUB, int BN, int STAGES>
+struct UmmaPairCfg {
+  static_assert(MSUB == 1 || MSUB == 2, "one or two 128-row sub-tiles per CTA");
+  static_assert(BN % 32 == 0 || (BN / 2) % 8 == 0, "half of B must keep whole 8-row swizzle groups");
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "UMMA N for M=256");
+  static constexpr int kAccStages = (MSUB == 1) ? 2 : 1;
+  static constexpr int kABytes = MSUB * 128 * kBlockK;
+  static constexpr int kBBytes = (BN / 2) * kBlockK;
+  static_assert(kBBytes % 1024 == 0, "B stage must keep 1024-byte alignment for SWIZZLE_128B");
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarBytes = (2 * STAGES + 2 * kAccStages) * 8 + 16;
+  static constexpr int kSmemBytes = STAGES * kStageBytes + kBarBytes + 1024;
+  static constexpr int kThreads = 128 + MSUB * 128;
+};
+
+template <int MSUB, int BN, int STAGES, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
+__global__ void __launch_bounds__(UmmaPairCfg<MSUB, BN, STAGES>::kThreads, 1)
+    umma_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const typename Sched::Params sp, const typename Epi::Params ep) {
+  using Cfg = UmmaPairCfg<MSUB, BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* full = bars;                          // used on the leader: both producers arrive, bytes of both CTAs
+  uint64_t* empty = bars + STAGES;                // per CTA: freed by the leader's multicast commit
+  uint64_t* tfull = bars + 2 * STAGES;            // per CTA: accumulator ready (multicast commit)
+  uint64_t* tempty = tfull + Cfg::kAccStages;     // used on the leader: both epilogues arrive
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + Cfg::kAccStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();
+  const bool leader = (crank == 0);
+  const int unit = blockIdx.x / 2;
+  const int nunits = gridDim.x / 2;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      ptx::mbar_init(&full[i], 2);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < Cfg::kAccStages; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], 2 * MSUB * 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc_pair(tmem_ptr, kTmemCols);
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      Sched sch(sp, unit, nunits, crank);
+      Job job;
+      uint32_t st = 0, ph = 0;
+      while (sch.next(job)) {
+        for (int kb = job.kb_begin; kb < job.kb_end; ++kb) {
+          ptx::mbar_wait(&empty[st], ph ^ 1);
+          uint8_t* sa = smem + st * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          if (leader) ptx::mbar_arrive_expect_tx(&full[st], 2 * Cfg::kStageBytes);
+          else ptx::mbar_arrive_remote(&full[st], 0);
+          ptx::tma_load_2d_pair(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, Sched::kHintA);
+          ptx::tma_load_2d_pair(&map_b, &full[st], sb, kb * kBlockK, job.b_row0 + static_cast<int>(crank) * (BN / 2),
+                                Sched::kHintB);
+          if (++st == STAGES) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- UMMA issuer (leader CTA only)
+    if (leader) {
+      constexpr uint32_t idesc = ptx::idesc_i8(256, BN, A_SIGNED, B_SIGNED);
+      Sched sch(sp, unit, nunits, crank);
+      Job job;
+      uint32_t st = 0, ph = 0, it = 0;
+      while (sch.next(job)) {
+        const uint32_t acc = it % Cfg::kAccStages;
+        const uint32_t accph = (it / Cfg::kAccStages) & 1;
+        ptx::mbar_wait(&tempty[acc], accph ^ 1);
+        ptx::tc_fence_after_sync();
+        for (int kb = job.kb_begin; kb < job.kb_end; ++kb) {
+          ptx::mbar_wait(&full[st], ph);
+          ptx::tc_fence_after_sync();
+          if (lane == 0) {
+            const uint32_t a_base = ptx::smem_u32(smem + st * Cfg::kStageBytes);
+            const uint32_t b_base = a_base + Cfg::kABytes;
+#pragma unroll
+            for (int s = 0; s < MSUB; ++s) {
+              const uint32_t d_col = tmem_base + (acc * MSUB + s) * kAccStride;
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint64_t da = ptx::smem_desc_k_sw128(a_base + s * 128 * kBlockK + k * kUmmaK);
+                const uint64_t db = ptx::smem_desc_k_sw128(b_base + k * kUmmaK);
+                ptx::umma_i8_ss_pair(d_col, da, db, idesc, (kb > job.kb_begin || k > 0) ? 1u : 0u);
+              }
+            }
+            ptx::umma_commit_pair_multicast(&empty[st], 3);
+            if (kb == job.kb_end - 1) ptx::umma_commit_pair_multicast(&tfull[acc], 3);
+          }
+          __syncwarp();
+          if (++st == STAGES) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+        ++it;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- epilogue (both CTAs)
+    const int sub = (warp - 4) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    Epi epi(ep);
+    Sched sch(sp, unit, nunits, crank);
+    Job job;
+    uint32_t it = 0;
+    while (sch.next(job)) {
+      const uint32_t acc = it % Cfg::kAccStages;
+      const uint32_t accph = (it / Cfg::kAccStages) & 1;
+      ptx::mbar_wait(&tfull[acc], accph);
+      ptx::tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * MSUB + sub) * kAccStride;
+      epi.run(job, taddr, sub, row);
+      ptx::tc_fence_before_sync();
+      if (leader) ptx::mbar_arrive(&tempty[acc]);
+      else ptx::mbar_arrive_remote(&tempty[acc], 0);
+      ++it;
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  ptx::cluster_sync();
+  if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
 // Host side: 2-D tensor map over a row-major uint8 matrix [rows][ld] with boxes of
 // (box_rows x 128 bytes), 128-byte swizzle, out-of-bounds rows read as zero.
 int make_tensor_map_u8(CUtensorMap* out, const void* base, uint64_t inner_bytes, uint64_t rows, uint64_t ld_bytes,
