@@ -29,6 +29,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "SNPs tested/sec (MLM P3D)"
 UNIT = "SNPs/s"
+# (taxa, markers per GPU, slices) -> dram__bytes_read.sum + dram__bytes_write.sum of one rotate_reduce launch (ncu)
+NCU_TRAFFIC_BYTES = {(5000, 500000, 6): 13.2e9}
 
 
 def parse():
@@ -363,9 +365,12 @@ def main():
     achieved = int8_ops / (scan_kernel_ms * 1e-3) / 1e12
     int8_meas = calibrate_int8_tops(dev)
     int8_peak = int8_meas if int8_meas else 2.0 * pk["bf16_tflops"]
-    roofline = {"bound": "tensor", "kernel": "umma_i8_kernel<ScanSched,ScanEpi> (rotate_reduce)",
+    # DRAM bytes (read + write) of one rotate_reduce launch from `ncu --set full` on this exact configuration
+    # (profiles/r1_ncu_full_pair_kernels_c2.csv); null for other shapes
+    traffic = NCU_TRAFFIC_BYTES.get((n, m, S))
+    roofline = {"bound": "tensor", "kernel": "umma_i8_pair_kernel<ScanSched,ScanEpi> (rotate_reduce, tcgen05 cta_group::2)",
                 "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s", "frac": achieved / int8_peak,
-                "traffic": None,
+                "traffic": traffic, "algorithmic_bytes": float(n) * m + float(n) * n * S,
                 "peak_note": ("int8 dense ceiling measured in this run: cuBLASLt int8 GEMM 8192^3 via torch._int_mm, best of 10 "
                               "(MEASURED_PEAKS.json holds no int8 figure)" if int8_meas else
                               f"2 x bf16_tflops of MEASURED_PEAKS.json ({pk['source']}); int8 calibration unavailable"),
@@ -393,7 +398,7 @@ def main():
         "cpu_baseline": cpu,
         "e2e": e2e,
         "gpu_launches": args.steps * 3,
-        "gpu_launches_note": "per scan step: vt_project + umma_i8 rotate_reduce + finalize",
+        "gpu_launches_note": "per scan step: vt_project + umma_i8_pair rotate_reduce + finalize",
         "clocks": clocks,
         "reml": {"delta": delta, "vg": vg},
         "min_p": float(np.nanmin(last["arrs"]["pvalue"])),
