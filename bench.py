@@ -353,7 +353,7 @@ def main():
         ns = args.cpu_sample
         if not ns:   # pilot, then size the sample for ~15 s of CPU work
             v0, _ = cpu_scan_sample(n, min(m, 16), 0, eig_L, reml_d, G_host, Y[:, 0], X0)
-            ns = int(max(16, min(m, 20.0 * v0)))
+            ns = int(max(16, min(m, 40.0 * v0)))
         v, dt = cpu_scan_sample(n, ns, 0, eig_L, reml_d, G_host, Y[:, 0], X0)
         cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                "sample": f"first {ns} of {m} markers ({dt:.1f} s); oracle restatement of GAPIT.EMMAxP3D.R:397-979 "
