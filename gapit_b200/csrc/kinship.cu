@@ -101,7 +101,7 @@ struct GramEpi {
   };
   Params p;
   __device__ explicit GramEpi(const Params& pp) : p(pp) {}
-  __device__ void run(const Job& job, uint32_t taddr, int sub, int row) {
+  __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int /*half*/, int /*nhalf*/) {
     int32_t* dst = p.G + (int64_t(job.a_row0) + sub * 128 + row) * p.ldg + job.b_row0;
 #pragma unroll 1
     for (int c0 = 0; c0 < 256; c0 += 16) {
@@ -220,15 +220,15 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ld
   if (const char* ev = getenv("GAPIT_PAIR")) pair = atoi(ev);
   if (cl == 2 && pair) {
     using PCfg = UmmaPairCfg<2, 256, 4>;
-    auto kern = umma_i8_pair_kernel<2, 256, 4, GramSched, GramEpi, 0, 0>;
+    auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpi, 0, 0>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
     GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
   } else if (cl == 2) {
-    auto kern = umma_i8_kernel<2, 256, 3, 2, GramSched, GramEpi, 0, 0>;
+    auto kern = umma_i8_kernel<2, 256, 3, 2, 1, GramSched, GramEpi, 0, 0>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
     GAPIT_CUDA(launch_umma(kern, nunits, 2, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
   } else {
-    auto kern = umma_i8_kernel<2, 256, 3, 1, GramSched, GramEpi, 0, 0>;
+    auto kern = umma_i8_kernel<2, 256, 3, 1, 1, GramSched, GramEpi, 0, 0>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
     GAPIT_CUDA(launch_umma(kern, nunits, 1, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
   }

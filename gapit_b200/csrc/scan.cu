@@ -197,7 +197,9 @@ struct ScanEpi {
 #pragma unroll
       for (int i = 0; i < Q + 2; ++i) acc[t][i] = 0.0;
   }
-  __device__ void run(const Job& job, uint32_t taddr, int sub, int row) {
+  // `half` of `nhalf` epilogue warps on this (sub-tile, quarter): column groups are dealt round-robin and every
+  // warp keeps its own partial sums (split index tag1 * nhalf + half in `part`)
+  __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int half, int nhalf) {
     if (job.group_first) {
 #pragma unroll
       for (int t = 0; t < TC; ++t)
@@ -208,7 +210,7 @@ struct ScanEpi {
     const int ntr = min(TC, p.T - t0);
     const double* gc = p.gconst + int64_t(t0) * p.gc_tstride + int64_t(job.tag0) * KPB * (Q + 2);
 #pragma unroll 1
-    for (int g = 0; g < BN / GC; ++g) {
+    for (int g = half; g < BN / GC; g += nhalf) {
       uint32_t r[GC];
 #pragma unroll
       for (int j = 0; j < GC / 8; ++j) ptx::tmem_ld_x8(taddr + g * GC + j * 8, *reinterpret_cast<uint32_t(*)[8]>(&r[j * 8]));
@@ -253,7 +255,7 @@ struct ScanEpi {
 #pragma unroll
         for (int t = 0; t < TC; ++t) {
           if (TC == 1 || t < ntr) {
-            double* dst = p.part + int64_t(t0 + t) * p.part_tstride + int64_t(job.tag1) * (Q + 2) * p.m_ld + mrk;
+            double* dst = p.part + int64_t(t0 + t) * p.part_tstride + int64_t(job.tag1 * nhalf + half) * (Q + 2) * p.m_ld + mrk;
 #pragma unroll
             for (int i = 0; i < Q + 2; ++i) dst[i * p.m_ld] = acc[t][i];
           }
@@ -310,7 +312,7 @@ struct GlmEpi {
   };
   Params p;
   __device__ explicit GlmEpi(const Params& pp) : p(pp) {}
-  __device__ void run(const Job& job, uint32_t taddr, int sub, int row) {
+  __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int /*half*/, int /*nhalf*/) {
     uint32_t r[BN];
 #pragma unroll
     for (int j = 0; j < BN / 8; ++j) ptx::tmem_ld_x8(taddr + j * 8, *reinterpret_cast<uint32_t(*)[8]>(&r[j * 8]));
@@ -542,6 +544,27 @@ static int pad_q(int q0) {
   return 16;
 }
 
+// Which form of the rotation kernel a shape gets: clusters of two CTAs need at least two marker tiles; the
+// single-trait epilogue (few registers) runs two warps per (sub-tile, lane quarter).  Environment switches are
+// A/B knobs for profiling.
+struct ScanMode {
+  int cl;     // CTAs per cluster
+  int pair;   // 1: tcgen05 cta_group::2 UMMA
+  int nhalf;  // epilogue warps per (sub-tile, quarter) = partial sums per eigen split
+};
+static ScanMode scan_mode(int64_t m_ld, int T) {
+  ScanMode md;
+  md.cl = (m_ld / 256 >= 2) ? 2 : 1;
+  if (const char* ev = getenv("GAPIT_CLUSTER")) md.cl = std::max(1, std::min(md.cl, atoi(ev)));
+  md.pair = 1;
+  if (const char* ev = getenv("GAPIT_PAIR")) md.pair = atoi(ev) ? 1 : 0;
+  if (md.cl != 2) md.pair = 0;
+  // a single trait always keeps two partial sums per eigen split (even / odd column groups), whatever kernel form
+  // runs it, so its fp64 summation order -- hence every output bit -- does not depend on tile count or chunking
+  md.nhalf = (T == 1) ? 2 : 1;
+  return md;
+}
+
 // one launch scans traits [0, T): gconst_dev/part_dev are the arrays of trait 0, strides in doubles
 template <int S, int BN, int Q, int TC>
 static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* gconst_dev, double* part_dev,
@@ -551,9 +574,8 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   CUtensorMap map_a, map_b;
   GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
                                  static_cast<uint64_t>(g->ldn), 256));
-  // clusters of two CTAs share (multicast) the eigen tile; a single marker tile cannot be paired
-  int cl = (m_ld / 256 >= 2) ? 2 : 1;
-  if (const char* ev = getenv("GAPIT_CLUSTER")) cl = std::max(1, std::min(cl, atoi(ev)));  // A/B switch for profiling
+  const ScanMode md = scan_mode(m_ld, T);
+  const int cl = md.cl;
   GAPIT_CHECK(make_tensor_map_u8(&map_b, e->Vs, static_cast<uint64_t>(e->ldn), static_cast<uint64_t>(e->nkq * BN),
                                  static_cast<uint64_t>(e->ldn), BN / cl));
   ScanSched::Params sp;
@@ -568,21 +590,21 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);  // A/B switch for profiling
   typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair, T, gc_tstride, part_tstride};
   const int nunits = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit * sp.nchunk);
-  int pair_mma = 1;  // cta_group::2 UMMA (one M=256 instruction per CTA pair) unless switched off for A/B profiling
-  if (const char* ev = getenv("GAPIT_PAIR")) pair_mma = atoi(ev);
-  if (cl == 2 && pair_mma) {
+  constexpr int EPIW = (TC == 1) ? 2 : 1;
+  constexpr int kThreadsEpi = 128 + 2 * 128 * EPIW;
+  if (md.pair) {
     using PCfg = UmmaPairCfg<2, BN, 4>;
-    auto kern = umma_i8_pair_kernel<2, BN, 4, ScanSched, Epi, 1, 1>;
+    auto kern = umma_i8_pair_kernel<2, BN, 4, EPIW, ScanSched, Epi, 1, 1>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, PCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
   } else if (cl == 2) {
-    auto kern = umma_i8_kernel<2, BN, 3, 2, ScanSched, Epi, 1, 1>;
+    auto kern = umma_i8_kernel<2, BN, 3, 2, EPIW, ScanSched, Epi, 1, 1>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 2, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
   } else {
-    auto kern = umma_i8_kernel<2, BN, 3, 1, ScanSched, Epi, 1, 1>;
+    auto kern = umma_i8_kernel<2, BN, 3, 1, EPIW, ScanSched, Epi, 1, 1>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 1, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+    GAPIT_CUDA(launch_umma(kern, nunits, 1, kThreadsEpi, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
   }
   return GAPIT_OK;
 }
@@ -633,7 +655,7 @@ static int launch_glm_bn(gapit_ctx* ctx, gapit_geno* g, const int8_t* Rs_dev, in
                                  static_cast<uint64_t>(g->ldn), BN));
   GlmSched::Params sp{static_cast<int>(m_ld / 256), static_cast<int>(g->ldn / kBlockK)};
   typename Epi::Params ep{scale_dev, g->colsumsq, part_dev, m_ld, g->m, nc, Q};
-  auto kern = umma_i8_kernel<2, BN, 4, 1, GlmSched, Epi, 1, 1>;
+  auto kern = umma_i8_kernel<2, BN, 4, 1, 1, GlmSched, Epi, 1, 1>;
   GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int grid = std::min(ctx->sm_count, sp.mtiles);
   GAPIT_CUDA(launch_umma(kern, grid, 1, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
@@ -843,7 +865,8 @@ static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, d
                     int64_t out_ld, int64_t out_off, cudaEvent_t after_reduce = nullptr) {
   const int Q = plan.Q;
   const int64_t m_ld = round_up(v.m, 256);
-  const int64_t part_tstride = int64_t(plan.gsplit) * (Q + 2) * m_ld;
+  const int nsplit = plan.glm ? 1 : plan.gsplit * scan_mode(m_ld, plan.T).nhalf;   // partial sums per marker
+  const int64_t part_tstride = int64_t(nsplit) * (Q + 2) * m_ld;
   double* part = nullptr;
   GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t(plan.T) * part_tstride, &part));
   gapit_geno view;  // borrowed pointers only
@@ -866,8 +889,10 @@ static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, d
   if (after_reduce) cudaEventRecord(after_reduce, ctx->stream);
   for (int t = 0; t < plan.T; ++t) {
     double* o = out_dev + t * out_tstride + out_off;
+    FinalizeConsts fc = plan.fc[t];
+    fc.gsplit = nsplit;
     finalize_kernel<<<static_cast<unsigned>((v.m + 255) / 256), 256, 0, ctx->stream>>>(
-        part + t * part_tstride, m_ld, v.m, v.colsum, v.colsumsq, plan.fc[t], o, o + out_ld, o + 2 * out_ld,
+        part + t * part_tstride, m_ld, v.m, v.colsum, v.colsumsq, fc, o, o + out_ld, o + 2 * out_ld,
         o + 3 * out_ld, o + 4 * out_ld, o + 5 * out_ld, o + 6 * out_ld);
   }
   GAPIT_CUDA(cudaGetLastError());

@@ -54,15 +54,15 @@ struct UmmaCfg {
 };
 
 // Sched: struct with `Params`, ctor(Params, unit, nunits, cta_rank), bool next(Job&).
-// Epi  : struct with `Params`, ctor(Params), run(job, taddr, sub, row).
+// Epi  : struct with `Params`, ctor(Params), run(job, taddr, sub, row, half, nhalf).
 //
 // CL == 2 runs the kernel as thread-block clusters of two CTAs that work on the same B tile with different
 // A tiles: each CTA fetches half of the B box and TMA-multicasts it into both CTAs' shared memory, so the
 // L2 -> SM operand traffic of a pair drops from 2(A+B) to 2A+B bytes.  A ring slot is released when the UMMAs of
 // BOTH CTAs have consumed it (tcgen05.commit multicast onto both `empty` barriers, arrival count 2).
 // map_b must then be encoded with boxes of BN/CL rows.
-template <int MSUB, int BN, int STAGES, int CL, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
-__global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
+template <int MSUB, int BN, int STAGES, int CL, int EPIW, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
+__global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
     umma_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const typename Sched::Params sp, const typename Epi::Params ep) {
   using Cfg = UmmaCfg<MSUB, BN, STAGES>;
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], MSUB * 128);
+      ptx::mbar_init(&tempty[i], MSUB * 128 * EPIW);
     }
     ptx::fence_barrier_init();
   }
@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
-    const int sub = (warp - 4) >> 2;
+    const int sub = ((warp - 4) >> 2) % MSUB;
+    const int half = ((warp - 4) >> 2) / MSUB;  // which share of the accumulator columns this warp drains (EPIW > 1)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = quarter * 32 + lane;
     Epi epi(ep);
@@ -187,7 +188,7 @@ __global__ void __launch_bounds__(UmmaCfg<MSUB, BN, STAGES>::kThreads, 1)
       ptx::mbar_wait(&tfull[acc], accph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * MSUB + sub) * kAccStride;
-      epi.run(job, taddr, sub, row);
+      epi.run(job, taddr, sub, row, half, EPIW);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&tempty[acc]);
       ++it;
@@ -225,8 +226,10 @@ struct UmmaPairCfg {
   static constexpr int kThreads = 128 + MSUB * 128;
 };
 
-template <int MSUB, int BN, int STAGES, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
-__global__ void __launch_bounds__(UmmaPairCfg<MSUB, BN, STAGES>::kThreads, 1)
+// EPIW epilogue warps share each (sub-tile, lane quarter): they split the accumulator columns between them and
+// halve the time the single TMEM stage is blocked (the epilogue keeps per-warp partial sums).
+template <int MSUB, int BN, int STAGES, int EPIW, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
+__global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
     umma_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const typename Sched::Params sp, const typename Epi::Params ep) {
   using Cfg = UmmaPairCfg<MSUB, BN, STAGES>;
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(UmmaPairCfg<MSUB, BN, STAGES>::kThreads, 1)
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], 2 * MSUB * 128);
+      ptx::mbar_init(&tempty[i], 2 * MSUB * 128 * EPIW);
     }
     ptx::fence_barrier_init();
   }
@@ -332,7 +335,8 @@ __global__ void __launch_bounds__(UmmaPairCfg<MSUB, BN, STAGES>::kThreads, 1)
     }
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue (both CTAs)
-    const int sub = (warp - 4) >> 2;
+    const int sub = ((warp - 4) >> 2) % MSUB;
+    const int half = ((warp - 4) >> 2) / MSUB;   // which share of the accumulator columns this warp drains
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     Epi epi(ep);
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(UmmaPairCfg<MSUB, BN, STAGES>::kThreads, 1)
       ptx::mbar_wait(&tfull[acc], accph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * MSUB + sub) * kAccStride;
-      epi.run(job, taddr, sub, row);
+      epi.run(job, taddr, sub, row, half, EPIW);
       ptx::tc_fence_before_sync();
       if (leader) ptx::mbar_arrive(&tempty[acc]);
       else ptx::mbar_arrive_remote(&tempty[acc], 0);

@@ -342,7 +342,8 @@ def test_multi_trait_matches_single_trait_calls(gpu_ctx):
                                 ctx=gpu_ctx)
     for t in range(3):
         one, b1 = gb().p3d_scan(geno, X0, Yt[:, t], eigsys=es, delta=[remls[t]["delta"]], vg=[remls[t]["vg"]], ctx=gpu_ctx)
-        assert np.array_equal(arrs["pvalue"][t], one["pvalue"][0], equal_nan=True)
+        # a single trait keeps two partial sums per eigen split, a trait chunk one: same numbers to rounding
+        assert np.allclose(arrs["pvalue"][t], one["pvalue"][0], rtol=1e-11, atol=0, equal_nan=True)
         ora = go.emmax_p3d(Yt[:, t], G.T, K, X0, eig_L=eL, reml=remls[t])
         with np.errstate(divide="ignore"):
             assert np.nanmax(np.abs(np.log10(arrs["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
