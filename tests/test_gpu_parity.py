@@ -452,3 +452,64 @@ def test_blup_pev_block(gpu_ctx, npc, ridge):
     assert np.allclose(res["BLUE"][:, 0], ora["BLUE"], rtol=1e-9, atol=1e-9)
     glm = gb().GAPIT_EMMAxP3D(Y, G.T, None, X0=X0, ctx=gpu_ctx)
     assert glm["BLUP"] == 0.0 and glm["PEV"] == glm["ves"] and np.isnan(glm["BLUP_Plus_Mean"])   # :872-875
+
+
+def test_full_size_c2_properties(gpu_ctx):
+    """BASELINE configs[1] at full size (5,000 taxa x 500,000 SNPs): the oracle cannot run this in seconds, so parity
+    is carried by size-independent properties -- exact Gram checksums, K 1 = 0, bit-identical rows for duplicated
+    columns in different tiles, shard independence of the scan, and spot rows against the dense Cholesky GLS."""
+    n, m = 5000, 500000
+    G = synth.make_genotypes(n, m, seed=20160302, threads=16)
+    G[499999] = G[123]          # duplicates far apart (different tiles, different stream chunks)
+    G[250000] = G[123]
+    Y = synth.make_phenotypes(G[:4096], seed=3)[:, 0]
+    X0 = np.ones((n, 1))
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    K, gram = gb().GAPIT_kinship_VanRaden(geno, ctx=gpu_ctx, return_gram=True, verbose=False)
+    cs, cq = geno.colsums()
+    c = cs.astype(np.int64)
+    assert int(gram.astype(np.int64).sum()) == int((c * c).sum())                 # sum_ij G_ij = sum_k c_k^2
+    assert int(np.trace(gram.astype(np.int64))) == int(cq.astype(np.int64).sum())  # tr G = sum x^2
+    sub = G[:, 4900:5000].astype(np.int64)
+    assert np.array_equal(gram[4900:, 4900:], sub.T @ sub)
+    assert np.abs(K.sum(1)).max() < 1e-8 and np.array_equal(K, K.T)
+    eL = gb().emma_eigen_L_wo_Z(K, ctx=gpu_ctx)
+    reml = gb().GAPIT_emma_REMLE(Y, X0, K, ctx=gpu_ctx)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    kw = dict(eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]], ctx=gpu_ctx)
+    full, _ = gb().p3d_scan(geno, X0, Y, **kw)
+    for key in ("pvalue", "tvalue", "effect", "rsquare", "loglm"):
+        assert full[key][0, 499999] == full[key][0, 123] == full[key][0, 250000], key
+    # a marker shard (what one rank of a multi-GPU run holds) reproduces its rows of the full scan bit for bit
+    shard = gb().Genotypes(G[300000:337000], ctx=gpu_ctx, marker_major=True)
+    part, _ = gb().p3d_scan(shard, X0, Y, **kw)
+    for key in ("pvalue", "tvalue", "effect"):
+        assert np.array_equal(part[key][0], full[key][0, 300000:337000], equal_nan=True), key
+    # the streaming host path too
+    host, _ = gb().p3d_scan_host(G, X0, Y, marker_major=True, **kw)
+    assert np.array_equal(host["pvalue"], full["pvalue"], equal_nan=True)
+    # spot rows against the dense GLS solve (Cholesky of K + delta I)
+    L = np.linalg.cholesky(K + reml["delta"] * np.eye(n))
+    yw = np.linalg.solve(L, Y)
+    x0w = np.linalg.solve(L, X0[:, 0])
+    for i in (0, 123, 77777, 499998):
+        if np.isnan(full["tvalue"][0, i]):
+            continue
+        Xw = np.column_stack([x0w, np.linalg.solve(L, G[i].astype(np.float64))])
+        iXX = np.linalg.inv(Xw.T @ Xw)
+        b = iXX @ (Xw.T @ yw)
+        se = np.sqrt(iXX[1, 1] * reml["vg"])
+        assert full["effect"][0, i] == pytest.approx(b[1], rel=1e-7, abs=1e-10)
+        assert full["se"][0, i] == pytest.approx(se, rel=1e-8)
+    # GLM rows against OLS with the reduced-model variance (:937)
+    glm, gbase = gb().p3d_scan(geno, X0, Y, glm=True, ctx=gpu_ctx)
+    ves = float(((Y - Y.mean()) ** 2).sum() / (n - 1))
+    assert gbase[0]["ves"] == pytest.approx(ves, rel=1e-10)
+    for i in (5, 400000):
+        x = G[i].astype(np.float64)
+        if x.min() == x.max():
+            continue
+        X = np.column_stack([X0[:, 0], x])
+        iXX = np.linalg.inv(X.T @ X)
+        b = iXX @ (X.T @ Y)
+        assert glm["tvalue"][0, i] == pytest.approx(b[1] / np.sqrt(iXX[1, 1] * ves), rel=1e-9)
