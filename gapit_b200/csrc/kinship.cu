@@ -99,8 +99,10 @@ struct GramEpi {
     int32_t* G;   // [ldg][ldg] row-major, zero-initialised
     int64_t ldg;
   };
+  static constexpr int kSmemBytes = 0;
   Params p;
-  __device__ explicit GramEpi(const Params& pp) : p(pp) {}
+  __device__ GramEpi(const Params& pp, uint8_t*) : p(pp) {}
+  __device__ void prepare(const Job&, int, int) {}
   __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int /*half*/, int /*nhalf*/) {
     int32_t* dst = p.G + (int64_t(job.a_row0) + sub * 128 + row) * p.ldg + job.b_row0;
 #pragma unroll 1

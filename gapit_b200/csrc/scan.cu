@@ -176,26 +176,34 @@ struct ScanEpi {
   static constexpr int KG = GC / S;
   static_assert(BN % GC == 0, "accumulator columns must split into whole digit groups");
   struct Params {
-    const double* gconst;  // [T][(nkq*KPB)][Q+2]: w c^2 | w c A_j ... | w c b   (per trait)
+    const double* gconst;  // [chunk][nkq*KPB][TC][Q+2]: w c^2 | w c A_j ... | w c b  for the TC traits of the chunk
     double* part;          // [T][gsplit][Q+2][m_ld]
     int64_t m_ld;
     int64_t m;
     int pair;              // 1: merge adjacent digit planes in int32 before converting (needs 65792 n < 2^31)
     int T;                 // traits; chunk c of a job covers traits [c*TC, min(T, (c+1)*TC))
-    int64_t gc_tstride;    // doubles between the constants of consecutive traits
+    int64_t gc_tstride;    // doubles between the constants of consecutive trait chunks (= nk * TC * (Q+2))
     int64_t part_tstride;  // doubles between the partial sums of consecutive traits
   };
+  // the constants of one job (KPB eigen indices x TC traits) are staged in shared memory while the job's MMAs run
+  static constexpr int kSmemDoubles = KPB * TC * (Q + 2);
+  static constexpr int kSmemBytes = kSmemDoubles * 8;
   Params p;
+  double* cs;
   double acc[TC][Q + 2];
   // exact int32 -> fp64: the bits 0x43300000:(x ^ 0x80000000) are the double 2^52 + 2^31 + x
   static __device__ __forceinline__ double i2d(int x) {
     return __hiloint2double(0x43300000, x ^ static_cast<int>(0x80000000u)) - 4503601774854144.0;
   }
-  __device__ explicit ScanEpi(const Params& pp) : p(pp) {
+  __device__ ScanEpi(const Params& pp, uint8_t* scratch) : p(pp), cs(reinterpret_cast<double*>(scratch)) {
 #pragma unroll
     for (int t = 0; t < TC; ++t)
 #pragma unroll
       for (int i = 0; i < Q + 2; ++i) acc[t][i] = 0.0;
+  }
+  __device__ void prepare(const Job& job, int tid, int nthreads) {
+    const double* src = p.gconst + int64_t(job.tag2) * p.gc_tstride + int64_t(job.tag0) * kSmemDoubles;
+    for (int i = tid; i < kSmemDoubles; i += nthreads) cs[i] = __ldg(src + i);
   }
   // `half` of `nhalf` epilogue warps on this (sub-tile, quarter): column groups are dealt round-robin and every
   // warp keeps its own partial sums (split index tag1 * nhalf + half in `part`)
@@ -208,7 +216,6 @@ struct ScanEpi {
     }
     const int t0 = job.tag2 * TC;
     const int ntr = min(TC, p.T - t0);
-    const double* gc = p.gconst + int64_t(t0) * p.gc_tstride + int64_t(job.tag0) * KPB * (Q + 2);
 #pragma unroll 1
     for (int g = half; g < BN / GC; g += nhalf) {
       uint32_t r[GC];
@@ -237,14 +244,14 @@ struct ScanEpi {
 #pragma unroll
           for (int s = S - 2; s >= 0; --s) u = fma(u, 256.0, i2d(d[s]));
         }
-        const double* c = gc + (g * KG + kk) * (Q + 2);
+        const double* c = cs + (g * KG + kk) * TC * (Q + 2);   // shared-memory broadcast reads
 #pragma unroll
         for (int t = 0; t < TC; ++t) {
           if (TC == 1 || t < ntr) {
-            const double* ct = c + int64_t(t) * p.gc_tstride;
-            acc[t][0] = fma(__ldg(ct) * u, u, acc[t][0]);
+            const double* ct = c + t * (Q + 2);
+            acc[t][0] = fma(ct[0] * u, u, acc[t][0]);
 #pragma unroll
-            for (int i = 1; i < Q + 2; ++i) acc[t][i] = fma(__ldg(ct + i), u, acc[t][i]);
+            for (int i = 1; i < Q + 2; ++i) acc[t][i] = fma(ct[i], u, acc[t][i]);
           }
         }
       }
@@ -310,8 +317,10 @@ struct GlmEpi {
     int nc;                    // q0 + 1 columns of R in use
     int qpad;
   };
+  static constexpr int kSmemBytes = 0;
   Params p;
-  __device__ explicit GlmEpi(const Params& pp) : p(pp) {}
+  __device__ GlmEpi(const Params& pp, uint8_t*) : p(pp) {}
+  __device__ void prepare(const Job&, int, int) {}
   __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int /*half*/, int /*nhalf*/) {
     uint32_t r[BN];
 #pragma unroll
@@ -544,6 +553,9 @@ static int pad_q(int q0) {
   return 16;
 }
 
+// traits that share one rotation pass (must match the TC template arguments picked in launch_scan_S)
+static int trait_chunk(int Q) { return Q <= 1 ? 16 : (Q <= 2 ? 12 : (Q <= 4 ? 8 : (Q <= 8 ? 4 : 2))); }
+
 // Which form of the rotation kernel a shape gets: clusters of two CTAs need at least two marker tiles; the
 // single-trait epilogue (few registers) runs two warps per (sub-tile, lane quarter).  Environment switches are
 // A/B knobs for profiling.
@@ -595,16 +607,16 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   if (md.pair) {
     using PCfg = UmmaPairCfg<2, BN, 4>;
     auto kern = umma_i8_pair_kernel<2, BN, 4, EPIW, ScanSched, Epi, 1, 1>;
-    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, PCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes + Epi::kSmemBytes + 16));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, PCfg::kSmemBytes + Epi::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
   } else if (cl == 2) {
     auto kern = umma_i8_kernel<2, BN, 3, 2, EPIW, ScanSched, Epi, 1, 1>;
-    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + Epi::kSmemBytes + 16));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, Cfg::kSmemBytes + Epi::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
   } else {
     auto kern = umma_i8_kernel<2, BN, 3, 1, EPIW, ScanSched, Epi, 1, 1>;
-    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 1, kThreadsEpi, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + Epi::kSmemBytes + 16));
+    GAPIT_CUDA(launch_umma(kern, nunits, 1, kThreadsEpi, Cfg::kSmemBytes + Epi::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
   }
   return GAPIT_OK;
 }
@@ -694,8 +706,9 @@ struct ScanPlan {
   int q0 = 0, Q = 0, T = 0, glm = 0, gsplit = 1;
   gapit_eigsys* e = nullptr;
   std::vector<FinalizeConsts> fc;   // per trait
-  double* gconst = nullptr;         // MLM: [T][nk][Q+2]
+  double* gconst = nullptr;         // MLM: [chunk][nk][TC][Q+2], TC traits per chunk share one rotation pass
   int64_t nk = 0;
+  int TC = 1;
   int8_t* Rs = nullptr;             // GLM: [T][128][ldn] digit planes of [X0 | y_t]
   double* Rscale = nullptr;         // GLM: [T][GAPIT_MAX_Q0+1]
 };
@@ -743,7 +756,9 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
     GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
     GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
     plan->nk = e->nkq * e->KPB;
-    GAPIT_CHECK(ctx_ws_t(ctx, WS_GCONST, size_t(T) * plan->nk * (Q + 2), &plan->gconst));
+    plan->TC = (T > 1) ? trait_chunk(Q) : 1;
+    const int nchunk = (T + plan->TC - 1) / plan->TC;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_GCONST, size_t(nchunk) * plan->nk * plan->TC * (Q + 2), &plan->gconst));
   } else {
     std::copy(X0, X0 + size_t(n) * q0, proj.begin());
     std::copy(Y, Y + size_t(n) * T, proj.begin() + size_t(n) * q0);
@@ -753,7 +768,7 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
   }
 
   std::vector<double> w(n), gconst;
-  if (!glm) gconst.assign(size_t(T) * plan->nk * (Q + 2), 0.0);
+  if (!glm) gconst.assign(size_t((T + plan->TC - 1) / plan->TC) * plan->nk * plan->TC * (Q + 2), 0.0);
   const double dn = static_cast<double>(n);
   const double two_pi = 2.0 * 3.14159265358979323846;
   for (int t = 0; t < T; ++t) {
@@ -832,10 +847,11 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
       b.singular_x0 = singular;
     }
     if (!glm) {
-      double* gt = gconst.data() + size_t(t) * plan->nk * (Q + 2);
+      const int TC = plan->TC;
+      double* gt = gconst.data() + size_t(t / TC) * plan->nk * TC * (Q + 2) + size_t(t % TC) * (Q + 2);
       for (int64_t k = 0; k < n; ++k) {
         const double c = e->h_scale[k];
-        double* gk = gt + size_t(k) * (Q + 2);
+        double* gk = gt + size_t(k) * TC * (Q + 2);
         gk[0] = w[k] * c * c;
         for (int j = 0; j < q0; ++j) gk[1 + j] = w[k] * c * proj[size_t(j) * n + k];
         gk[Q + 1] = w[k] * c * yt[k];
@@ -880,7 +896,7 @@ static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, d
   if (!plan.glm) {
     // one launch for all traits: the rotation of a marker tile is shared by a chunk of traits
     GAPIT_CHECK(launch_scan(ctx, &view, plan.e, Q, plan.gconst, part, m_ld, plan.gsplit, plan.T,
-                            plan.nk * (Q + 2), part_tstride));
+                            plan.nk * plan.TC * (Q + 2), part_tstride));
   } else {
     for (int t = 0; t < plan.T; ++t)
       GAPIT_CHECK(launch_glm(ctx, &view, plan.Rs + size_t(t) * 128 * plan.ldn, 128,

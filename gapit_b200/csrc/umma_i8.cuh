@@ -54,7 +54,8 @@ struct UmmaCfg {
 };
 
 // Sched: struct with `Params`, ctor(Params, unit, nunits, cta_rank), bool next(Job&).
-// Epi  : struct with `Params`, ctor(Params), run(job, taddr, sub, row, half, nhalf).
+// Epi  : struct with `Params`, `kSmemBytes`, ctor(Params, smem scratch), prepare(job, tid, nthreads),
+//        run(job, taddr, sub, row, half, nhalf).
 //
 // CL == 2 runs the kernel as thread-block clusters of two CTAs that work on the same B tile with different
 // A tiles: each CTA fetches half of the B box and TMA-multicasts it into both CTAs' shared memory, so the
@@ -82,6 +83,8 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + Cfg::kAccStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + Cfg::kAccStages);
+  // epilogue scratch (Epi::kSmemBytes, 16-byte aligned) behind the barriers; the launch adds it to the dynamic size
+  uint8_t* epi_smem = smem + ((STAGES * Cfg::kStageBytes + Cfg::kBarBytes + 15) & ~15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,13 +181,20 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
     const int half = ((warp - 4) >> 2) / MSUB;  // which share of the accumulator columns this warp drains (EPIW > 1)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = quarter * 32 + lane;
-    Epi epi(ep);
+    Epi epi(ep, epi_smem);
     Sched sch(sp, unit, nunits, crank);
     Job job;
     uint32_t it = 0;
+    constexpr int kEpiThreads = MSUB * 128 * EPIW;
     while (sch.next(job)) {
       const uint32_t acc = it % Cfg::kAccStages;
       const uint32_t accph = (it / Cfg::kAccStages) & 1;
+      if (Epi::kSmemBytes > 0) {
+        // stage the job's epilogue constants while its MMAs run: nobody may still read the previous job's copy
+        ptx::named_bar_sync(1, kEpiThreads);
+        epi.prepare(job, threadIdx.x - 128, kEpiThreads);
+        ptx::named_bar_sync(1, kEpiThreads);
+      }
       ptx::mbar_wait(&tfull[acc], accph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * MSUB + sub) * kAccStride;
@@ -241,6 +251,8 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
   uint64_t* tfull = bars + 2 * STAGES;            // per CTA: accumulator ready (multicast commit)
   uint64_t* tempty = tfull + Cfg::kAccStages;     // used on the leader: both epilogues arrive
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + Cfg::kAccStages);
+  // epilogue scratch (Epi::kSmemBytes, 16-byte aligned) behind the barriers; the launch adds it to the dynamic size
+  uint8_t* epi_smem = smem + ((STAGES * Cfg::kStageBytes + Cfg::kBarBytes + 15) & ~15);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -339,13 +351,20 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
     const int half = ((warp - 4) >> 2) / MSUB;   // which share of the accumulator columns this warp drains
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    Epi epi(ep);
+    Epi epi(ep, epi_smem);
     Sched sch(sp, unit, nunits, crank);
     Job job;
     uint32_t it = 0;
+    constexpr int kEpiThreads = MSUB * 128 * EPIW;
     while (sch.next(job)) {
       const uint32_t acc = it % Cfg::kAccStages;
       const uint32_t accph = (it / Cfg::kAccStages) & 1;
+      if (Epi::kSmemBytes > 0) {
+        // stage the job's epilogue constants while its MMAs run: nobody may still read the previous job's copy
+        ptx::named_bar_sync(1, kEpiThreads);
+        epi.prepare(job, threadIdx.x - 128, kEpiThreads);
+        ptx::named_bar_sync(1, kEpiThreads);
+      }
       ptx::mbar_wait(&tfull[acc], accph);
       ptx::tc_fence_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + (acc * MSUB + sub) * kAccStride;
