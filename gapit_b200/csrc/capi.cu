@@ -9,7 +9,6 @@ namespace gapit {
 
 static thread_local std::string g_last_error;
 
-void set_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;

@@ -13,7 +13,6 @@
 
 namespace gapit {
 
-void set_error(const std::string& msg);
 int fail(int code, const std::string& msg);
 
 #define GAPIT_CUDA(call)                                                                          \

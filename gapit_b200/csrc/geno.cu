@@ -192,7 +192,6 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
     return cleanup(fail(GAPIT_ERR_CUDA, std::string("gapit_geno_pack: cudaMalloc: ") + cudaGetErrorString(e)));
 
   cudaEventRecord(ctx->ev0, ctx->stream);
-  int rc = GAPIT_OK;
   if (dtype == GAPIT_I8) {
     if (g->ldn != n) cudaMemsetAsync(g->mk, 0, size_t(m) * g->ldn, ctx->stream);
     if (ld == n && g->ldn != n) {
@@ -250,7 +249,7 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
     return cleanup(fail(GAPIT_ERR_ARG, "gapit_geno_pack: unknown dtype"));
   }
   cudaEventRecord(ctx->ev1, ctx->stream);
-  rc = run_colstats(g);
+  const int rc = run_colstats(g);
   if (rc != GAPIT_OK) return cleanup(rc);
   *out = g;
   return GAPIT_OK;
