@@ -994,10 +994,13 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
   cudaEventRecord(ctx->ev0, ctx->stream);
   // the copy stream must not start before the workspaces are initialised
   GAPIT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev0, 0));
-  const int64_t nchunks = (m + chunk - 1) / chunk;
+  // the first block's upload cannot overlap anything, so it is a quarter-size one
+  const int64_t first = std::min<int64_t>(m, std::max<int64_t>(256, chunk / 4 / 256 * 256));
+  const int64_t nchunks = 1 + (m - first + chunk - 1) / chunk;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int b = static_cast<int>(c & 1);
-    const int64_t k0 = c * chunk, mc = std::min(chunk, m - k0);
+    const int64_t k0 = (c == 0) ? 0 : first + (c - 1) * chunk;
+    const int64_t mc = (c == 0) ? first : std::min(chunk, m - k0);
     const char* src = static_cast<const char*>(snps) + size_t(k0) * ld * esz;
     if (c >= 2) GAPIT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_free[b], 0));   // buffer b scanned
     if (dtype == GAPIT_I8 && stage[b]) {
