@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="markers of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--reml-route", default="eigL", choices=["eigL", "eigR"],
+                    help="eigL: REML from the spectrum of K alone (one eigendecomposition); eigR: the reference's "
+                         "second decomposition of S(K+I)S (emma.txt:82-89)")
     return ap.parse_args()
 
 
@@ -290,12 +293,15 @@ def main():
         t0 = time.perf_counter()
         eL = gb.emma_eigen_L_wo_Z(K_host, ctx=ctx)
         setup["eigh_L_ms"] = (time.perf_counter() - t0) * 1e3
+        eR = None
+        if args.reml_route == "eigR":
+            t0 = time.perf_counter()
+            eR = gb.emma_eigen_R_wo_Z(K_host, X0, ctx=ctx)
+            setup["eigen_R_ms"] = (time.perf_counter() - t0) * 1e3
         t0 = time.perf_counter()
-        eR = gb.emma_eigen_R_wo_Z(K_host, X0, ctx=ctx)
-        setup["eigen_R_ms"] = (time.perf_counter() - t0) * 1e3
-        t0 = time.perf_counter()
-        reml = gb.GAPIT_emma_REMLE(Y[:, 0], X0, K_host, eig_R=eR, ctx=ctx)
+        reml = gb.GAPIT_emma_REMLE(Y[:, 0], X0, K_host, eig_L=eL, eig_R=eR, ctx=ctx)
         setup["reml_ms"] = (time.perf_counter() - t0) * 1e3
+        setup["reml_route"] = args.reml_route
         del eR
         vec_t.copy_(torch.from_numpy(np.ascontiguousarray(eL["vectors"].T)))   # row r of vec_t = eigenvector r
         val_t.copy_(torch.from_numpy(eL["values"]))

@@ -208,11 +208,21 @@ def GAPIT_emma_REMLE(y, X, K, Z=None, ngrids=100, llim=-10, ulim=10, esp=1e-10, 
     n, q = X.shape
     if np.linalg.det(X.T @ X) == 0:                      # GAPIT.emma.REMLE.R:15-18
         return {"REML": 0.0, "delta": 0.0, "ve": 0.0, "vg": 0.0}
+    out = _lib.RemlOut()
+    if eig_R is None and eig_L is not None:
+        # eig.L given, eig.R not: the same likelihood from the spectrum of K alone (gapit_reml_eigL) --
+        # no second eigendecomposition
+        V = eig_L["vectors"]
+        lam = np.ascontiguousarray(eig_L["values"], dtype=np.float64)
+        Vty = np.ascontiguousarray(V.T @ y)
+        VtX = np.asfortranarray(V.T @ X)
+        check(_lib.load().gapit_reml_eigL(_ptr(lam), _ptr(Vty), _ptr(VtX), n, q, int(ngrids), float(llim), float(ulim),
+                                          float(esp), C.byref(out)))
+        return {"REML": out.REML, "delta": out.delta, "ve": out.ve, "vg": out.vg}
     if eig_R is None:                                    # :22-24
         eig_R = emma_eigen_R_wo_Z(K, X, ctx=ctx)
     lam = np.ascontiguousarray(eig_R["values"], dtype=np.float64)
     etas = np.ascontiguousarray(eig_R["vectors"].T @ y)  # :25 (n-q dot products; host)
-    out = _lib.RemlOut()
     check(_lib.load().gapit_reml(_ptr(lam), _ptr(etas), lam.shape[0], int(ngrids), float(llim), float(ulim),
                                  float(esp), C.byref(out)))
     return {"REML": out.REML, "delta": out.delta, "ve": out.ve, "vg": out.vg}
@@ -324,13 +334,15 @@ def _timmer(Timmer, label):
 def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=None, GI=None, GP=None,
                    fullGD=True, SNP_P3D=True, Timmer=None, Memory=None, optOnly=False, SNP_effect="Add",
                    SNP_impute="Middle", ngrids=100, llim=-10, ulim=10, esp=1e-10, name_of_trait=None,
-                   Create_indicator=False, ctx=None, eig_L=None, reml=None):
+                   Create_indicator=False, ctx=None, eig_L=None, reml=None, reml_route="eigL"):
     """The accelerated branch of GAPIT.EMMAxP3D: Z NULL or square, SNP.P3D, fullGD, no indicators, !optOnly.
 
     Returns the reference's named list (GAPIT.EMMAxP3D.R:1018-1020) as a dict; per-marker
     entries are (m, 1) arrays like the reference's m x g matrices with g = 1.  ``eig_L`` /
     ``reml`` may be injected (tests feed both sides identical spectra); they are otherwise
-    computed exactly where the reference computes them (:48, :58, :202).
+    computed where the reference computes them (:48, :58, :202).  ``reml_route="eigL"`` (default) evaluates the REML
+    likelihood from eig.L alone (``gapit_reml_eigL``: same function of delta, measured agreement 1e-13 in delta), so
+    the eig.R decomposition of :58 is skipped; ``reml_route="eigR"`` runs the reference's two-decomposition route.
     Other argument combinations are the reference's other code paths and are not provided here.
     """
     ctx = ctx or default_context()
@@ -361,6 +373,8 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
         if eig_L is None:
             eig_L = emma_eigen_L_wo_Z(K, ctx=ctx)                         # :48
         Timmer = _timmer(Timmer, "eig.L")
+        if reml is None and reml_route == "eigL":
+            reml = GAPIT_emma_REMLE(ys, X0, K, None, ngrids, llim, ulim, esp, eig_L=eig_L, ctx=ctx)    # :202
         if reml is None:
             try:
                 eig_R = emma_eigen_R_wo_Z(K, X0, ctx=ctx)                 # :58

@@ -39,9 +39,15 @@ struct RemlFn {
     const double v = 0.5 * (static_cast<double>(nq) * a / b - c);
     return scaled ? delta * v : v;
   }
+  double vg(double delta) const {
+    double s = 0.0;
+    for (int64_t i = 0; i < nq; ++i) s += etasq[i] / (lambda[i] + delta);
+    return s / static_cast<double>(nq);
+  }
 };
 
-static double zeroin(const RemlFn& f, double ax, double bx, double fa, double fb, double tol, int maxit, bool* ok) {
+template <class Fn>
+static double zeroin(const Fn& f, double ax, double bx, double fa, double fb, double tol, int maxit, bool* ok) {
   double a = ax, b = bx, c = a, fc = fa;
   *ok = true;
   if (fa == 0.0) return a;
@@ -84,16 +90,10 @@ static double zeroin(const RemlFn& f, double ax, double bx, double fa, double fb
   return b;
 }
 
-}  // namespace gapit
-
-using namespace gapit;
-
-extern "C" int gapit_reml(const double* lambda, const double* etas, int64_t nq, int ngrids, double llim, double ulim,
-                          double esp, gapit_reml_out* out) {
-  if (!lambda || !etas || !out || nq < 1 || ngrids < 2) return fail(GAPIT_ERR_ARG, "gapit_reml: bad argument");
-  std::vector<double> etasq(nq);
-  for (int64_t i = 0; i < nq; ++i) etasq[i] = etas[i] * etas[i];
-  RemlFn f{lambda, etasq.data(), nq};
+// GAPIT.emma.REMLE.R:27-54, 96-110 over any function object with LL / dLL / vg: the grid of log(delta), the bracketed
+// uniroot calls, the boundary candidates and the which.max rule.
+template <class Fn>
+static int reml_search(const Fn& f, int ngrids, double llim, double ulim, double esp, gapit_reml_out* out) {
   const int m = ngrids + 1;
   std::vector<double> logdelta(m), dLL(m);
   for (int i = 0; i < m; ++i) {
@@ -126,11 +126,157 @@ extern "C" int gapit_reml(const double* lambda, const double* etas, int64_t nq, 
     if (!std::isnan(optLL[i]) && (best < 0 || optLL[i] > optLL[best])) best = static_cast<int>(i);
   if (best < 0) return fail(GAPIT_ERR_NUMERIC, "gapit_reml: all candidate likelihoods are NaN");
   const double maxdelta = std::exp(optlogdelta[best]);
-  double s = 0.0;
-  for (int64_t i = 0; i < nq; ++i) s += etasq[i] / (lambda[i] + maxdelta);  // :103
   out->REML = optLL[best];
   out->delta = maxdelta;
-  out->vg = s / static_cast<double>(nq);
-  out->ve = out->vg * maxdelta;  // :108
+  out->vg = f.vg(maxdelta);       // :103
+  out->ve = out->vg * maxdelta;   // :108
   return GAPIT_OK;
+}
+
+// The same restricted likelihood evaluated from the spectrum of K alone (eig.L), so that the second O(n^3)
+// eigendecomposition of the reference (eig.R of S(K+I)S, emma.txt:82-89) is not needed.  With d = 1/(lambda+delta),
+// yt = V'y, Xt = V'X, A = Xt'D Xt, r = yt - Xt A^-1 Xt'D yt and P = S(S H S)^+ S, H = K + delta I:
+//   sum eta^2/(lambdaR+delta)   = y'P y  = sum d r^2
+//   sum eta^2/(lambdaR+delta)^2 = y'PP y = sum d^2 r^2
+//   sum 1/(lambdaR+delta)       = tr P   = sum d - tr(A^-1 Xt'D^2 Xt)
+//   sum log(lambdaR+delta)      = sum log(lambda+delta) + log|A| - log|X'X|
+// which are exactly the four sums emma.delta.REML.{LL,dLL}.wo.Z take over eig.R (emma.txt:145-164).
+struct RemlFnL {
+  const double* lambda;  // n eigenvalues of K
+  const double* yt;      // n
+  const double* Xt;      // n x q column-major
+  int64_t n;
+  int q;
+  double logdetXX;       // log|X'X| (= log|Xt'Xt|, V orthogonal)
+  struct Sums {
+    double r1, r2, trP, logdet;
+    bool ok;
+  };
+  // Cholesky of a q x q SPD matrix (row-major, lower); false if not positive definite
+  static bool chol(int q, std::vector<double>& A) {
+    for (int i = 0; i < q; ++i) {
+      for (int j = 0; j <= i; ++j) {
+        double s = A[i * q + j];
+        for (int k = 0; k < j; ++k) s -= A[i * q + k] * A[j * q + k];
+        if (i == j) {
+          if (!(s > 0.0)) return false;
+          A[i * q + i] = std::sqrt(s);
+        } else {
+          A[i * q + j] = s / A[j * q + j];
+        }
+      }
+    }
+    return true;
+  }
+  static void chol_solve(int q, const std::vector<double>& L, double* b) {
+    for (int i = 0; i < q; ++i) {
+      double s = b[i];
+      for (int k = 0; k < i; ++k) s -= L[i * q + k] * b[k];
+      b[i] = s / L[i * q + i];
+    }
+    for (int i = q - 1; i >= 0; --i) {
+      double s = b[i];
+      for (int k = i + 1; k < q; ++k) s -= L[k * q + i] * b[k];
+      b[i] = s / L[i * q + i];
+    }
+  }
+  Sums sums(double delta) const {
+    Sums o{0.0, 0.0, 0.0, 0.0, true};
+    std::vector<double> A(q * q, 0.0), A2(q * q, 0.0), b(q, 0.0);
+    double sd = 0.0, sl = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+      const double ld = lambda[i] + delta;
+      const double d = 1.0 / ld;
+      sd += d;
+      sl += std::log(ld);
+      for (int a = 0; a < q; ++a) {
+        const double xa = Xt[a * n + i] * d;
+        b[a] += xa * yt[i];
+        for (int c = 0; c <= a; ++c) {
+          const double v = xa * Xt[c * n + i];
+          A[a * q + c] += v;
+          A2[a * q + c] += v * d;
+        }
+      }
+    }
+    for (int a = 0; a < q; ++a)
+      for (int c = a + 1; c < q; ++c) {
+        A[a * q + c] = A[c * q + a];
+        A2[a * q + c] = A2[c * q + a];
+      }
+    std::vector<double> L(A);
+    if (!chol(q, L)) {
+      o.ok = false;
+      return o;
+    }
+    std::vector<double> beta(b);
+    chol_solve(q, L, beta.data());
+    double r1 = 0.0, r2 = 0.0;
+    for (int64_t i = 0; i < n; ++i) {
+      double r = yt[i];
+      for (int a = 0; a < q; ++a) r -= Xt[a * n + i] * beta[a];
+      const double d = 1.0 / (lambda[i] + delta);
+      const double dr2 = d * r * r;
+      r1 += dr2;
+      r2 += dr2 * d;
+    }
+    double tr = 0.0, ldA = 0.0;
+    std::vector<double> col(q);
+    for (int c = 0; c < q; ++c) {  // tr(A^-1 A2) column by column
+      for (int a = 0; a < q; ++a) col[a] = A2[a * q + c];
+      chol_solve(q, L, col.data());
+      tr += col[c];
+      ldA += 2.0 * std::log(L[c * q + c]);
+    }
+    o.r1 = r1;
+    o.r2 = r2;
+    o.trP = sd - tr;
+    o.logdet = sl + ldA - logdetXX;
+    return o;
+  }
+  double LL(double logdelta) const {
+    const Sums s = sums(std::exp(logdelta));
+    if (!s.ok) return NAN;
+    const double dnq = static_cast<double>(n - q);
+    return 0.5 * (dnq * (std::log(dnq / (2.0 * M_PI)) - 1.0 - std::log(s.r1)) - s.logdet);
+  }
+  double dLL(double logdelta, bool scaled) const {
+    const double delta = std::exp(logdelta);
+    const Sums s = sums(delta);
+    if (!s.ok) return NAN;
+    const double v = 0.5 * (static_cast<double>(n - q) * s.r2 / s.r1 - s.trP);
+    return scaled ? delta * v : v;
+  }
+  double vg(double delta) const { return sums(delta).r1 / static_cast<double>(n - q); }
+};
+
+}  // namespace gapit
+
+using namespace gapit;
+
+extern "C" int gapit_reml(const double* lambda, const double* etas, int64_t nq, int ngrids, double llim, double ulim,
+                          double esp, gapit_reml_out* out) {
+  if (!lambda || !etas || !out || nq < 1 || ngrids < 2) return fail(GAPIT_ERR_ARG, "gapit_reml: bad argument");
+  std::vector<double> etasq(nq);
+  for (int64_t i = 0; i < nq; ++i) etasq[i] = etas[i] * etas[i];
+  RemlFn f{lambda, etasq.data(), nq};
+  return reml_search(f, ngrids, llim, ulim, esp, out);
+}
+
+extern "C" int gapit_reml_eigL(const double* lambda, const double* Vty, const double* VtX, int64_t n, int q, int ngrids,
+                               double llim, double ulim, double esp, gapit_reml_out* out) {
+  if (!lambda || !Vty || !VtX || !out || q < 1 || q > GAPIT_MAX_Q0 || n <= q || ngrids < 2)
+    return fail(GAPIT_ERR_ARG, "gapit_reml_eigL: bad argument");
+  std::vector<double> XX(q * q, 0.0);
+  for (int a = 0; a < q; ++a)
+    for (int c = 0; c <= a; ++c) {
+      double s = 0.0;
+      for (int64_t i = 0; i < n; ++i) s += VtX[a * n + i] * VtX[c * n + i];
+      XX[a * q + c] = XX[c * q + a] = s;
+    }
+  if (!RemlFnL::chol(q, XX)) return fail(GAPIT_ERR_NUMERIC, "gapit_reml_eigL: X'X is singular");
+  double ld = 0.0;
+  for (int a = 0; a < q; ++a) ld += 2.0 * std::log(XX[a * q + a]);
+  RemlFnL f{lambda, Vty, VtX, n, q, ld};
+  return reml_search(f, ngrids, llim, ulim, esp, out);
 }

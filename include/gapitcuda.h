@@ -111,6 +111,12 @@ typedef struct {
 } gapit_reml_out;
 int gapit_reml(const double* lambda, const double* etas, int64_t nq, int ngrids, double llim, double ulim,
                double esp, gapit_reml_out* out);
+/* Same optimisation (grid :27-33, uniroot :46-54, which.max :96-108) with the four sums of
+ * emma.delta.REML.{LL,dLL}.wo.Z (emma.txt:145-164) evaluated from the spectrum of K alone: lambda = the n values of
+ * gapit_eigh(K), Vty = vectors' y (n), VtX = vectors' X (n x q column-major).  Mathematically the same function of
+ * delta as gapit_reml on eig.R, so the second O(n^3) eigendecomposition (emma.txt:82-89) can be skipped. */
+int gapit_reml_eigL(const double* lambda, const double* Vty, const double* VtX, int64_t n, int q, int ngrids,
+                    double llim, double ulim, double esp, gapit_reml_out* out);
 
 /* ---- P3D / EMMAx marker scan (GAPIT.EMMAxP3D.R:397-979) -------------------
  * Inputs: eigen-system of K (vectors n x n column-major, values), covariates

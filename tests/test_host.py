@@ -67,6 +67,34 @@ def test_reml_host_code_matches_oracle():
             assert got[k] == pytest.approx(ref[k], rel=1e-10), k
 
 
+def test_reml_from_eigL_alone_matches_the_eigR_route():
+    """gapit_reml_eigL evaluates emma.delta.REML.{LL,dLL}.wo.Z (emma.txt:145-164) from eig.L only; it must land on
+    the optimum the reference's eig.R route (GAPIT.emma.REMLE.R:21-54) finds."""
+    import gapit_b200 as gb
+    for seed, n, m, npc in [(3, 90, 300, 0), (4, 120, 500, 2), (9, 200, 900, 5), (11, 64, 200, 1)]:
+        G = synth.make_genotypes(n, m, seed=seed, threads=1)
+        Y = synth.make_phenotypes(G, seed=seed)[:, 0]
+        X0 = synth.make_covariates(G, npc=npc)
+        K = go.kinship_vanraden(G.T)
+        ref = go.emma_REMLE(Y, X0, K)
+        got = gb.GAPIT_emma_REMLE(Y, X0, K, eig_L=go.emma_eigen_L_wo_Z(K))
+        for k in ("REML", "delta", "ve", "vg"):
+            assert got[k] == pytest.approx(ref[k], rel=1e-10), (k, seed)
+    # collinear covariates: X'X singular is an error, not a crash
+    lib = _lib.load()
+    lam = np.linspace(2.0, 0.0, 10)
+    X = np.ones((10, 2))
+    out = _lib.RemlOut()
+    rc = lib.gapit_reml_eigL(lam.ctypes.data_as(C.c_void_p), lam.ctypes.data_as(C.c_void_p),
+                             np.asfortranarray(X).ctypes.data_as(C.c_void_p), 10, 2, 100, -10.0, 10.0, 1e-10, C.byref(out))
+    assert rc == _lib_err("GAPIT_ERR_NUMERIC")
+
+
+def _lib_err(name):
+    return {"GAPIT_ERR_ARG": -1, "GAPIT_ERR_CUDA": -2, "GAPIT_ERR_NO_DEVICE": -3, "GAPIT_ERR_DATA": -4,
+            "GAPIT_ERR_NUMERIC": -5}[name]
+
+
 def test_reml_boundary_optimum():
     # pure-noise phenotype on a near-identity kinship: the optimum sits on the grid boundary (:37-44)
     lib = _lib.load()
