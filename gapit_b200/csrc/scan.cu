@@ -6,7 +6,7 @@
 //   K3a slice_v          V (fp64) -> S int8 digit planes per eigenvector (balanced base-256 digits of
 //                        V_jk / 2^e_k; "Ozaki split").  The genotype operand is exactly int8, so
 //                        D_s[k,i] = sum_j digit_s(V_jk) x_ji are exact int32 and
-//                        W_ki = c_k sum_s 256^s D_s[k,i] reproduces the fp64 product to ~2^-(8S-2)
+//                        W_ki = c_k sum_s 256^s D_s[k,i] reproduces the fp64 product to ~2^-(8S-1)
 //                        relative to max_j |V_jk|, deterministically (integer sums are order-free).
 //   K3  rotate_reduce    tcgen05 kind::i8, M = markers (TMEM lanes), N = (k, slice) columns.  Each epilogue
 //                        thread owns one marker: it rebuilds W_ki from the S int32 slices and accumulates
@@ -52,7 +52,7 @@ struct gapit_eigsys {
   int64_t nkq = 0;    // number of BN-row tiles of Vs
   int8_t* Vs = nullptr;      // [(nkq*BN)][ldn] row (k*S + s) = digit plane s of eigenvector k
   double* V = nullptr;       // n x n column-major
-  double* scale = nullptr;   // [nkq*KPB] c_k = 2^(e_k - (8S-2)), 0 beyond n
+  double* scale = nullptr;   // [nkq*KPB] c_k = max_j |V_jk| / (126 * 256^(S-1)), 0 beyond n
   std::vector<double> values;  // host, descending
   std::vector<double> h_scale;
 };
@@ -80,15 +80,13 @@ __global__ void slice_v_kernel(const double* __restrict__ V, int64_t n, int S, i
   }
   __syncthreads();
   mx = red[0];
-  int e = 0;
-  if (mx > 0.0) {
-    frexp(mx, &e);  // mx = f * 2^e, f in [0.5, 1)  =>  |v| * 2^-e < 1
-  }
-  const int B = 8 * S - 2;
-  const double up = ldexp(1.0, B - e);
-  if (threadIdx.x == 0) scale[k] = ldexp(1.0, e - B);
+  // |q| <= 126 * 256^(S-1): the balanced digits below then stay within int8 (top digit <= 127).  The scale is not a
+  // power of two: against 2^e >= max it keeps 1-2 more bits of every element (q is rounded to nearest either way).
+  const double qmax = ldexp(126.0, 8 * (S - 1));
+  const double up = (mx > 0.0) ? qmax / mx : 0.0;
+  if (threadIdx.x == 0) scale[k] = (mx > 0.0) ? mx / qmax : 0.0;
   for (int64_t j = threadIdx.x; j < n; j += blockDim.x) {
-    long long q = __double2ll_rn(v[j] * up);  // |q| <= 2^(8S-2)
+    long long q = __double2ll_rn(v[j] * up);
     for (int s = 0; s < S; ++s) {
       const long long d = ((q + 128) & 255) - 128;  // balanced digit in [-128, 127]
       Vs[(k * S + s) * ldn + j] = static_cast<int8_t>(d);
@@ -309,7 +307,7 @@ template <int S, int BN>
 struct GlmEpi {
   static constexpr int NCMAX = BN / S;
   struct Params {
-    const double* scale;       // [nc] c_j = 2^(e_j - (8S-2)) of column j of R
+    const double* scale;       // [nc] c_j = max_i |R_ij| / (126 * 256^(S-1)) of column j of R
     const int32_t* colsumsq;   // [m]
     double* part;              // [qpad+2][m_ld]
     int64_t m_ld;

@@ -238,7 +238,7 @@ def test_mlm_scan_slice_counts(gpu_ctx, slices):
     finally:
         gpu_ctx.set_slices(6)
     r, a = rel_err(res["effect.est"][:, 0], ora.effect_est, 1e-3)
-    assert r < (1e-6 if slices == 5 else BETA_RTOL)
+    assert r < BETA_RTOL   # 5 planes: ~1e-9 (tools/slice_accuracy.py); 6 and up: the oracle's own rounding
     with np.errstate(divide="ignore"):
         assert np.nanmax(np.abs(np.log10(res["ps"][:, 0]) - np.log10(ora.ps))) < LOGP_ATOL
 
