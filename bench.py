@@ -355,6 +355,19 @@ def main():
                "note": "host int8 dosages (pinned) -> gapit_p3d_scan_host (chunked upload overlapped with the scan) -> host result arrays; "
                        "eigen-system resident (one-off per trait set, see setup_ms)"}
 
+        # same call fed 2-bit packed host rows (GAPIT_B2): a quarter of the PCIe bytes, expanded on the device
+        P2 = gb.Packed2.from_dosages(G_host, marker_major=True, pinned=True)
+
+        def e2e_packed_step():
+            arrs, _ = gb.p3d_scan_host(P2, X0, Y[:, :1], eigsys=es, delta=[delta], vg=[vg], ctx=ctx, pinned=True)
+            last["e2e_packed_min_p"] = float(np.nanmin(arrs["pvalue"]))
+        e2p_ms, _ = timed(e2e_packed_step, args.steps, 1)
+        e2e["packed2"] = {"value": m_total / (e2p_ms * 1e-3), "unit": UNIT, "ms_per_step": e2p_ms,
+                          "h2d_bytes_per_step": int(P2.data.nbytes) + 8 * n * 2, "d2h_bytes_per_step": 7 * 8 * int(m),
+                          "note": "host genotypes at 2 bits each (GAPIT_B2, PLINK .bed bit order), unpack kernel on the copy stream"}
+        assert last["e2e_packed_min_p"] == last["e2e_min_p"]
+        del P2
+
     # ---------------- CPU baseline beside it (rank 0, N=1) ----------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

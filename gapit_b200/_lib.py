@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgapitcuda.so")
 
 GAPIT_MAX_Q0 = 16
-GAPIT_F64, GAPIT_I32, GAPIT_I8 = 0, 1, 2
+GAPIT_F64, GAPIT_I32, GAPIT_I8, GAPIT_B2 = 0, 1, 2, 3
 IMPUTE = {None: -1, "None": -1, "Minor": 0, "Middle": 1, "Major": 2}
 
 

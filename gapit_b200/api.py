@@ -72,6 +72,41 @@ def default_context():
     return _default_ctx
 
 
+class Packed2:
+    """Host genotypes at 2 bits each (GAPIT_B2): ``data`` is (m, ceil(n/4)) uint8, marker-major, taxon i of a marker in
+    byte i//4 at bits 2(i%4).. (PLINK .bed bit order); code 0/1/2 = dosage, 3 = NA.  A quarter of the int8 bytes
+    over PCIe; the device expands it to the int8 operand layout."""
+
+    def __init__(self, data, n):
+        self.data = np.ascontiguousarray(data, dtype=np.uint8)
+        self.n = int(n)
+        assert self.data.ndim == 2 and self.data.shape[1] >= (self.n + 3) // 4
+        self.m = int(self.data.shape[0])
+
+    @staticmethod
+    def from_dosages(a, marker_major=False, pinned=False):
+        """(n, m) dosages (or (m, n) with ``marker_major``), values 0/1/2, NaN or negative = NA."""
+        a = np.asarray(a)
+        if not marker_major:
+            a = a.T
+        m, n = a.shape
+        nb = (n + 3) // 4
+        if a.dtype.kind == "f":
+            c = np.where(np.isnan(a), 3, a).astype(np.uint8)
+        else:
+            c = np.where(a < 0, 3, a).astype(np.uint8)
+        pad = np.zeros((m, nb * 4), dtype=np.uint8)
+        pad[:, :n] = c
+        q = pad.reshape(m, nb, 4)
+        out = (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).astype(np.uint8)
+        if pinned:
+            import torch
+            t = torch.empty((m, nb), dtype=torch.uint8).pin_memory()
+            t.numpy()[:] = out
+            out = t.numpy()
+        return Packed2(out, n)
+
+
 class Genotypes:
     """Device-resident dosage matrix (gapit_geno): int8, marker-major, plus column statistics."""
 
@@ -80,6 +115,13 @@ class Genotypes:
         ``marker_major=True`` an (m, n) C-contiguous array (= R's column-major memory)."""
         self.ctx = ctx or default_context()
         lib = self.ctx.lib
+        if isinstance(snps, Packed2):
+            h = C.c_void_p()
+            check(lib.gapit_geno_pack(self.ctx.h, _ptr(snps.data), _lib.GAPIT_B2, snps.n, snps.m, snps.data.shape[1],
+                                      _lib.IMPUTE[impute], C.byref(h)))
+            self.h = h
+            self.n, self.m = snps.n, snps.m
+            return
         a = np.asarray(snps)
         if not marker_major:
             # n x m: column-major memory is what the C ABI wants (element (i,k) at i + k*ld)
@@ -285,8 +327,12 @@ def p3d_scan_host(snps, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=
     """Streaming scan straight from a host genotype matrix (H2D overlapped with the scan).  Same returns as
     :func:`p3d_scan`."""
     ctx = ctx or default_context()
-    a, dtype = _host_geno(snps, marker_major)
-    m, n = a.shape
+    if isinstance(snps, Packed2):
+        a, dtype, m, n, ld = snps.data, _lib.GAPIT_B2, snps.m, snps.n, snps.data.shape[1]
+    else:
+        a, dtype = _host_geno(snps, marker_major)
+        m, n = a.shape
+        ld = n
     X0 = np.asfortranarray(X0, dtype=np.float64)
     Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n, -1))
     q0, T = X0.shape[1], Y.shape[1]
@@ -297,7 +343,7 @@ def p3d_scan_host(snps, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=
     base = (_lib.ScanBase * T)()
     d = np.ascontiguousarray(delta, dtype=np.float64).reshape(-1) if delta is not None else None
     v = np.ascontiguousarray(vg, dtype=np.float64).reshape(-1) if vg is not None else None
-    check(ctx.lib.gapit_p3d_scan_host(ctx.h, _ptr(a), dtype, n, m, n, _lib.IMPUTE[impute],
+    check(ctx.lib.gapit_p3d_scan_host(ctx.h, _ptr(a), dtype, n, m, ld, _lib.IMPUTE[impute],
                                       eigsys.h if eigsys is not None else None, _ptr(X0), q0, _ptr(Y), T, _ptr(d), _ptr(v),
                                       1 if glm else 0, C.byref(so), base))
     bases = [{"logL0": b.logL0, "logLM_base": b.logLM_base, "rsquare_base": b.rsquare_base, "ves": b.ves,
@@ -362,7 +408,7 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
     # :20-24 (NA -> SNP.impute value).  A host matrix is streamed (upload overlapped with the scan); an
     # already-resident Genotypes handle is scanned in place.
     resident = isinstance(xs, Genotypes)
-    m = xs.m if resident else np.asarray(xs).shape[1]
+    m = xs.m if isinstance(xs, (Genotypes, Packed2)) else np.asarray(xs).shape[1]
 
     def run_scan(**kw):
         if resident:

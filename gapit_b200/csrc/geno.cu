@@ -42,6 +42,44 @@ __global__ void convert_kernel(const T* __restrict__ src, int64_t ld, int64_t n,
   }
 }
 
+// ---- 2-bit packed -> int8 ---------------------------------------------------
+// src: `mc` dense rows of nb = ceil(n/4) bytes; taxon i of a marker sits in byte i/4 at bits 2(i%4)..2(i%4)+1
+// (PLINK .bed bit order), code 0/1/2 = dosage, 3 = NA.  One thread expands 4 packed bytes into 16 output bytes
+// (one 128-bit store) and zero-fills the row padding up to ldn.
+__global__ void unpack2_kernel(const uint8_t* __restrict__ src, int64_t nb, int64_t n, int64_t mc, int8_t* __restrict__ dst,
+                               int64_t ldn, int impute, int* __restrict__ bad) {
+  const int64_t groups = ldn / 16;  // ldn is a multiple of 128
+  const int64_t total = mc * groups;
+  const uint32_t na = impute < 0 ? 0u : static_cast<uint32_t>(impute);
+  int flag = 0;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t k = t / groups;
+    const int64_t gi = t - k * groups;
+    const uint8_t* row = src + k * nb;
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t byte = gi * 4 + j;
+      if (byte < nb) {
+        const uint32_t pk = __ldg(row + byte);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v = (pk >> (2 * c)) & 3u;
+          if (byte * 4 + c >= n) {
+            v = 0u;  // bits past the last taxon are ignored
+          } else if (v == 3u) {
+            if (impute < 0) flag = 2;
+            v = na;
+          }
+          w[j] |= v << (8 * c);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + k * ldn + gi * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (flag) atomicOr(bad, flag);
+}
+
 // ---- per-marker statistics: one warp per marker, 16-byte loads -------------
 __global__ void colstats_kernel(const int8_t* __restrict__ mk, int64_t ldn, int64_t n, int64_t m,
                                 int32_t* __restrict__ colsum, int32_t* __restrict__ colsumsq, int* __restrict__ bad) {
@@ -142,6 +180,16 @@ int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_
   return GAPIT_OK;
 }
 
+// stage: `mc` dense rows of ceil(n/4) packed bytes already on the device
+int launch_unpack2(gapit_ctx* ctx, cudaStream_t st, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
+                   int impute, int* bad_dev) {
+  const int64_t total = mc * (ldn / 16);
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16)));
+  unpack2_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(stage), (n + 3) / 4, n, mc, dst, ldn, impute, bad_dev);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
 static int run_colstats(gapit_geno* g) {
   gapit_ctx* ctx = g->ctx;
   int* bad = nullptr;
@@ -174,7 +222,8 @@ using namespace gapit;
 
 extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
                                gapit_impute impute, gapit_geno** out) {
-  if (!ctx || !snps || !out || n <= 0 || m <= 0 || ld < n) return fail(GAPIT_ERR_ARG, "gapit_geno_pack: bad argument");
+  if (!ctx || !snps || !out || n <= 0 || m <= 0 || ld < (dtype == GAPIT_B2 ? (n + 3) / 4 : n))
+    return fail(GAPIT_ERR_ARG, "gapit_geno_pack: bad argument");
   GAPIT_CUDA(cudaSetDevice(ctx->device));
   gapit_geno* g = new gapit_geno();
   g->ctx = ctx;
@@ -245,6 +294,28 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
     if (e != cudaSuccess) return cleanup(fail(GAPIT_ERR_CUDA, std::string("genotype conversion: ") + cudaGetErrorString(e)));
     if (hbad & 2) return cleanup(fail(GAPIT_ERR_DATA, "genotype matrix holds NA and no impute rule was given"));
     if (hbad & 1) return cleanup(fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}"));
+  } else if (dtype == GAPIT_B2) {
+    const int64_t nb = (n + 3) / 4;
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(256) << 20) / nb));
+    void* stage = nullptr;
+    int* bad = nullptr;
+    int rc2 = ctx_ws(ctx, WS_STAGE0, size_t(chunk) * nb, &stage);
+    if (rc2 == GAPIT_OK) rc2 = ctx_ws_t(ctx, WS_BAD, 4, &bad);
+    if (rc2 != GAPIT_OK) return cleanup(rc2);
+    e = cudaMemsetAsync(bad, 0, 4, ctx->stream);
+    for (int64_t k0 = 0; k0 < m && e == cudaSuccess; k0 += chunk) {
+      const int64_t mc = std::min(chunk, m - k0);
+      const char* src = static_cast<const char*>(snps) + size_t(k0) * ld;
+      if (ld == nb) e = cudaMemcpyAsync(stage, src, size_t(mc) * nb, cudaMemcpyHostToDevice, ctx->stream);
+      else e = cudaMemcpy2DAsync(stage, nb, src, ld, nb, mc, cudaMemcpyHostToDevice, ctx->stream);
+      if (e == cudaSuccess && launch_unpack2(ctx, ctx->stream, stage, n, mc, g->mk + k0 * g->ldn, g->ldn, int(impute), bad) != GAPIT_OK)
+        return cleanup(GAPIT_ERR_CUDA);
+    }
+    int hbad = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) return cleanup(fail(GAPIT_ERR_CUDA, std::string("packed genotype upload: ") + cudaGetErrorString(e)));
+    if (hbad & 2) return cleanup(fail(GAPIT_ERR_DATA, "genotype matrix holds NA and no impute rule was given"));
   } else {
     return cleanup(fail(GAPIT_ERR_ARG, "gapit_geno_pack: unknown dtype"));
   }

@@ -695,6 +695,8 @@ int launch_colstats(gapit_ctx* ctx, cudaStream_t st, const int8_t* mk, int64_t l
                     int32_t* colsumsq, int* bad_dev);
 int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
                    int impute, int* bad_dev);
+int launch_unpack2(gapit_ctx* ctx, cudaStream_t st, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
+                   int impute, int* bad_dev);
 
 // Everything about a scan that does not depend on the markers: the marker-free model of every trait
 // (i = 0 of the reference loop), the per-eigenvalue constants of the rotation epilogue (MLM) or the digit
@@ -963,12 +965,15 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
 static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
                           gapit_impute impute, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
                           const double* delta, const double* vg, int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
-  if (!snps || n <= 0 || m <= 0 || ld < n) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan_host: bad genotype argument");
+  const int64_t nb2 = (n + 3) / 4;   // bytes per marker of the 2-bit packed form
+  if (!snps || n <= 0 || m <= 0 || ld < (dtype == GAPIT_B2 ? nb2 : n))
+    return fail(GAPIT_ERR_ARG, "gapit_p3d_scan_host: bad genotype argument");
   GAPIT_CHECK(check_out(out));
   const int64_t ldn = round_up(n, 128);
   ScanPlan plan;
   GAPIT_CHECK(scan_prepare(ctx, n, ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
   const size_t esz = dtype == GAPIT_F64 ? 8 : (dtype == GAPIT_I32 ? 4 : 1);
+  const size_t row_bytes = dtype == GAPIT_B2 ? size_t(nb2) : size_t(n) * esz;   // dense bytes of one marker on the host
   // marker block: ~320 MB of int8 (multiple of 256 markers), at most 65535 for the convert grid
   int64_t chunk = std::max<int64_t>(256, (int64_t(320) << 20) / ldn / 256 * 256);
   if (const char* ev = getenv("GAPIT_STREAM_CHUNK")) chunk = std::max<int64_t>(256, atoll(ev) / 256 * 256);  // tests
@@ -983,8 +988,8 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
     GAPIT_CHECK(ctx_ws_t(ctx, WS_CHUNK0 + b, size_t(chunk) * ldn, &mk[b]));
     GAPIT_CHECK(ctx_ws_t(ctx, WS_CS0 + b, size_t(chunk), &cs[b]));
     GAPIT_CHECK(ctx_ws_t(ctx, WS_CQ0 + b, size_t(chunk), &cq[b]));
-    if (dtype != GAPIT_I8 || (ld == n && ldn != n)) GAPIT_CHECK(ctx_ws(ctx, WS_STAGE0 + b, size_t(chunk) * n * esz, &stage[b]));
-    if (ldn != n) GAPIT_CUDA(cudaMemsetAsync(mk[b], 0, size_t(chunk) * ldn, ctx->stream));
+    if (dtype != GAPIT_I8 || (ld == n && ldn != n)) GAPIT_CHECK(ctx_ws(ctx, WS_STAGE0 + b, size_t(chunk) * row_bytes, &stage[b]));
+    if (ldn != n && dtype != GAPIT_B2) GAPIT_CUDA(cudaMemsetAsync(mk[b], 0, size_t(chunk) * ldn, ctx->stream));
   }
   GAPIT_CHECK(ctx_ws_t(ctx, WS_BAD, 4, &bad));
   GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(T) * 7 * m, &o));
@@ -1007,6 +1012,11 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
       GAPIT_CUDA(cudaMemcpy2DAsync(mk[b], ldn, stage[b], n, n, mc, cudaMemcpyDeviceToDevice, ctx->copy_stream));
     } else if (dtype == GAPIT_I8) {
       GAPIT_CUDA(cudaMemcpy2DAsync(mk[b], ldn, src, ld, n, mc, cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else if (dtype == GAPIT_B2) {
+      // a quarter of the int8 bytes over PCIe, expanded to the int8 operand layout on the device
+      if (ld == nb2) GAPIT_CUDA(cudaMemcpyAsync(stage[b], src, size_t(mc) * nb2, cudaMemcpyHostToDevice, ctx->copy_stream));
+      else GAPIT_CUDA(cudaMemcpy2DAsync(stage[b], nb2, src, ld, nb2, mc, cudaMemcpyHostToDevice, ctx->copy_stream));
+      GAPIT_CHECK(launch_unpack2(ctx, ctx->copy_stream, stage[b], n, mc, mk[b], ldn, int(impute), bad));
     } else {
       GAPIT_CUDA(cudaMemcpy2DAsync(stage[b], size_t(n) * esz, src, size_t(ld) * esz, size_t(n) * esz, mc,
                                    cudaMemcpyHostToDevice, ctx->copy_stream));

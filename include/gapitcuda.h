@@ -39,8 +39,10 @@ extern "C" {
 typedef struct gapit_ctx gapit_ctx;
 typedef struct gapit_geno gapit_geno;
 
-/* element type of a host genotype matrix */
-typedef enum { GAPIT_F64 = 0, GAPIT_I32 = 1, GAPIT_I8 = 2 } gapit_dtype;
+/* element type of a host genotype matrix.  GAPIT_B2: 2 bits per genotype, marker-major: marker k starts at byte
+ * k*ld (ld >= ceil(n/4) BYTES), taxon i in byte i/4 at bits 2(i%4)..2(i%4)+1 (the bit order of a PLINK .bed row);
+ * code 0/1/2 = dosage, 3 = NA (imputed by the gapit_impute rule, rejected with GAPIT_IMPUTE_NONE). */
+typedef enum { GAPIT_F64 = 0, GAPIT_I32 = 1, GAPIT_I8 = 2, GAPIT_B2 = 3 } gapit_dtype;
 /* NA rule for GAPIT_F64 input (GAPIT.EMMAxP3D.R:20-24, SNP.impute): NaN -> value; NONE rejects NaN */
 typedef enum { GAPIT_IMPUTE_NONE = -1, GAPIT_IMPUTE_MINOR = 0, GAPIT_IMPUTE_MIDDLE = 1, GAPIT_IMPUTE_MAJOR = 2 } gapit_impute;
 

@@ -87,6 +87,55 @@ def test_pack_and_column_stats(gpu_ctx, n, m):
         g.close()
 
 
+@pytest.mark.parametrize("n,m", [(5, 3), (127, 129), (281, 3093), (1001, 517)])
+def test_packed_2bit_ingestion_is_bit_identical(gpu_ctx, n, m):
+    """GAPIT_B2 host rows (4 genotypes per byte) must land on the device exactly like the int8 rows."""
+    G, Y, X0 = case(n, m, edge=False)
+    x = G.astype(np.int64)
+    P = gb().Packed2.from_dosages(G, marker_major=True)
+    assert P.data.shape == (m, (n + 3) // 4)
+    g = gb().Genotypes(P, ctx=gpu_ctx)
+    cs, cq = g.colsums()
+    assert np.array_equal(cs, x.sum(1)) and np.array_equal(cq, (x * x).sum(1))
+    K2, gram2 = gb().GAPIT_kinship_VanRaden(g, ctx=gpu_ctx, return_gram=True, verbose=False)
+    g.close()
+    K1, gram1 = gb().GAPIT_kinship_VanRaden(G.T, ctx=gpu_ctx, return_gram=True, verbose=False)
+    assert np.array_equal(gram1, gram2) and np.array_equal(K1, K2)
+    # NA code 3: rejected without a rule, imputed with one (GAPIT.EMMAxP3D.R:20-24); a padded row pitch is honoured
+    na = G.astype(np.int64).copy()
+    na[m // 2, n // 2] = -1
+    Pn = gb().Packed2.from_dosages(na, marker_major=True)
+    with pytest.raises(gb().GapitCudaError):
+        gb().Genotypes(Pn, ctx=gpu_ctx)
+    wide = np.full((m, Pn.data.shape[1] + 3), 0xFF, dtype=np.uint8)
+    wide[:, :Pn.data.shape[1]] = Pn.data
+    for rule, val in [("Middle", 1), ("Major", 2), ("Minor", 0)]:
+        g = gb().Genotypes(gb().Packed2(wide, n), ctx=gpu_ctx, impute=rule)
+        ref = x.copy()
+        ref[m // 2, n // 2] = val
+        assert np.array_equal(g.colsums()[0], ref.sum(1))
+        g.close()
+
+
+def test_packed_2bit_streaming_scan_equals_int8_scan(gpu_ctx, monkeypatch):
+    G, Y, X0 = case(300, 2100, npc=2)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    monkeypatch.setenv("GAPIT_STREAM_CHUNK", "512")      # several blocks, ragged tail
+    kw = dict(eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]], ctx=gpu_ctx)
+    a8, _ = gb().p3d_scan_host(G, X0, Y, marker_major=True, **kw)
+    a2, _ = gb().p3d_scan_host(gb().Packed2.from_dosages(G, marker_major=True), X0, Y, **kw)
+    for k in a8:
+        assert np.array_equal(a8[k], a2[k], equal_nan=True), k
+    g8, _ = gb().p3d_scan_host(G, X0, Y, marker_major=True, glm=True, ctx=gpu_ctx)
+    g2, _ = gb().p3d_scan_host(gb().Packed2.from_dosages(G, marker_major=True), X0, Y, glm=True, ctx=gpu_ctx)
+    for k in g8:
+        assert np.array_equal(g8[k], g2[k], equal_nan=True), k
+    es.close()
+
+
 def test_pack_rejects_bad_values_and_imputes_na(gpu_ctx):
     G, _, _ = case(40, 60, edge=False)
     bad = G.T.astype(np.float64)

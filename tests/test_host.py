@@ -112,6 +112,23 @@ def test_reml_boundary_optimum():
     assert lib.gapit_reml(None, None, 0, 100, -10.0, 10.0, 1e-10, C.byref(out)) == -1
 
 
+def test_packed2_host_layout():
+    """Packed2.from_dosages: taxon i of marker k in byte i//4 of row k at bits 2(i%4).., NA = 3."""
+    import gapit_b200 as gb
+    rng = np.random.default_rng(5)
+    G = rng.integers(0, 3, size=(7, 13)).astype(np.int8)      # (m, n)
+    G[2, 5] = -1
+    P = gb.Packed2.from_dosages(G, marker_major=True)
+    assert P.data.shape == (7, 4) and P.n == 13 and P.m == 7
+    for k in range(7):
+        for i in range(13):
+            code = (int(P.data[k, i // 4]) >> (2 * (i % 4))) & 3
+            assert code == (3 if G[k, i] < 0 else G[k, i])
+    assert (int(P.data[0, 3]) >> 2) == 0                       # bits past the last taxon are zero
+    Pf = gb.Packed2.from_dosages(np.where(G.T < 0, np.nan, G.T.astype(float)))
+    assert np.array_equal(Pf.data, P.data)
+
+
 def test_marker_shards_cover_in_order():
     for m, w in [(10, 3), (500000, 8), (7, 8), (3093, 2)]:
         parts = [shard.marker_shard(m, r, w) for r in range(w)]
