@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libgapitcuda.so")
 GAPIT_MAX_Q0 = 16
 GAPIT_F64, GAPIT_I32, GAPIT_I8, GAPIT_B2 = 0, 1, 2, 3
 IMPUTE = {None: -1, "None": -1, "Minor": 0, "Middle": 1, "Major": 2}
+EFFECT = {"Add": 0, "Dom": 1, "Left": 2, "Right": 3}
 
 
 class GapitCudaError(RuntimeError):
@@ -54,14 +55,21 @@ SIGNATURES = {
     "gapit_ctx_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "gapit_ctx_set_stream": (C.c_int, [_P, _P]),
     "gapit_geno_pack": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _I64, C.c_int, C.POINTER(_P)]),
+    "gapit_geno_from_device": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(_P)]),
     "gapit_geno_free": (None, [_P]),
     "gapit_geno_n": (_I64, [_P]),
     "gapit_geno_m": (_I64, [_P]),
     "gapit_geno_colsums": (C.c_int, [_P, _P, _P]),
+    "gapit_hapmap_index": (C.c_int, [_P, _I64, C.c_int, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(C.c_int), _P, _I64,
+                                     C.POINTER(_I64)]),
+    "gapit_hapmap_numericalize": (C.c_int, [_P, _P, _I64, _P, C.c_int, C.c_int, _I64, _I64, C.c_int, C.c_int, C.c_int, _P,
+                                            C.POINTER(_P)]),
     "gapit_vanraden": (C.c_int, [_P, _P, _P, _P]),
     "gapit_gram_ld": (_I64, [_I64]),
     "gapit_vanraden_gram": (C.c_int, [_P, _P, _P, _P]),
     "gapit_vanraden_finish": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
+    "gapit_zhang": (C.c_int, [_P, _P, _P]),
+    "gapit_pca": (C.c_int, [_P, _P, _I64, _P, _P]),
     "gapit_eigh": (C.c_int, [_P, _P, _I64, _P, _P]),
     "gapit_eigen_R": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P]),
     "gapit_reml": (C.c_int, [_P, _P, _I64, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(RemlOut)]),

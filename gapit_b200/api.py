@@ -140,6 +140,18 @@ class Genotypes:
         self.h = h
         self.n, self.m = int(n), int(m)
 
+    @classmethod
+    def from_device(cls, data_ptr, n, m, ld=None, ctx=None):
+        """int8 dosages already on the context's device (marker-major, marker k at data_ptr + k*ld), e.g.
+        ``t.data_ptr()`` of a contiguous (m, n) torch.int8 CUDA tensor."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        h = C.c_void_p()
+        check(self.ctx.lib.gapit_geno_from_device(self.ctx.h, C.c_void_p(int(data_ptr)), int(n), int(m),
+                                                  int(ld if ld is not None else n), C.byref(h)))
+        self.h, self.n, self.m = h, int(n), int(m)
+        return self
+
     def colsums(self):
         cs = np.empty(self.m, dtype=np.int32)
         cq = np.empty(self.m, dtype=np.int32)
@@ -184,6 +196,77 @@ class EigenSystem:
             pass
 
 
+# ---------------------------------------------------------------------------
+# GAPIT.HapMap(G, SNP.effect, SNP.impute, heading, Create.indicator, Major.allele.zero)   GAPIT.HapMap.R:1-66
+# GAPIT.Numericalization(x, bit, effect, impute, Create.indicator, Major.allele.zero)      GAPIT.Numericalization.R
+# ---------------------------------------------------------------------------
+def _numericalize(ctx, text, row_off, bit, stride, n, m, effect, impute, maz, want_gd, want_geno):
+    buf = np.frombuffer(text, dtype=np.uint8)
+    off = np.ascontiguousarray(row_off, dtype=np.int64)
+    gd = np.empty((m, n), dtype=np.int8) if want_gd else None
+    h = C.c_void_p()
+    check(ctx.lib.gapit_hapmap_numericalize(ctx.h, _ptr(buf), buf.shape[0], _ptr(off), int(bit), int(stride), n, m,
+                                            _lib.EFFECT[effect], _lib.IMPUTE[impute], 1 if maz else 0, _ptr(gd),
+                                            C.byref(h) if want_geno else None))
+    geno = None
+    if want_geno:
+        geno = Genotypes.__new__(Genotypes)
+        geno.ctx, geno.h, geno.n, geno.m = ctx, h, int(n), int(m)
+    return gd, geno
+
+
+def GAPIT_Numericalization(x, bit=2, effect="Add", impute="None", Create_indicator=False, Major_allele_zero=False,
+                           byRow=True, ctx=None):
+    """One marker's genotype strings -> n x 1 (or 1 x n) numeric matrix, NaN = NA (GAPIT.Numericalization.R:1-112)."""
+    ctx = ctx or default_context()
+    codes = [str(v).encode() for v in x]
+    if any(len(c) != bit for c in codes):
+        raise ValueError("every genotype code must have `bit` characters")
+    n = len(codes)
+    gd, _ = _numericalize(ctx, b"".join(codes), [0], bit, bit, n, 1, effect, impute, Major_allele_zero, True, False)
+    out = np.where(gd[0] < 0, np.nan, gd[0].astype(np.float64))
+    return out.reshape(n, 1) if byRow else out.reshape(1, n)
+
+
+def GAPIT_HapMap(G, SNP_effect="Add", SNP_impute="Middle", heading=True, Create_indicator=False,
+                 Major_allele_zero=False, ctx=None, device=False):
+    """HapMap table -> {"GT": taxa, "GD": n x m dosages, "GI": (SNP, Chromosome, Position)} (GAPIT.HapMap.R:1-66).
+
+    ``G`` is the text of the table (bytes, or a path to the file): what the reference receives as a data frame from
+    ``read.table(file, head=FALSE)``.  The per-marker loop of :34-38 runs on the GPU on the raw text.  GD is int8
+    (n, m) with the reference's column-major memory; -1 marks NA (only with ``SNP_impute="None"``).
+    ``device=True`` also returns the device-resident ``Genotypes`` under "geno" for the kinship / scan calls."""
+    ctx = ctx or default_context()
+    if Create_indicator:
+        raise NotImplementedError("Create.indicator keeps the character table (GAPIT.HapMap.R:36): reference path")
+    if isinstance(G, str):
+        with open(G, "rb") as f:
+            G = f.read()
+    lib = ctx.lib
+    buf = np.frombuffer(G, dtype=np.uint8)
+    n, m, bit, hoff = C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
+    check(lib.gapit_hapmap_index(_ptr(buf), buf.shape[0], 1 if heading else 0, C.byref(n), C.byref(m), C.byref(bit), None,
+                                 0, C.byref(hoff)))
+    off = np.empty(m.value, dtype=np.int64)
+    check(lib.gapit_hapmap_index(_ptr(buf), buf.shape[0], 1 if heading else 0, C.byref(n), C.byref(m), C.byref(bit),
+                                 _ptr(off), m.value, C.byref(hoff)))
+    gd, geno = _numericalize(ctx, G, off, bit.value, bit.value + 1, n.value, m.value, SNP_effect, SNP_impute,
+                             Major_allele_zero, True, device)
+    GT = None
+    if heading:                                                            # :14-16
+        end = G.find(b"\n", hoff.value)
+        GT = G[hoff.value:end if end >= 0 else len(G)].rstrip(b"\r").decode().split("\t")
+    GI = []                                                                # :15,:18  columns 1, 3, 4
+    for k in range(m.value):
+        start = G.rfind(b"\n", 0, off[k]) + 1
+        f = G[start:off[k]].split(b"\t", 4)
+        GI.append((f[0].decode(), f[2].decode(), f[3].decode()))
+    out = {"GT": GT, "GD": gd.T, "GI": GI}
+    if device:
+        out["geno"] = geno
+    return out
+
+
 def _as_geno(snps, ctx, impute=None):
     if isinstance(snps, Genotypes):
         return snps, False
@@ -212,6 +295,48 @@ def GAPIT_kinship_VanRaden(snps, hasInbred=True, ctx=None, return_gram=False, ve
         g.close()
     say("Calculating kinship with VanRaden method: done")
     return (K, G) if return_gram else K
+
+
+# ---------------------------------------------------------------------------
+# GAPIT.kinship.ZHANG(snps, hasInbred=TRUE)          GAPIT.kinship.ZHANG.R:1-66
+# GAPIT.PCA(X, taxa, PC.number, file.output, PCA.total)   GAPIT.PCA.R:1-73
+# ---------------------------------------------------------------------------
+def GAPIT_kinship_ZHANG(snps, hasInbred=True, ctx=None, verbose=True):
+    """n x m dosages (array or Genotypes) -> n x n ZHANG relationship; the reference's progress prints are kept."""
+    ctx = ctx or default_context()
+    say = print if verbose else (lambda *_: None)
+    say("Calculating ZHANG relationship defined by Zhiwu Zhang...")
+    g, owned = _as_geno(snps, ctx)
+    K = np.empty((g.n, g.n), dtype=np.float64, order="F")
+    say("substracting mean...")
+    say("Getting X'X...")
+    check(ctx.lib.gapit_zhang(ctx.h, g.h, _ptr(K)))
+    say("Adjusting...")
+    if owned:
+        g.close()
+    say("Calculating kinship with Zhang method: done")
+    return K
+
+
+def GAPIT_PCA(X, taxa=None, PC_number=None, file_output=False, PCA_total=0, ctx=None, verbose=True):
+    """prcomp of the n x m dosage matrix (GAPIT.PCA.R:10).  Returns {"PCs": n x PC_number scores (the reference binds
+    `taxa` in front, :54), "EV": all min(n, m) variances (:73), "nPCs": None}.  Plots and csv files (:17-51, :63-69)
+    stay in R (file_output must be False here)."""
+    if file_output:
+        raise NotImplementedError("plots and csv output of GAPIT.PCA stay in R")
+    ctx = ctx or default_context()
+    say = print if verbose else (lambda *_: None)
+    say("Calling prcomp...")
+    g, owned = _as_geno(X, ctx)
+    rank = min(g.n, g.m)
+    k = rank if PC_number is None else int(min(PC_number, rank))
+    scores = np.empty((g.n, k), dtype=np.float64, order="F")
+    ev = np.empty(rank, dtype=np.float64)
+    check(ctx.lib.gapit_pca(ctx.h, g.h, k, _ptr(scores), _ptr(ev)))
+    if owned:
+        g.close()
+    say("Joining taxa...")
+    return {"PCs": scores, "taxa": taxa, "EV": ev, "nPCs": None}
 
 
 # ---------------------------------------------------------------------------

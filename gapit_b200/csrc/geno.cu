@@ -326,6 +326,36 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
   return GAPIT_OK;
 }
 
+extern "C" int gapit_geno_from_device(gapit_ctx* ctx, const int8_t* mk_dev, int64_t n, int64_t m, int64_t ld,
+                                      gapit_geno** out) {
+  if (!ctx || !mk_dev || !out || n <= 0 || m <= 0 || ld < n) return fail(GAPIT_ERR_ARG, "gapit_geno_from_device: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  gapit_geno* g = new gapit_geno();
+  g->ctx = ctx;
+  g->n = n;
+  g->m = m;
+  g->ldn = round_up(n, 128);
+  cudaError_t e;
+  if ((e = cudaMalloc(&g->mk, size_t(m) * g->ldn)) != cudaSuccess || (e = cudaMalloc(&g->colsum, size_t(m) * 4)) != cudaSuccess ||
+      (e = cudaMalloc(&g->colsumsq, size_t(m) * 4)) != cudaSuccess) {
+    gapit_geno_free(g);
+    return fail(GAPIT_ERR_CUDA, std::string("gapit_geno_from_device: cudaMalloc: ") + cudaGetErrorString(e));
+  }
+  if (g->ldn != n) e = cudaMemsetAsync(g->mk, 0, size_t(m) * g->ldn, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(g->mk, g->ldn, mk_dev, ld, n, m, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (e != cudaSuccess) {
+    gapit_geno_free(g);
+    return fail(GAPIT_ERR_CUDA, std::string("gapit_geno_from_device: ") + cudaGetErrorString(e));
+  }
+  const int rc = run_colstats(g);
+  if (rc != GAPIT_OK) {
+    gapit_geno_free(g);
+    return rc;
+  }
+  *out = g;
+  return GAPIT_OK;
+}
+
 extern "C" void gapit_geno_free(gapit_geno* g) {
   if (!g) return;
   if (g->ctx) cudaSetDevice(g->ctx->device);

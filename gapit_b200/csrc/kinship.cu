@@ -190,6 +190,112 @@ __global__ void vanraden_epilogue_kernel(const int32_t* __restrict__ G, int64_t 
   }
 }
 
+// Centred cross-product C_ij = sum_k (x_ik - c_k/n)(x_jk - c_k/n) = (n^2 G_ij - n (s_i + s_j) + sum c^2) / n^2:
+// the matrix GAPIT.kinship.ZHANG.R:21-26 calls K before its adjustments and the X X' of prcomp(X) (GAPIT.PCA.R:10).
+// Monomorphic columns contribute exactly 0, so nothing has to be dropped.  Exact int64 numerator, one division.
+__global__ void centered_gram_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n, const long long* __restrict__ s,
+                                     const unsigned long long* __restrict__ sums, double* __restrict__ K) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long nn = n;
+  const long long c2 = static_cast<long long>(sums[1]);
+  const long long si = s[i];
+  const double d = static_cast<double>(nn) * static_cast<double>(nn);
+  for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
+    const long long num = nn * nn * static_cast<long long>(G[j * ldg + i]) - nn * (si + s[j]) + c2;
+    K[i + j * n] = static_cast<double>(num) / d;
+  }
+}
+
+// per-taxon number of heterozygous calls: het_i = sum_k [x_ik == 1] = sum_k x_ik (2 - x_ik) (GAPIT.kinship.ZHANG.R:14-15);
+// one warp per taxon over the taxa-major copy, 16-byte loads, dp4a
+__global__ void taxa_het_kernel(const int8_t* __restrict__ tx, int64_t ldm, int64_t n, long long* __restrict__ het) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const uint4* r = reinterpret_cast<const uint4*>(tx + row * ldm);
+  long long acc = 0;
+  for (int64_t c = lane; c * 16 < ldm; c += 32) {
+    const uint4 v = __ldg(r + c);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    int s1 = 0, s2 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      s1 = __dp4a(static_cast<int>(w[j]), 0x01010101, s1);
+      s2 = __dp4a(static_cast<int>(w[j]), static_cast<int>(w[j]), s2);
+    }
+    acc += 2 * s1 - s2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) het[row] = acc;
+}
+
+// per-block partials of: min over all entries, min / max of the diagonal, max of the off-diagonal
+__global__ void zhang_reduce_kernel(const double* __restrict__ K, int64_t n, double* __restrict__ part) {
+  double mn = INFINITY, dmin = INFINITY, dmax = -INFINITY, omax = -INFINITY;
+  const int64_t total = n * n;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const double v = K[t];
+    const int64_t j = t / n, i = t - j * n;
+    mn = fmin(mn, v);
+    if (i == j) {
+      dmin = fmin(dmin, v);
+      dmax = fmax(dmax, v);
+    } else {
+      omax = fmax(omax, v);
+    }
+  }
+  __shared__ double red[4][8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+    dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    omax = fmax(omax, __shfl_xor_sync(0xffffffffu, omax, o));
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+    red[0][w] = mn;
+    red[1][w] = dmin;
+    red[2][w] = dmax;
+    red[3][w] = omax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; ++k) {
+      red[0][0] = fmin(red[0][0], red[0][k]);
+      red[1][0] = fmin(red[1][0], red[1][k]);
+      red[2][0] = fmax(red[2][0], red[2][k]);
+      red[3][0] = fmax(red[3][0], red[3][k]);
+    }
+    for (int k = 0; k < 4; ++k) part[blockIdx.x * 4 + k] = red[k][0];
+  }
+}
+
+struct ZhangAdj {
+  double top, floor, range;   // K <- top (K - floor) / range                       (:46)
+  int adj_diag;               // Dmin < 1                                          (:50)
+  double Dmin, diag_den, off_mul;   // diag <- (diag - Dmin + 1) / diag_den, off <- off * off_mul   (:52-53)
+  int adj_off;                // Omax > top                                        (:58)
+  double off_mul2;            // off <- off * (top / Omax)                         (:60)
+};
+
+__global__ void zhang_adjust_kernel(double* __restrict__ K, int64_t n, const ZhangAdj a) {
+  const int64_t total = n * n;
+  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t j = t / n, i = t - j * n;
+    double v = a.top * (K[t] - a.floor) / a.range;
+    if (i == j) {
+      if (a.adj_diag) v = (v - a.Dmin + 1.0) / a.diag_den;
+    } else {
+      if (a.adj_diag) v = v * a.off_mul;
+      if (a.adj_off) v = v * a.off_mul2;
+    }
+    K[t] = v;
+  }
+}
+
 static int choose_ksplit(int ntri, int kblocks, int sms) {
   // enough jobs for >= ~6 waves, each job keeping >= 32 k-blocks of work
   int ks = 1;
@@ -315,4 +421,138 @@ extern "C" int gapit_vanraden(gapit_ctx* ctx, gapit_geno* g, double* K_out, int3
   cudaFree(G_dev);
   cudaFree(sums);
   return rc;
+}
+
+namespace gapit {
+int syevd_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* w_dev);
+
+// mirrored Gram + row sums + centred cross-product of every marker of `g` into K_dev (n x n column-major)
+static int centered_gram_dev(gapit_ctx* ctx, gapit_geno* g, double* K_dev, int32_t** G_keep, int64_t** sums_keep) {
+  const int64_t n = g->n, ldg = gapit_gram_ld(n);
+  int32_t* G_dev = nullptr;
+  int64_t* sums = nullptr;
+  long long* s = nullptr;
+  GAPIT_CUDA(cudaMalloc(&G_dev, size_t(ldg) * ldg * 4));
+  if (cudaMalloc(&sums, 3 * 8) != cudaSuccess) {
+    cudaFree(G_dev);
+    return fail(GAPIT_ERR_CUDA, "centered_gram: cudaMalloc");
+  }
+  int rc = gapit_vanraden_gram(ctx, g, G_dev, sums);
+  if (rc == GAPIT_OK) rc = ctx_ws_t(ctx, WS_R, size_t(n), &s);
+  if (rc == GAPIT_OK) {
+    dim3 grid(static_cast<unsigned>(ldg / 32), static_cast<unsigned>(ldg / 32));
+    gram_mirror_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg);
+    gram_rowsum_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(G_dev, ldg, n, s);
+    dim3 g2(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(std::min<int64_t>(n, 65535)));
+    centered_gram_kernel<<<g2, 256, 0, ctx->stream>>>(G_dev, ldg, n, s, reinterpret_cast<const unsigned long long*>(sums), K_dev);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(GAPIT_ERR_CUDA, "centered_gram: launch failed");
+  }
+  if (rc == GAPIT_OK && G_keep) {
+    *G_keep = G_dev;
+    *sums_keep = sums;
+    return rc;
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(G_dev);
+  cudaFree(sums);
+  return rc;
+}
+}  // namespace gapit
+
+// GAPIT.kinship.ZHANG(snps)  GAPIT.kinship.ZHANG.R:1-66
+extern "C" int gapit_zhang(gapit_ctx* ctx, gapit_geno* g, double* K_out) {
+  if (!ctx || !g || !K_out) return fail(GAPIT_ERR_ARG, "gapit_zhang: NULL argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = g->n;
+  double* K_dev = nullptr;
+  long long* het = nullptr;
+  double* part = nullptr;
+  const int nblk = std::max(1, std::min(ctx->sm_count * 8, int((n * n + 255) / 256)));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(n) * n, &K_dev));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(n), &het));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t(nblk) * 4, &part));
+  int32_t* G_dev = nullptr;
+  int64_t* sums = nullptr;
+  GAPIT_CHECK(centered_gram_dev(ctx, g, K_dev, &G_dev, &sums));
+  taxa_het_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(g->tx, g->ldm, n, het);
+  zhang_reduce_kernel<<<nblk, 256, 0, ctx->stream>>>(K_dev, n, part);
+  std::vector<long long> h_het(n);
+  std::vector<double> h_part(size_t(nblk) * 4);
+  std::vector<int32_t> h_cs(g->m);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_het.data(), het, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_part.data(), part, h_part.size() * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_cs.data(), g->colsum, size_t(g->m) * 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(G_dev);
+  cudaFree(sums);
+  if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("gapit_zhang: ") + cudaGetErrorString(e));
+  // :9-11 markers kept (0 < fa < 1); :14-17 inbreeding from the per-taxon heterozygosity
+  int64_t nsnp = 0;
+  for (int64_t k = 0; k < g->m; ++k) nsnp += (h_cs[k] > 0 && h_cs[k] < 2 * n);
+  if (nsnp == 0) return fail(GAPIT_ERR_DATA, "gapit_zhang: every marker is monomorphic");
+  double fmin_i = INFINITY;
+  for (int64_t i = 0; i < n; ++i) fmin_i = std::min(fmin_i, static_cast<double>(h_het[i]) / (2.0 * static_cast<double>(nsnp)));
+  const double inbreeding = 1.0 - fmin_i;
+  double floor_ = INFINITY, DL = INFINITY, DU = -INFINITY, omax_raw = -INFINITY;
+  for (int b = 0; b < nblk; ++b) {
+    floor_ = std::min(floor_, h_part[b * 4 + 0]);
+    DL = std::min(DL, h_part[b * 4 + 1]);
+    DU = std::max(DU, h_part[b * 4 + 2]);
+    omax_raw = std::max(omax_raw, h_part[b * 4 + 3]);
+  }
+  ZhangAdj a{};
+  a.top = 1.0 + inbreeding;                                  // :45
+  a.floor = floor_;
+  a.range = DU - floor_;
+  a.Dmin = a.top * (DL - floor_) / a.range;                  // :47
+  double omax = a.top * (omax_raw - floor_) / a.range;       // the adjustments are monotone: Omax follows the raw maximum
+  a.adj_diag = a.Dmin < 1.0;                                 // :50
+  if (a.adj_diag) {
+    a.diag_den = (a.top + 1.0 - a.Dmin) * .5;                // :52
+    a.off_mul = 1.0 / a.Dmin;                                // :53
+    omax = omax * a.off_mul;
+  }
+  a.adj_off = (n > 1) && omax > a.top;                       // :57-58
+  if (a.adj_off) a.off_mul2 = a.top / omax;                  // :60
+  zhang_adjust_kernel<<<nblk, 256, 0, ctx->stream>>>(K_dev, n, a);
+  GAPIT_CUDA(cudaGetLastError());
+  GAPIT_CUDA(cudaMemcpyAsync(K_out, K_dev, size_t(n) * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GAPIT_OK;
+}
+
+// prcomp(X) of GAPIT.PCA.R:10 from the centred cross-product: X_c X_c' = V diag(l) V'  =>  scores PCA.X$x = V sqrt(l),
+// variances PCA.X$sdev^2 = l / (n - 1); min(n, m) components, descending.
+extern "C" int gapit_pca(gapit_ctx* ctx, gapit_geno* g, int64_t ncomp, double* scores_out, double* ev_out) {
+  if (!ctx || !g || ncomp < 0 || (ncomp > 0 && !scores_out)) return fail(GAPIT_ERR_ARG, "gapit_pca: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = g->n, rank = std::min(n, g->m);
+  if (ncomp > rank) return fail(GAPIT_ERR_ARG, "gapit_pca: more components than min(n, m)");
+  double *K_dev = nullptr, *w_dev = nullptr;
+  GAPIT_CUDA(cudaMalloc(&K_dev, size_t(n) * n * 8));
+  if (cudaMalloc(&w_dev, size_t(n) * 8) != cudaSuccess) {
+    cudaFree(K_dev);
+    return fail(GAPIT_ERR_CUDA, "gapit_pca: cudaMalloc");
+  }
+  int rc = centered_gram_dev(ctx, g, K_dev, nullptr, nullptr);
+  if (rc == GAPIT_OK) rc = syevd_dev(ctx, K_dev, n, w_dev);   // ascending, vectors in place
+  std::vector<double> w(n), col(n);
+  cudaError_t e = cudaSuccess;
+  if (rc == GAPIT_OK) e = cudaMemcpyAsync(w.data(), w_dev, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  if (rc == GAPIT_OK && e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  for (int64_t c = 0; rc == GAPIT_OK && e == cudaSuccess && c < rank; ++c) {
+    const double l = std::max(w[n - 1 - c], 0.0);
+    if (ev_out) ev_out[c] = l / static_cast<double>(n - 1);
+    if (c < ncomp) {
+      e = cudaMemcpy(col.data(), K_dev + (n - 1 - c) * n, size_t(n) * 8, cudaMemcpyDeviceToHost);
+      const double sd = std::sqrt(l);
+      for (int64_t i = 0; i < n; ++i) scores_out[c * n + i] = col[i] * sd;
+    }
+  }
+  cudaFree(K_dev);
+  cudaFree(w_dev);
+  if (rc != GAPIT_OK) return rc;
+  if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("gapit_pca: ") + cudaGetErrorString(e));
+  return GAPIT_OK;
 }

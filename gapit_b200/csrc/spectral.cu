@@ -59,7 +59,7 @@ __global__ void reverse_cols_kernel(const double* __restrict__ src, int64_t n, i
 }
 
 // in-place syevd on a device matrix; eigenvalues (ascending) into w_dev
-static int syevd_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* w_dev) {
+int syevd_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* w_dev) {
   GAPIT_CHECK(ensure_solver(ctx));
   if (n > 46000) return fail(GAPIT_ERR_ARG, "eigh: n above the 32-bit cuSOLVER workspace limit");
   int lwork = 0;

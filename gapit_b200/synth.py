@@ -99,3 +99,48 @@ def make_covariates(G, npc=0, ncols=4096):
         u, s, _ = np.linalg.svd(sub, full_matrices=False)
         X0 = np.column_stack([X0, u[:, :npc] * s[:npc]])
     return X0
+
+
+_IUPAC = {frozenset("AG"): "R", frozenset("CT"): "Y", frozenset("GT"): "K", frozenset("AC"): "M",
+          frozenset("CG"): "S", frozenset("AT"): "W"}
+
+
+def make_hapmap_text(G, bit=2, missing=0.02, seed=BASE_SEED, heading=True, crlf=False, odd_rows=True):
+    """Dosages (m, n) -> the text of a HapMap table (bytes): 11 leading columns, tab separated, one row per marker.
+
+    Alleles are drawn per marker; dosage 0/2 are the two homozygotes, 1 the heterozygote (``bit=2``: "AG";
+    ``bit=1``: the IUPAC letter).  ``missing`` of the calls become one of the reference's missing codes
+    (GAPIT.Numericalization.R:8-22).  ``odd_rows`` adds the table shapes the reference special-cases: both
+    heterozygote spellings in one row (four levels -> all zero, :76), a monomorphic row and a row with no heterozygote."""
+    rng = np.random.Generator(np.random.PCG64(seed + 13))
+    m, n = G.shape
+    miss2, miss1 = ["NN", "XX", "--", "++", "//"], ["N", "X", "-", "+", "/"]
+    lines = []
+    if heading:
+        lines.append("\t".join(["rs#", "alleles", "chrom", "pos", "strand", "assembly#", "center", "protLSID", "assayLSID",
+                                "panelLSID", "QCcode"] + [f"taxa{i:05d}" for i in range(n)]))
+    for k in range(m):
+        a, b = rng.choice(list("ACGT"), size=2, replace=False)
+        if bit == 2:
+            codes = np.array([a + a, a + b, b + b])
+        else:
+            codes = np.array([a, _IUPAC[frozenset((a, b))], b])
+        row = codes[G[k]].astype(object)
+        if odd_rows and bit == 2 and k % 17 == 5:
+            het = np.nonzero(G[k] == 1)[0]
+            row[het[::2]] = b + a                                   # second spelling of the heterozygote
+        if odd_rows and k % 23 == 7:
+            row[:] = codes[0]                                       # monomorphic
+        if odd_rows and k % 29 == 11:
+            row[G[k] == 1] = codes[2]                               # two levels only
+        if missing > 0:
+            na = np.nonzero(rng.random(n) < missing)[0]
+            row[na] = rng.choice(miss2 if bit == 2 else miss1, size=na.size)
+        lines.append("\t".join([f"rs{k}", f"{a}/{b}", str(1 + k % 10), str(1000 + 37 * k), "+", "NA", "NA", "NA", "NA",
+                                "NA", "NA"] + list(row)))
+    return (("\r\n" if crlf else "\n").join(lines) + ("\r\n" if crlf else "\n")).encode()
+
+
+def hapmap_rows(text):
+    """The same table as the list of string rows R's read.table(head=FALSE) would hold."""
+    return [ln.rstrip("\r").split("\t") for ln in text.decode().split("\n") if ln.strip("\r")]

@@ -9,6 +9,7 @@
  *   emma.eigen.L.wo.Z / emma.eigen.R.wo.Z   emma.txt:58-61, 82-89           -> gapit_eigh, gapit_eigen_R
  *   GAPIT.emma.REMLE (Z = NULL)             GAPIT.emma.REMLE.R:21-54,96-110 -> gapit_reml
  *   GAPIT.EMMAxP3D marker loop              GAPIT.EMMAxP3D.R:397-979        -> gapit_p3d_scan
+ *   GAPIT.HapMap / GAPIT.Numericalization   GAPIT.HapMap.R:19-37            -> gapit_hapmap_numericalize
  *
  * Conventions: plain pointers and sizes only.  Host buffers are caller-owned,
  * read-only unless named *_out; device memory lives behind opaque handles.
@@ -74,11 +75,33 @@ int gapit_ctx_set_stream(gapit_ctx* ctx, void* cuda_stream);
  * GAPIT.Main.R:427. */
 int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
                     gapit_impute impute, gapit_geno** out);
+/* The same handle from int8 dosages already resident on this context's device (marker k at mk_dev + k*ld, ld >= n):
+ * one device-to-device re-pitch plus the column statistics; values outside {0,1,2} are rejected. */
+int gapit_geno_from_device(gapit_ctx* ctx, const int8_t* mk_dev, int64_t n, int64_t m, int64_t ld, gapit_geno** out);
 void gapit_geno_free(gapit_geno* g);
 int64_t gapit_geno_n(const gapit_geno* g);
 int64_t gapit_geno_m(const gapit_geno* g);
 /* per-marker allele-count sums (host out, length m) */
 int gapit_geno_colsums(const gapit_geno* g, int32_t* colsum_out, int32_t* colsumsq_out);
+
+/* ---- HapMap ingestion (GAPIT.HapMap.R:19-37 looping GAPIT.Numericalization.R:1-112 per marker) --------------
+ * gapit_hapmap_index (host): scans the text of a HapMap table (tab separated, 11 leading columns, one row per
+ * marker, optional heading row) and returns taxa count n, marker count m, genotype width `bit` (1 or 2 characters,
+ * nchar(G[2,12]) at GAPIT.HapMap.R:28) and, when row_off_out != NULL (capacity row_cap), the byte offset of the first
+ * genotype character of every data row; header_off_out (may be NULL) gets the offset of the first taxa name of the
+ * heading row or -1.  Call once with row_off_out = NULL to size the array.
+ * gapit_hapmap_numericalize (device): the text goes to the GPU as is; genotype i of marker k is the `bit` bytes at
+ * text[row_off[k] + i*stride] (stride = bit + 1 for tab-separated text, bit for a dense code matrix).  Rules of
+ * GAPIT.Numericalization: missing codes (:8-22), sorted levels and counts (:25-37), Major.allele.zero (:41-62),
+ * dosage by level (:76-86), impute None/Middle/Minor/Major (:92-101), effect 0 Add / 1 Dom / 2 Left / 3 Right
+ * (:105-107).  Outputs: gd_out (may be NULL) m x n int8 marker-major (= R's n x m column-major GD), NA = -1;
+ * geno_out (may be NULL) the device-resident genotype handle the kinship and scan calls take (fails with
+ * GAPIT_ERR_DATA if NA remain). */
+int gapit_hapmap_index(const char* text, int64_t bytes, int heading, int64_t* n_out, int64_t* m_out, int* bit_out,
+                       int64_t* row_off_out, int64_t row_cap, int64_t* header_off_out);
+int gapit_hapmap_numericalize(gapit_ctx* ctx, const char* text, int64_t bytes, const int64_t* row_off, int bit, int stride,
+                              int64_t n, int64_t m, int effect, gapit_impute impute, int major_allele_zero,
+                              int8_t* gd_out, gapit_geno** geno_out);
 
 /* ---- VanRaden kinship (GAPIT.kinship.VanRaden.R:11-32) -------------------
  * K_out: n x n fp64 column-major (symmetric).  G_out (optional, may be NULL):
@@ -96,6 +119,15 @@ int64_t gapit_gram_ld(int64_t n);
 int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t* sums_dev);
 int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, const int64_t* sums_dev, double* K_dev_out,
                           double* K_host_out, int32_t* G_host_out);
+
+/* ---- ZHANG kinship and PCA covariates from the same integer cross-product ----------------------------
+ * gapit_zhang: GAPIT.kinship.ZHANG(snps) (GAPIT.kinship.ZHANG.R:1-66): centred cross-product (:21-26), range
+ * scaling to [0, 1 + inbreeding] (:43-47) and the two diagonal / off-diagonal adjustments (:50-61).  K_out n x n fp64.
+ * gapit_pca: prcomp(X) of GAPIT.PCA.R:10 for the n x m dosage matrix: the first `ncomp` columns of PCA.X$x
+ * (scores_out, n x ncomp column-major; sign of a component is arbitrary as in LAPACK) and all min(n, m) variances
+ * PCA.X$sdev^2 (ev_out, may be NULL), from the eigen-system of the centred cross-product X_c X_c'. */
+int gapit_zhang(gapit_ctx* ctx, gapit_geno* g, double* K_out);
+int gapit_pca(gapit_ctx* ctx, gapit_geno* g, int64_t ncomp, double* scores_out, double* ev_out);
 
 /* ---- spectral pieces (emma.txt:58-61, 82-89) ------------------------------
  * gapit_eigh: eigen(A, symmetric=TRUE): values descending, vectors n x n

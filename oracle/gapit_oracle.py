@@ -445,3 +445,127 @@ def blup_pev(ys, X0, K, eig_L, reml, CVI=None, CV_Inheritance=None):
         BLUE = XCV @ beta_inh if XCV.shape[1] == beta_inh.shape[0] else None
     return {"BLUP": BLUP, "BLUP_Plus_Mean": BLUP_Plus_Mean, "PEV": PEV, "BLUE": BLUE, "beta": beta,
             "used_ginv_K": used_ginv}
+
+
+# --------------------------------------------------------------------------
+# GAPIT.Numericalization  (GAPIT.Numericalization.R:1-112) and the HapMap loop
+# around it (GAPIT.HapMap.R:19-37)
+# --------------------------------------------------------------------------
+def _r_order(values, decreasing=False):
+    """R's order(): stable, ties keep their original order in both directions (radix method)."""
+    idx = list(range(len(values)))
+    return sorted(idx, key=lambda i: -values[i] if decreasing else values[i])
+
+
+def numericalization(x, bit=2, effect="Add", impute="None", Major_allele_zero=False):
+    """One marker: list of genotype strings -> float vector (NaN = NA).  Line references are to
+    GAPIT.Numericalization.R.  Factor levels are sorted by byte value (R's sort in the C locale; identical to any
+    locale for the upper-case nucleotide codes HapMap files hold)."""
+    x = [str(v) for v in x]
+    if bit == 1:                                                            # :8-14
+        x = ["N" if v in ("X", "-", "+", "/") else v for v in x]
+        x = ["Z" if v == "K" else v for v in x]
+    if bit == 2:                                                            # :16-22
+        x = ["N" if v in ("XX", "--", "++", "//", "NN") else v for v in x]
+    n = len(x)
+    lev = sorted(set(x) - {"N"}, key=lambda s: s.encode())                  # :25-26
+    ln = len(lev)                                                           # :28
+    count = [sum(1 for v in x if v == l) for l in lev]                      # :34-37
+    if Major_allele_zero and 1 < ln <= 3:                                   # :41-62
+        ct = [(count[i], i) for i in range(ln)]
+        if bit == 1:
+            if ln == 3:
+                ct = ct[:2]
+            o = _r_order([c for c, _ in ct], decreasing=True)
+            order = [ct[i][1] for i in o] + ([2] if ln == 3 else [])
+        else:
+            if ln == 3:
+                ct = [ct[0], ct[2]]
+            o = _r_order([c for c, _ in ct], decreasing=True)
+            order = [ct[o[0]][1], 1, ct[o[1]][1]] if ln == 3 else [ct[i][1] for i in o]
+        count = [count[i] for i in order]
+        lev = [lev[i] for i in order]
+    if bit == 1 and ln == 3:                                                # :67-71
+        count[1], count[2] = count[2], count[1]
+    position = [p + 1 for p in _r_order(count)]                             # :72 (1-based)
+    nan = float("nan")
+    if ln <= 1 or ln > 3:                                                   # :76
+        out = [0.0] * n
+    elif ln == 2:                                                           # :79
+        out = [nan if v == "N" else (0.0 if v == lev[0] else 2.0) for v in x]
+    elif bit == 1:                                                          # :82-83
+        out = [nan if v == "N" else (0.0 if v == lev[0] else (1.0 if v == lev[2] else 2.0)) for v in x]
+    else:                                                                   # :85
+        out = [nan if v == "N" else (0.0 if v == lev[0] else (2.0 if v == lev[2] else 1.0)) for v in x]
+    out = np.array(out, dtype=np.float64)
+    na = np.isnan(out)
+    if impute == "Middle":                                                  # :92
+        out[na] = 1.0
+    if ln == 3:                                                             # :94-97
+        if impute == "Minor":
+            out[na] = position[0] - 1
+        if impute == "Major":
+            out[na] = position[ln - 1] - 1
+    elif ln >= 1:                                                           # :99-101 (position is empty for ln == 0)
+        if impute == "Minor":
+            out[na] = 2 * (position[0] - 1)
+        if impute == "Major":
+            out[na] = 2 * (position[ln - 1] - 1)
+    na = np.isnan(out)
+    if effect == "Dom":                                                     # :105
+        out = np.where(na, np.nan, np.where(out == 1.0, 1.0, 0.0))
+    if effect == "Left":                                                    # :106
+        out[out == 1.0] = 0.0
+    if effect == "Right":                                                   # :107
+        out[out == 1.0] = 2.0
+    return out
+
+
+def hapmap(rows, SNP_effect="Add", SNP_impute="Middle", heading=True, Major_allele_zero=False):
+    """GAPIT.HapMap (GAPIT.HapMap.R:1-66) on a table given as a list of rows (each a list of strings, 11 leading
+    HapMap columns).  Returns GT (taxa), GD (n x m float, NaN = NA), GI (SNP, Chromosome, Position)."""
+    body = rows[1:] if heading else rows
+    GT = list(rows[0][11:]) if heading else None                            # :14-16
+    GI = [(r[0], r[2], r[3]) for r in body]                                 # :15,:18
+    bit = len(str(rows[1][11]))                                             # :28  nchar(G[2,12])
+    GD = np.column_stack([numericalization(r[11:], bit=bit, effect=SNP_effect, impute=SNP_impute,
+                                           Major_allele_zero=Major_allele_zero) for r in body])   # :34-38
+    return {"GT": GT, "GD": GD, "GI": GI}
+
+
+# --------------------------------------------------------------------------
+# GAPIT.kinship.ZHANG  (GAPIT.kinship.ZHANG.R:1-66)  and  prcomp of GAPIT.PCA.R:10
+# --------------------------------------------------------------------------
+def kinship_zhang(snps: np.ndarray) -> np.ndarray:
+    """n x m dosages -> n x n ZHANG relationship, line by line."""
+    snps = np.asarray(snps, dtype=np.float64)
+    fa = snps.sum(axis=0) / (2.0 * snps.shape[0])                            # :9
+    snps = snps[:, ~((fa >= 1.0) | (fa <= 0.0))]                             # :10-11
+    het = 1.0 - np.abs(snps - 1.0)                                           # :13
+    fi = het.sum(axis=1) / (2.0 * snps.shape[1])                             # :14-15
+    inbreeding = 1.0 - fi.min()                                              # :16
+    n = snps.shape[0]
+    Z = snps.T - snps.mean(axis=0)[:, None]                                  # :21-23
+    K = Z.T @ Z                                                              # :26
+    d = np.diag(K).copy()                                                    # :31-35
+    DL, DU, floor = d.min(), d.max(), K.min()                                # :36-38
+    top = 1.0 + inbreeding                                                   # :42
+    K = top * (K - floor) / (DU - floor)                                     # :43
+    Dmin = top * (DL - floor) / (DU - floor)                                 # :44
+    diag = np.eye(n, dtype=bool)
+    if Dmin < 1.0:                                                           # :47-51
+        K[diag] = (K[diag] - Dmin + 1.0) / ((top + 1.0 - Dmin) * .5)
+        K[~diag] = K[~diag] * (1.0 / Dmin)
+    Omax = K[~diag].max()                                                    # :54
+    if Omax > top:                                                           # :55-58
+        K[~diag] = K[~diag] * (top / Omax)
+    return K
+
+
+def prcomp(X: np.ndarray):
+    """stats::prcomp(X) as GAPIT.PCA.R:10 calls it (centre, no scaling): svd of the centred matrix.
+    Returns (x = scores n x min(n,m), sdev^2)."""
+    X = np.asarray(X, dtype=np.float64)
+    Xc = X - X.mean(axis=0, keepdims=True)
+    u, s, _ = np.linalg.svd(Xc, full_matrices=False)
+    return u * s, s * s / (X.shape[0] - 1.0)

@@ -136,6 +136,64 @@ def test_packed_2bit_streaming_scan_equals_int8_scan(gpu_ctx, monkeypatch):
     es.close()
 
 
+# ------------------------------------------------------------------ HapMap numericalization
+@pytest.mark.parametrize("bit", [1, 2])
+@pytest.mark.parametrize("maz", [False, True])
+def test_hapmap_numericalization_matches_oracle(gpu_ctx, bit, maz):
+    """The text of a HapMap table through gapit_hapmap_numericalize against GAPIT.Numericalization restated
+    (oracle.hapmap), byte for byte, for every impute rule and effect model."""
+    G, _, _ = case(203, 331, edge=False)
+    text = synth.make_hapmap_text(G, bit=bit, missing=0.03, crlf=(bit == 1))
+    rows = synth.hapmap_rows(text)
+    for impute in ("None", "Middle", "Minor", "Major"):
+        for effect in ("Add", "Dom", "Left", "Right"):
+            ref = go.hapmap(rows, SNP_effect=effect, SNP_impute=impute, Major_allele_zero=maz)
+            got = gb().GAPIT_HapMap(text, SNP_effect=effect, SNP_impute=impute, Major_allele_zero=maz, ctx=gpu_ctx)
+            gd = got["GD"].astype(np.float64)
+            gd[gd < 0] = np.nan
+            assert np.array_equal(gd, ref["GD"], equal_nan=True), (impute, effect)
+            assert got["GT"] == ref["GT"] and got["GI"] == ref["GI"]
+
+
+def test_hapmap_to_device_genotypes_and_single_marker_call(gpu_ctx):
+    G, _, _ = case(150, 260, edge=False)
+    text = synth.make_hapmap_text(G, bit=2, missing=0.02, heading=False)
+    hm = gb().GAPIT_HapMap(text, heading=False, SNP_impute="Major", ctx=gpu_ctx, device=True)
+    assert hm["GT"] is None and hm["GD"].shape == (150, 260)
+    x = hm["GD"].astype(np.int64)
+    cs, cq = hm["geno"].colsums()
+    assert np.array_equal(cs, x.sum(0)) and np.array_equal(cq, (x * x).sum(0))
+    K1 = gb().GAPIT_kinship_VanRaden(hm["geno"], ctx=gpu_ctx, verbose=False)
+    K2 = gb().GAPIT_kinship_VanRaden(hm["GD"], ctx=gpu_ctx, verbose=False)
+    assert np.array_equal(K1, K2)
+    hm["geno"].close()
+    # impute None leaves NA: fine for GD, an error for a device handle
+    with pytest.raises(gb().GapitCudaError):
+        gb().GAPIT_HapMap(text, heading=False, SNP_impute="None", ctx=gpu_ctx, device=True)
+    # the per-marker entry point (dense code vector, GAPIT.HMP2Num.R:36)
+    row = synth.hapmap_rows(text)[7][11:]
+    for impute in ("None", "Minor"):
+        got = gb().GAPIT_Numericalization(row, bit=2, impute=impute, ctx=gpu_ctx)
+        assert got.shape == (150, 1)
+        assert np.array_equal(got[:, 0], go.numericalization(row, impute=impute), equal_nan=True)
+
+
+def test_device_resident_ingestion(gpu_ctx):
+    import torch
+    G, _, _ = case(131, 257, edge=False)
+    t = torch.from_numpy(G).cuda()
+    g = gb().Genotypes.from_device(t.data_ptr(), 131, 257, ctx=gpu_ctx)
+    x = G.astype(np.int64)
+    cs, cq = g.colsums()
+    assert np.array_equal(cs, x.sum(1)) and np.array_equal(cq, (x * x).sum(1))
+    K1 = gb().GAPIT_kinship_VanRaden(g, ctx=gpu_ctx, verbose=False)
+    assert np.array_equal(K1, gb().GAPIT_kinship_VanRaden(G.T, ctx=gpu_ctx, verbose=False))
+    g.close()
+    t[5, 7] = 3
+    with pytest.raises(gb().GapitCudaError):
+        gb().Genotypes.from_device(t.data_ptr(), 131, 257, ctx=gpu_ctx)
+
+
 def test_pack_rejects_bad_values_and_imputes_na(gpu_ctx):
     G, _, _ = case(40, 60, edge=False)
     bad = G.T.astype(np.float64)
@@ -210,6 +268,25 @@ def test_vanraden_sharded_partials_sum_exactly(gpu_ctx):
                                          K.ctypes.data_as(C.c_void_p), None))
     K1 = gb().GAPIT_kinship_VanRaden(gb().Genotypes(G, ctx=gpu_ctx, marker_major=True), ctx=gpu_ctx, verbose=False)
     assert np.array_equal(K, K1), "sharded and one-shot kinship must be bit-identical"
+
+
+@pytest.mark.parametrize("n,m", [(60, 500), (281, 3093), (300, 1000)])
+def test_zhang_kinship_and_pca(gpu_ctx, n, m):
+    """GAPIT.kinship.ZHANG and prcomp (GAPIT.PCA.R:10) from the same exact integer cross-product."""
+    G, _, _ = case(n, m)
+    Kz = gb().GAPIT_kinship_ZHANG(G.T, ctx=gpu_ctx, verbose=False)
+    ref = go.kinship_zhang(G.T)
+    assert np.abs(Kz - ref).max() <= 1e-11 * np.abs(ref).max()
+    assert np.array_equal(Kz, Kz.T)
+    pc = gb().GAPIT_PCA(G.T, PC_number=5, ctx=gpu_ctx, verbose=False)
+    x, ev = go.prcomp(G.T)
+    assert pc["EV"].shape == (min(n, m),)
+    assert np.abs(pc["EV"] - ev).max() <= 1e-10 * ev[0]
+    for c in range(5):                     # leading components are well separated; the sign is LAPACK's to choose
+        a, b = pc["PCs"][:, c], x[:, c]
+        sgn = 1.0 if np.dot(a, b) > 0 else -1.0
+        gap = min(ev[c - 1] - ev[c] if c else np.inf, ev[c] - ev[c + 1])
+        assert np.abs(sgn * a - b).max() <= 1e-9 * np.abs(b).max() * ev[0] / gap
 
 
 def test_gram_checksums_at_scale(gpu_ctx):

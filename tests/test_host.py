@@ -129,6 +129,35 @@ def test_packed2_host_layout():
     assert np.array_equal(Pf.data, P.data)
 
 
+def test_hapmap_index_host_code():
+    """gapit_hapmap_index: row offsets, n, m, genotype width; CRLF and missing heading; malformed rows are errors."""
+    lib = _lib.load()
+    G = synth.make_genotypes(7, 30, seed=2, threads=1)
+    for bit, crlf, heading in [(2, False, True), (1, True, True), (2, True, False)]:
+        text = synth.make_hapmap_text(G, bit=bit, crlf=crlf, heading=heading)
+        buf = np.frombuffer(text, dtype=np.uint8)
+        n, m, b, h = C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
+        off = np.empty(30, dtype=np.int64)
+        rc = lib.gapit_hapmap_index(buf.ctypes.data_as(C.c_void_p), len(text), int(heading), C.byref(n), C.byref(m),
+                                    C.byref(b), off.ctypes.data_as(C.c_void_p), 30, C.byref(h))
+        assert rc == 0 and (n.value, m.value, b.value) == (7, 30, bit)
+        rows = synth.hapmap_rows(text)[1 if heading else 0:]
+        for k in (0, 13, 29):
+            got = text[off[k]: off[k] + 7 * (bit + 1) - 1].decode().split("\t")
+            assert got == rows[k][11:]
+        assert (h.value >= 0) == heading
+        if heading:
+            assert text[h.value:h.value + 9] == b"taxa00000"
+    bad = text.replace(b"\t", b" ", 3)   # fewer than 12 tab-separated columns in the first row
+    buf = np.frombuffer(bad, dtype=np.uint8)
+    assert lib.gapit_hapmap_index(buf.ctypes.data_as(C.c_void_p), len(bad), 0, C.byref(n), C.byref(m), C.byref(b), None, 0,
+                                  None) == _lib_err("GAPIT_ERR_DATA")
+    ragged = text[:-6]                   # last row one genotype short
+    buf = np.frombuffer(ragged, dtype=np.uint8)
+    assert lib.gapit_hapmap_index(buf.ctypes.data_as(C.c_void_p), len(ragged), 0, C.byref(n), C.byref(m), C.byref(b), None,
+                                  0, None) == _lib_err("GAPIT_ERR_DATA")
+
+
 def test_marker_shards_cover_in_order():
     for m, w in [(10, 3), (500000, 8), (7, 8), (3093, 2)]:
         parts = [shard.marker_shard(m, r, w) for r in range(w)]

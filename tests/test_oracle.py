@@ -176,3 +176,55 @@ def test_golden_c1_reproduces(c1_golden):
     assert np.allclose(np.diag(K), g["K_diag"], rtol=1e-12)
     glm = go.emmax_p3d(Y, G.T, None, X0, ncol_CVI=1)
     assert np.allclose(glm.ps, g["glm_ps"], rtol=1e-10, equal_nan=True)
+
+
+# ------------------------------------------------------------------ HapMap numericalization (GAPIT.Numericalization.R)
+def test_numericalization_hand_cases():
+    f = go.numericalization
+    nan = np.nan
+    x = ["AA", "AG", "GG", "NN", "AA", "GG", "GG"]
+    assert np.array_equal(f(x), [0, 1, 2, nan, 0, 2, 2], equal_nan=True)              # :85, impute None keeps NA
+    assert np.array_equal(f(x, impute="Middle"), [0, 1, 2, 1, 0, 2, 2])                # :92
+    assert np.array_equal(f(x, impute="Minor"), [0, 1, 2, 1, 0, 2, 2])                 # :95 rarest class is the het
+    assert np.array_equal(f(x, impute="Major"), [0, 1, 2, 2, 0, 2, 2])                 # :96
+    # Major.allele.zero: the more frequent homozygote (GG) becomes 0 (:53-57)
+    assert np.array_equal(f(x, impute="Major", Major_allele_zero=True), [2, 1, 0, 0, 2, 0, 0])
+    # one-character codes: het letter sorts last, K -> Z (:13), X - + / -> N (:9-12)
+    assert np.array_equal(f(["A", "G", "R", "N", "A", "G", "G"], bit=1, impute="Major"), [0, 2, 1, 2, 0, 2, 2])
+    assert np.array_equal(f(["G", "T", "K", "X", "T"], bit=1), [0, 2, 1, nan, 2], equal_nan=True)
+    # two levels: 0 / 2 (:79); Major/Minor impute on the 0/2 scale (:99-100)
+    assert np.array_equal(f(["AA", "TT", "--", "TT"], impute="Major"), [0, 2, 2, 2])
+    assert np.array_equal(f(["AA", "TT", "//", "TT"], impute="Minor"), [0, 2, 0, 2])
+    # one level or more than three: all zero, NA included (:76)
+    assert np.array_equal(f(["AA", "AA", "NN"]), [0, 0, 0])
+    assert np.array_equal(f(["AA", "AC", "CA", "CC"]), [0, 0, 0, 0])
+    # effects (:105-107)
+    assert np.array_equal(f(x, impute="Middle", effect="Dom"), [0, 1, 0, 1, 0, 0, 0])
+    assert np.array_equal(f(x, impute="Middle", effect="Left"), [0, 0, 2, 0, 0, 2, 2])
+    assert np.array_equal(f(x, impute="Middle", effect="Right"), [0, 2, 2, 2, 0, 2, 2])
+    # ties in the counts keep the sorted level order (R's stable order())
+    assert np.array_equal(f(["AA", "GG", "NN"], impute="Major", Major_allele_zero=True), [0, 2, 2])
+
+
+def test_hapmap_table_restatement():
+    G = synth.make_genotypes(9, 40, seed=4, threads=1)
+    text = synth.make_hapmap_text(G, bit=2, missing=0.0, odd_rows=False)
+    hm = go.hapmap(synth.hapmap_rows(text), SNP_impute="Middle")
+    assert hm["GT"][0] == "taxa00000" and len(hm["GT"]) == 9 and hm["GI"][3] == ("rs3", "4", "1111")
+    # without missing calls a three-level row is the dosage itself or its mirror image (levels sort by allele letter)
+    for k in range(40):
+        col = hm["GD"][:, k]
+        if len(set(G[k])) == 3:
+            assert np.array_equal(col, G[k]) or np.array_equal(col, 2 - G[k])
+
+
+def test_zhang_and_prcomp_restatements():
+    G = synth.make_genotypes(40, 300, seed=8, threads=1)
+    X = G.T.astype(np.float64)
+    K = go.kinship_zhang(X)
+    top = 1.0 + (1.0 - ((X == 1).sum(1) / (2.0 * ((X.sum(0) > 0) & (X.sum(0) < 80)).sum())).min())
+    off = K[~np.eye(40, dtype=bool)]
+    assert np.allclose(K, K.T) and off.max() <= top * (1 + 1e-12) and np.diag(K).min() >= 1.0 - 1e-12   # :47-58
+    x, ev = go.prcomp(X)
+    Xc = X - X.mean(0)
+    assert np.allclose(x @ x.T, Xc @ Xc.T, atol=1e-8) and np.isclose(ev.sum(), Xc.var(0, ddof=1).sum())
