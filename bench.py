@@ -233,7 +233,8 @@ def main():
     X0 = np.ones((n, 1))
 
     ctx = gb.Context(local, slices=S)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # one non-default stream for torch, NCCL and libgapitcuda alike
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     lib = ctx.lib
     geno = gb.Genotypes(G_host, ctx=ctx, marker_major=True)

@@ -39,8 +39,13 @@ class Context:
             check(self.lib.gapit_set_slices(self.h, int(slices)))
 
     def set_stream(self, cuda_stream):
-        """Run on a caller-owned stream (e.g. ``torch.cuda.current_stream().cuda_stream``); None restores."""
-        check(self.lib.gapit_ctx_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """Run on a caller-owned stream (e.g. ``torch.cuda.current_stream().cuda_stream``); None restores the
+        context's own stream.  Handle 0 is the legacy default stream (what torch uses until a stream is made
+        current): it is passed as cudaStreamLegacy, because NULL means "restore" in the C ABI."""
+        if cuda_stream is None:
+            check(self.lib.gapit_ctx_set_stream(self.h, None))
+        else:
+            check(self.lib.gapit_ctx_set_stream(self.h, C.c_void_p(int(cuda_stream) or 1)))
 
     def set_slices(self, slices):
         check(self.lib.gapit_set_slices(self.h, int(slices)))

@@ -76,7 +76,9 @@ int gapit_ctx_set_stream(gapit_ctx* ctx, void* cuda_stream);
 int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
                     gapit_impute impute, gapit_geno** out);
 /* The same handle from int8 dosages already resident on this context's device (marker k at mk_dev + k*ld, ld >= n):
- * one device-to-device re-pitch plus the column statistics; values outside {0,1,2} are rejected. */
+ * one device-to-device re-pitch plus the column statistics; values outside {0,1,2} are rejected.  The copy runs on
+ * the context's stream: either share that stream with the producer of mk_dev (gapit_ctx_set_stream) or
+ * synchronise the producer first. */
 int gapit_geno_from_device(gapit_ctx* ctx, const int8_t* mk_dev, int64_t n, int64_t m, int64_t ld, gapit_geno** out);
 void gapit_geno_free(gapit_geno* g);
 int64_t gapit_geno_n(const gapit_geno* g);

@@ -190,6 +190,7 @@ def test_device_resident_ingestion(gpu_ctx):
     assert np.array_equal(K1, gb().GAPIT_kinship_VanRaden(G.T, ctx=gpu_ctx, verbose=False))
     g.close()
     t[5, 7] = 3
+    torch.cuda.synchronize()        # the context runs on its own stream: the producer must have finished
     with pytest.raises(gb().GapitCudaError):
         gb().Genotypes.from_device(t.data_ptr(), 131, 257, ctx=gpu_ctx)
 

@@ -28,7 +28,7 @@ def gen_block(n, mb, seed, dev, pop):
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
     out = torch.empty((mb, n), dtype=torch.int8, device=dev)
-    step = max(1, (1 << 28) // n)
+    step = 4096   # fixed sub-block: the first rows of a block do not depend on how many rows are asked for
     for k0 in range(0, mb, step):
         k1 = min(mb, k0 + step)
         p = torch.rand(k1 - k0, generator=g, device=dev) * 0.45 + 0.05
@@ -65,7 +65,8 @@ def main():
     bounds = [(b * m) // nblocks for b in range(nblocks + 1)]
     mine = [b for b in range(nblocks) if b % world == rank]
     ctx = gb.Context(local, slices=args.slices)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # one non-default stream for torch, NCCL and libgapitcuda alike
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     lib = ctx.lib
     g0 = torch.Generator(device=dev)
