@@ -3,6 +3,7 @@
 // plus the taxa-major transposed copy the kinship cross-product contracts over.
 // All three kernels are HBM-bound byte shuffles (128-bit loads, coalesced rows).
 #include <algorithm>
+#include <climits>
 #include <vector>
 
 #include "common.cuh"
@@ -10,72 +11,112 @@
 namespace gapit {
 
 // ---- f64 / i32 -> int8 with validation ------------------------------------
-// src: chunk of `mc` markers, element (i,k) at src[i + k*ld]; dst row k at dst + k*ldn.
+// src: chunk of `mc` markers, element (i,k) at src[i + k*ld]; dst row k at dst + k*ldn (128-byte aligned rows).
+// One thread converts four consecutive elements and writes one 32-bit word, so a warp reads 1 KB (f64) / 512 B
+// (i32) of contiguous input and writes 128 contiguous bytes; the row padding up to ldn is written as zeros.
 template <typename T>
-__global__ void convert_kernel(const T* __restrict__ src, int64_t ld, int64_t n, int64_t mc, int8_t* __restrict__ dst,
-                               int64_t ldn, int impute, int* __restrict__ bad) {
-  const int64_t k = blockIdx.y;
-  if (k >= mc) return;
-  const T* s = src + k * ld;
-  int8_t* d = dst + k * ldn;
-  for (int64_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-    double v = static_cast<double>(s[i]);
-    int8_t o;
-    if (v != v) {  // NA
-      if (impute < 0) {
-        atomicOr(bad, 2);
-        o = 0;
+__global__ void __launch_bounds__(256) convert_kernel(const T* __restrict__ src, int64_t ld, int64_t n, int64_t mc,
+                                                      int8_t* __restrict__ dst, int64_t ldn, int impute,
+                                                      int* __restrict__ bad) {
+  const int64_t words = ldn >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(ld * sizeof(T))) & 15) == 0;
+  int flag = 0;
+  for (int64_t k = blockIdx.y; k < mc; k += gridDim.y) {
+    const T* s = src + k * ld;
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst + k * ldn);
+    for (int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < words; w += int64_t(gridDim.x) * blockDim.x) {
+      // classification on the bit patterns (no fp64 pipe): code 0/1/2, 3 = NA, 4 = not a dosage
+      uint32_t code[4] = {0u, 0u, 0u, 0u};
+      const int64_t i0 = w * 4;
+      if (sizeof(T) == 4) {
+        int q[4] = {0, 0, 0, 0};
+        if (vec && i0 + 3 < n) {   // one 16-byte load when every row start is 16-byte aligned
+          const int4 v = __ldg(reinterpret_cast<const int4*>(s + i0));
+          q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (i0 + c < n) q[c] = static_cast<int>(s[i0 + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)   // R's NA_integer_ is INT_MIN
+          code[c] = static_cast<unsigned>(q[c]) <= 2u ? static_cast<uint32_t>(q[c]) : (q[c] == INT_MIN ? 3u : 4u);
       } else {
-        o = static_cast<int8_t>(impute);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (i0 + c < n) {
+            const unsigned long long bits = __ldg(reinterpret_cast<const unsigned long long*>(s) + i0 + c);
+            const unsigned long long mag = bits & 0x7FFFFFFFFFFFFFFFull;
+            code[c] = mag == 0ull ? 0u
+                      : bits == 0x3FF0000000000000ull ? 1u
+                      : bits == 0x4000000000000000ull ? 2u
+                      : mag > 0x7FF0000000000000ull ? 3u : 4u;   // NaN / NA_real_ -> NA (GAPIT.EMMAxP3D.R:20-24)
+          }
+        }
       }
-    } else if (v == 0.0) {
-      o = 0;
-    } else if (v == 1.0) {
-      o = 1;
-    } else if (v == 2.0) {
-      o = 2;
-    } else {
-      atomicOr(bad, 1);
-      o = 0;
+      uint32_t o = 0u;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v = code[c];
+        if (v == 3u) {
+          if (impute < 0) flag |= 2;
+          v = impute < 0 ? 0u : static_cast<uint32_t>(impute);
+        } else if (v == 4u) {
+          flag |= 1;
+          v = 0u;
+        }
+        o |= v << (8 * c);
+      }
+      d[w] = o;
     }
-    d[i] = o;
   }
+  if (flag) atomicOr(bad, flag);
 }
 
 // ---- 2-bit packed -> int8 ---------------------------------------------------
-// src: `mc` dense rows of nb = ceil(n/4) bytes; taxon i of a marker sits in byte i/4 at bits 2(i%4)..2(i%4)+1
-// (PLINK .bed bit order), code 0/1/2 = dosage, 3 = NA.  One thread expands 4 packed bytes into 16 output bytes
-// (one 128-bit store) and zero-fills the row padding up to ldn.
-__global__ void unpack2_kernel(const uint8_t* __restrict__ src, int64_t nb, int64_t n, int64_t mc, int8_t* __restrict__ dst,
-                               int64_t ldn, int impute, int* __restrict__ bad) {
-  const int64_t groups = ldn / 16;  // ldn is a multiple of 128
-  const int64_t total = mc * groups;
+// src: `mc` dense rows of nb = ceil(n/4) bytes (rows are NOT word aligned in general); taxon i of a marker sits in
+// byte i/4 at bits 2(i%4)..2(i%4)+1 (PLINK .bed bit order), code 0/1/2 = dosage, 3 = NA.  One thread expands 4 packed
+// bytes (fetched as two aligned words and a funnel shift) into 16 output bytes with bit spreads and writes them as
+// one 128-bit store; the row padding up to ldn is written as zeros.  The staging buffer carries 8 bytes of slack.
+__device__ __forceinline__ uint32_t spread2(uint32_t b) {   // 4 x 2-bit fields of a byte -> 4 bytes
+  uint32_t v = (b | (b << 12)) & 0x000F000Fu;
+  return (v | (v << 6)) & 0x03030303u;
+}
+
+__global__ void __launch_bounds__(256) unpack2_kernel(const uint8_t* __restrict__ src, int64_t nb, int64_t n, int64_t mc,
+                                                      int8_t* __restrict__ dst, int64_t ldn, int impute,
+                                                      int* __restrict__ bad) {
+  const int groups = static_cast<int>(ldn >> 4);  // ldn is a multiple of 128
   const uint32_t na = impute < 0 ? 0u : static_cast<uint32_t>(impute);
+  const uint32_t* src32 = reinterpret_cast<const uint32_t*>(src);
   int flag = 0;
-  for (int64_t t = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; t < total; t += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t k = t / groups;
-    const int64_t gi = t - k * groups;
-    const uint8_t* row = src + k * nb;
-    uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t byte = gi * 4 + j;
-      if (byte < nb) {
-        const uint32_t pk = __ldg(row + byte);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v = (pk >> (2 * c)) & 3u;
-          if (byte * 4 + c >= n) {
-            v = 0u;  // bits past the last taxon are ignored
-          } else if (v == 3u) {
-            if (impute < 0) flag = 2;
-            v = na;
-          }
-          w[j] |= v << (8 * c);
-        }
+  for (int64_t k = blockIdx.y; k < mc; k += gridDim.y) {
+    const int64_t row_off = k * nb;
+    uint4* drow = reinterpret_cast<uint4*>(dst + k * ldn);
+    for (int gi = blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += gridDim.x * blockDim.x) {
+      const int64_t byte0 = int64_t(gi) * 4;
+      uint32_t pk = 0u;
+      if (byte0 < nb) {
+        const int64_t off = row_off + byte0;
+        const uint32_t lo = __ldg(src32 + (off >> 2));
+        const uint32_t hi = __ldg(src32 + (off >> 2) + 1);
+        pk = __funnelshift_r(lo, hi, static_cast<uint32_t>(off & 3) * 8u);
+        const int64_t left = n - byte0 * 4;              // genotypes of this row from byte0 on
+        if (left < 16) pk &= (1u << (2 * static_cast<int>(left))) - 1u;   // bits past the last taxon are ignored
       }
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t v = spread2((pk >> (8 * j)) & 0xFFu);
+        const uint32_t m3 = v & (v >> 1) & 0x01010101u;   // bytes holding code 3
+        if (m3) {
+          if (impute < 0) flag = 2;
+          v = (v & ~(m3 * 3u)) | (m3 * na);
+        }
+        w[j] = v;
+      }
+      drow[gi] = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    *reinterpret_cast<uint4*>(dst + k * ldn + gi * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   if (flag) atomicOr(bad, flag);
 }
@@ -115,47 +156,51 @@ __global__ void colstats_kernel(const int8_t* __restrict__ mk, int64_t ldn, int6
 }
 
 // ---- marker-major -> taxa-major byte transpose -----------------------------
-// 128 markers x 128 taxa per block; each thread owns a 4x4 byte block that is
-// transposed in registers (prmt), staged through shared memory and written
-// back as coalesced 128-byte rows.
+// 128 markers x 256 taxa per block (two 128 x 128 tiles whose 8 loads per thread are all issued up front, which
+// keeps ~64 KB of reads in flight per SM); each thread owns a 4x4 byte block per tile that is transposed in
+// registers (prmt), staged through shared memory and written back as coalesced 128-byte rows.
 __global__ void __launch_bounds__(1024) transpose_kernel(const int8_t* __restrict__ mk, int64_t ldn, int64_t n,
                                                          int64_t m, int8_t* __restrict__ tx, int64_t ldm,
                                                          int64_t n_rows_t) {
-  __shared__ uint32_t tile[128][33];
+  __shared__ uint32_t tile[2][128][33];
   const int txi = threadIdx.x;  // 0..31: taxa chunk (4 taxa)
   const int tyi = threadIdx.y;  // 0..31: marker chunk (4 markers)
   const int64_t k0 = int64_t(blockIdx.x) * 128;  // marker tile
-  const int64_t i0 = int64_t(blockIdx.y) * 128;  // taxa tile
-  uint32_t w[4];
+  const int64_t i00 = int64_t(blockIdx.y) * 256;  // first of the two taxa tiles
+  uint32_t w[2][4];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int64_t k = k0 + tyi * 4 + r;
-    const int64_t i = i0 + txi * 4;
-    w[r] = (k < m && i < ldn) ? __ldg(reinterpret_cast<const uint32_t*>(mk + k * ldn + i)) : 0u;
-  }
-  // 4x4 byte transpose: o[c] = { w[0].c, w[1].c, w[2].c, w[3].c }
-  const uint32_t t0 = __byte_perm(w[0], w[1], 0x5140);  // w0.b0 w1.b0 w0.b1 w1.b1
-  const uint32_t t1 = __byte_perm(w[0], w[1], 0x7362);  // w0.b2 w1.b2 w0.b3 w1.b3
-  const uint32_t t2 = __byte_perm(w[2], w[3], 0x5140);
-  const uint32_t t3 = __byte_perm(w[2], w[3], 0x7362);
-  uint32_t o[4];
-  o[0] = __byte_perm(t0, t2, 0x5410);
-  o[1] = __byte_perm(t0, t2, 0x7632);
-  o[2] = __byte_perm(t1, t3, 0x5410);
-  o[3] = __byte_perm(t1, t3, 0x7632);
+  for (int h = 0; h < 2; ++h)
 #pragma unroll
-  for (int c = 0; c < 4; ++c) tile[txi * 4 + c][tyi] = o[c];
-  __syncthreads();
-  // row `txi + 32*j` of the tile = one taxon, 32 words = 128 markers
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int rrow = tyi + 32 * j;
-    const int64_t i = i0 + rrow;
-    if (i < n_rows_t) {
-      uint32_t v = (i < n) ? tile[rrow][txi] : 0u;
-      *reinterpret_cast<uint32_t*>(tx + i * ldm + k0 + txi * 4) = v;
+    for (int r = 0; r < 4; ++r) {
+      const int64_t k = k0 + tyi * 4 + r;
+      const int64_t i = i00 + h * 128 + txi * 4;
+      w[h][r] = (k < m && i < ldn) ? __ldg(reinterpret_cast<const uint32_t*>(mk + k * ldn + i)) : 0u;
     }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    // 4x4 byte transpose: o[c] = { w[0].c, w[1].c, w[2].c, w[3].c }
+    const uint32_t t0 = __byte_perm(w[h][0], w[h][1], 0x5140);  // w0.b0 w1.b0 w0.b1 w1.b1
+    const uint32_t t1 = __byte_perm(w[h][0], w[h][1], 0x7362);  // w0.b2 w1.b2 w0.b3 w1.b3
+    const uint32_t t2 = __byte_perm(w[h][2], w[h][3], 0x5140);
+    const uint32_t t3 = __byte_perm(w[h][2], w[h][3], 0x7362);
+    tile[h][txi * 4 + 0][tyi] = __byte_perm(t0, t2, 0x5410);
+    tile[h][txi * 4 + 1][tyi] = __byte_perm(t0, t2, 0x7632);
+    tile[h][txi * 4 + 2][tyi] = __byte_perm(t1, t3, 0x5410);
+    tile[h][txi * 4 + 3][tyi] = __byte_perm(t1, t3, 0x7632);
   }
+  __syncthreads();
+  // row `tyi + 32*j` of a tile = one taxon, 32 words = 128 markers
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rrow = tyi + 32 * j;
+      const int64_t i = i00 + h * 128 + rrow;
+      if (i < n_rows_t) {
+        const uint32_t v = (i < n) ? tile[h][rrow][txi] : 0u;
+        *reinterpret_cast<uint32_t*>(tx + i * ldm + k0 + txi * 4) = v;
+      }
+    }
 }
 
 // asynchronous pieces shared with the streaming scan (scan.cu)
@@ -171,11 +216,13 @@ int launch_colstats(gapit_ctx* ctx, cudaStream_t st, const int8_t* mk, int64_t l
 // stage: `mc` markers of n elements (dense, ld = n) already on the device
 int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
                    int impute, int* bad_dev) {
-  dim3 grid(static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64)), static_cast<unsigned>(mc));
+  const int64_t words = ldn / 4;
+  const int threads = words >= 256 ? 256 : 64;
+  dim3 grid(static_cast<unsigned>((words + threads - 1) / threads), static_cast<unsigned>(std::min<int64_t>(mc, 65535)));
   if (dtype == GAPIT_F64)
-    convert_kernel<double><<<grid, 256, 0, st>>>(static_cast<const double*>(stage), n, n, mc, dst, ldn, impute, bad_dev);
+    convert_kernel<double><<<grid, threads, 0, st>>>(static_cast<const double*>(stage), n, n, mc, dst, ldn, impute, bad_dev);
   else
-    convert_kernel<int32_t><<<grid, 256, 0, st>>>(static_cast<const int32_t*>(stage), n, n, mc, dst, ldn, impute, bad_dev);
+    convert_kernel<int32_t><<<grid, threads, 0, st>>>(static_cast<const int32_t*>(stage), n, n, mc, dst, ldn, impute, bad_dev);
   GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
 }
@@ -183,9 +230,12 @@ int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_
 // stage: `mc` dense rows of ceil(n/4) packed bytes already on the device
 int launch_unpack2(gapit_ctx* ctx, cudaStream_t st, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
                    int impute, int* bad_dev) {
-  const int64_t total = mc * (ldn / 16);
-  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((total + 255) / 256, int64_t(ctx->sm_count) * 16)));
-  unpack2_kernel<<<blocks, 256, 0, st>>>(static_cast<const uint8_t*>(stage), (n + 3) / 4, n, mc, dst, ldn, impute, bad_dev);
+  const int64_t groups = ldn / 16;
+  int threads = 64;   // CTA width with the fewest idle threads in a row's last CTA
+  for (int t : {128, 256})
+    if ((groups + t - 1) / t * t <= (groups + threads - 1) / threads * threads) threads = t;
+  dim3 grid(static_cast<unsigned>((groups + threads - 1) / threads), static_cast<unsigned>(std::min<int64_t>(mc, 65535)));
+  unpack2_kernel<<<grid, threads, 0, st>>>(static_cast<const uint8_t*>(stage), (n + 3) / 4, n, mc, dst, ldn, impute, bad_dev);
   GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
 }
@@ -210,7 +260,7 @@ int geno_build_taxa_major(gapit_geno* g) {
   g->ldm = round_up(g->m, 128);
   GAPIT_CUDA(cudaMalloc(&g->tx, size_t(g->n_rows_t) * g->ldm));
   dim3 block(32, 32);
-  dim3 grid(static_cast<unsigned>(g->ldm / 128), static_cast<unsigned>(g->n_rows_t / 128));
+  dim3 grid(static_cast<unsigned>(g->ldm / 128), static_cast<unsigned>(g->n_rows_t / 256));   // n_rows_t is a multiple of 256
   transpose_kernel<<<grid, block, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, g->tx, g->ldm, g->n_rows_t);
   GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
@@ -277,13 +327,11 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
       e = cudaMemcpy2DAsync(stage, size_t(n) * esz, src, size_t(ld) * esz, size_t(n) * esz, mc, cudaMemcpyHostToDevice,
                             ctx->stream);
       if (e != cudaSuccess) break;
-      dim3 grid(static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 64)), static_cast<unsigned>(mc));
-      if (dtype == GAPIT_F64)
-        convert_kernel<double><<<grid, 256, 0, ctx->stream>>>(static_cast<const double*>(stage), n, n, mc,
-                                                              g->mk + k0 * g->ldn, g->ldn, int(impute), bad);
-      else
-        convert_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(static_cast<const int32_t*>(stage), n, n, mc,
-                                                               g->mk + k0 * g->ldn, g->ldn, int(impute), bad);
+      if (launch_convert(ctx->stream, dtype, stage, n, mc, g->mk + k0 * g->ldn, g->ldn, int(impute), bad) != GAPIT_OK) {
+        cudaFree(stage);
+        cudaFree(bad);
+        return cleanup(GAPIT_ERR_CUDA);
+      }
       e = cudaGetLastError();
     }
     int hbad = 0;
@@ -299,7 +347,7 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(256) << 20) / nb));
     void* stage = nullptr;
     int* bad = nullptr;
-    int rc2 = ctx_ws(ctx, WS_STAGE0, size_t(chunk) * nb, &stage);
+    int rc2 = ctx_ws(ctx, WS_STAGE0, size_t(chunk) * nb + 8, &stage);
     if (rc2 == GAPIT_OK) rc2 = ctx_ws_t(ctx, WS_BAD, 4, &bad);
     if (rc2 != GAPIT_OK) return cleanup(rc2);
     e = cudaMemsetAsync(bad, 0, 4, ctx->stream);

@@ -5,7 +5,8 @@
 //   numericalize_kernel         one CTA per marker: distinct genotype strings (<= 3 matter), their counts, the
 //                               reference's level ordering / Major.allele.zero / impute / effect rules, then the
 //                               0/1/2 dosages straight into the int8 marker-major operand layout of the scan
-// Byte work: the file text is read twice from L2/HBM (levels, then counts + write), 1 byte per genotype is written.
+// Byte work: the text row of a marker is staged once in shared memory with 16-byte loads, the three passes (levels,
+// counts, dosages) read it there, and 1 byte per genotype is written as 32-bit words.
 #include <algorithm>
 #include <cstring>
 #include <vector>
@@ -63,9 +64,14 @@ __device__ void order3(const int* c, int len, bool decreasing, int* idx) {
     }
 }
 
-__global__ void __launch_bounds__(128) numericalize_kernel(const NumParams p) {
-  __shared__ uint32_t slots[4];
-  __shared__ int overflow;
+// STAGE: the marker's text row is first copied to shared memory with 16-byte loads (rows up to kStageBytes) and the
+// three passes read it from there; otherwise they read global memory (very wide rows).
+constexpr int kStageBytes = 48 * 1024;
+
+template <bool STAGE>
+__global__ void __launch_bounds__(256) numericalize_kernel(const NumParams p) {
+  extern __shared__ uint4 stage_raw[];
+  __shared__ uint32_t wmin[8];
   __shared__ uint32_t lev[3];
   __shared__ int len_s;
   __shared__ int cnt[3];
@@ -73,44 +79,53 @@ __global__ void __launch_bounds__(128) numericalize_kernel(const NumParams p) {
   __shared__ int na_val;    // value of a missing genotype after the impute rule (-1 = stays NA)
   const int tid = threadIdx.x;
   for (int64_t k = p.k0 + blockIdx.x; k < p.k1; k += gridDim.x) {
-    const uint8_t* row = p.text + (p.row_off[k] - p.text_base);
-    if (tid < 4) slots[tid] = kKeyEmpty;
+    const uint8_t* grow = p.text + (p.row_off[k] - p.text_base);
+    const uint8_t* row = grow;
+    if (STAGE) {
+      const uintptr_t a = reinterpret_cast<uintptr_t>(grow);
+      const int lead = static_cast<int>(a & 15);
+      const uint4* g16 = reinterpret_cast<const uint4*>(a - lead);
+      const int nvec = static_cast<int>((lead + (p.n - 1) * p.stride + p.bit + 15) >> 4);
+      for (int v = tid; v < nvec; v += blockDim.x) stage_raw[v] = __ldg(g16 + v);
+      row = reinterpret_cast<const uint8_t*>(stage_raw) + lead;
+    }
     if (tid < 3) cnt[tid] = 0;
-    if (tid == 0) overflow = 0;
     __syncthreads();
-    // ---- pass 1: the distinct genotype strings (only "more than three" matters beyond three)
-    uint32_t lk[4];
-    int nl = 0;
+    // ---- pass 1: the distinct genotype strings of this thread's share (only "more than three" matters beyond three)
+    uint32_t k0 = kKeyEmpty, k1 = kKeyEmpty, k2 = kKeyEmpty, k3 = kKeyEmpty;   // registers, no indexed array
     for (int64_t i = tid; i < p.n; i += blockDim.x) {
       const uint32_t key = read_key(row + i * p.stride, p.bit);
-      if (key == kKeyNA) continue;
-      bool seen = false;
-      for (int j = 0; j < nl; ++j) seen |= (lk[j] == key);
-      if (!seen && nl < 4) lk[nl++] = key;
+      if (key == kKeyNA || key == k0 || key == k1 || key == k2 || key == k3) continue;
+      if (k0 == kKeyEmpty) k0 = key;
+      else if (k1 == kKeyEmpty) k1 = key;
+      else if (k2 == kKeyEmpty) k2 = key;
+      else if (k3 == kKeyEmpty) k3 = key;
     }
-    for (int j = 0; j < nl; ++j) {
-      bool placed = false;
-      for (int s = 0; s < 4 && !placed; ++s) {
-        const uint32_t old = atomicCAS(&slots[s], kKeyEmpty, lk[j]);
-        placed = (old == kKeyEmpty || old == lk[j]);
-      }
-      if (!placed) atomicExch(&overflow, 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t v[4];
+    // levels(as.factor(x)) (:25): the sorted distinct strings, found as successive block-wide minima (no atomics)
+    {
+      uint32_t prev = 0u;   // every key is > 0
       int len = 0;
-      for (int s = 0; s < 4; ++s)
-        if (slots[s] != kKeyEmpty) v[len++] = slots[s];
-      if (overflow) len = 4;
-      for (int i = 1; i < len; ++i)   // levels(as.factor(x)): sorted (:25)
-        for (int j = i; j > 0 && v[j] < v[j - 1]; --j) {
-          const uint32_t t = v[j];
-          v[j] = v[j - 1];
-          v[j - 1] = t;
-        }
-      len_s = len;
-      for (int i = 0; i < 3; ++i) lev[i] = (i < len) ? v[i] : kKeyEmpty;
+      for (int r = 0; r < 4; ++r) {
+        uint32_t cand = kKeyEmpty;
+        if (k0 > prev && k0 < cand) cand = k0;
+        if (k1 > prev && k1 < cand) cand = k1;
+        if (k2 > prev && k2 < cand) cand = k2;
+        if (k3 > prev && k3 < cand) cand = k3;
+        cand = __reduce_min_sync(0xffffffffu, cand);
+        if ((tid & 31) == 0) wmin[tid >> 5] = cand;
+        __syncthreads();
+        uint32_t mn = kKeyEmpty;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) mn = min(mn, wmin[w]);
+        __syncthreads();
+        if (mn == kKeyEmpty) break;   // uniform across the block
+        if (r < 3 && tid == 0) lev[r] = mn;
+        ++len;
+        prev = mn;
+      }
+      if (tid == 0) {
+        for (int i = len; i < 3; ++i) lev[i] = kKeyEmpty;
+        len_s = len;
+      }
     }
     __syncthreads();
     const int len = len_s;
@@ -201,22 +216,28 @@ __global__ void __launch_bounds__(128) numericalize_kernel(const NumParams p) {
       }
       __syncthreads();
     }
-    // ---- pass 3: dosages
-    int8_t* dst = p.out + (k - p.k0) * p.ldo;
+    // ---- pass 3: dosages, four per thread, one 32-bit store (rows are padded to ldo, a multiple of 128)
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.out + (k - p.k0) * p.ldo);
+    const int words = static_cast<int>(p.ldo >> 2);
     bool left_na = false;
     if (len < 2 || len > 3) {   // :76  x = 0
-      for (int64_t i = tid; i < p.ldo; i += blockDim.x) dst[i] = 0;
+      for (int w = tid; w < words; w += blockDim.x) dst[w] = 0u;
     } else {
       const uint32_t l0 = lev[0], l1 = lev[1];
       const int v0 = code[0], v1 = code[1], v2 = code[2], vn = na_val;
-      for (int64_t i = tid; i < p.ldo; i += blockDim.x) {
-        int v = 0;
-        if (i < p.n) {
-          const uint32_t key = read_key(row + i * p.stride, p.bit);
-          v = (key == kKeyNA) ? vn : (key == l0 ? v0 : (key == l1 ? v1 : v2));
-          left_na |= (v < 0);
+      for (int w = tid; w < words; w += blockDim.x) {
+        uint32_t o = 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int64_t i = int64_t(w) * 4 + c;
+          if (i < p.n) {
+            const uint32_t key = read_key(row + i * p.stride, p.bit);
+            const int v = (key == kKeyNA) ? vn : (key == l0 ? v0 : (key == l1 ? v1 : v2));
+            left_na |= (v < 0);
+            o |= (static_cast<uint32_t>(v) & 0xFFu) << (8 * c);
+          }
         }
-        dst[i] = static_cast<int8_t>(v);
+        dst[w] = o;
       }
     }
     if (left_na) atomicOr(p.has_na, 1);
@@ -321,7 +342,7 @@ extern "C" int gapit_hapmap_numericalize(gapit_ctx* ctx, const char* text, int64
     max_span = std::max(max_span, row_off[k1 - 1] + row_span - row_off[k0]);
     k0 = k1;
   }
-  if ((e = cudaMalloc(&text_dev, size_t(max_span))) != cudaSuccess)
+  if ((e = cudaMalloc(&text_dev, size_t(max_span) + 32)) != cudaSuccess)
     return cleanup(fail(GAPIT_ERR_CUDA, std::string("gapit_hapmap_numericalize: cudaMalloc: ") + cudaGetErrorString(e)));
   cudaEventRecord(ctx->ev0, ctx->stream);
   e = cudaMemcpyAsync(off_dev, row_off, size_t(m) * 8, cudaMemcpyHostToDevice, ctx->stream);
@@ -334,8 +355,15 @@ extern "C" int gapit_hapmap_numericalize(gapit_ctx* ctx, const char* text, int64
     if (e != cudaSuccess) break;
     NumParams p{text_dev, off_dev, row_off[k0], k0, k1, n, bit, stride, effect, int(impute), major_allele_zero,
                 g->mk + k0 * ldn, ldn, flag_dev};
-    const int blocks = static_cast<int>(std::min<int64_t>(k1 - k0, int64_t(ctx->sm_count) * 16));
-    numericalize_kernel<<<blocks, 128, 0, ctx->stream>>>(p);
+    // one CTA per marker; narrow tables use one-warp CTAs so that more markers are in flight per SM
+    const int threads = n <= 4096 ? 32 : (n <= 16384 ? 128 : 256);
+    const int blocks = static_cast<int>(std::min<int64_t>(k1 - k0, int64_t(ctx->sm_count) * (2048 / threads)));
+    if (row_span + 32 <= kStageBytes) {
+      const size_t smem = size_t((row_span + 15 + 15) / 16) * 16;
+      numericalize_kernel<true><<<blocks, threads, smem, ctx->stream>>>(p);
+    } else {
+      numericalize_kernel<false><<<blocks, threads, 0, ctx->stream>>>(p);
+    }
     e = cudaGetLastError();
     k0 = k1;
   }

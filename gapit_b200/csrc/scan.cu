@@ -988,7 +988,7 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
     GAPIT_CHECK(ctx_ws_t(ctx, WS_CHUNK0 + b, size_t(chunk) * ldn, &mk[b]));
     GAPIT_CHECK(ctx_ws_t(ctx, WS_CS0 + b, size_t(chunk), &cs[b]));
     GAPIT_CHECK(ctx_ws_t(ctx, WS_CQ0 + b, size_t(chunk), &cq[b]));
-    if (dtype != GAPIT_I8 || (ld == n && ldn != n)) GAPIT_CHECK(ctx_ws(ctx, WS_STAGE0 + b, size_t(chunk) * row_bytes, &stage[b]));
+    if (dtype != GAPIT_I8 || (ld == n && ldn != n)) GAPIT_CHECK(ctx_ws(ctx, WS_STAGE0 + b, size_t(chunk) * row_bytes + 8, &stage[b]));
     if (ldn != n && dtype != GAPIT_B2) GAPIT_CUDA(cudaMemsetAsync(mk[b], 0, size_t(chunk) * ldn, ctx->stream));
   }
   GAPIT_CHECK(ctx_ws_t(ctx, WS_BAD, 4, &bad));

@@ -209,12 +209,22 @@ def test_pack_rejects_bad_values_and_imputes_na(gpu_ctx):
     na[2, 4] = np.nan
     with pytest.raises(gb().GapitCudaError):
         gb().Genotypes(na, ctx=gpu_ctx)
+    nai = G.T.astype(np.int32)
+    nai[2, 4] = np.iinfo(np.int32).min                                 # R's NA_integer_
+    with pytest.raises(gb().GapitCudaError):
+        gb().Genotypes(nai, ctx=gpu_ctx)
     for rule, val in [("Middle", 1), ("Major", 2), ("Minor", 0)]:      # GAPIT.EMMAxP3D.R:20-24
-        g = gb().Genotypes(na, ctx=gpu_ctx, impute=rule)
-        ref = G.T.astype(np.int64).copy()
-        ref[2, 4] = val
-        assert np.array_equal(g.colsums()[0], ref.sum(0))
-        g.close()
+        for arr in (na, nai):
+            g = gb().Genotypes(arr, ctx=gpu_ctx, impute=rule)
+            ref = G.T.astype(np.int64).copy()
+            ref[2, 4] = val
+            assert np.array_equal(g.colsums()[0], ref.sum(0))
+            g.close()
+    neg0 = G.T.astype(np.float64)
+    neg0[neg0 == 0] = -0.0                                             # -0 is a valid dosage 0
+    g = gb().Genotypes(neg0, ctx=gpu_ctx)
+    assert np.array_equal(g.colsums()[0], G.T.astype(np.int64).sum(0))
+    g.close()
 
 
 # ------------------------------------------------------------------ kinship
