@@ -285,39 +285,47 @@ def main():
     gram_tops_local = float(n) * (n + 1) * m / (gram_ms * 1e-3) / 1e12
 
     # ---------------- spectra + REML (rank 0; one-off per trait set; timed separately) ----------------
+    # device-resident: K_dev -> eigenvectors in place (cuSOLVER syevd) -> digit planes; REML from V'y, V'X0
     setup = {}
-    vec_t = torch.empty((n, n), dtype=torch.float64, device=dev)
     val_t = torch.empty(n, dtype=torch.float64, device=dev)
     dv_t = torch.empty(2, dtype=torch.float64, device=dev)
+    es = None
     if rank == 0:
-        K_host = np.asfortranarray(K_dev.cpu().numpy())   # symmetric, so the row/column-major view is immaterial
+        K_host = np.asfortranarray(K_dev.cpu().numpy()) if args.reml_route == "eigR" else None
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        eL = gb.emma_eigen_L_wo_Z(K_host, ctx=ctx)
+        values = gb.eigh_dev(K_dev.data_ptr(), n, ctx=ctx)          # K_dev now holds V (row r = eigenvector r)
         setup["eigh_L_ms"] = (time.perf_counter() - t0) * 1e3
-        eR = None
+        val_t.copy_(torch.from_numpy(values))
+    if world > 1:
+        dist.broadcast(K_dev, 0)
+        dist.broadcast(val_t, 0)
+    torch.cuda.synchronize()
+    values = val_t.cpu().numpy()
+    t0 = time.perf_counter()
+    es = gb.EigenSystem.from_device(values, K_dev.data_ptr(), ctx=ctx)
+    setup["eigsys_slice_ms"] = (time.perf_counter() - t0) * 1e3
+    if rank == 0:
+        t0 = time.perf_counter()
         if args.reml_route == "eigR":
-            t0 = time.perf_counter()
             eR = gb.emma_eigen_R_wo_Z(K_host, X0, ctx=ctx)
             setup["eigen_R_ms"] = (time.perf_counter() - t0) * 1e3
-        t0 = time.perf_counter()
-        reml = gb.GAPIT_emma_REMLE(Y[:, 0], X0, K_host, eig_L=eL, eig_R=eR, ctx=ctx)
+            t0 = time.perf_counter()
+            reml = gb.GAPIT_emma_REMLE(Y[:, 0], X0, K_host, eig_R=eR, ctx=ctx)
+            del eR, K_host
+        else:
+            proj = es.project(np.column_stack([Y[:, 0], X0]))
+            reml = gb.reml_from_projections(values, proj[:, 0], proj[:, 1:])
         setup["reml_ms"] = (time.perf_counter() - t0) * 1e3
         setup["reml_route"] = args.reml_route
-        del eR
-        vec_t.copy_(torch.from_numpy(np.ascontiguousarray(eL["vectors"].T)))   # row r of vec_t = eigenvector r
-        val_t.copy_(torch.from_numpy(eL["values"]))
         dv_t.copy_(torch.tensor([reml["delta"], reml["vg"]], dtype=torch.float64))
     if world > 1:
-        dist.broadcast(vec_t, 0)
-        dist.broadcast(val_t, 0)
         dist.broadcast(dv_t, 0)
-    vectors = np.asfortranarray(vec_t.cpu().numpy().T)
-    values = val_t.cpu().numpy()
     delta, vg = [float(x) for x in dv_t.cpu().numpy()]
-    del vec_t
-    t0 = time.perf_counter()
-    es = gb.EigenSystem(values, vectors, ctx=ctx)
-    setup["eigsys_upload_slice_ms"] = (time.perf_counter() - t0) * 1e3
+    vectors = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        vectors = np.asfortranarray(K_dev.cpu().numpy().T)          # host copy for the CPU baseline only
+    del K_dev
 
     # ---------------- the timed hot path: MLM P3D scan ----------------
     gather_buf = [torch.empty(m, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None

@@ -71,6 +71,7 @@ SIGNATURES = {
     "gapit_zhang": (C.c_int, [_P, _P, _P]),
     "gapit_pca": (C.c_int, [_P, _P, _I64, _P, _P]),
     "gapit_eigh": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "gapit_eigh_dev": (C.c_int, [_P, _P, _I64, _P]),
     "gapit_eigen_R": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P]),
     "gapit_reml": (C.c_int, [_P, _P, _I64, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(RemlOut)]),
     "gapit_reml_eigL": (C.c_int, [_P, _P, _P, _I64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
@@ -78,6 +79,8 @@ SIGNATURES = {
     "gapit_p3d_scan": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
                                  C.POINTER(ScanOut), C.POINTER(ScanBase)]),
     "gapit_eigsys_upload": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),
+    "gapit_eigsys_from_device": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),
+    "gapit_eigsys_project": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "gapit_eigsys_free": (None, [_P]),
     "gapit_p3d_scan_dev": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
                                      C.POINTER(ScanOut), C.POINTER(ScanBase)]),

@@ -189,6 +189,26 @@ class EigenSystem:
         self.h = h
         self.n = n
 
+    @classmethod
+    def from_device(cls, values, vectors_ptr, ctx=None):
+        """Eigenvectors already on the context's device (n x n column-major, descending; e.g. after ``eigh_dev``)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        self.values = np.ascontiguousarray(values, dtype=np.float64)
+        n = self.values.shape[0]
+        h = C.c_void_p()
+        check(self.ctx.lib.gapit_eigsys_from_device(self.ctx.h, C.c_void_p(int(vectors_ptr)), _ptr(self.values), n,
+                                                    C.byref(h)))
+        self.h, self.n = h, n
+        return self
+
+    def project(self, R):
+        """V'R for an n x nc host matrix (the rotated phenotypes / covariates REML starts from)."""
+        R = np.asfortranarray(np.asarray(R, dtype=np.float64).reshape(self.n, -1))
+        out = np.empty_like(R, order="F")
+        check(self.ctx.lib.gapit_eigsys_project(self.ctx.h, self.h, _ptr(R), R.shape[1], _ptr(out)))
+        return out
+
     def close(self):
         if getattr(self, "h", None):
             self.ctx.lib.gapit_eigsys_free(self.h)
@@ -355,6 +375,26 @@ def emma_eigen_L_wo_Z(K, ctx=None):
     vectors = np.empty((n, n), order="F")
     check(ctx.lib.gapit_eigh(ctx.h, _ptr(K), n, _ptr(values), _ptr(vectors)))
     return {"values": values, "vectors": vectors}
+
+
+def eigh_dev(K_ptr, n, ctx=None):
+    """In-place eigendecomposition of a device-resident symmetric matrix (gapit_eigh_dev): the n x n column-major
+    buffer at ``K_ptr`` becomes the eigenvectors (descending); returns the eigenvalues."""
+    ctx = ctx or default_context()
+    values = np.empty(int(n))
+    check(ctx.lib.gapit_eigh_dev(ctx.h, C.c_void_p(int(K_ptr)), int(n), _ptr(values)))
+    return values
+
+
+def reml_from_projections(values, Vty, VtX, ngrids=100, llim=-10, ulim=10, esp=1e-10):
+    """gapit_reml_eigL on rotated inputs (EigenSystem.project): {"REML", "delta", "ve", "vg"}."""
+    lam = np.ascontiguousarray(values, dtype=np.float64)
+    Vty = np.ascontiguousarray(Vty, dtype=np.float64).reshape(-1)
+    VtX = np.asfortranarray(np.asarray(VtX, dtype=np.float64).reshape(lam.shape[0], -1))
+    out = _lib.RemlOut()
+    check(_lib.load().gapit_reml_eigL(_ptr(lam), _ptr(Vty), _ptr(VtX), lam.shape[0], VtX.shape[1], int(ngrids),
+                                      float(llim), float(ulim), float(esp), C.byref(out)))
+    return {"REML": out.REML, "delta": out.delta, "ve": out.ve, "vg": out.vg}
 
 
 def emma_eigen_R_wo_Z(K, X, ctx=None):

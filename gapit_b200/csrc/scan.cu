@@ -1051,8 +1051,8 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
 
 using namespace gapit;
 
-extern "C" int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const double* values, int64_t n,
-                                   gapit_eigsys** out) {
+static int eigsys_build(gapit_ctx* ctx, const double* vectors, cudaMemcpyKind kind, const double* values, int64_t n,
+                        gapit_eigsys** out) {
   if (!ctx || !vectors || !values || !out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_eigsys_upload: bad argument");
   GAPIT_CUDA(cudaSetDevice(ctx->device));
   gapit_eigsys* e = new gapit_eigsys();
@@ -1069,7 +1069,7 @@ extern "C" int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const 
   cudaError_t err = cudaMalloc(&e->V, size_t(n) * n * 8);
   if (err == cudaSuccess) err = cudaMalloc(&e->Vs, size_t(e->nkq) * e->BN * e->ldn);
   if (err == cudaSuccess) err = cudaMalloc(&e->scale, size_t(nk) * 8);
-  if (err == cudaSuccess) err = cudaMemcpyAsync(e->V, vectors, size_t(n) * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(e->V, vectors, size_t(n) * n * 8, kind, ctx->stream);
   if (err == cudaSuccess) err = cudaMemsetAsync(e->Vs, 0, size_t(e->nkq) * e->BN * e->ldn, ctx->stream);
   if (err == cudaSuccess) err = cudaMemsetAsync(e->scale, 0, size_t(nk) * 8, ctx->stream);
   if (err == cudaSuccess) {
@@ -1084,6 +1084,33 @@ extern "C" int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const 
     return fail(GAPIT_ERR_CUDA, std::string("gapit_eigsys_upload: ") + cudaGetErrorString(err));
   }
   *out = e;
+  return GAPIT_OK;
+}
+
+extern "C" int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const double* values, int64_t n,
+                                   gapit_eigsys** out) {
+  return eigsys_build(ctx, vectors, cudaMemcpyHostToDevice, values, n, out);
+}
+
+extern "C" int gapit_eigsys_from_device(gapit_ctx* ctx, const double* vectors_dev, const double* values, int64_t n,
+                                        gapit_eigsys** out) {
+  return eigsys_build(ctx, vectors_dev, cudaMemcpyDeviceToDevice, values, n, out);
+}
+
+// out[c*n + k] = sum_j V[j + k n] R[j + c n]: the projections V'R the REML search and the reduced model start from
+extern "C" int gapit_eigsys_project(gapit_ctx* ctx, gapit_eigsys* e, const double* R, int nc, double* out) {
+  if (!ctx || !e || !R || !out || nc < 1) return fail(GAPIT_ERR_ARG, "gapit_eigsys_project: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int64_t n = e->n;
+  double *dR = nullptr, *dP = nullptr;
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n) * nc, &dR));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(n) * nc, &dP));
+  GAPIT_CUDA(cudaMemcpyAsync(dR, R, size_t(n) * nc * 8, cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned blocks = static_cast<unsigned>((n * 32 + 255) / 256);
+  for (int c0 = 0; c0 < nc; c0 += 8) vt_project_kernel<8><<<blocks, 256, 0, ctx->stream>>>(e->V, n, dR, nc, c0, dP);
+  GAPIT_CUDA(cudaGetLastError());
+  GAPIT_CUDA(cudaMemcpyAsync(out, dP, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
   return GAPIT_OK;
 }
 

@@ -58,6 +58,17 @@ __global__ void reverse_cols_kernel(const double* __restrict__ src, int64_t n, i
   for (int64_t c = blockIdx.y; c < ncols; c += gridDim.y) dst[i + c * n] = src[i + (n - 1 - c) * n];
 }
 
+// column c <-> column n-1-c, in place (ascending -> descending order of the eigenvectors)
+__global__ void swap_cols_kernel(double* __restrict__ A, int64_t n) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int64_t c = blockIdx.y; c < n / 2; c += gridDim.y) {
+    const double a = A[i + c * n], b = A[i + (n - 1 - c) * n];
+    A[i + c * n] = b;
+    A[i + (n - 1 - c) * n] = a;
+  }
+}
+
 // in-place syevd on a device matrix; eigenvalues (ascending) into w_dev
 int syevd_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* w_dev) {
   GAPIT_CHECK(ensure_solver(ctx));
@@ -122,6 +133,30 @@ extern "C" int gapit_eigh(gapit_ctx* ctx, const double* A, int64_t n, double* va
   cudaFree(A_dev);
   cudaFree(w_dev);
   return rc;
+}
+
+extern "C" int gapit_eigh_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* values_out) {
+  if (!ctx || !A_dev || !values_out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_eigh_dev: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  double* w_dev = nullptr;
+  GAPIT_CUDA(cudaMalloc(&w_dev, size_t(n) * 8));
+  int rc = syevd_dev(ctx, A_dev, n, w_dev);
+  std::vector<double> w(n);
+  cudaError_t e = cudaSuccess;
+  if (rc == GAPIT_OK) {
+    if (n >= 2) {
+      dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(std::min<int64_t>(n / 2, 65535)));
+      swap_cols_kernel<<<grid, 256, 0, ctx->stream>>>(A_dev, n);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w.data(), w_dev, size_t(n) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
+  cudaFree(w_dev);
+  if (rc != GAPIT_OK) return rc;
+  if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("gapit_eigh_dev: ") + cudaGetErrorString(e));
+  for (int64_t c = 0; c < n; ++c) values_out[c] = w[n - 1 - c];
+  return GAPIT_OK;
 }
 
 extern "C" int gapit_eigen_R(gapit_ctx* ctx, const double* K, const double* X, int64_t n, int64_t q, double* values_out,

@@ -135,6 +135,9 @@ int gapit_pca(gapit_ctx* ctx, gapit_geno* g, int64_t ncomp, double* scores_out, 
  * gapit_eigh: eigen(A, symmetric=TRUE): values descending, vectors n x n
  * column-major in matching order (cuSOLVER syevd; timed separately). */
 int gapit_eigh(gapit_ctx* ctx, const double* A, int64_t n, double* values_out, double* vectors_out);
+/* Device-resident form: A_dev (n x n column-major, e.g. K_dev_out of gapit_vanraden_finish) is overwritten by the
+ * eigenvectors in descending order of the eigenvalues (values_out: host, n) -- no n^2 host round trip. */
+int gapit_eigh_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* values_out);
 /* gapit_eigen_R: eigen(S (K+I) S) with S = I - X (X'X)^-1 X'; returns the first
  * n-q values minus 1 and the first n-q vectors (n x (n-q) column-major). */
 int gapit_eigen_R(gapit_ctx* ctx, const double* K, const double* X, int64_t n, int64_t q, double* values_out,
@@ -193,6 +196,10 @@ int gapit_p3d_scan(gapit_ctx* ctx, gapit_geno* g, const double* vectors, const d
  * eigen-system once (slices V for the int8 rotation), then scan. */
 typedef struct gapit_eigsys gapit_eigsys;
 int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const double* values, int64_t n, gapit_eigsys** out);
+/* the same from eigenvectors already on the device (gapit_eigh_dev), and the projections V'R (R: n x nc column-major
+ * host, out: n x nc host) that gapit_reml_eigL takes (V'y, V'X) */
+int gapit_eigsys_from_device(gapit_ctx* ctx, const double* vectors_dev, const double* values, int64_t n, gapit_eigsys** out);
+int gapit_eigsys_project(gapit_ctx* ctx, gapit_eigsys* e, const double* R, int nc, double* out);
 void gapit_eigsys_free(gapit_eigsys* e);
 int gapit_p3d_scan_dev(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
                        const double* delta, const double* vg, int glm, gapit_scan_out* out,

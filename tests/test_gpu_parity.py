@@ -339,6 +339,33 @@ def test_eigh_eigenR_reml_match_oracle(gpu_ctx):
         assert r1[k] == pytest.approx(r2[k], rel=1e-7), k
 
 
+def test_device_resident_spectra_match_host_route(gpu_ctx):
+    """K on the device -> gapit_eigh_dev in place -> gapit_eigsys_from_device -> projections -> gapit_reml_eigL:
+    same numbers as the host-buffer route (gapit_eigh + gapit_eigsys_upload + eig.R REML)."""
+    import torch
+    G, Y, X0 = case(200, 900, npc=2)
+    K = gb().GAPIT_kinship_VanRaden(G.T, ctx=gpu_ctx, verbose=False)
+    eL = gb().emma_eigen_L_wo_Z(K, ctx=gpu_ctx)
+    r_ref = gb().GAPIT_emma_REMLE(Y, X0, K, ctx=gpu_ctx)                  # eig.R route (GAPIT.emma.REMLE.R:21-54)
+    Kd = torch.from_numpy(np.ascontiguousarray(K)).cuda()
+    torch.cuda.synchronize()
+    vals = gb().eigh_dev(Kd.data_ptr(), 200, ctx=gpu_ctx)
+    assert np.abs(vals - eL["values"]).max() < 1e-12 * np.abs(vals).max()
+    es = gb().EigenSystem.from_device(vals, Kd.data_ptr(), ctx=gpu_ctx)
+    proj = es.project(np.column_stack([Y, X0]))
+    Vd = Kd.cpu().numpy().T                                               # column k = eigenvector k
+    assert np.abs(proj - Vd.T @ np.column_stack([Y, X0])).max() < 1e-11
+    r = gb().reml_from_projections(vals, proj[:, 0], proj[:, 1:])
+    for k in ("REML", "delta", "ve", "vg"):
+        assert r[k] == pytest.approx(r_ref[k], rel=1e-9), k
+    a1, _ = gb().p3d_scan(gb().Genotypes(G, ctx=gpu_ctx, marker_major=True), X0, Y, eigsys=es, delta=[r["delta"]],
+                          vg=[r["vg"]], ctx=gpu_ctx)
+    ora = go.emmax_p3d(Y, G.T, K, X0, eig_L=go.emma_eigen_L_wo_Z(K), reml=r_ref)
+    rr, _ = rel_err(a1["effect"][0], ora.effect_est, 1e-3)
+    assert rr < 1e-7                                                      # two independent eigen-solvers + REML searches
+    es.close()
+
+
 # ------------------------------------------------------------------ the scan
 @pytest.mark.parametrize("n,m,npc", [(48, 160, 2), (281, 3093, 0), (200, 700, 3), (333, 900, 6), (150, 300, 12)])
 def test_mlm_scan_parity_injected_spectrum(gpu_ctx, n, m, npc):
