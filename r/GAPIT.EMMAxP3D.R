@@ -31,16 +31,24 @@ glm <- is.null(K)
 if(!glm){
   eig.L <- .Call("gapit_R_eigen_L", K)                                        # :48
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="eig.L"); Memory=GAPIT.Memory(Memory=Memory,Infor="eig.L")
-  eig.R <- try(.Call("gapit_R_eigen_R", K, X0), silent=TRUE)                  # :58
+  # :58, :202  the REML likelihood is evaluated from eig.L alone (gapit_reml_eigL: the same function of delta as
+  # emma.delta.REML.{LL,dLL}.wo.Z on eig.R, delta agrees to 1e-13), so the second eigendecomposition is skipped.
+  # options(gapit.reml.route="eigR") runs the reference's route (gapit_R_eigen_R + gapit_R_reml) instead.
+  if(identical(getOption("gapit.reml.route"), "eigR")){
+    eig.R <- try(.Call("gapit_R_eigen_R", K, X0), silent=TRUE)                # :58
+    if(inherits(eig.R, "try-error"))                                          # :70-74
+      return(list(ps = NULL, REMLs = NA, stats = NULL, effect.est = NULL, dfs = NULL,maf=NULL,nobs = NULL,Timmer=Timmer,Memory=Memory,
+          vgs = NA, ves = NA, BLUP = NULL, BLUP_Plus_Mean = NULL, PEV = NULL, BLUE=NULL))
+    etas <- crossprod(eig.R$vectors, y)                                       # GAPIT.emma.REMLE.R:25
+    r <- .Call("gapit_R_reml", eig.R$values, as.numeric(etas), as.integer(ngrids), llim, ulim, esp)   # :202
+    rm(eig.R)
+  } else {
+    Vt <- crossprod(eig.L$vectors, cbind(y, X0))
+    r <- .Call("gapit_R_reml_eigL", eig.L$values, as.numeric(Vt[,1]), Vt[,-1,drop=FALSE], as.integer(ngrids), llim, ulim, esp)
+  }
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="eig.R"); Memory=GAPIT.Memory(Memory=Memory,Infor="eig.R")
-  if(inherits(eig.R, "try-error"))                                            # :70-74
-    return(list(ps = NULL, REMLs = NA, stats = NULL, effect.est = NULL, dfs = NULL,maf=NULL,nobs = NULL,Timmer=Timmer,Memory=Memory,
-        vgs = NA, ves = NA, BLUP = NULL, BLUP_Plus_Mean = NULL, PEV = NULL, BLUE=NULL))
-  etas <- crossprod(eig.R$vectors, y)                                         # GAPIT.emma.REMLE.R:25
-  r <- .Call("gapit_R_reml", eig.R$values, as.numeric(etas), as.integer(ngrids), llim, ulim, esp)   # :202
   REMLs <- r[1]; REMLE_delta <- r[2]; ves <- r[3]; vgs <- r[4]
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="REML"); Memory=GAPIT.Memory(Memory=Memory,Infor="REML")
-  rm(eig.R)
   bp <- .Call("gapit_R_blup_pev", eig.L$vectors, eig.L$values, X0, y, REMLE_delta, vgs)      # :779-839
   BLUP <- bp[[1]]; PEV <- bp[[2]]; BLUP_Plus_Mean <- bp[[3]][1] + BLUP                        # :818-819
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="PEV"); Memory=GAPIT.Memory(Memory=Memory,Infor="PEV")

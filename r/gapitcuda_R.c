@@ -170,3 +170,82 @@ SEXP gapit_R_blup_pev(SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP delta, SE
   UNPROTECT(4);
   return out;
 }
+
+/* REML from eig.L alone: c(REML, delta, ve, vg).  values = eig.L$values, Vty = crossprod(eig.L$vectors, y),
+ * VtX = crossprod(eig.L$vectors, X0)   (same likelihood as gapit_R_reml on eig.R; GAPIT.emma.REMLE.R:27-54, 96-108) */
+SEXP gapit_R_reml_eigL(SEXP values, SEXP Vty, SEXP VtX, SEXP ngrids, SEXP llim, SEXP ulim, SEXP esp) {
+  gapit_reml_out r;
+  const int64_t n = XLENGTH(values);
+  const int q = (int)(XLENGTH(VtX) / n);
+  int rc = gapit_reml_eigL(REAL(values), REAL(Vty), REAL(VtX), n, q, Rf_asInteger(ngrids), Rf_asReal(llim), Rf_asReal(ulim),
+                           Rf_asReal(esp), &r);
+  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  SEXP out = PROTECT(Rf_allocVector(REALSXP, 4));
+  REAL(out)[0] = r.REML;
+  REAL(out)[1] = r.delta;
+  REAL(out)[2] = r.ve;
+  REAL(out)[3] = r.vg;
+  UNPROTECT(1);
+  return out;
+}
+
+/* GAPIT.kinship.ZHANG(snps): n x m matrix -> n x n double matrix (GAPIT.kinship.ZHANG.R:1-66) */
+SEXP gapit_R_zhang(SEXP snps) {
+  SEXP dim = Rf_getAttrib(snps, R_DimSymbol);
+  const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
+  gapit_geno* g = NULL;
+  if (gapit_geno_pack(ctx(), sexp_data(snps), sexp_dtype(snps), n, m, n, GAPIT_IMPUTE_NONE, &g) != GAPIT_OK)
+    Rf_error("gapitcuda: %s", gapit_last_error());   /* :27 "Missing data is not allowed for numerical genotype data" */
+  SEXP K = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
+  int rc = gapit_zhang(ctx(), g, REAL(K));
+  gapit_geno_free(g);
+  UNPROTECT(1);
+  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  return K;
+}
+
+/* prcomp(X) of GAPIT.PCA.R:10: list(x = n x ncomp scores, sdev2 = min(n, m) variances) */
+SEXP gapit_R_pca(SEXP X, SEXP ncomp) {
+  SEXP dim = Rf_getAttrib(X, R_DimSymbol);
+  const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1], k = Rf_asInteger(ncomp), rank = n < m ? n : m;
+  gapit_geno* g = NULL;
+  if (gapit_geno_pack(ctx(), sexp_data(X), sexp_dtype(X), n, m, n, GAPIT_IMPUTE_NONE, &g) != GAPIT_OK)
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  SEXP x = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)k));
+  SEXP ev = PROTECT(Rf_allocVector(REALSXP, rank));
+  int rc = gapit_pca(ctx(), g, k, REAL(x), REAL(ev));
+  gapit_geno_free(g);
+  if (rc != GAPIT_OK) {
+    UNPROTECT(2);
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  }
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SET_VECTOR_ELT(out, 0, x);
+  SET_VECTOR_ELT(out, 1, ev);
+  UNPROTECT(3);
+  return out;
+}
+
+/* The numericalization loop of GAPIT.HapMap (GAPIT.HapMap.R:34-38 over GAPIT.Numericalization.R) on a raw vector:
+ * `text` = the bytes of the HapMap file (readBin(path, "raw", file.size(path))), heading TRUE/FALSE.
+ * effect 0 Add / 1 Dom / 2 Left / 3 Right, impute -1 None / 0 Minor / 1 Middle / 2 Major.
+ * Returns the n x m integer matrix GD (NA_integer_ where a call stays missing). */
+SEXP gapit_R_hapmap(SEXP text, SEXP heading, SEXP effect, SEXP impute, SEXP maz) {
+  const char* t = (const char*)RAW(text);
+  const int64_t bytes = XLENGTH(text);
+  int64_t n = 0, m = 0, hoff = 0;
+  int bit = 0;
+  if (gapit_hapmap_index(t, bytes, Rf_asLogical(heading), &n, &m, &bit, NULL, 0, &hoff) != GAPIT_OK)
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  int64_t* off = (int64_t*)R_alloc((size_t)m, sizeof(int64_t));
+  gapit_hapmap_index(t, bytes, Rf_asLogical(heading), &n, &m, &bit, off, m, &hoff);
+  int8_t* gd = (int8_t*)R_alloc((size_t)n * (size_t)m, 1);
+  int rc = gapit_hapmap_numericalize(ctx(), t, bytes, off, bit, bit + 1, n, m, Rf_asInteger(effect),
+                                     (gapit_impute)Rf_asInteger(impute), Rf_asLogical(maz), gd, NULL);
+  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  SEXP GD = PROTECT(Rf_allocMatrix(INTSXP, (int)n, (int)m));   /* marker-major bytes == column-major n x m */
+  int* o = INTEGER(GD);
+  for (int64_t i = 0; i < n * m; ++i) o[i] = gd[i] < 0 ? NA_INTEGER : gd[i];
+  UNPROTECT(1);
+  return GD;
+}
