@@ -450,10 +450,11 @@ def _host_array(shape, pinned):
     return np.empty(shape, dtype=np.float64)
 
 
-def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None, pinned=False):
+def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None, pinned=False, out=None):
     """Scan all markers of ``geno`` for T traits.  Returns (dict of (T, m) arrays, list of per-trait base dicts).
     ``pinned=True`` puts the result arrays in page-locked host memory (needs torch) so the D2H copy runs at
-    full PCIe rate."""
+    full PCIe rate; ``out`` reuses the array dict of an earlier call of the same shape (page-locking gigabytes per call
+    costs more than the copy)."""
     ctx = ctx or geno.ctx
     X0 = np.asfortranarray(X0, dtype=np.float64)
     Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(geno.n, -1))
@@ -461,8 +462,11 @@ def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None,
     T = Y.shape[1]
     m = geno.m
     names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
-    arrs = {k: _host_array((T, m), pinned) for k in names}
-    arrs["maf"] = _host_array((m,), pinned)
+    if out is not None and out["effect"].shape == (T, m) and out["maf"].shape == (m,):
+        arrs = out
+    else:
+        arrs = {k: _host_array((T, m), pinned) for k in names}
+        arrs["maf"] = _host_array((m,), pinned)
     so = _lib.ScanOut(**{k: arrs[k].ctypes.data_as(C.POINTER(C.c_double)) for k in arrs})
     base = (_lib.ScanBase * T)()
     d = np.ascontiguousarray(delta, dtype=np.float64).reshape(-1) if delta is not None else None

@@ -207,28 +207,29 @@ __global__ void centered_gram_kernel(const int32_t* __restrict__ G, int64_t ldg,
   }
 }
 
-// per-taxon number of heterozygous calls: het_i = sum_k [x_ik == 1] = sum_k x_ik (2 - x_ik) (GAPIT.kinship.ZHANG.R:14-15);
-// one warp per taxon over the taxa-major copy, 16-byte loads, dp4a
-__global__ void taxa_het_kernel(const int8_t* __restrict__ tx, int64_t ldm, int64_t n, long long* __restrict__ het) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (row >= n) return;
-  const uint4* r = reinterpret_cast<const uint4*>(tx + row * ldm);
-  long long acc = 0;
-  for (int64_t c = lane; c * 16 < ldm; c += 32) {
-    const uint4 v = __ldg(r + c);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    int s1 = 0, s2 = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      s1 = __dp4a(static_cast<int>(w[j]), 0x01010101, s1);
-      s2 = __dp4a(static_cast<int>(w[j]), static_cast<int>(w[j]), s2);
+// per-taxon number of heterozygous calls: het_i = sum_k [x_ik == 1] (GAPIT.kinship.ZHANG.R:14-15), straight from the
+// marker-major matrix: a thread owns four taxa (one 32-bit word of every marker row), walks a slab of markers and
+// counts the bytes equal to 1 in four packed 8-bit lanes (flushed before they can overflow); coalesced row reads.
+__global__ void taxa_het_kernel(const int8_t* __restrict__ mk, int64_t ldn, int64_t m, int64_t rows_per_slab,
+                                unsigned long long* __restrict__ het /* [ldn], zero-initialised */) {
+  const int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (w * 4 >= ldn) return;
+  const int64_t k0 = int64_t(blockIdx.y) * rows_per_slab;
+  const int64_t k1 = min(m, k0 + rows_per_slab);
+  unsigned int c[4] = {0u, 0u, 0u, 0u};
+  for (int64_t kb = k0; kb < k1; kb += 255) {
+    uint32_t lanes = 0u;
+    const int64_t ke = min(k1, kb + 255);
+    for (int64_t k = kb; k < ke; ++k) {
+      const uint32_t x = __ldg(reinterpret_cast<const uint32_t*>(mk + k * ldn) + w);
+      lanes += x & ~(x >> 1) & 0x01010101u;   // byte == 1 (values are 0, 1, 2)
     }
-    acc += 2 * s1 - s2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) c[j] += (lanes >> (8 * j)) & 0xFFu;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) het[row] = acc;
+  for (int j = 0; j < 4; ++j)
+    if (c[j]) atomicAdd(het + w * 4 + j, static_cast<unsigned long long>(c[j]));
 }
 
 // per-block partials of: min over all entries, min / max of the diagonal, max of the off-diagonal
@@ -303,8 +304,19 @@ static int choose_ksplit(int ntri, int kblocks, int sms) {
   return ks;
 }
 
+// The cta_group::2 form reads the marker-major matrix directly as MN-major operands (taxa contiguous, one marker per
+// 128-byte row): no taxa-major copy, no transpose pass.  Smaller problems keep the K-major kernels on the copy.
+static bool gram_mn_major(const gapit_geno* g) {
+  if (g->n <= 256) return false;
+  if (const char* ev = getenv("GAPIT_PAIR")) if (!atoi(ev)) return false;
+  if (const char* ev = getenv("GAPIT_CLUSTER")) if (atoi(ev) < 2) return false;
+  if (const char* ev = getenv("GAPIT_GRAM_MN")) return atoi(ev) != 0;   // A/B switch for profiling
+  return true;
+}
+
 static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ldg) {
-  GAPIT_CHECK(geno_build_taxa_major(g));
+  const bool mn = gram_mn_major(g);
+  if (!mn) GAPIT_CHECK(geno_build_taxa_major(g));
   GramSched::Params sp;
   sp.tiles_side = static_cast<int>((g->n + 255) / 256);
   // clusters of two CTAs take two block-rows against one block-column and multicast that column's panel
@@ -315,15 +327,25 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ld
   sp.cl = cl;
   sp.ntri = 0;
   for (int R = 0; R < TR; ++R) sp.ntri += std::min(cl * (R + 1), sp.tiles_side);
-  sp.kblocks = static_cast<int>(g->ldm / kBlockK);
+  sp.kblocks = static_cast<int>(round_up(g->m, 128) / kBlockK);
   sp.ksplit = choose_ksplit(sp.ntri * cl, sp.kblocks, ctx->sm_count);
   CUtensorMap map_a, map_b;
+  GramEpi::Params ep{G_dev, ldg};
+  const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
+  if (mn) {
+    // one map for both operands: [m markers][ldn bytes of taxa], boxes of 128 markers x 128 taxa
+    GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
+                                   static_cast<uint64_t>(g->ldn), 128));
+    using PCfg = UmmaPairCfg<2, 256, 4>;
+    auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpi, 0, 0, true>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_a, sp, ep));
+    return GAPIT_OK;
+  }
   GAPIT_CHECK(make_tensor_map_u8(&map_a, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
                                  static_cast<uint64_t>(g->ldm), 256));
   GAPIT_CHECK(make_tensor_map_u8(&map_b, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
                                  static_cast<uint64_t>(g->ldm), 256 / cl));
-  GramEpi::Params ep{G_dev, ldg};
-  const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
   int pair = 1;  // cta_group::2 UMMA (one M=256 instruction per CTA pair) unless switched off for A/B profiling
   if (const char* ev = getenv("GAPIT_PAIR")) pair = atoi(ev);
   if (cl == 2 && pair) {
@@ -361,7 +383,7 @@ extern "C" int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev
   cudaEvent_t evt;
   GAPIT_CUDA(cudaEventCreate(&evt));
   cudaEventRecord(evt, ctx->stream);
-  GAPIT_CHECK(geno_build_taxa_major(g));  // no-op when the taxa-major copy already exists
+  if (!gram_mn_major(g)) GAPIT_CHECK(geno_build_taxa_major(g));  // no-op when the taxa-major copy already exists
   cudaEventRecord(ctx->ev0, ctx->stream);
   GAPIT_CHECK(launch_gram(ctx, g, G_dev, ldg));
   cudaEventRecord(ctx->ev1, ctx->stream);
@@ -469,12 +491,20 @@ extern "C" int gapit_zhang(gapit_ctx* ctx, gapit_geno* g, double* K_out) {
   double* part = nullptr;
   const int nblk = std::max(1, std::min(ctx->sm_count * 8, int((n * n + 255) / 256)));
   GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(n) * n, &K_dev));
-  GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(n), &het));
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(g->ldn), &het));
   GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t(nblk) * 4, &part));
   int32_t* G_dev = nullptr;
   int64_t* sums = nullptr;
   GAPIT_CHECK(centered_gram_dev(ctx, g, K_dev, &G_dev, &sums));
-  taxa_het_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(g->tx, g->ldm, n, het);
+  {
+    const int64_t words = g->ldn / 4;
+    const int64_t slabs = std::max<int64_t>(1, std::min<int64_t>(1024, (int64_t(ctx->sm_count) * 8 * 128) / std::max<int64_t>(words, 1)));
+    const int64_t rows_per_slab = (g->m + slabs - 1) / slabs;
+    dim3 grid(static_cast<unsigned>((words + 127) / 128), static_cast<unsigned>((g->m + rows_per_slab - 1) / rows_per_slab));
+    cudaMemsetAsync(het, 0, size_t(g->ldn) * 8, ctx->stream);
+    taxa_het_kernel<<<grid, 128, 0, ctx->stream>>>(g->mk, g->ldn, g->m, rows_per_slab,
+                                                  reinterpret_cast<unsigned long long*>(het));
+  }
   zhang_reduce_kernel<<<nblk, 256, 0, ctx->stream>>>(K_dev, n, part);
   std::vector<long long> h_het(n);
   std::vector<double> h_part(size_t(nblk) * 4);

@@ -221,11 +221,27 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
   return d;
 }
 
+// MN-major operand (the MN index is contiguous in memory, one K index per 128-byte row), 128-byte swizzle: the tile
+// is [K rows][128 bytes of MN], 8-row swizzle atoms of 1024 bytes.  Canonical layout in 16-byte units
+// ((8,n),(8,k)):((1,LBO),(8,SBO)): SBO = bytes between groups of 8 K rows, LBO = bytes between 128-byte MN chunks
+// (unused when the operand is one chunk wide: 128 int8 rows per CTA).
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
 // Instruction descriptor for kind::i8, int32 accumulate, both operands K-major:
 //   [4,6) D format: 2 = S32      [7,10) A format: 0 = u8, 1 = s8   [10,13) B format
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3   [24,29) M >> 4
-__host__ __device__ constexpr uint32_t idesc_i8(uint32_t m, uint32_t n, uint32_t a_signed, uint32_t b_signed) {
-  return (2u << 4) | (a_signed << 7) | (b_signed << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_i8(uint32_t m, uint32_t n, uint32_t a_signed, uint32_t b_signed,
+                                                uint32_t mn_major = 0) {
+  return (2u << 4) | (a_signed << 7) | (b_signed << 10) | (mn_major << 15) | (mn_major << 16) | ((n >> 3) << 17) |
+         ((m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -686,7 +686,9 @@ static int launch_glm(gapit_ctx* ctx, gapit_geno* g, const int8_t* Rs_dev, int64
 // inside ~48 MB of L2.  Depends on n only, so results do not change with the marker shard or SM count.
 static int choose_gsplit(int64_t ldn, int64_t nkq) {
   const double bytes = 148.0 * 256.0 * static_cast<double>(ldn);
-  int g = static_cast<int>(std::ceil(bytes / 48.0e6));
+  double budget = 48.0e6;
+  if (const char* ev = getenv("GAPIT_GSPLIT_MB")) budget = std::max(1.0, atof(ev)) * 1.0e6;   // A/B switch for profiling
+  int g = static_cast<int>(std::ceil(bytes / budget));
   g = std::max(1, g);
   return static_cast<int>(std::min<int64_t>(g, nkq));
 }

@@ -238,7 +238,11 @@ struct UmmaPairCfg {
 
 // EPIW epilogue warps share each (sub-tile, lane quarter): they split the accumulator columns between them and
 // halve the time the single TMEM stage is blocked (the epilogue keeps per-warp partial sums).
-template <int MSUB, int BN, int STAGES, int EPIW, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
+// MNMAJ: both operands are MN-major (the contracted index is the ROW of the global matrix): a ring slot holds, per
+// 128-row operand chunk, a [kBlockK contracted rows][128 bytes] box.  job.a_row0 / b_row0 are then byte offsets along
+// the rows and kb walks the row axis.  Needs BN == 256 (one 128-wide chunk of B per CTA).
+template <int MSUB, int BN, int STAGES, int EPIW, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED,
+          bool MNMAJ = false>
 __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
     umma_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const typename Sched::Params sp, const typename Epi::Params ep) {
@@ -295,9 +299,19 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
           uint8_t* sb = sa + Cfg::kABytes;
           if (leader) ptx::mbar_arrive_expect_tx(&full[st], 2 * Cfg::kStageBytes);
           else ptx::mbar_arrive_remote(&full[st], 0);
-          ptx::tma_load_2d_pair(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, Sched::kHintA);
-          ptx::tma_load_2d_pair(&map_b, &full[st], sb, kb * kBlockK, job.b_row0 + static_cast<int>(crank) * (BN / 2),
-                                Sched::kHintB);
+          if (MNMAJ) {
+            static_assert(!MNMAJ || BN == 256, "MN-major B: one 128-wide chunk per CTA");
+#pragma unroll
+            for (int s = 0; s < MSUB; ++s)
+              ptx::tma_load_2d_pair(&map_a, &full[st], sa + s * 128 * kBlockK, job.a_row0 + s * 128, kb * kBlockK,
+                                    Sched::kHintA);
+            ptx::tma_load_2d_pair(&map_b, &full[st], sb, job.b_row0 + static_cast<int>(crank) * (BN / 2), kb * kBlockK,
+                                  Sched::kHintB);
+          } else {
+            ptx::tma_load_2d_pair(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, Sched::kHintA);
+            ptx::tma_load_2d_pair(&map_b, &full[st], sb, kb * kBlockK, job.b_row0 + static_cast<int>(crank) * (BN / 2),
+                                  Sched::kHintB);
+          }
           if (++st == STAGES) {
             st = 0;
             ph ^= 1;
@@ -308,7 +322,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
   } else if (warp == 1) {
     // ------------------------------------------------------------- UMMA issuer (leader CTA only)
     if (leader) {
-      constexpr uint32_t idesc = ptx::idesc_i8(256, BN, A_SIGNED, B_SIGNED);
+      constexpr uint32_t idesc = ptx::idesc_i8(256, BN, A_SIGNED, B_SIGNED, MNMAJ ? 1u : 0u);
       Sched sch(sp, unit, nunits, crank);
       Job job;
       uint32_t st = 0, ph = 0, it = 0;
@@ -328,8 +342,11 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
               const uint32_t d_col = tmem_base + (acc * MSUB + s) * kAccStride;
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                const uint64_t da = ptx::smem_desc_k_sw128(a_base + s * 128 * kBlockK + k * kUmmaK);
-                const uint64_t db = ptx::smem_desc_k_sw128(b_base + k * kUmmaK);
+                // K-major: 32 bytes along the 128-byte rows per step; MN-major: 32 rows of 128 bytes per step
+                const uint64_t da = MNMAJ ? ptx::smem_desc_mn_sw128(a_base + s * 128 * kBlockK + k * kUmmaK * 128, 128 * kBlockK)
+                                          : ptx::smem_desc_k_sw128(a_base + s * 128 * kBlockK + k * kUmmaK);
+                const uint64_t db = MNMAJ ? ptx::smem_desc_mn_sw128(b_base + k * kUmmaK * 128, 128 * kBlockK)
+                                          : ptx::smem_desc_k_sw128(b_base + k * kUmmaK);
                 ptx::umma_i8_ss_pair(d_col, da, db, idesc, (kb > job.kb_begin || k > 0) ? 1u : 0u);
               }
             }

@@ -155,6 +155,22 @@ def test_hapmap_numericalization_matches_oracle(gpu_ctx, bit, maz):
             assert got["GT"] == ref["GT"] and got["GI"] == ref["GI"]
 
 
+@pytest.mark.parametrize("n,m,bit", [(4100, 37, 2), (16500, 21, 2), (16500, 21, 1), (3, 9, 2)])
+def test_hapmap_row_widths(gpu_ctx, n, m, bit):
+    """CTA width and staging depend on the row width: one-warp CTAs (n <= 4096), 128 / 256 threads, and rows too wide
+    for the shared-memory stage (read from global memory)."""
+    rng = np.random.default_rng(n + bit)
+    G = rng.integers(0, 3, size=(m, n)).astype(np.int8)
+    text = synth.make_hapmap_text(G, bit=bit, missing=0.01, odd_rows=(n > 10))
+    rows = synth.hapmap_rows(text)
+    for impute, maz in (("Minor", True), ("None", False)):
+        ref = go.hapmap(rows, SNP_impute=impute, Major_allele_zero=maz)
+        got = gb().GAPIT_HapMap(text, SNP_impute=impute, Major_allele_zero=maz, ctx=gpu_ctx)
+        gd = got["GD"].astype(np.float64)
+        gd[gd < 0] = np.nan
+        assert np.array_equal(gd, ref["GD"], equal_nan=True), (impute, maz)
+
+
 def test_hapmap_to_device_genotypes_and_single_marker_call(gpu_ctx):
     G, _, _ = case(150, 260, edge=False)
     text = synth.make_hapmap_text(G, bit=2, missing=0.02, heading=False)

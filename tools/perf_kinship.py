@@ -35,8 +35,8 @@ tot = int(G_t[:n, :n].to(torch.int64).sum().item())
 tr = int(torch.diagonal(G_t[:n, :n]).to(torch.int64).sum().item())
 print("sum G == sum c^2:", tot == int((c * c).sum()), " trace G == sum x^2:", tr == int(cq.astype(np.int64).sum()))
 sym = bool(torch.equal(G_t[:4096, :4096], G_t[:4096, :4096].T))
-sub = G[:, -300:].astype(np.int64)   # last taxa: exercises the last tile band
-ref = sub.T @ sub
+sub = G[:, -300:].astype(np.float64)   # last taxa: exercises the last tile band (fp64 BLAS: exact below 2^53)
+ref = (sub.T @ sub).astype(np.int64)
 got = G_t[n - 300:n, n - 300:n].cpu().numpy()
 print("symmetric block:", sym, " last 300x300 block exact:", np.array_equal(got, ref))
 rs = K_t.sum(dim=1).abs().max().item()
