@@ -35,8 +35,8 @@ struct GramSched {
     int ksplit;      // splits of the marker axis
     int kblocks;     // marker axis in units of kBlockK
   };
-  static constexpr uint64_t kHintA = ptx::kEvictNormal;
-  static constexpr uint64_t kHintB = ptx::kEvictNormal;
+  __device__ uint64_t hint_a() const { return ptx::kEvictNormal; }
+  __device__ uint64_t hint_b() const { return ptx::kEvictNormal; }
   static constexpr int kBandRows = 12;  // block-rows per band
   Params p;
   int next_job, stride, crank;

@@ -132,9 +132,11 @@ struct ScanSched {
     int kblocks;  // taxa axis in units of kBlockK
     int bn;
     int nchunk;   // trait chunks: every chunk repeats the rotation of the tile with its own epilogue constants
+    uint64_t hint_a;  // L2 eviction hints (default: marker tile evict_last -- it is re-read for every eigen tile;
+    uint64_t hint_b;  //  eigen tiles evict_normal -- streamed, shared by the CTAs running together)
   };
-  static constexpr uint64_t kHintA = ptx::kEvictLast;    // marker tile: re-read for every eigen tile
-  static constexpr uint64_t kHintB = ptx::kEvictNormal;  // eigen tiles: streamed, shared by concurrent CTAs
+  __device__ uint64_t hint_a() const { return p.hint_a; }
+  __device__ uint64_t hint_b() const { return p.hint_b; }
   Params p;
   int gid, stride, kq, kq_begin, kq_end, mt, ks, tc, crank;
   __device__ ScanSched(const Params& pp, int unit, int nunits, uint32_t cta_rank)
@@ -280,8 +282,8 @@ struct GlmSched {
     int mtiles;   // 256-marker tiles
     int kblocks;  // taxa axis in units of kBlockK
   };
-  static constexpr uint64_t kHintA = ptx::kEvictFirst;  // genotypes: read once
-  static constexpr uint64_t kHintB = ptx::kEvictLast;   // digit planes of R: re-read by every tile
+  __device__ uint64_t hint_a() const { return ptx::kEvictFirst; }  // genotypes: read once
+  __device__ uint64_t hint_b() const { return ptx::kEvictLast; }   // digit planes of R: re-read by every tile
   Params p;
   int tile, stride;
   __device__ GlmSched(const Params& pp, int unit, int nunits, uint32_t) : p(pp), tile(unit), stride(nunits) {}
@@ -596,6 +598,14 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   sp.kblocks = static_cast<int>(g->ldn / kBlockK);
   sp.bn = BN;
   sp.nchunk = (T + TC - 1) / TC;
+  auto hint = [](const char* name, uint64_t dflt) {   // A/B switch for profiling: 0 normal, 1 evict_first, 2 evict_last
+    const char* ev = getenv(name);
+    if (!ev) return dflt;
+    const int v = atoi(ev);
+    return v == 1 ? ptx::kEvictFirst : (v == 2 ? ptx::kEvictLast : ptx::kEvictNormal);
+  };
+  sp.hint_a = hint("GAPIT_HINT_A", ptx::kEvictLast);
+  sp.hint_b = hint("GAPIT_HINT_B", ptx::kEvictNormal);
   int pair = (65792ll * g->n < 2147483647ll) ? 1 : 0;
   if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);  // A/B switch for profiling
   typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair, T, gc_tstride, part_tstride};

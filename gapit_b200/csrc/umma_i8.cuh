@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
           uint8_t* sa = smem + st * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           ptx::mbar_arrive_expect_tx(&full[st], Cfg::kStageBytes);
-          ptx::tma_load_2d(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, Sched::kHintA);
+          ptx::tma_load_2d(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, sch.hint_a());
           if (CL > 1)
             ptx::tma_load_2d_multicast(&map_b, &full[st], sb + crank * kBShare, kb * kBlockK,
-                                       job.b_row0 + static_cast<int>(crank) * (BN / CL), kClusterMask, Sched::kHintB);
+                                       job.b_row0 + static_cast<int>(crank) * (BN / CL), kClusterMask, sch.hint_b());
           else
-            ptx::tma_load_2d(&map_b, &full[st], sb, kb * kBlockK, job.b_row0, Sched::kHintB);
+            ptx::tma_load_2d(&map_b, &full[st], sb, kb * kBlockK, job.b_row0, sch.hint_b());
           if (++st == STAGES) {
             st = 0;
             ph ^= 1;
@@ -304,13 +304,13 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
 #pragma unroll
             for (int s = 0; s < MSUB; ++s)
               ptx::tma_load_2d_pair(&map_a, &full[st], sa + s * 128 * kBlockK, job.a_row0 + s * 128, kb * kBlockK,
-                                    Sched::kHintA);
+                                    sch.hint_a());
             ptx::tma_load_2d_pair(&map_b, &full[st], sb, job.b_row0 + static_cast<int>(crank) * (BN / 2), kb * kBlockK,
-                                  Sched::kHintB);
+                                  sch.hint_b());
           } else {
-            ptx::tma_load_2d_pair(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, Sched::kHintA);
+            ptx::tma_load_2d_pair(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, sch.hint_a());
             ptx::tma_load_2d_pair(&map_b, &full[st], sb, kb * kBlockK, job.b_row0 + static_cast<int>(crank) * (BN / 2),
-                                  Sched::kHintB);
+                                  sch.hint_b());
           }
           if (++st == STAGES) {
             st = 0;
