@@ -56,7 +56,7 @@ struct gapit_ctx {
 
 namespace gapit {
 enum WsSlot { WS_R = 0, WS_PROJ, WS_GCONST, WS_PART, WS_OUT, WS_RG, WS_RS, WS_RSCALE, WS_BAD, WS_CHUNK0, WS_CHUNK1,
-              WS_CS0, WS_CS1, WS_CQ0, WS_CQ1, WS_STAGE0, WS_STAGE1 };
+              WS_CS0, WS_CS1, WS_CQ0, WS_CQ1, WS_STAGE0, WS_STAGE1, WS_SYNC };
 // device workspace of at least `bytes` in `slot` (contents are not preserved when it grows)
 int ctx_ws(gapit_ctx* ctx, int slot, size_t bytes, void** out);
 template <class T>

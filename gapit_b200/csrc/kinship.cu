@@ -34,9 +34,23 @@ struct GramSched {
     int ntri;        // jobs per marker split = sum over row groups R of min(CL (R+1), T)
     int ksplit;      // splits of the marker axis
     int kblocks;     // marker axis in units of kBlockK
+    unsigned int* round_ctr;  // [rounds] zeroed before the launch, or nullptr (see ScanSched::align_round)
+    int round_wait;           // spin budget in clock cycles
   };
   __device__ uint64_t hint_a() const { return ptx::kEvictNormal; }
   __device__ uint64_t hint_b() const { return ptx::kEvictNormal; }
+  // All jobs have the same length; starting each unit's r-th job together keeps the tiles in flight on the same marker
+  // window, so the ~24 row panels they share are fetched from DRAM once.  Soft barrier, bounded wait (no hang).
+  __device__ void align_round() const {
+    if (!p.round_ctr) return;
+    const int job = next_job - stride;   // the job next() just handed out
+    const int r = job / stride;
+    const unsigned int expect = static_cast<unsigned int>(min(stride, p.ntri * p.ksplit - r * stride));
+    volatile unsigned int* c = p.round_ctr + r;
+    atomicAdd(p.round_ctr + r, 1u);
+    const long long t0 = clock64();
+    while (*c < expect && clock64() - t0 < p.round_wait) __nanosleep(64);
+  }
   static constexpr int kBandRows = 12;  // block-rows per band
   Params p;
   int next_job, stride, crank;
@@ -332,6 +346,14 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ld
   CUtensorMap map_a, map_b;
   GramEpi::Params ep{G_dev, ldg};
   const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
+  sp.round_ctr = nullptr;
+  sp.round_wait = 100000;
+  if (const char* ev = getenv("GAPIT_ROUND_WAIT")) sp.round_wait = atoi(ev);   // 0 switches the alignment off
+  if (mn && sp.round_wait > 0) {
+    const size_t rounds = size_t((sp.ntri * sp.ksplit + nunits - 1) / nunits) + 1;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_SYNC, rounds, &sp.round_ctr));
+    GAPIT_CUDA(cudaMemsetAsync(sp.round_ctr, 0, rounds * sizeof(unsigned int), ctx->stream));
+  }
   if (mn) {
     // one map for both operands: [m markers][ldn bytes of taxa], boxes of 128 markers x 128 taxa
     GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),

@@ -134,9 +134,25 @@ struct ScanSched {
     int nchunk;   // trait chunks: every chunk repeats the rotation of the tile with its own epilogue constants
     uint64_t hint_a;  // L2 eviction hints (default: marker tile evict_last -- it is re-read for every eigen tile;
     uint64_t hint_b;  //  eigen tiles evict_normal -- streamed, shared by the CTAs running together)
+    unsigned int* round_ctr;  // [rounds] zeroed before the launch, or nullptr: soft alignment of the units per round
+    int round_wait;           // spin budget (clock cycles) before a unit gives up waiting for the others
   };
   __device__ uint64_t hint_a() const { return p.hint_a; }
   __device__ uint64_t hint_b() const { return p.hint_b; }
+  // Every unit (CTA pair) starts round r = gid / stride (its r-th marker tile x eigen split) together with the others:
+  // the ~15 pairs that stream the same window of digit planes then stay in step, so the window is fetched from DRAM
+  // once and hit in L2 by the rest.  It is a soft barrier: arrival is counted, waiting is bounded by `round_wait`
+  // cycles, so a unit that cannot be co-resident (shared GPU) only costs its peers that bounded wait, never a hang.
+  __device__ void align_round() const {
+    if (!p.round_ctr) return;
+    const int total = p.mtiles * p.gsplit * p.nchunk;
+    const int r = gid / stride;
+    const unsigned int expect = static_cast<unsigned int>(min(stride, total - r * stride));
+    volatile unsigned int* c = p.round_ctr + r;
+    atomicAdd(p.round_ctr + r, 1u);
+    const long long t0 = clock64();
+    while (*c < expect && clock64() - t0 < p.round_wait) __nanosleep(64);
+  }
   Params p;
   int gid, stride, kq, kq_begin, kq_end, mt, ks, tc, crank;
   __device__ ScanSched(const Params& pp, int unit, int nunits, uint32_t cta_rank)
@@ -284,6 +300,7 @@ struct GlmSched {
   };
   __device__ uint64_t hint_a() const { return ptx::kEvictFirst; }  // genotypes: read once
   __device__ uint64_t hint_b() const { return ptx::kEvictLast; }   // digit planes of R: re-read by every tile
+  __device__ void align_round() const {}
   Params p;
   int tile, stride;
   __device__ GlmSched(const Params& pp, int unit, int nunits, uint32_t) : p(pp), tile(unit), stride(nunits) {}
@@ -606,12 +623,21 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   };
   sp.hint_a = hint("GAPIT_HINT_A", ptx::kEvictLast);
   sp.hint_b = hint("GAPIT_HINT_B", ptx::kEvictNormal);
+  sp.round_ctr = nullptr;
+  sp.round_wait = 100000;   // ~50 us
+  if (const char* ev = getenv("GAPIT_ROUND_WAIT")) sp.round_wait = atoi(ev);   // 0 switches the alignment off
   int pair = (65792ll * g->n < 2147483647ll) ? 1 : 0;
   if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);  // A/B switch for profiling
   typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair, T, gc_tstride, part_tstride};
   const int nunits = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit * sp.nchunk);
   constexpr int EPIW = (TC == 1) ? 2 : 1;
   constexpr int kThreadsEpi = 128 + 2 * 128 * EPIW;
+  if (md.pair && sp.round_wait > 0) {
+    const int nun = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit * sp.nchunk);
+    const size_t rounds = size_t((sp.mtiles * sp.gsplit * sp.nchunk + nun - 1) / nun) + 1;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_SYNC, rounds, &sp.round_ctr));
+    GAPIT_CUDA(cudaMemsetAsync(sp.round_ctr, 0, rounds * sizeof(unsigned int), ctx->stream));
+  }
   if (md.pair) {
     using PCfg = UmmaPairCfg<2, BN, 4>;
     auto kern = umma_i8_pair_kernel<2, BN, 4, EPIW, ScanSched, Epi, 1, 1>;

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
       Job job;
       uint32_t st = 0, ph = 0;
       while (sch.next(job)) {
+        if (leader && job.group_first) sch.align_round();   // keep the pairs that share an operand window in step
         for (int kb = job.kb_begin; kb < job.kb_end; ++kb) {
           ptx::mbar_wait(&empty[st], ph ^ 1);
           uint8_t* sa = smem + st * Cfg::kStageBytes;
