@@ -450,6 +450,14 @@ def _host_array(shape, pinned):
     return np.empty(shape, dtype=np.float64)
 
 
+def alloc_scan_out(T, m, pinned=True):
+    """Result arrays of a scan of m markers x T traits, for the ``out=`` argument of :func:`p3d_scan`: page-locking
+    gigabytes of host memory takes seconds, so callers that scan block after block allocate once."""
+    arrs = {k: _host_array((T, m), pinned) for k in ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")}
+    arrs["maf"] = _host_array((m,), pinned)
+    return arrs
+
+
 def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None, pinned=False, out=None):
     """Scan all markers of ``geno`` for T traits.  Returns (dict of (T, m) arrays, list of per-trait base dicts).
     ``pinned=True`` puts the result arrays in page-locked host memory (needs torch) so the D2H copy runs at

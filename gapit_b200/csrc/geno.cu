@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(256) convert_kernel(const T* __restrict__ src,
     const T* s = src + k * ld;
     uint32_t* d = reinterpret_cast<uint32_t*>(dst + k * ldn);
     for (int64_t w = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; w < words; w += int64_t(gridDim.x) * blockDim.x) {
-      // classification on the bit patterns (no fp64 pipe): code 0/1/2, 3 = NA, 4 = not a dosage
+      // classification: code 0/1/2, 3 = NA, 4 = not a dosage
       uint32_t code[4] = {0u, 0u, 0u, 0u};
       const int64_t i0 = w * 4;
       if (sizeof(T) == 4) {
@@ -45,12 +45,10 @@ __global__ void __launch_bounds__(256) convert_kernel(const T* __restrict__ src,
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (i0 + c < n) {
-            const unsigned long long bits = __ldg(reinterpret_cast<const unsigned long long*>(s) + i0 + c);
-            const unsigned long long mag = bits & 0x7FFFFFFFFFFFFFFFull;
-            code[c] = mag == 0ull ? 0u
-                      : bits == 0x3FF0000000000000ull ? 1u
-                      : bits == 0x4000000000000000ull ? 2u
-                      : mag > 0x7FF0000000000000ull ? 3u : 4u;   // NaN / NA_real_ -> NA (GAPIT.EMMAxP3D.R:20-24)
+            const double v = static_cast<double>(s[i0 + c]);
+            const int q = __double2int_rn(v);
+            code[c] = (v != v) ? 3u                                                   // NaN / NA_real_ -> NA
+                      : (static_cast<double>(q) == v && static_cast<unsigned>(q) <= 2u) ? static_cast<uint32_t>(q) : 4u;
           }
         }
       }

@@ -19,6 +19,7 @@
 //   K4  finalize         per marker: Schur complement of [X0t xst]'[X0t xst] (:736-748), beta (:772),
 //                        t (:936-937), p = 2 pt(|t|, df) (:939), logLM and R^2 (:955-967).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <vector>
@@ -976,7 +977,14 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
   if (!g) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL genotype handle");
   GAPIT_CHECK(check_out(out));
   ScanPlan plan;
+  const bool trace = getenv("GAPIT_TRACE") != nullptr;   // host-side phase times on stderr
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(now() - t0).count();
+  };
+  auto t_start = now();
   GAPIT_CHECK(scan_prepare(ctx, g->n, g->ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
+  if (trace) fprintf(stderr, "[gapit] scan_prepare %.2f ms\n", ms_since(t_start));
   const int64_t m = g->m;
   double* o = nullptr;
   GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(T) * 7 * m, &o));
@@ -986,7 +994,9 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
   cudaEventRecord(ctx->ev1, ctx->stream);
   for (int t = 0; t < T; ++t) GAPIT_CHECK(fetch_outputs(ctx, o + size_t(t) * 7 * m, m, m, t, out));
   cudaEventRecord(ctx->ev2, ctx->stream);
+  if (trace) fprintf(stderr, "[gapit] launches enqueued at %.2f ms\n", ms_since(t_start));
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (trace) fprintf(stderr, "[gapit] scan done at %.2f ms\n", ms_since(t_start));
   float ms = 0.f;
   ctx->stats = gapit_stats{};
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev3);
