@@ -76,6 +76,8 @@ SIGNATURES = {
     "gapit_reml": (C.c_int, [_P, _P, _I64, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(RemlOut)]),
     "gapit_reml_eigL": (C.c_int, [_P, _P, _P, _I64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                   C.POINTER(RemlOut)]),
+    "gapit_reml_eigL_multi": (C.c_int, [_P, _P, _P, _I64, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+                                        C.POINTER(RemlOut), _P]),
     "gapit_p3d_scan": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
                                  C.POINTER(ScanOut), C.POINTER(ScanBase)]),
     "gapit_eigsys_upload": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),

@@ -397,6 +397,19 @@ def reml_from_projections(values, Vty, VtX, ngrids=100, llim=-10, ulim=10, esp=1
     return {"REML": out.REML, "delta": out.delta, "ve": out.ve, "vg": out.vg}
 
 
+def reml_from_projections_multi(values, VtY, VtX, ngrids=100, llim=-10, ulim=10, esp=1e-10):
+    """T traits at once (VtY: n x T): list of {"REML", "delta", "ve", "vg"}; the searches run on the host's threads."""
+    lam = np.ascontiguousarray(values, dtype=np.float64)
+    n = lam.shape[0]
+    VtY = np.asfortranarray(np.asarray(VtY, dtype=np.float64).reshape(n, -1))
+    VtX = np.asfortranarray(np.asarray(VtX, dtype=np.float64).reshape(n, -1))
+    T = VtY.shape[1]
+    outs = (_lib.RemlOut * T)()
+    check(_lib.load().gapit_reml_eigL_multi(_ptr(lam), _ptr(VtY), _ptr(VtX), n, VtX.shape[1], T, int(ngrids), float(llim),
+                                            float(ulim), float(esp), outs, None))
+    return [{"REML": o.REML, "delta": o.delta, "ve": o.ve, "vg": o.vg} for o in outs]
+
+
 def emma_eigen_R_wo_Z(K, X, ctx=None):
     ctx = ctx or default_context()
     K = np.asfortranarray(K, dtype=np.float64)

@@ -4,6 +4,8 @@
 // netlib zeroin.c: tol = DBL_EPSILON^0.25, maxiter = 1000, end-point values pre-evaluated).
 #include <cfloat>
 #include <cmath>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -279,4 +281,43 @@ extern "C" int gapit_reml_eigL(const double* lambda, const double* Vty, const do
   for (int a = 0; a < q; ++a) ld += 2.0 * std::log(XX[a * q + a]);
   RemlFnL f{lambda, Vty, VtX, n, q, ld};
   return reml_search(f, ngrids, llim, ulim, esp, out);
+}
+
+// T traits that share X and the spectrum (BASELINE configs[4]): the searches are independent, so they run on the host's
+// threads.  VtY: n x T column-major; out: T entries.  A failing trait sets its status in rc_out (may be NULL) and the
+// call returns the first failure.
+extern "C" int gapit_reml_eigL_multi(const double* lambda, const double* VtY, const double* VtX, int64_t n, int q, int T,
+                                     int ngrids, double llim, double ulim, double esp, gapit_reml_out* out, int* rc_out) {
+  if (!lambda || !VtY || !VtX || !out || T < 1 || q < 1 || q > GAPIT_MAX_Q0 || n <= q || ngrids < 2)
+    return fail(GAPIT_ERR_ARG, "gapit_reml_eigL_multi: bad argument");
+  std::vector<double> XX(q * q, 0.0);
+  for (int a = 0; a < q; ++a)
+    for (int c = 0; c <= a; ++c) {
+      double s = 0.0;
+      for (int64_t i = 0; i < n; ++i) s += VtX[a * n + i] * VtX[c * n + i];
+      XX[a * q + c] = XX[c * q + a] = s;
+    }
+  if (!RemlFnL::chol(q, XX)) return fail(GAPIT_ERR_NUMERIC, "gapit_reml_eigL_multi: X'X is singular");
+  double ld = 0.0;
+  for (int a = 0; a < q; ++a) ld += 2.0 * std::log(XX[a * q + a]);
+  std::vector<int> rcs(T, GAPIT_OK);
+  const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  const int nthreads = static_cast<int>(std::min<unsigned>(hw, static_cast<unsigned>(T)));
+  std::atomic<int> next{0};
+  auto work = [&] {
+    for (int t = next.fetch_add(1); t < T; t = next.fetch_add(1)) {
+      RemlFnL f{lambda, VtY + size_t(t) * n, VtX, n, q, ld};
+      rcs[t] = reml_search(f, ngrids, llim, ulim, esp, &out[t]);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int i = 1; i < nthreads; ++i) pool.emplace_back(work);
+  work();
+  for (auto& th : pool) th.join();
+  int first = GAPIT_OK;
+  for (int t = 0; t < T; ++t) {
+    if (rc_out) rc_out[t] = rcs[t];
+    if (first == GAPIT_OK && rcs[t] != GAPIT_OK) first = rcs[t];
+  }
+  return first;
 }

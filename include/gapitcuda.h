@@ -156,6 +156,10 @@ int gapit_reml(const double* lambda, const double* etas, int64_t nq, int ngrids,
  * delta as gapit_reml on eig.R, so the second O(n^3) eigendecomposition (emma.txt:82-89) can be skipped. */
 int gapit_reml_eigL(const double* lambda, const double* Vty, const double* VtX, int64_t n, int q, int ngrids,
                     double llim, double ulim, double esp, gapit_reml_out* out);
+/* T traits sharing X and the spectrum (VtY: n x T column-major; out: T entries; rc_out: per-trait status or NULL):
+ * the independent searches run on the host's threads. */
+int gapit_reml_eigL_multi(const double* lambda, const double* VtY, const double* VtX, int64_t n, int q, int T,
+                          int ngrids, double llim, double ulim, double esp, gapit_reml_out* out, int* rc_out);
 
 /* ---- P3D / EMMAx marker scan (GAPIT.EMMAxP3D.R:397-979) -------------------
  * Inputs: eigen-system of K (vectors n x n column-major, values), covariates

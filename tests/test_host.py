@@ -80,6 +80,15 @@ def test_reml_from_eigL_alone_matches_the_eigR_route():
         got = gb.GAPIT_emma_REMLE(Y, X0, K, eig_L=go.emma_eigen_L_wo_Z(K))
         for k in ("REML", "delta", "ve", "vg"):
             assert got[k] == pytest.approx(ref[k], rel=1e-10), (k, seed)
+    # many traits on the host's threads: identical to the one-trait calls
+    Yt = synth.make_phenotypes(G, ntraits=7, seed=5)
+    eL = go.emma_eigen_L_wo_Z(K)
+    V = eL["vectors"]
+    P = V.T @ Yt
+    multi = gb.reml_from_projections_multi(eL["values"], P, V.T @ X0)
+    for t in range(7):
+        one = gb.reml_from_projections(eL["values"], P[:, t], V.T @ X0)
+        assert multi[t] == one
     # collinear covariates: X'X singular is an error, not a crash
     lib = _lib.load()
     lam = np.linspace(2.0, 0.0, 10)

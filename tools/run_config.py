@@ -174,10 +174,8 @@ def main():
     if rank == 0:
         t1 = time.perf_counter()
         proj = es.project(np.column_stack([X0, Y]))          # V'[X0 | Y] on the device
-        dl, vg = np.empty(T), np.empty(T)
-        for t in range(T):
-            r = gb.reml_from_projections(es.values, proj[:, 1 + t], proj[:, :1])
-            dl[t], vg[t] = r["delta"], r["vg"]
+        rs = gb.reml_from_projections_multi(es.values, proj[:, 1:], proj[:, :1])   # all traits, host threads
+        dl, vg = np.array([r["delta"] for r in rs]), np.array([r["vg"] for r in rs])
         T_["reml_all_traits_s"] = time.perf_counter() - t1
         dv_t[0].copy_(torch.from_numpy(dl))
         dv_t[1].copy_(torch.from_numpy(vg))
