@@ -3,6 +3,8 @@
 // S (K+I) S without the reference's two n^3 GEMMs and puts the spectrum in R's order.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "common.cuh"
@@ -69,30 +71,51 @@ __global__ void swap_cols_kernel(double* __restrict__ A, int64_t n) {
   }
 }
 
-// in-place syevd on a device matrix; eigenvalues (ascending) into w_dev
+// in-place syevd on a device matrix; eigenvalues (ascending) into w_dev.  The 64-bit API (cusolverDnXsyevd) has no
+// 32-bit workspace limit; GAPIT_SYEVD=legacy selects the int-indexed cusolverDnDsyevd (n <= 46,000) for A/B timing.
 int syevd_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* w_dev) {
   GAPIT_CHECK(ensure_solver(ctx));
-  if (n > 46000) return fail(GAPIT_ERR_ARG, "eigh: n above the 32-bit cuSOLVER workspace limit");
-  int lwork = 0;
-  if (cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, int(n), A_dev, int(n),
-                                  w_dev, &lwork) != CUSOLVER_STATUS_SUCCESS)
-    return fail(GAPIT_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed");
-  double* work = nullptr;
+  const char* ev = getenv("GAPIT_SYEVD");
+  const bool legacy = ev && std::string(ev) == "legacy";
   int* info = nullptr;
-  GAPIT_CUDA(cudaMalloc(&work, size_t(lwork) * 8));
-  cudaError_t e = cudaMalloc(&info, 4);
-  if (e != cudaSuccess) {
-    cudaFree(work);
-    return fail(GAPIT_ERR_CUDA, "eigh: cudaMalloc");
+  void* work = nullptr;
+  std::vector<char> hwork;
+  cusolverStatus_t st;
+  cusolverDnParams_t params = nullptr;
+  GAPIT_CUDA(cudaMalloc(&info, 4));
+  if (legacy) {
+    if (n > 46000) {
+      cudaFree(info);
+      return fail(GAPIT_ERR_ARG, "eigh: n above the 32-bit cuSOLVER workspace limit");
+    }
+    int lwork = 0;
+    st = cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, int(n), A_dev, int(n),
+                                     w_dev, &lwork);
+    if (st == CUSOLVER_STATUS_SUCCESS && cudaMalloc(&work, size_t(lwork) * 8) != cudaSuccess) st = CUSOLVER_STATUS_ALLOC_FAILED;
+    if (st == CUSOLVER_STATUS_SUCCESS)
+      st = cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, int(n), A_dev, int(n), w_dev,
+                            static_cast<double*>(work), lwork, info);
+  } else {
+    size_t dbytes = 0, hbytes = 0;
+    st = cusolverDnCreateParams(&params);
+    if (st == CUSOLVER_STATUS_SUCCESS)
+      st = cusolverDnXsyevd_bufferSize(ctx->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F,
+                                       A_dev, n, CUDA_R_64F, w_dev, CUDA_R_64F, &dbytes, &hbytes);
+    if (st == CUSOLVER_STATUS_SUCCESS && cudaMalloc(&work, std::max<size_t>(dbytes, 16)) != cudaSuccess)
+      st = CUSOLVER_STATUS_ALLOC_FAILED;
+    if (st == CUSOLVER_STATUS_SUCCESS) {
+      hwork.resize(std::max<size_t>(hbytes, 16));
+      st = cusolverDnXsyevd(ctx->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A_dev, n,
+                            CUDA_R_64F, w_dev, CUDA_R_64F, work, dbytes, hwork.data(), hbytes, info);
+    }
   }
-  cusolverStatus_t st = cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, int(n), A_dev,
-                                         int(n), w_dev, work, lwork, info);
   int hinfo = -1;
-  e = cudaMemcpyAsync(&hinfo, info, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaMemcpyAsync(&hinfo, info, 4, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   cudaFree(work);
   cudaFree(info);
-  if (st != CUSOLVER_STATUS_SUCCESS) return fail(GAPIT_ERR_CUDA, "cusolverDnDsyevd failed, status " + std::to_string(int(st)));
+  if (params) cusolverDnDestroyParams(params);
+  if (st != CUSOLVER_STATUS_SUCCESS) return fail(GAPIT_ERR_CUDA, "cuSOLVER syevd failed, status " + std::to_string(int(st)));
   if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("eigh: ") + cudaGetErrorString(e));
   if (hinfo != 0) return fail(GAPIT_ERR_NUMERIC, "syevd did not converge, info " + std::to_string(hinfo));
   return GAPIT_OK;
