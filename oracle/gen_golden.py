@@ -67,7 +67,49 @@ def make_case(name, n, m, npc, seed, store_inputs):
     print(name, "->", path, os.path.getsize(path) // 1024, "KiB; delta", reml["delta"])
 
 
+def make_ingest_case(name, n, m, seed):
+    """HapMap text -> dosages (GAPIT.HapMap / GAPIT.Numericalization), ZHANG kinship and prcomp on the result."""
+    G = synth.make_genotypes(n, m, seed=seed, threads=1)
+    out = {"n": n, "m": m, "seed": seed}
+    for bit in (1, 2):
+        text = synth.make_hapmap_text(G, bit=bit, missing=0.04, seed=seed, crlf=(bit == 1))
+        rows = synth.hapmap_rows(text)
+        out[f"text{bit}"] = np.frombuffer(text, dtype=np.uint8)
+        for impute in ("None", "Middle", "Minor", "Major"):
+            for maz in (False, True):
+                gd = go.hapmap(rows, SNP_impute=impute, Major_allele_zero=maz)["GD"]
+                # independent check of the reference's rules: no value outside {0,1,2,NA}; NA only without a rule
+                assert np.all(np.isnan(gd) | np.isin(gd, (0.0, 1.0, 2.0)))
+                assert impute == "None" or not np.isnan(gd).any()
+                out[f"GD{bit}_{impute}_{int(maz)}"] = np.where(np.isnan(gd), -1, gd).astype(np.int8)
+        out[f"GD{bit}_Dom"] = go.hapmap(rows, SNP_effect="Dom", SNP_impute="Middle")["GD"].astype(np.int8)
+    X = out["GD2_Major_0"].astype(np.float64)
+    Kz = go.kinship_zhang(X)
+    # independent derivation of the ZHANG raw matrix: centred cross-product from exact integers
+    keep = (X.sum(0) > 0) & (X.sum(0) < 2 * n)
+    xi = X[:, keep].astype(np.int64)
+    c = xi.sum(0)
+    num = n * n * (xi @ xi.T) - n * ((xi @ c)[:, None] + (xi @ c)[None, :]) + int((c * c).sum())
+    raw = num / float(n * n)
+    top = 1.0 + (1.0 - ((xi == 1).sum(1) / (2.0 * xi.shape[1])).min())
+    chk = top * (raw - raw.min()) / (np.diag(raw).max() - raw.min())
+    diag = np.eye(n, dtype=bool)
+    Dmin = chk[diag].min()
+    if Dmin < 1.0:
+        chk[diag] = (chk[diag] - Dmin + 1.0) / ((top + 1.0 - Dmin) * .5)
+        chk[~diag] = chk[~diag] * (1.0 / Dmin)
+    if chk[~diag].max() > top:
+        chk[~diag] = chk[~diag] * (top / chk[~diag].max())
+    assert np.abs(chk - Kz).max() <= 1e-11 * np.abs(Kz).max()
+    x, ev = go.prcomp(X)
+    out.update({"zhang": Kz, "pca_ev": ev, "pca_x_abs": np.abs(x[:, :4])})
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def main():
+    make_ingest_case("ingest_n37_m90", 37, 90, 77)
     # tiny case with every input stored (self-contained known-answer vector)
     make_case("tiny_n48_m160_q3", 48, 160, 2, 101, store_inputs=True)
     # BASELINE configs[0] shape; inputs are re-generated from the seed (synth is deterministic)

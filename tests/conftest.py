@@ -25,6 +25,11 @@ def c1_golden():
     return dict(np.load(os.path.join(GOLDEN, "c1_n281_m3093_q1.npz")))
 
 
+@pytest.fixture(scope="session")
+def ingest_golden():
+    return dict(np.load(os.path.join(GOLDEN, "ingest_n37_m90.npz")))
+
+
 def c1_inputs(g):
     """Re-generate the inputs of the C1 golden case exactly as oracle/gen_golden.py did."""
     from gapit_b200 import synth

@@ -155,6 +155,26 @@ def test_hapmap_numericalization_matches_oracle(gpu_ctx, bit, maz):
             assert got["GT"] == ref["GT"] and got["GI"] == ref["GI"]
 
 
+def test_ingest_golden_fixture(gpu_ctx, ingest_golden):
+    """The committed known-answer vectors of the widened rows: text -> dosages byte for byte, ZHANG within 1e-11, PCA
+    variances within 1e-10 and leading scores up to sign."""
+    g = ingest_golden
+    for bit in (1, 2):
+        text = g[f"text{bit}"].tobytes()
+        for impute in ("None", "Middle", "Minor", "Major"):
+            for maz in (False, True):
+                got = gb().GAPIT_HapMap(text, SNP_impute=impute, Major_allele_zero=maz, ctx=gpu_ctx)["GD"]
+                assert np.array_equal(got, g[f"GD{bit}_{impute}_{int(maz)}"]), (bit, impute, maz)
+        dom = gb().GAPIT_HapMap(text, SNP_effect="Dom", SNP_impute="Middle", ctx=gpu_ctx)["GD"]
+        assert np.array_equal(dom, g[f"GD{bit}_Dom"])
+    X = g["GD2_Major_0"]
+    Kz = gb().GAPIT_kinship_ZHANG(X, ctx=gpu_ctx, verbose=False)
+    assert np.abs(Kz - g["zhang"]).max() <= 1e-11 * np.abs(g["zhang"]).max()
+    pc = gb().GAPIT_PCA(X, PC_number=4, ctx=gpu_ctx, verbose=False)
+    assert np.abs(pc["EV"] - g["pca_ev"]).max() <= 1e-10 * g["pca_ev"][0]
+    assert np.abs(np.abs(pc["PCs"]) - g["pca_x_abs"]).max() <= 1e-8 * np.abs(g["pca_x_abs"]).max()
+
+
 @pytest.mark.parametrize("n,m,bit", [(4100, 37, 2), (16500, 21, 2), (16500, 21, 1), (3, 9, 2)])
 def test_hapmap_row_widths(gpu_ctx, n, m, bit):
     """CTA width and staging depend on the row width: one-warp CTAs (n <= 4096), 128 / 256 threads, and rows too wide

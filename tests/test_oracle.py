@@ -228,3 +228,18 @@ def test_zhang_and_prcomp_restatements():
     x, ev = go.prcomp(X)
     Xc = X - X.mean(0)
     assert np.allclose(x @ x.T, Xc @ Xc.T, atol=1e-8) and np.isclose(ev.sum(), Xc.var(0, ddof=1).sum())
+
+
+def test_golden_ingest_reproduces(ingest_golden):
+    """tests/golden/ingest_n37_m90.npz (oracle/gen_golden.py): HapMap text -> dosages for every impute rule and both
+    genotype widths, ZHANG kinship and prcomp variances of the result."""
+    g = ingest_golden
+    for bit in (1, 2):
+        rows = synth.hapmap_rows(g[f"text{bit}"].tobytes())
+        for impute in ("None", "Middle", "Minor", "Major"):
+            for maz in (False, True):
+                gd = go.hapmap(rows, SNP_impute=impute, Major_allele_zero=maz)["GD"]
+                assert np.array_equal(np.where(np.isnan(gd), -1, gd).astype(np.int8), g[f"GD{bit}_{impute}_{int(maz)}"])
+    X = g["GD2_Major_0"].astype(np.float64)
+    assert np.array_equal(go.kinship_zhang(X), g["zhang"])
+    assert np.allclose(go.prcomp(X)[1], g["pca_ev"], rtol=1e-12, atol=1e-12)
