@@ -167,6 +167,27 @@ def test_hapmap_index_host_code():
                                   0, None) == _lib_err("GAPIT_ERR_DATA")
 
 
+def test_r_shim_type_checks_against_the_header():
+    """r/gapitcuda_R.c cannot be built here (no R), but it must stay in step with include/gapitcuda.h: compile it for
+    syntax and types against a minimal stand-in for R's headers (tests/rstub)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "rstub"),
+                        "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "r", "gapitcuda_R.c")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # every .Call target the R replacement bodies use is defined by the shim
+    import re
+    shim = open(os.path.join(ROOT, "r", "gapitcuda_R.c")).read()
+    defined = set(re.findall(r"^SEXP (gapit_R_\w+)\(", shim, flags=re.M))
+    for fn in os.listdir(os.path.join(ROOT, "r")):
+        if fn.endswith(".R"):
+            for call in re.findall(r'\.Call\("(gapit_R_\w+)"', open(os.path.join(ROOT, "r", fn)).read()):
+                assert call in defined, (fn, call)
+
+
 def test_marker_shards_cover_in_order():
     for m, w in [(10, 3), (500000, 8), (7, 8), (3093, 2)]:
         parts = [shard.marker_shard(m, r, w) for r in range(w)]
