@@ -112,13 +112,26 @@ struct GramEpi {
   struct Params {
     int32_t* G;   // [ldg][ldg] row-major, zero-initialised
     int64_t ldg;
+    // Fused exchange over NVLink (sharded kinship, one process per GPU), all buffers at the same symmetric layout:
+    //   mode 1: reduce-scatter -- the tile of block-row I is added into the buffer of the rank that owns I (peer RED)
+    //   mode 2: all-reduce in the switch -- every add goes to the NVLS multicast address (multimem.red), so each
+    //           rank's buffer receives the sum of all ranks
+    int mode;
+    int world;
+    int tiles_side;
+    int32_t* peers[8];
+    int32_t* mc;
   };
   static constexpr int kSmemBytes = 0;
   Params p;
   __device__ GramEpi(const Params& pp, uint8_t*) : p(pp) {}
   __device__ void prepare(const Job&, int, int) {}
   __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int /*half*/, int /*nhalf*/) {
-    int32_t* dst = p.G + (int64_t(job.a_row0) + sub * 128 + row) * p.ldg + job.b_row0;
+    const int64_t off = (int64_t(job.a_row0) + sub * 128 + row) * p.ldg + job.b_row0;
+    int32_t* base = p.G;
+    if (p.mode == 1) base = p.peers[min(p.world - 1, (job.tag0 * p.world) / p.tiles_side)];
+    if (p.mode == 2) base = p.mc;
+    int32_t* dst = base + off;
 #pragma unroll 1
     for (int c0 = 0; c0 < 256; c0 += 16) {
       uint32_t r[16];
@@ -127,7 +140,12 @@ struct GramEpi {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int v = static_cast<int>(r[i]);
-        if (v != 0) atomicAdd(dst + c0 + i, v);
+        if (v != 0) {
+          if (p.mode == 2)
+            asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(dst + c0 + i), "r"(r[i]) : "memory");
+          else
+            atomicAdd(dst + c0 + i, v);
+        }
       }
     }
   }
@@ -328,7 +346,14 @@ static bool gram_mn_major(const gapit_geno* g) {
   return true;
 }
 
-static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ldg) {
+struct GramExchange {   // fused NVLink exchange of the sharded kinship (mode 0: none)
+  int mode = 0;
+  int world = 1;
+  int32_t* peers[8] = {};
+  int32_t* mc = nullptr;
+};
+
+static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ldg, const GramExchange& ex = GramExchange()) {
   const bool mn = gram_mn_major(g);
   if (!mn) GAPIT_CHECK(geno_build_taxa_major(g));
   GramSched::Params sp;
@@ -344,7 +369,15 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ld
   sp.kblocks = static_cast<int>(round_up(g->m, 128) / kBlockK);
   sp.ksplit = choose_ksplit(sp.ntri * cl, sp.kblocks, ctx->sm_count);
   CUtensorMap map_a, map_b;
-  GramEpi::Params ep{G_dev, ldg};
+  GramEpi::Params ep{};
+  ep.G = G_dev;
+  ep.ldg = ldg;
+  ep.mode = ex.mode;
+  ep.world = ex.world;
+  ep.tiles_side = sp.tiles_side;
+  for (int r = 0; r < 8; ++r) ep.peers[r] = ex.peers[r];
+  ep.mc = ex.mc;
+  if (ex.mode != 0 && !mn) return fail(GAPIT_ERR_ARG, "fused kinship exchange needs the pair kernel (n > 256)");
   const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
   sp.round_ctr = nullptr;
   sp.round_wait = 100000;
@@ -417,6 +450,59 @@ extern "C" int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats.kernel_ms = ms;
   cudaEventDestroy(evt);
+  return GAPIT_OK;
+}
+
+// Sharded kinship with the exchange fused into the Gram kernel's epilogue (see GramEpi): every rank calls this with
+// the same symmetric buffers (peers[r] = rank r's buffer, mc = their NVLS multicast address or NULL), all zeroed and
+// fenced by a barrier BEFORE anyone starts; after the kernels of all ranks have completed (stream sync + barrier)
+//   mode 1: rank r holds the fully summed block-rows it owns, gapit_gram_owned_rows() (lower triangle);
+//   mode 2: every rank holds the full sum (lower triangle), as after an all-reduce.
+extern "C" int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int32_t* mc, int world,
+                                         int rank, int mode, int64_t* sums_dev) {
+  if (!ctx || !g || !peers || !sums_dev || world < 1 || world > 8 || rank < 0 || rank >= world || mode < 1 || mode > 2 ||
+      (mode == 2 && !mc))
+    return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram_fused: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  const int64_t ldg = gapit_gram_ld(g->n);
+  GramExchange ex;
+  ex.mode = mode;
+  ex.world = world;
+  ex.mc = mc;
+  for (int r = 0; r < world; ++r) {
+    if (!peers[r]) return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram_fused: NULL peer buffer");
+    ex.peers[r] = peers[r];
+  }
+  GAPIT_CUDA(cudaMemsetAsync(sums_dev, 0, 3 * 8, ctx->stream));
+  colsum_reduce_kernel<<<std::min<int64_t>(1024, (g->m + 255) / 256), 256, 0, ctx->stream>>>(
+      g->colsum, g->m, 2 * g->n, reinterpret_cast<unsigned long long*>(sums_dev));
+  GAPIT_CUDA(cudaGetLastError());
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  GAPIT_CHECK(launch_gram(ctx, g, peers[rank], ldg, ex));
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  ctx->stats = gapit_stats{};
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats.kernel_ms = ms;
+  return GAPIT_OK;
+}
+
+// block-rows [lo, hi) (units of 256 taxa rows) whose sums land on `rank` in mode 1
+extern "C" int gapit_gram_owned_rows(int64_t n, int world, int rank, int64_t* row_lo, int64_t* row_hi) {
+  if (n <= 0 || world < 1 || rank < 0 || rank >= world || !row_lo || !row_hi) return fail(GAPIT_ERR_ARG, "gapit_gram_owned_rows");
+  const int64_t T = (n + 255) / 256;
+  int64_t lo = T, hi = 0;
+  for (int64_t I = 0; I < T; ++I) {
+    const int64_t o = std::min<int64_t>(world - 1, (I * world) / T);
+    if (o == rank) {
+      lo = std::min(lo, I);
+      hi = std::max(hi, I + 1);
+    }
+  }
+  if (hi <= lo) lo = hi = 0;
+  *row_lo = lo * 256;
+  *row_hi = std::min<int64_t>(hi * 256, gapit_gram_ld(n));
   return GAPIT_OK;
 }
 

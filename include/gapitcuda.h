@@ -121,6 +121,18 @@ int64_t gapit_gram_ld(int64_t n);
 int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t* sums_dev);
 int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, const int64_t* sums_dev, double* K_dev_out,
                           double* K_host_out, int32_t* G_host_out);
+/* The same partial cross-product with the exchange FUSED into the kernel's epilogue over NVLink peer memory, instead of
+ * a collective after it.  peers[r] = rank r's Gram buffer (gapit_gram_ld(n)^2 int32 each, same layout everywhere,
+ * peer-mapped into this process: e.g. torch symmetric memory or cudaIpc handles), mc = the NVLS multicast address of
+ * the same buffers (mode 2 only).  Protocol: every rank zeroes its buffer, all ranks pass a barrier, every rank calls
+ * this, all ranks synchronise their streams and pass a barrier again.  Then
+ *   mode 1 (reduce-scatter by peer RED.ADD): rank r holds the complete sums of the block-rows
+ *          gapit_gram_owned_rows(n, world, r) (lower triangle) -- copy them to the finishing rank;
+ *   mode 2 (all-reduce in the switch by multimem.red): every rank holds the complete lower triangle.
+ * gapit_vanraden_finish then runs on the complete buffer.  Integer adds: bit-identical to the NCCL route. */
+int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int32_t* mc, int world, int rank,
+                              int mode, int64_t* sums_dev);
+int gapit_gram_owned_rows(int64_t n, int world, int rank, int64_t* row_lo, int64_t* row_hi);
 
 /* ---- ZHANG kinship and PCA covariates from the same integer cross-product ----------------------------
  * gapit_zhang: GAPIT.kinship.ZHANG(snps) (GAPIT.kinship.ZHANG.R:1-66): centred cross-product (:21-26), range
