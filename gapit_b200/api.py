@@ -292,6 +292,53 @@ def GAPIT_HapMap(G, SNP_effect="Add", SNP_impute="Middle", heading=True, Create_
     return out
 
 
+def p3d_scan_hapmap(G, X0, Y, eigsys=None, delta=None, vg=None, glm=False, file_fragment=65536, SNP_effect="Add",
+                    SNP_impute="Middle", Major_allele_zero=False, heading=True, ctx=None):
+    """The by-file branch of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:262-330) on a HapMap file: fragments of
+    ``file_fragment`` markers (GAPIT.Fragment.R:14-77) are numericalized on the GPU straight from the text
+    (GAPIT.HapMap.R:34-38) and scanned with the shared eigen-system and variance components; nothing but the file text
+    crosses PCIe.  ``G``: bytes of the table or a path.  Taxa must be in the order of ``Y`` (the reference's
+    ``GTindex`` re-ordering is the caller's).  Returns (arrays (T, m), per-trait bases, GT, GI)."""
+    ctx = ctx or default_context()
+    if isinstance(G, str):
+        with open(G, "rb") as f:
+            G = f.read()
+    lib = ctx.lib
+    buf = np.frombuffer(G, dtype=np.uint8)
+    n, m, bit, hoff = C.c_int64(), C.c_int64(), C.c_int(), C.c_int64()
+    check(lib.gapit_hapmap_index(_ptr(buf), buf.shape[0], 1 if heading else 0, C.byref(n), C.byref(m), C.byref(bit), None,
+                                 0, C.byref(hoff)))
+    off = np.empty(m.value, dtype=np.int64)
+    check(lib.gapit_hapmap_index(_ptr(buf), buf.shape[0], 1 if heading else 0, C.byref(n), C.byref(m), C.byref(bit),
+                                 _ptr(off), m.value, C.byref(hoff)))
+    n, m, bit = n.value, m.value, bit.value
+    Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n, -1))
+    T = Y.shape[1]
+    names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
+    arrs = {k: np.empty((T, m)) for k in names}
+    arrs["maf"] = np.empty(m)
+    bases = None
+    for k0 in range(0, m, int(file_fragment)):                            # one fragment = one GAPIT.Fragment call
+        k1 = min(m, k0 + int(file_fragment))
+        _, geno = _numericalize(ctx, G, off[k0:k1], bit, bit + 1, n, k1 - k0, SNP_effect, SNP_impute, Major_allele_zero,
+                                False, True)
+        part, bases = p3d_scan(geno, X0, Y, eigsys=eigsys, delta=delta, vg=vg, glm=glm, ctx=ctx)
+        geno.close()
+        for k in names:
+            arrs[k][:, k0:k1] = part[k]
+        arrs["maf"][k0:k1] = part["maf"]
+    GT = None
+    if heading:
+        end = G.find(b"\n", hoff.value)
+        GT = G[hoff.value:end if end >= 0 else len(G)].rstrip(b"\r").decode().split("\t")
+    GI = []
+    for k in range(m):
+        start = G.rfind(b"\n", 0, off[k]) + 1
+        f = G[start:off[k]].split(b"\t", 4)
+        GI.append((f[0].decode(), f[2].decode(), f[3].decode()))
+    return arrs, bases, GT, GI
+
+
 def _as_geno(snps, ctx, impute=None):
     if isinstance(snps, Genotypes):
         return snps, False

@@ -191,6 +191,34 @@ def test_hapmap_row_widths(gpu_ctx, n, m, bit):
         assert np.array_equal(gd, ref["GD"], equal_nan=True), (impute, maz)
 
 
+def test_by_file_scan_from_hapmap_text(gpu_ctx):
+    """GAPIT.EMMAxP3D's by-file branch (:262-330): fragments of the HapMap text are numericalized and scanned on the GPU;
+    the result must equal the oracle's numericalization followed by the oracle's scan, fragment size notwithstanding."""
+    G, Y, X0 = case(180, 700, npc=1, edge=False)
+    text = synth.make_hapmap_text(G, bit=2, missing=0.02)
+    GD = go.hapmap(synth.hapmap_rows(text), SNP_impute="Middle")["GD"]          # n x m, what the reference would scan
+    K = go.kinship_vanraden(GD)
+    eL = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    ora = go.emmax_p3d(Y, GD, K, X0, eig_L=eL, reml=reml)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    res = {}
+    for frag in (97, 256, 100000):
+        arrs, bases, GT, GI = gb().p3d_scan_hapmap(text, X0, Y, eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]],
+                                                   file_fragment=frag, ctx=gpu_ctx)
+        res[frag] = arrs
+        assert len(GT) == 180 and len(GI) == 700 and GI[5][0] == "rs5"
+    for k in res[97]:
+        assert np.array_equal(res[97][k], res[256][k], equal_nan=True) and np.array_equal(res[97][k], res[100000][k], equal_nan=True)
+    a = res[256]
+    assert np.array_equal(np.isnan(a["tvalue"][0]), np.isnan(ora.stats))
+    r, _ = rel_err(a["effect"][0], ora.effect_est, 1e-4)
+    assert r < BETA_RTOL
+    with np.errstate(divide="ignore"):
+        assert np.nanmax(np.abs(np.log10(a["pvalue"][0]) - np.log10(ora.ps))) < LOGP_ATOL
+    es.close()
+
+
 def test_hapmap_to_device_genotypes_and_single_marker_call(gpu_ctx):
     G, _, _ = case(150, 260, edge=False)
     text = synth.make_hapmap_text(G, bit=2, missing=0.02, heading=False)
