@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -108,7 +109,8 @@ struct GramSched {
   }
 };
 
-struct GramEpi {
+template <int MODE>   // 0: local buffer; 1 / 2: fused NVLink exchange (below) -- compile-time so the local path keeps its plain RED
+struct GramEpiT {
   struct Params {
     int32_t* G;   // [ldg][ldg] row-major, zero-initialised
     int64_t ldg;
@@ -124,13 +126,13 @@ struct GramEpi {
   };
   static constexpr int kSmemBytes = 0;
   Params p;
-  __device__ GramEpi(const Params& pp, uint8_t*) : p(pp) {}
+  __device__ GramEpiT(const Params& pp, uint8_t*) : p(pp) {}
   __device__ void prepare(const Job&, int, int) {}
   __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int /*half*/, int /*nhalf*/) {
     const int64_t off = (int64_t(job.a_row0) + sub * 128 + row) * p.ldg + job.b_row0;
     int32_t* base = p.G;
-    if (p.mode == 1) base = p.peers[min(p.world - 1, (job.tag0 * p.world) / p.tiles_side)];
-    if (p.mode == 2) base = p.mc;
+    if (MODE == 1) base = p.peers[min(p.world - 1, (job.tag0 * p.world) / p.tiles_side)];
+    if (MODE == 2) base = p.mc;
     int32_t* dst = base + off;
 #pragma unroll 1
     for (int c0 = 0; c0 < 256; c0 += 16) {
@@ -141,8 +143,10 @@ struct GramEpi {
       for (int i = 0; i < 16; ++i) {
         const int v = static_cast<int>(r[i]);
         if (v != 0) {
-          if (p.mode == 2)
+          if (MODE == 2)
             asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(dst + c0 + i), "r"(r[i]) : "memory");
+          else if (MODE == 1)   // fire-and-forget reduction on a peer-mapped address (an atom would wait for the reply)
+            asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(dst + c0 + i), "r"(v) : "memory");
           else
             atomicAdd(dst + c0 + i, v);
         }
@@ -151,6 +155,7 @@ struct GramEpi {
   }
 };
 
+using GramEpi = GramEpiT<0>;
 using GramCfg = UmmaCfg<2, 256, 3>;
 
 // ------------------------------------------------------------------ K2 pieces
@@ -392,9 +397,27 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ld
     GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
                                    static_cast<uint64_t>(g->ldn), 128));
     using PCfg = UmmaPairCfg<2, 256, 4>;
-    auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpi, 0, 0, true>;
-    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_a, sp, ep));
+    if (ex.mode == 0) {
+      auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpi, 0, 0, true>;
+      GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
+      GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_a, sp, ep));
+    } else {
+      // the exchange variants share the parameter block (same layout for every MODE)
+      typename GramEpiT<1>::Params e1;
+      static_assert(sizeof(e1) == sizeof(ep), "GramEpiT<MODE>::Params must not depend on MODE");
+      memcpy(&e1, &ep, sizeof(ep));
+      if (ex.mode == 1) {
+        auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpiT<1>, 0, 0, true>;
+        GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
+        GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_a, sp, e1));
+      } else {
+        typename GramEpiT<2>::Params e2;
+        memcpy(&e2, &ep, sizeof(ep));
+        auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpiT<2>, 0, 0, true>;
+        GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
+        GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_a, sp, e2));
+      }
+    }
     return GAPIT_OK;
   }
   GAPIT_CHECK(make_tensor_map_u8(&map_a, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
