@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="markers of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kinship-exchange", default="fused", choices=["fused", "nccl"],
+                    help="N > 1: exchange of the Gram partials fused into the kernel over NVLink peer memory, or ncclAllReduce")
     ap.add_argument("--reml-route", default="eigL", choices=["eigL", "eigR"],
                     help="eigL: REML from the spectrum of K alone (one eigendecomposition); eigR: the reference's "
                          "second decomposition of S(K+I)S (emma.txt:82-89)")
@@ -267,23 +269,61 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps, float(np.mean(kms))
 
-    # ---------------- kinship: gram (+ all-reduce) + epilogue ----------------
+    # ---------------- kinship: gram (+ exchange) + epilogue ----------------
+    # N > 1: the exchange is fused into the Gram kernel -- every rank's epilogue adds its tiles into rank 0's buffer over
+    # NVLink as bulk tensor reduce-adds (gapit_vanraden_gram_fused, mode 3, root 0; buffers from torch symmetric memory).
+    # `--kinship-exchange nccl` (or a box without peer access) runs Gram -> ncclAllReduce instead.
+    import ctypes
     ldg = lib.gapit_gram_ld(n)
-    G_t = torch.empty((ldg, ldg), dtype=torch.int32, device=dev)
     sums_t = torch.empty(3, dtype=torch.int64, device=dev)
     K_dev = torch.empty((n, n), dtype=torch.float64, device=dev)
+    hdl = None
+    exchange = "none" if world == 1 else "nccl"
+    if world > 1 and args.kinship_exchange == "fused":
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            G_t = symm_mem.empty((ldg, ldg), dtype=torch.int32, device=dev)
+            hdl = symm_mem.rendezvous(G_t, dist.group.WORLD)
+            peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            exchange = "fused: bulk tensor reduce-add into rank 0 over NVLink (TMA), no collective"
+        except Exception as exc:
+            hdl = None
+            exchange = f"nccl (symmetric memory unavailable: {exc!r})"[:160]
+    if hdl is None:
+        G_t = torch.empty((ldg, ldg), dtype=torch.int32, device=dev)
 
     def kinship_step():
-        _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_t.data_ptr(), sums_t.data_ptr()))
-        if world > 1:
-            dist.all_reduce(G_t)
+        if hdl is not None:
+            if rank == 0:
+                G_t.zero_()
+            hdl.barrier()
+            _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, None, world, rank, 3, 0, sums_t.data_ptr()))
+            st = ctx.stats()
+            hdl.barrier()
             dist.all_reduce(sums_t)
-        st = ctx.stats()
-        _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_t.data_ptr(), sums_t.data_ptr(), K_dev.data_ptr(), None, None))
+            if rank == 0:
+                _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_t.data_ptr(), sums_t.data_ptr(), K_dev.data_ptr(), None, None))
+        else:
+            _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_t.data_ptr(), sums_t.data_ptr()))
+            if world > 1:
+                dist.all_reduce(G_t)
+                dist.all_reduce(sums_t)
+            st = ctx.stats()
+            _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_t.data_ptr(), sums_t.data_ptr(), K_dev.data_ptr(), None, None))
         ctx._last_gram_ms = st["kernel_ms"]
 
     kin_ms, _ = timed(kinship_step, args.steps, args.warmup)
     gram_ms = ctx._last_gram_ms
+    exchange_ok = None
+    if hdl is not None:   # once, outside the timed region: the fused sums against Gram + ncclAllReduce, bit for bit
+        G_ref = torch.empty((ldg, ldg), dtype=torch.int32, device=dev)
+        s_ref = torch.empty(3, dtype=torch.int64, device=dev)
+        _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_ref.data_ptr(), s_ref.data_ptr()))
+        dist.all_reduce(G_ref)
+        if rank == 0:
+            # G_t was mirrored in place by the last finish: compare the lower triangle
+            exchange_ok = bool(torch.equal(torch.tril(G_ref[:n, :n]), torch.tril(G_t[:n, :n])))
+        del G_ref, s_ref
     m_total = m * world
     kin_ops = float(n) * (n + 1) * m_total            # one multiply + one add per lower-triangle pair per marker
     kin_tops = kin_ops / (kin_ms * 1e-3) / 1e12
@@ -429,7 +469,8 @@ def main():
         "kinship": {"tops": kin_tops, "ms": kin_ms, "gram_kernel_ms": gram_ms, "gram_kernel_tops_per_gpu": gram_tops_local,
                     "ops": "n(n+1)m integer multiply-adds counted once per lower-triangle pair",
                     "frac_of_int8_peak": gram_tops_local / int8_peak,
-                    "includes": "gram + NCCL all-reduce (N>1) + fp64 epilogue"},
+                    "includes": "gram + exchange (N>1) + fp64 epilogue", "exchange": exchange,
+                    "exchange_matches_nccl_bit_for_bit": exchange_ok},
         "glm": {"snps_per_s": m_total / (glm_ms * 1e-3), "ms": glm_ms, "kernel_ms": glm_kernel_ms,
                 "hbm_gbs": glm_bytes / (glm_kernel_ms * 1e-3) / 1e9,
                 "frac_of_hbm_peak": glm_bytes / (glm_kernel_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},

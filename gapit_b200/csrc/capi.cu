@@ -50,6 +50,24 @@ int make_tensor_map_u8(CUtensorMap* out, const void* base, uint64_t inner_bytes,
   return GAPIT_OK;
 }
 
+// 2-D tensor map over a row-major int32 matrix [rows][ld] with boxes of 32 x 32 elements (128-byte rows, 128-byte
+// swizzle): the destination of the Gram epilogue's bulk reduce-adds (local or peer-mapped memory).
+int make_tensor_map_i32_box32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_bytes) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return fail(GAPIT_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if (ld_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 127) != 0)
+    return fail(GAPIT_ERR_ARG, "make_tensor_map_i32_box32: misaligned tensor");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_bytes};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(GAPIT_ERR_CUDA, "cuTensorMapEncodeTiled (int32) failed, CUresult " + std::to_string(int(r)));
+  return GAPIT_OK;
+}
+
 int ctx_ws(gapit_ctx* ctx, int slot, size_t bytes, void** out) {
   if (slot < 0 || slot >= gapit_ctx::kWsSlots) return fail(GAPIT_ERR_ARG, "ctx_ws: bad slot");
   if (bytes == 0) bytes = 16;

@@ -221,6 +221,18 @@ __device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
   return d;
 }
 
+// ---- bulk tensor reduce-add: shared-memory box -> global tensor (local or peer-mapped), element type from the map ----
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int32_t crd0, int32_t crd1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(desc)),
+               "r"(smem_u32(smem_src)), "r"(crd0), "r"(crd1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // MN-major operand (the MN index is contiguous in memory, one K index per 128-byte row), 128-byte swizzle: the tile
 // is [K rows][128 bytes of MN], 8-row swizzle atoms of 1024 bytes.  Canonical layout in 16-byte units
 // ((8,n),(8,k)):((1,LBO),(8,SBO)): SBO = bytes between groups of 8 K rows, LBO = bytes between 128-byte MN chunks

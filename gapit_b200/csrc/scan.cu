@@ -218,6 +218,7 @@ struct ScanEpi {
 #pragma unroll
       for (int i = 0; i < Q + 2; ++i) acc[t][i] = 0.0;
   }
+  __device__ void finish() {}
   __device__ void prepare(const Job& job, int tid, int nthreads) {
     const double* src = p.gconst + int64_t(job.tag2) * p.gc_tstride + int64_t(job.tag0) * kSmemDoubles;
     for (int i = tid; i < kSmemDoubles; i += nthreads) cs[i] = __ldg(src + i);
@@ -339,6 +340,7 @@ struct GlmEpi {
   Params p;
   __device__ GlmEpi(const Params& pp, uint8_t*) : p(pp) {}
   __device__ void prepare(const Job&, int, int) {}
+  __device__ void finish() {}
   __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int /*half*/, int /*nhalf*/) {
     uint32_t r[BN];
 #pragma unroll

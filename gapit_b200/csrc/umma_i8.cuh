@@ -55,7 +55,8 @@ struct UmmaCfg {
 
 // Sched: struct with `Params`, ctor(Params, unit, nunits, cta_rank), bool next(Job&).
 // Epi  : struct with `Params`, `kSmemBytes`, ctor(Params, smem scratch), prepare(job, tid, nthreads),
-//        run(job, taddr, sub, row, half, nhalf).
+//        run(job, taddr, sub, row, half, nhalf), finish() (after the last job, before the CTA may exit).
+//        The parameter block is a __grid_constant__, so an epilogue may hand tensor maps inside it to TMA.
 //
 // CL == 2 runs the kernel as thread-block clusters of two CTAs that work on the same B tile with different
 // A tiles: each CTA fetches half of the B box and TMA-multicasts it into both CTAs' shared memory, so the
@@ -65,7 +66,7 @@ struct UmmaCfg {
 template <int MSUB, int BN, int STAGES, int CL, int EPIW, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
 __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
     umma_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   const typename Sched::Params sp, const typename Epi::Params ep) {
+                   const typename Sched::Params sp, const __grid_constant__ typename Epi::Params ep) {
   using Cfg = UmmaCfg<MSUB, BN, STAGES>;
   static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
   static_assert((BN / CL) % 8 == 0, "each CTA's share of the B box must keep the 8-row swizzle groups whole");
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
       ptx::mbar_arrive(&tempty[acc]);
       ++it;
     }
+    epi.finish();
   }
 
   ptx::tc_fence_before_sync();
@@ -245,7 +247,7 @@ template <int MSUB, int BN, int STAGES, int EPIW, class Sched, class Epi, uint32
           bool MNMAJ = false>
 __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
     umma_i8_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                        const typename Sched::Params sp, const typename Epi::Params ep) {
+                        const typename Sched::Params sp, const __grid_constant__ typename Epi::Params ep) {
   using Cfg = UmmaPairCfg<MSUB, BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -392,6 +394,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
       else ptx::mbar_arrive_remote(&tempty[acc], 0);
       ++it;
     }
+    epi.finish();
   }
 
   ptx::tc_fence_before_sync();

@@ -126,12 +126,13 @@ int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, const int64
  * peer-mapped into this process: e.g. torch symmetric memory or cudaIpc handles), mc = the NVLS multicast address of
  * the same buffers (mode 2 only).  Protocol: every rank zeroes its buffer, all ranks pass a barrier, every rank calls
  * this, all ranks synchronise their streams and pass a barrier again.  Then
- *   mode 1 (reduce-scatter by peer RED.ADD): rank r holds the complete sums of the block-rows
- *          gapit_gram_owned_rows(n, world, r) (lower triangle) -- copy them to the finishing rank;
- *   mode 2 (all-reduce in the switch by multimem.red): every rank holds the complete lower triangle.
- * gapit_vanraden_finish then runs on the complete buffer.  Integer adds: bit-identical to the NCCL route. */
+ *   mode 3 (bulk tensor reduce-adds through TMA, 32 x 32 int32 boxes; the fast one) and mode 1 (4-byte RED.ADD on peer
+ *          pointers): root >= 0: rank `root` holds the complete lower triangle (reduce to root); root < 0: rank r holds
+ *          the complete block-rows gapit_gram_owned_rows(n, world, r) (reduce-scatter);
+ *   mode 2 (NVLS multimem.red): every rank holds the complete lower triangle (all-reduce in the switch).
+ * gapit_vanraden_finish then runs on a complete buffer.  Integer adds: bit-identical to the NCCL route. */
 int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int32_t* mc, int world, int rank,
-                              int mode, int64_t* sums_dev);
+                              int mode, int root, int64_t* sums_dev);
 int gapit_gram_owned_rows(int64_t n, int world, int rank, int64_t* row_lo, int64_t* row_hi);
 
 /* ---- ZHANG kinship and PCA covariates from the same integer cross-product ----------------------------

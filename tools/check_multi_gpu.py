@@ -49,18 +49,22 @@ try:
     peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
     mc = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
     s_f = torch.empty(3, dtype=torch.int64, device=dev)
-    for mode in ((1, 2) if mc else (1,)):
+    for mode, root in (((1, -1), (2, -1), (3, -1), (3, 0)) if mc else ((1, -1), (3, -1), (3, 0))):
         G_sym.zero_()
         torch.cuda.synchronize()
         hdl.barrier()
         t0 = time.perf_counter()
-        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, ctypes.c_void_p(mc), world, rank, mode, s_f.data_ptr()))
+        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, ctypes.c_void_p(mc), world, rank, mode, root,
+                                                 s_f.data_ptr()))
         torch.cuda.synchronize()
         hdl.barrier()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         full = G_sym.clone()
-        if mode == 1:   # every rank pulls the block-rows the others own (the finishing rank would do only this)
+        if root >= 0:   # reduce to root: only that rank holds the sums; hand them to the others for the comparison
+            full = hdl.get_buffer(root, (ldg, ldg), torch.int32).clone()
+            torch.cuda.synchronize()
+        elif mode != 2:   # reduce-scatter modes: every rank pulls the block-rows the others own (the finishing rank would do only this)
             for r in range(world):
                 lo, hi = ctypes.c_int64(), ctypes.c_int64()
                 _lib.check(lib.gapit_gram_owned_rows(n, world, r, ctypes.byref(lo), ctypes.byref(hi)))
@@ -71,7 +75,7 @@ try:
         # compare the lower triangle (by 256-tiles) with the all-reduced one
         ref_t = torch.tril(G_t[:n, :n])
         got_t = torch.tril(full[:n, :n])
-        fused[mode] = {"bit_identical": bool(torch.equal(ref_t, got_t)), "call_ms": dt * 1e3}
+        fused[f"mode{mode}_root{root}"] = {"bit_identical": bool(torch.equal(ref_t, got_t)), "call_ms": dt * 1e3}
 except Exception as exc:   # no peer access / symmetric memory on this box: the NCCL route stays the product path
     fused = {"unavailable": repr(exc)[:200]}
 vec = torch.empty((n, n), dtype=torch.float64, device=dev)
