@@ -81,16 +81,36 @@ def main():
 
     T_ = {}
     # ---------------- kinship: per-block Gram partials, summed, one epilogue ----------------
+    # The exchange is fused into the Gram kernel: every block of every rank adds its tiles straight into rank 0's buffer
+    # (bulk tensor reduce-adds through TMA, over NVLink for the other ranks), so there is neither a per-block
+    # accumulation pass nor a collective.  Without peer access: per-rank accumulation + ncclAllReduce.
     ldg = lib.gapit_gram_ld(n)
-    G_acc = torch.zeros((ldg, ldg), dtype=torch.int32, device=dev)
-    G_t = torch.empty((ldg, ldg), dtype=torch.int32, device=dev)
     s_acc = torch.zeros(3, dtype=torch.int64, device=dev)
     s_t = torch.empty(3, dtype=torch.int64, device=dev)
+    hdl = None
+    if world > 1:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            G_acc = symm_mem.empty((ldg, ldg), dtype=torch.int32, device=dev)
+            hdl = symm_mem.rendezvous(G_acc, dist.group.WORLD)
+            peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+        except Exception as exc:
+            print("symmetric memory unavailable, using ncclAllReduce:", repr(exc)[:200], flush=True)
+            hdl = None
+    if hdl is None:
+        G_acc = torch.zeros((ldg, ldg), dtype=torch.int32, device=dev)
+        peers = (ctypes.c_void_p * 1)(G_acc.data_ptr())
+    fused = hdl is not None or world == 1
+    G_t = None if fused else torch.empty((ldg, ldg), dtype=torch.int32, device=dev)
     gram_ms = pack_ms = 0.0
     keep = {}
     sync()
     t_gen = 0.0
     t0 = time.perf_counter()
+    if fused:
+        G_acc.zero_()
+        if hdl is not None:
+            hdl.barrier()
     for b in mine:
         tg = time.perf_counter()
         blk = gen_block(n, bounds[b + 1] - bounds[b], 1000 + b, dev, pop)
@@ -98,11 +118,15 @@ def main():
         t_gen += time.perf_counter() - tg
         geno = gb.Genotypes.from_device(blk.data_ptr(), n, blk.shape[0], ctx=ctx)
         del blk
-        _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_t.data_ptr(), s_t.data_ptr()))
+        if fused:
+            _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, None, world if hdl is not None else 1,
+                                                     rank if hdl is not None else 0, 3, 0, s_t.data_ptr()))
+        else:
+            _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_t.data_ptr(), s_t.data_ptr()))
+            G_acc += G_t
         st = ctx.stats()
         gram_ms += st["kernel_ms"]
         pack_ms += st["pack_ms"]
-        G_acc += G_t
         s_acc += s_t
         if cfg["scan"] and len(mine) == 1:
             keep[b] = geno           # one block per rank: keep it resident for the scan
@@ -110,10 +134,14 @@ def main():
             geno.close()
     if world > 1:
         ta = time.perf_counter()
-        dist.all_reduce(G_acc)
+        if hdl is not None:
+            hdl.barrier()
+        else:
+            dist.all_reduce(G_acc)
         dist.all_reduce(s_acc)
         torch.cuda.synchronize()
-        T_["allreduce_s"] = time.perf_counter() - ta
+        T_["exchange_tail_s"] = time.perf_counter() - ta
+    T_["exchange"] = "fused-tma-to-root" if hdl is not None else ("nccl" if world > 1 else "none")
     del G_t
     K_dev = torch.empty((n, n), dtype=torch.float64, device=dev)
     tf = time.perf_counter()
