@@ -49,7 +49,11 @@ try:
     peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
     mc = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
     s_f = torch.empty(3, dtype=torch.int64, device=dev)
-    for mode, root in (((1, -1), (2, -1), (3, -1), (3, 0)) if mc else ((1, -1), (3, -1), (3, 0))):
+    # the product path is mode 3 (bulk tensor reduce-adds); CHK_ALL_MODES=1 also runs the 4-byte transports
+    variants = [(3, -1), (3, 0)]
+    if os.environ.get("CHK_ALL_MODES"):
+        variants = [(1, -1)] + ([(2, -1)] if mc else []) + variants
+    for mode, root in variants:
         G_sym.zero_()
         torch.cuda.synchronize()
         hdl.barrier()
