@@ -1,4 +1,5 @@
-"""First-light diagnostics on a B200: each stage against the oracle, verbose."""
+"""First-light diagnostics on a B200: each stage against the oracle, verbose (run by hand: python tests/diag_first_light.py).
+Lives under tests/ because it uses the oracle, which only tests, smoke() and bench.py's CPU legs may touch."""
 import os, sys, time, traceback
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -2,8 +2,7 @@
 
 For each taxa count the scan is run with S = 8 (62 bits of every eigenvector element, beyond fp64's 53) as the
 reference and with S = 4..7; reported per S: max |d beta| / max(|beta|, 1e-3) (the parity tests' measure),
-max |d beta| / SE (error in t units), max |d SE| / SE, max |d log10 p|, and kernel time.  For n <= 600 the CPU
-oracle is the second reference.
+max |d beta| / SE (error in t units), max |d SE| / SE, max |d log10 p|, and kernel time.
 """
 import os, sys
 import numpy as np
@@ -45,11 +44,4 @@ for n, m in shapes:
             dlp = np.nanmax(np.abs(np.log10(a["pvalue"][0][ok]) - np.log10(ref["pvalue"][0][ok])))
         print(f"S={S}: beta rel(floor 1e-3) {rel:.3e}  |dbeta|/SE {tun:.3e}  SE rel {dse:.3e}  dlog10p {dlp:.3e}  "
               f"kernel {km:.3f} ms ({m / km / 1e3:.2f} M SNPs/s)", flush=True)
-    if n <= 600:
-        from oracle import gapit_oracle as go
-        ora = go.emmax_p3d(Y[:, 0], G.T.astype(np.float64), K, X0, eig_L=eL, reml=reml)
-        for S in (8, 6, 5):
-            a = res[S][0]
-            db = np.abs(a["effect"][0][ok] - ora.effect_est[ok])
-            print(f"vs oracle S={S}: beta rel(floor 1e-3) {np.max(db / np.maximum(np.abs(ora.effect_est[ok]), 1e-3)):.3e}")
     geno.close()
