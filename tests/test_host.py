@@ -199,6 +199,24 @@ def test_r_shim_type_checks_against_the_header():
                 assert call in defined, (fn, call)
 
 
+def test_gram_owned_rows_partition_the_block_rows():
+    """gapit_gram_owned_rows (reduce-scatter form of the fused kinship exchange): the ranks' row ranges are disjoint,
+    ordered, 256-aligned and cover the Gram buffer's block-rows exactly once."""
+    lib = _lib.load()
+    for n in (257, 700, 5000, 20000, 50000):
+        T = (n + 255) // 256
+        for world in (1, 2, 3, 4, 8):
+            covered = []
+            for r in range(world):
+                lo, hi = C.c_int64(), C.c_int64()
+                assert lib.gapit_gram_owned_rows(n, world, r, C.byref(lo), C.byref(hi)) == 0
+                assert lo.value % 256 == 0 and lo.value <= hi.value <= lib.gapit_gram_ld(n)
+                covered += list(range(lo.value // 256, (hi.value + 255) // 256))
+            assert covered == list(range(T)) or (world > T and sorted(set(covered)) == list(range(T))), (n, world)
+    lo, hi = C.c_int64(), C.c_int64()
+    assert lib.gapit_gram_owned_rows(700, 2, 2, C.byref(lo), C.byref(hi)) == -1     # rank out of range
+
+
 def test_marker_shards_cover_in_order():
     for m, w in [(10, 3), (500000, 8), (7, 8), (3093, 2)]:
         parts = [shard.marker_shard(m, r, w) for r in range(w)]
