@@ -55,6 +55,7 @@ SIGNATURES = {
     "gapit_ctx_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "gapit_ctx_set_stream": (C.c_int, [_P, _P]),
     "gapit_geno_pack": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _I64, C.c_int, C.POINTER(_P)]),
+    "gapit_pack2_host": (C.c_int, [_P, C.c_int, _I64, _I64, _I64, _P, C.c_int]),
     "gapit_geno_from_device": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(_P)]),
     "gapit_geno_free": (None, [_P]),
     "gapit_geno_n": (_I64, [_P]),

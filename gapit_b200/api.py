@@ -89,26 +89,31 @@ class Packed2:
         self.m = int(self.data.shape[0])
 
     @staticmethod
-    def from_dosages(a, marker_major=False, pinned=False):
-        """(n, m) dosages (or (m, n) with ``marker_major``), values 0/1/2, NaN or negative = NA."""
+    def from_dosages(a, marker_major=False, pinned=False, threads=0):
+        """(n, m) dosages (or (m, n) with ``marker_major``), values 0/1/2, NaN / NA_integer_ / negative int8 = NA.
+        Packed by the library on the host's threads (gapit_pack2_host)."""
         a = np.asarray(a)
         if not marker_major:
             a = a.T
+        if a.dtype == np.int8 or a.dtype == np.uint8:
+            dtype = _lib.GAPIT_I8
+        elif a.dtype == np.int32:
+            dtype = _lib.GAPIT_I32
+        elif a.dtype.kind in "iu":
+            a = np.where(a < 0, np.iinfo(np.int32).min, a).astype(np.int32)
+            dtype = _lib.GAPIT_I32
+        else:
+            a = a.astype(np.float64, copy=False)
+            dtype = _lib.GAPIT_F64
+        a = np.ascontiguousarray(a)
         m, n = a.shape
         nb = (n + 3) // 4
-        if a.dtype.kind == "f":
-            c = np.where(np.isnan(a), 3, a).astype(np.uint8)
-        else:
-            c = np.where(a < 0, 3, a).astype(np.uint8)
-        pad = np.zeros((m, nb * 4), dtype=np.uint8)
-        pad[:, :n] = c
-        q = pad.reshape(m, nb, 4)
-        out = (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).astype(np.uint8)
         if pinned:
             import torch
-            t = torch.empty((m, nb), dtype=torch.uint8).pin_memory()
-            t.numpy()[:] = out
-            out = t.numpy()
+            out = torch.empty((m, nb), dtype=torch.uint8).pin_memory().numpy()
+        else:
+            out = np.empty((m, nb), dtype=np.uint8)
+        check(_lib.load().gapit_pack2_host(_ptr(a), dtype, n, m, n, _ptr(out), int(threads)))
         return Packed2(out, n)
 
 

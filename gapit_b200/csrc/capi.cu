@@ -174,3 +174,80 @@ extern "C" int gapit_set_slices(gapit_ctx* ctx, int slices) {
   ctx->slices = slices;
   return GAPIT_OK;
 }
+
+// Host-side packer for the GAPIT_B2 upload format: R-layout double / integer / int8 dosages -> 2 bits per call, on the
+// host's threads, so that a caller holding R doubles (8 bytes per call) ships 1/32 of the bytes over PCIe.
+// NaN / NA_integer_ / negative int8 -> code 3 (NA); anything else outside {0,1,2} -> GAPIT_ERR_DATA.
+#include <atomic>
+#include <climits>
+#include <thread>
+#include <vector>
+
+namespace {
+template <typename T>
+inline unsigned code_of(T v, bool* bad);
+template <>
+inline unsigned code_of<double>(double v, bool* bad) {
+  if (v != v) return 3u;
+  if (v == 0.0) return 0u;
+  if (v == 1.0) return 1u;
+  if (v == 2.0) return 2u;
+  *bad = true;
+  return 0u;
+}
+template <>
+inline unsigned code_of<int32_t>(int32_t v, bool* bad) {
+  if (v == INT_MIN) return 3u;
+  if (v >= 0 && v <= 2) return static_cast<unsigned>(v);
+  *bad = true;
+  return 0u;
+}
+template <>
+inline unsigned code_of<int8_t>(int8_t v, bool* bad) {
+  if (v < 0) return 3u;
+  if (v <= 2) return static_cast<unsigned>(v);
+  *bad = true;
+  return 0u;
+}
+
+template <typename T>
+bool pack_rows(const T* src, int64_t n, int64_t ld, int64_t k0, int64_t k1, uint8_t* out, int64_t nb) {
+  bool bad = false;
+  for (int64_t k = k0; k < k1; ++k) {
+    const T* s = src + k * ld;
+    uint8_t* o = out + k * nb;
+    int64_t i = 0;
+    for (int64_t b = 0; b < nb; ++b) {
+      unsigned byte = 0u;
+      for (int c = 0; c < 4 && i < n; ++c, ++i) byte |= code_of<T>(s[i], &bad) << (2 * c);
+      o[b] = static_cast<uint8_t>(byte);
+    }
+  }
+  return !bad;
+}
+}  // namespace
+
+extern "C" int gapit_pack2_host(const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld, uint8_t* out,
+                                int nthreads) {
+  if (!snps || !out || n <= 0 || m <= 0 || ld < n || (dtype != GAPIT_F64 && dtype != GAPIT_I32 && dtype != GAPIT_I8))
+    return fail(GAPIT_ERR_ARG, "gapit_pack2_host: bad argument");
+  const int64_t nb = (n + 3) / 4;
+  unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+  int nt = nthreads > 0 ? nthreads : static_cast<int>(hw);
+  nt = static_cast<int>(std::min<int64_t>(nt, std::max<int64_t>(1, m / 64)));
+  std::atomic<int> ok{1};
+  auto work = [&](int t) {
+    const int64_t k0 = m * t / nt, k1 = m * (t + 1) / nt;
+    bool good = true;
+    if (dtype == GAPIT_F64) good = pack_rows(static_cast<const double*>(snps), n, ld, k0, k1, out, nb);
+    else if (dtype == GAPIT_I32) good = pack_rows(static_cast<const int32_t*>(snps), n, ld, k0, k1, out, nb);
+    else good = pack_rows(static_cast<const int8_t*>(snps), n, ld, k0, k1, out, nb);
+    if (!good) ok.store(0);
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nt; ++t) pool.emplace_back(work, t);
+  work(0);
+  for (auto& th : pool) th.join();
+  if (!ok.load()) return fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}");
+  return GAPIT_OK;
+}

@@ -75,6 +75,11 @@ int gapit_ctx_set_stream(gapit_ctx* ctx, void* cuda_stream);
  * GAPIT.Main.R:427. */
 int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
                     gapit_impute impute, gapit_geno** out);
+/* Host-side packer for GAPIT_B2 (runs on the host's threads; nthreads 0 = all): an R-layout F64 / I32 / I8 matrix
+ * (element (i,k) at snps[i + k*ld]) -> m rows of ceil(n/4) bytes in `out`.  NaN, NA_integer_ and negative int8 become
+ * code 3 (NA); any other value outside {0,1,2} is GAPIT_ERR_DATA.  A caller holding R doubles then uploads 1/32 of the
+ * bytes (gapit_geno_pack / gapit_p3d_scan_host with GAPIT_B2). */
+int gapit_pack2_host(const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld, uint8_t* out, int nthreads);
 /* The same handle from int8 dosages already resident on this context's device (marker k at mk_dev + k*ld, ld >= n):
  * one device-to-device re-pitch plus the column statistics; values outside {0,1,2} are rejected.  The copy runs on
  * the context's stream: either share that stream with the producer of mk_dev (gapit_ctx_set_stream) or

@@ -31,13 +31,26 @@ static gapit_dtype sexp_dtype(SEXP x) {
 
 static const void* sexp_data(SEXP x) { return TYPEOF(x) == REALSXP ? (const void*)REAL(x) : (const void*)INTEGER(x); }
 
+/* An R matrix holds 8 (numeric) or 4 (integer) bytes per genotype call: pack it to 2 bits per call on the host's
+ * threads (gapit_pack2_host) so that 1/32 (1/16) of the bytes cross PCIe.  R_alloc memory is freed by R at the end of
+ * the .Call, also on error.  NA becomes code 3 and meets the impute rule on the device, as in GAPIT.EMMAxP3D.R:20-24. */
+static uint8_t* pack_matrix(SEXP x, int64_t n, int64_t m, int64_t* nb_out) {
+  const int64_t nb = (n + 3) / 4;
+  uint8_t* packed = (uint8_t*)R_alloc((size_t)m * (size_t)nb, 1);
+  if (gapit_pack2_host(sexp_data(x), sexp_dtype(x), n, m, n, packed, 0) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  *nb_out = nb;
+  return packed;
+}
+
 /* GAPIT.kinship.VanRaden(snps): n x m matrix -> n x n double matrix (GAPIT.kinship.VanRaden.R:1-37) */
 SEXP gapit_R_vanraden(SEXP snps) {
   SEXP dim = Rf_getAttrib(snps, R_DimSymbol);
   const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
   gapit_geno* g = NULL;
+  int64_t nb = 0;
+  const uint8_t* packed = pack_matrix(snps, n, m, &nb);
   /* the reference does not impute here: NA propagates to a NaN matrix, so NA is an error for us */
-  int rc = gapit_geno_pack(ctx(), sexp_data(snps), sexp_dtype(snps), n, m, n, GAPIT_IMPUTE_NONE, &g);
+  int rc = gapit_geno_pack(ctx(), packed, GAPIT_B2, n, m, nb, GAPIT_IMPUTE_NONE, &g);
   if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
   SEXP K = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
   rc = gapit_vanraden(ctx(), g, REAL(K), NULL);
@@ -118,6 +131,8 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP 
   const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
   const int q0 = INTEGER(Rf_getAttrib(X0, R_DimSymbol))[1];
   const int is_glm = Rf_asLogical(glm);
+  int64_t nb = 0;
+  const uint8_t* packed = pack_matrix(xs, n, m, &nb);   /* may Rf_error: before any device resource is held */
   gapit_eigsys* e = NULL;
   if (!is_glm && gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e) != GAPIT_OK)
     Rf_error("gapitcuda: %s", gapit_last_error());
@@ -126,7 +141,7 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP 
   gapit_scan_out out = {r, r + m, r + 2 * m, r + 3 * m, r + 4 * m, r + 5 * m, r + 6 * m};
   gapit_scan_base base;
   double d = is_glm ? 0.0 : Rf_asReal(delta), v = is_glm ? 0.0 : Rf_asReal(vg);
-  int rc = gapit_p3d_scan_host(ctx(), sexp_data(xs), sexp_dtype(xs), n, m, n, (gapit_impute)Rf_asInteger(impute), e,
+  int rc = gapit_p3d_scan_host(ctx(), packed, GAPIT_B2, n, m, nb, (gapit_impute)Rf_asInteger(impute), e,
                                REAL(X0), q0, REAL(y), 1, &d, &v, is_glm, &out, &base);
   gapit_eigsys_free(e);
   if (rc != GAPIT_OK) {

@@ -147,6 +147,20 @@ def test_packed2_host_layout():
     assert (int(P.data[0, 3]) >> 2) == 0                       # bits past the last taxon are zero
     Pf = gb.Packed2.from_dosages(np.where(G.T < 0, np.nan, G.T.astype(float)))
     assert np.array_equal(Pf.data, P.data)
+    Pi = gb.Packed2.from_dosages(np.where(G < 0, np.iinfo(np.int32).min, G.astype(np.int32)), marker_major=True)
+    assert np.array_equal(Pi.data, P.data)
+    # the threaded packer against a numpy restatement on a bigger ragged shape, every thread count
+    G2 = rng.integers(-1, 3, size=(1001, 517)).astype(np.int8)
+    pad = np.zeros((1001, 520), dtype=np.uint8)
+    pad[:, :517] = np.where(G2 < 0, 3, G2)
+    q = pad.reshape(1001, 130, 4)
+    ref = (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).astype(np.uint8)
+    for threads in (1, 3, 0):
+        assert np.array_equal(gb.Packed2.from_dosages(G2, marker_major=True, threads=threads).data, ref)
+    bad = G2.astype(np.float64)
+    bad[5, 7] = 2.5
+    with pytest.raises(gb.GapitCudaError):
+        gb.Packed2.from_dosages(bad, marker_major=True)
 
 
 def test_hapmap_index_host_code():
