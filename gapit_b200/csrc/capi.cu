@@ -210,16 +210,57 @@ inline unsigned code_of<int8_t>(int8_t v, bool* bad) {
   return 0u;
 }
 
+// fast path: four calls per output byte, branch-free; any call that is not exactly 0, 1 or 2 sends the byte to the
+// careful path (NA codes, error detection)
+inline bool fast4(const double* s, unsigned* byte) {
+  static const uint64_t pat[4] = {0ull, 0x3FF0000000000000ull, 0x4000000000000000ull, ~0ull};
+  uint64_t b[4];
+  memcpy(b, s, 32);
+  unsigned out = 0u;
+  uint64_t diff = 0ull;
+  for (int c = 0; c < 4; ++c) {
+    const unsigned hi = static_cast<unsigned>(b[c] >> 32);
+    const unsigned code = ((hi >> 30) & 1u) * 2u + ((hi >> 29) & 1u);   // 0.0 -> 0, 1.0 -> 1, 2.0 -> 2
+    diff |= b[c] ^ pat[code];
+    out |= code << (2 * c);
+  }
+  *byte = out;
+  return diff == 0ull;
+}
+inline bool fast4(const int32_t* s, unsigned* byte) {
+  unsigned out = 0u, over = 0u;
+  for (int c = 0; c < 4; ++c) {
+    const unsigned v = static_cast<unsigned>(s[c]);
+    over |= (v > 2u);
+    out |= (v & 3u) << (2 * c);
+  }
+  *byte = out;
+  return over == 0u;
+}
+inline bool fast4(const int8_t* s, unsigned* byte) {
+  unsigned out = 0u, over = 0u;
+  for (int c = 0; c < 4; ++c) {
+    const unsigned v = static_cast<uint8_t>(s[c]);
+    over |= (v > 2u);
+    out |= (v & 3u) << (2 * c);
+  }
+  *byte = out;
+  return over == 0u;
+}
+
 template <typename T>
 bool pack_rows(const T* src, int64_t n, int64_t ld, int64_t k0, int64_t k1, uint8_t* out, int64_t nb) {
   bool bad = false;
+  const int64_t full = n / 4;
   for (int64_t k = k0; k < k1; ++k) {
     const T* s = src + k * ld;
     uint8_t* o = out + k * nb;
-    int64_t i = 0;
     for (int64_t b = 0; b < nb; ++b) {
       unsigned byte = 0u;
-      for (int c = 0; c < 4 && i < n; ++c, ++i) byte |= code_of<T>(s[i], &bad) << (2 * c);
+      if (b >= full || !fast4(s + 4 * b, &byte)) {
+        byte = 0u;
+        for (int c = 0; c < 4 && 4 * b + c < n; ++c) byte |= code_of<T>(s[4 * b + c], &bad) << (2 * c);
+      }
       o[b] = static_cast<uint8_t>(byte);
     }
   }
