@@ -523,6 +523,16 @@ def alloc_scan_out(T, m, pinned=True):
     return arrs
 
 
+def _check_scan_shapes(n, X0, T, delta, vg, glm):
+    """The C ABI takes raw pointers: row counts and per-trait vector lengths are checked here, before it reads them."""
+    if X0.ndim != 2 or X0.shape[0] != n:
+        raise ValueError(f"X0 must have {n} rows (one per taxon), got shape {X0.shape}")
+    if not glm:
+        for name, v in (("delta", delta), ("vg", vg)):
+            if v is not None and np.size(v) != T:
+                raise ValueError(f"{name} must hold one value per trait ({T}), got {np.size(v)}")
+
+
 def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None, pinned=False, out=None):
     """Scan all markers of ``geno`` for T traits.  Returns (dict of (T, m) arrays, list of per-trait base dicts).
     ``pinned=True`` puts the result arrays in page-locked host memory (needs torch) so the D2H copy runs at
@@ -534,6 +544,7 @@ def p3d_scan(geno, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None,
     n, q0 = X0.shape
     T = Y.shape[1]
     m = geno.m
+    _check_scan_shapes(geno.n, X0, T, delta, vg, glm)
     names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
     if out is not None and out["effect"].shape == (T, m) and out["maf"].shape == (m,):
         arrs = out
@@ -583,6 +594,7 @@ def p3d_scan_host(snps, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=
     X0 = np.asfortranarray(X0, dtype=np.float64)
     Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n, -1))
     q0, T = X0.shape[1], Y.shape[1]
+    _check_scan_shapes(n, X0, T, delta, vg, glm)
     names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
     arrs = {k: _host_array((T, m), pinned) for k in names}
     arrs["maf"] = _host_array((m,), pinned)
@@ -734,3 +746,63 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
         "logLM": col(arrs["loglm"][0]), "effect.snp": col(arrs["effect"][0]), "effect.cv": b["beta0"],
         "se": col(arrs["se"][0]), "delta": (None if glm else reml["delta"]),
     }
+
+
+# ---------------------------------------------------------------------------
+# Compression glue GAPIT.Main.R:386-400 runs before every GAPIT.EMMAxP3D call.
+# Host-side table bookkeeping, no kernel: the point is NOT to run dist() + hclust() (O(n^3) scalar R,
+# GAPIT.Compress.R:37-38) nor the dense Z %*% DS (GAPIT.ZmatrixCompress.R:34) at the two group settings the
+# MLM (GN = n) and GLM (GN = 1) models use, where their results are known in closed form.
+# Tables: KI = (names, n x n array); GA rows = (taxon, group); GAU rows = (taxon, group, block, ID);
+# Z = (row taxa, column taxa, array).
+# ---------------------------------------------------------------------------
+def GAPIT_Compress(line_names, KI, kinship_cluster="average", kinship_group="Mean", GN=None):
+    """GAPIT.Compress at GN >= n (every taxon its own group, numbered in row order as cutree numbers clusters by
+    first appearance; KG = KI, :59-61 with b = I) and GN == 1 (one group; KG = the 1 x 1 Mean / Max / Min / Median
+    of KI).  Other group counts are the compressed-MLM path, which stays with the reference's R body."""
+    KI = np.asarray(KI, dtype=np.float64)
+    n = KI.shape[0]
+    GN = n if GN is None else int(GN)
+    if GN >= n:
+        return [(str(t), i + 1) for i, t in enumerate(line_names)], KI.copy()
+    if GN == 1:
+        f = {"Mean": np.mean, "Max": np.max, "Min": np.min, "Median": np.median}[kinship_group]
+        return [(str(t), 1) for t in line_names], np.array([[f(KI)]])
+    raise NotImplementedError("compressed MLM (1 < GN < n) keeps the reference's GAPIT.Compress body")
+
+
+def GAPIT_Block(Z_col_taxa, GA, KG):
+    """GAPIT.Block (GAPIT.Block.R:14-64): groups with a phenotyped member -> KW, the rest -> KO; GAU rows in
+    merge()'s order (group key sorted as character)."""
+    zset = set(str(t) for t in Z_col_taxa)
+    blk = [1 if t in zset else 2 for t, _ in GA]
+    grp1 = list(dict.fromkeys(g for (_, g), b in zip(GA, blk) if b == 1))
+    in1 = set(grp1)
+    grp2 = [g for g in dict.fromkeys(g for _, g in GA) if g not in in1]
+    gid = {g: (1, i + 1) for i, g in enumerate(grp1)}
+    gid.update({g: (2, i + 1) for i, g in enumerate(grp2)})
+    rows = sorted(range(len(GA)), key=lambda i: blk[i])
+    rows.sort(key=lambda i: str(GA[i][1]))
+    GAU = [(GA[i][0], GA[i][1], (blk[i] + gid[GA[i][1]][0]) / 2.0, gid[GA[i][1]][1]) for i in rows]
+    i1 = np.asarray(grp1, dtype=np.int64) - 1
+    i2 = np.asarray(grp2, dtype=np.int64) - 1
+    KG = np.asarray(KG)
+    return GAU, KG[np.ix_(i1, i1)], KG[np.ix_(i2, i2)], KG[np.ix_(i1, i2)]
+
+
+def GAPIT_ZmatrixCompress(Z_row_taxa, Z_col_taxa, Zmat, GAU):
+    """GAPIT.ZmatrixCompress: Z %*% DS with DS = diag(n)[x,] (:24,:34) is a column scatter-add -- O(n^2), not the
+    reference's dense n^3 product; rows sorted by taxon (:41)."""
+    zset = set(str(t) for t in Z_col_taxa)
+    GAU1 = sorted((r for r in GAU if r[0] in zset), key=lambda r: r[0])
+    n = max(r[3] for r in GAU1 if r[2] < 2)
+    x = np.asarray([r[3] for r in GAU1], dtype=np.int64) - 1
+    order_Z = sorted(range(len(Z_col_taxa)), key=lambda i: str(Z_col_taxa[i]))
+    Zs = np.asarray(Zmat, dtype=np.float64)[:, order_Z]
+    out = np.zeros((Zs.shape[0], n))
+    if len(set(x.tolist())) == len(x):
+        out[:, x] = Zs
+    else:
+        np.add.at(out.T, x, Zs.T)
+    order_rows = sorted(range(len(Z_row_taxa)), key=lambda i: str(Z_row_taxa[i]))
+    return [str(Z_row_taxa[i]) for i in order_rows], out[order_rows, :]

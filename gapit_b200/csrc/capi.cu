@@ -123,6 +123,8 @@ extern "C" int gapit_ctx_create(int device, gapit_ctx** out) {
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev2);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev3);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_blk, cudaEventDisableTiming);
   for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
     e = cudaEventCreateWithFlags(&ctx->ev_ready[i], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_free[i], cudaEventDisableTiming);
@@ -143,11 +145,13 @@ extern "C" void gapit_ctx_destroy(gapit_ctx* ctx) {
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev2) cudaEventDestroy(ctx->ev2);
   if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+  if (ctx->ev_blk) cudaEventDestroy(ctx->ev_blk);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_ready[i]) cudaEventDestroy(ctx->ev_ready[i]);
     if (ctx->ev_free[i]) cudaEventDestroy(ctx->ev_free[i]);
   }
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
   for (int i = 0; i < gapit_ctx::kWsSlots; ++i)
     if (ctx->ws_ptr[i]) cudaFree(ctx->ws_ptr[i]);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

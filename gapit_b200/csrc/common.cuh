@@ -46,17 +46,19 @@ struct gapit_ctx {
   gapit_stats stats = {};
   int slices = 6;  // int8 slices of V used by the rotation (Ozaki split)
   // grow-only device workspaces reused across calls (no cudaMalloc/cudaFree on the hot path)
-  static constexpr int kWsSlots = 24;
+  static constexpr int kWsSlots = 32;
   void* ws_ptr[kWsSlots] = {};
   size_t ws_cap[kWsSlots] = {};
   cudaStream_t copy_stream = nullptr;   // H2D of the next genotype chunk while the current one is scanned
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;
   cudaEvent_t ev_ready[2] = {}, ev_free[2] = {};
+  cudaStream_t d2h_stream = nullptr;   // finished result rows go to the host while the next marker block is computed
+  cudaEvent_t ev_blk = nullptr;        // results of a marker block are final
 };
 
 namespace gapit {
 enum WsSlot { WS_R = 0, WS_PROJ, WS_GCONST, WS_PART, WS_OUT, WS_RG, WS_RS, WS_RSCALE, WS_BAD, WS_CHUNK0, WS_CHUNK1,
-              WS_CS0, WS_CS1, WS_CQ0, WS_CQ1, WS_STAGE0, WS_STAGE1, WS_SYNC };
+              WS_CS0, WS_CS1, WS_CQ0, WS_CQ1, WS_STAGE0, WS_STAGE1, WS_SYNC, WS_FC, WS_WBUF, WS_WT, WS_XX, WS_KSCALE, WS_Z };
 // device workspace of at least `bytes` in `slot` (contents are not preserved when it grows)
 int ctx_ws(gapit_ctx* ctx, int slot, size_t bytes, void** out);
 template <class T>

@@ -358,7 +358,8 @@ extern "C" int gapit_hapmap_numericalize(gapit_ctx* ctx, const char* text, int64
     // one CTA per marker; narrow tables use one-warp CTAs so that more markers are in flight per SM
     const int threads = n <= 4096 ? 32 : (n <= 16384 ? 128 : 256);
     const int blocks = static_cast<int>(std::min<int64_t>(k1 - k0, int64_t(ctx->sm_count) * (2048 / threads)));
-    if (row_span + 32 <= kStageBytes) {
+    // the kernel also holds ~100 bytes of static shared memory: keep static + dynamic inside the 48 KB default limit
+    if (row_span + 32 + 512 <= kStageBytes) {
       const size_t smem = size_t((row_span + 15 + 15) / 16) * 16;
       numericalize_kernel<true><<<blocks, threads, smem, ctx->stream>>>(p);
     } else {

@@ -51,7 +51,9 @@ struct gapit_eigsys {
   int S = 0, BN = 0, KPB = 0;
   int64_t ldn = 0;    // bytes per row of Vs
   int64_t nkq = 0;    // number of BN-row tiles of Vs
-  int8_t* Vs = nullptr;      // [(nkq*BN)][ldn] row (k*S + s) = digit plane s of eigenvector k
+  int8_t* Vs = nullptr;      // [(tiles_cap*BN)][ldn] row (k*S + s) = digit plane s of eigenvector k; tiles beyond nkq:
+                             // digit planes of the back-rotated columns of a multi-trait scan (rewritten per call)
+  int64_t tiles_cap = 0;
   double* V = nullptr;       // n x n column-major
   double* scale = nullptr;   // [nkq*KPB] c_k = max_j |V_jk| / (126 * 256^(S-1)), 0 beyond n
   std::vector<double> values;  // host, descending
@@ -290,6 +292,73 @@ struct ScanEpi {
   }
 };
 
+// ------------------------------------------------------------------ K3m
+// Many traits sharing one eigendecomposition (BASELINE configs[4]; GAPIT.R:101-132 calls GAPIT.EMMAxP3D per trait and
+// every call repeats the rotation :634).  W = V'X does not depend on the trait; only w_t = 1/(lambda + delta_t) does:
+//   xx_t(i)   = sum_k w_tk W_ki^2                      needs the rotation (quadratic in x_i)
+//   xa_tj(i)  = x_i' H_t^-1 X0_j,  num_t(i) = x_i' H_t^-1 (y_t - X0 beta0_t)     are LINEAR in x_i
+// (H_t = K + delta_t I = V diag(1/w_t) V').  So the B operand of ONE rotation launch is the digit planes of V followed
+// by the digit planes of the back-rotated columns R = [H_t^-1 X0 | H_t^-1 r_t]_t, and this epilogue only rebuilds the
+// fp64 value of every accumulator column and stores it: W_ki^2 for the eigenvector rows (row k of `wbuf`), the finished
+// linear sums for the R rows.  A DMMA GEMM (xx_contract, contract.cu) then forms xx_t for all traits from W^2 -- the
+// rotation runs once for any number of traits and no trait-sized accumulator block has to fit in registers.
+template <int S, int BN>
+struct StoreEpi {
+  static constexpr int KPB = BN / S;
+  static constexpr int GC = (S == 4 || S == 8) ? 8 : (S == 5 ? 40 : (S == 6 ? 24 : 56));  // lcm(S, 8)
+  static constexpr int KG = GC / S;
+  struct Params {
+    const double* kscale;  // [rows] c_k of every B row group (eigenvectors, then R columns)
+    double* wbuf;          // [rows][m_ld]
+    int64_t m_ld;
+    int nk_sq;             // rows below this index are squared (eigenvector rows)
+    int pair;              // 1: merge adjacent digit planes in int32 first
+  };
+  static constexpr int kSmemBytes = 0;
+  Params p;
+  static __device__ __forceinline__ double i2d(int x) {
+    return __hiloint2double(0x43300000, x ^ static_cast<int>(0x80000000u)) - 4503601774854144.0;
+  }
+  __device__ StoreEpi(const Params& pp, uint8_t*) : p(pp) {}
+  __device__ void prepare(const Job&, int, int) {}
+  __device__ void finish() {}
+  __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int half, int nhalf) {
+    const int64_t mrk = int64_t(job.a_row0) + sub * 128 + row;
+    const bool live = mrk < p.m_ld;
+#pragma unroll 1
+    for (int g = half; g < BN / GC; g += nhalf) {
+      uint32_t r[GC];
+#pragma unroll
+      for (int j = 0; j < GC / 8; ++j) ptx::tmem_ld_x8(taddr + g * GC + j * 8, *reinterpret_cast<uint32_t(*)[8]>(&r[j * 8]));
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int kk = 0; kk < KG; ++kk) {
+        const int* d = reinterpret_cast<const int*>(&r[kk * S]);
+        double u;
+        if (p.pair) {
+          if (S & 1) {
+            u = i2d(d[S - 1]);
+#pragma unroll
+            for (int s = S - 3; s >= 0; s -= 2) u = fma(u, 65536.0, i2d(d[s + 1] * 256 + d[s]));
+          } else {
+            u = i2d(d[S - 1] * 256 + d[S - 2]);
+#pragma unroll
+            for (int s = S - 4; s >= 0; s -= 2) u = fma(u, 65536.0, i2d(d[s + 1] * 256 + d[s]));
+          }
+        } else {
+          u = i2d(d[S - 1]);
+#pragma unroll
+          for (int s = S - 2; s >= 0; --s) u = fma(u, 256.0, i2d(d[s]));
+        }
+        const int k = job.tag0 * KPB + g * KG + kk;
+        double v = u * __ldg(p.kscale + k);
+        if (k < p.nk_sq) v *= v;
+        if (live) p.wbuf[int64_t(k) * p.m_ld + mrk] = v;
+      }
+    }
+  }
+};
+
 // ------------------------------------------------------------------ K3g
 // GLM (K = NULL, U = I): xa_j = sum_i X0_ij x_i and xy = sum_i y_i x_i are the product of the marker tile
 // with R = [X0 | y] (n x (q0+1)), so the same int8 UMMA main loop is used with the digit planes of R as the
@@ -377,7 +446,6 @@ struct FinalizeConsts {
   double lbeta;       // log Beta(df/2, 1/2)
   int q0;
   int qpad;    // covariate width the reduction kernels were instantiated for (>= q0)
-  int gsplit;  // partial sums per marker (splits of the eigen index)
 };
 
 // continued fraction of the incomplete beta function (modified Lentz)
@@ -427,29 +495,46 @@ __device__ double two_sided_t_pvalue(double t, double df, double lbeta) {
   return 1.0 - exp(b * ln_y + a * ln_x - lbeta - log(b)) * betacf(b, a, y);
 }
 
-__global__ void finalize_kernel(const double* __restrict__ part, int64_t m_ld, int64_t m, const int32_t* __restrict__ colsum,
-                                const int32_t* __restrict__ colsumsq, FinalizeConsts fc, double* __restrict__ effect,
-                                double* __restrict__ tvalue, double* __restrict__ se, double* __restrict__ pvalue,
-                                double* __restrict__ rsquare, double* __restrict__ loglm, double* __restrict__ maf) {
+// where the per-marker sums of trait t live: xx[t*xx_t + g*xx_g + k], xa_j[t*xa_t + g*xa_g + j*xa_j + k],
+// xy[t*xy_t + g*xy_g + k], g = 0..nsplit-1 partial sums added in index order
+struct FinalizeSrc {
+  const double* xx;
+  const double* xa;
+  const double* xy;
+  int64_t xx_t, xx_g, xa_t, xa_g, xa_j, xy_t, xy_g;
+  int nsplit;
+};
+
+// grid (marker blocks, traits); outputs of trait t at out + t*out_t + a*out_ld + k, a = 0..6
+__global__ void finalize_kernel(FinalizeSrc src, int64_t m, const int32_t* __restrict__ colsum,
+                                const int32_t* __restrict__ colsumsq, const FinalizeConsts* __restrict__ fcs,
+                                double* __restrict__ out, int64_t out_t, int64_t out_ld) {
   const int64_t k = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (k >= m) return;
+  const int t = blockIdx.y;
+  const FinalizeConsts& fc = fcs[t];
+  double* effect = out + t * out_t + k;
+  double* tvalue = effect + out_ld;
+  double* se = effect + 2 * out_ld;
+  double* pvalue = effect + 3 * out_ld;
+  double* rsquare = effect + 4 * out_ld;
+  double* loglm = effect + 5 * out_ld;
   const int q0 = fc.q0;
   const double NaN = __longlong_as_double(0x7ff8000000000000LL);
   const long long ss = colsum[k], sq = colsumsq[k];
   const double half_freq = 0.5 * static_cast<double>(ss) / fc.n;
-  if (maf) maf[k] = fmin(half_freq, 1.0 - half_freq);
+  if (t == 0) effect[6 * out_ld] = fmin(half_freq, 1.0 - half_freq);
   // constant marker (min == max  <=>  n sum x^2 == (sum x)^2): GAPIT.EMMAxP3D.R:499-511
   if (static_cast<long long>(fc.n) * sq == ss * ss) {
-    effect[k] = NaN; tvalue[k] = NaN; se[k] = NaN; pvalue[k] = 1.0; rsquare[k] = NaN; loglm[k] = NaN;
+    *effect = NaN; *tvalue = NaN; *se = NaN; *pvalue = 1.0; *rsquare = NaN; *loglm = NaN;
     return;
   }
   double xx = 0.0, xy = 0.0, xa[GAPIT_MAX_Q0];
   for (int j = 0; j < q0; ++j) xa[j] = 0.0;
-  for (int g = 0; g < fc.gsplit; ++g) {  // fixed order: deterministic for any grid
-    const double* pp = part + int64_t(g) * (fc.qpad + 2) * m_ld + k;
-    xx += pp[0];
-    for (int j = 0; j < q0; ++j) xa[j] += pp[(1 + j) * m_ld];
-    xy += pp[int64_t(fc.qpad + 1) * m_ld];
+  for (int g = 0; g < src.nsplit; ++g) {  // fixed order: deterministic for any grid
+    xx += src.xx[t * src.xx_t + g * src.xx_g + k];
+    for (int j = 0; j < q0; ++j) xa[j] += src.xa[t * src.xa_t + g * src.xa_g + j * src.xa_j + k];
+    xy += src.xy[t * src.xy_t + g * src.xy_g + k];
   }
   // Schur complement of the bordered normal equations (:736-748)
   double quad = 0.0, num = xy;
@@ -462,17 +547,17 @@ __global__ void finalize_kernel(const double* __restrict__ part, int64_t m_ld, i
   const double B22 = xx - quad;
   const double beta = num / B22;                      // :772 last element
   const double sdev = sqrt(fc.var_scale / B22);       // sqrt(iXX[q1,q1] * vg|ve)
-  const double t = beta / sdev;                       // :936-937
-  double p = two_sided_t_pvalue(t, fc.df, fc.lbeta);  // :939
+  const double tv = beta / sdev;                      // :936-937
+  double p = two_sided_t_pvalue(tv, fc.df, fc.lbeta); // :939
   if (p != p) p = 1.0;                                // :940
   const double rss = fc.rss0 - num * beta;            // ||U'(y - X beta)||^2 (:957) via the Schur update
   const double ll = 0.5 * (-fc.n * log((2.0 * 3.14159265358979323846 / fc.n) * rss) - fc.sumlog - fc.n);  // :958
-  effect[k] = beta;
-  tvalue[k] = t;
-  se[k] = sdev;
-  pvalue[k] = p;
-  loglm[k] = ll;
-  rsquare[k] = 1.0 - exp(-(2.0 / fc.n) * (ll - fc.logL0));  // :967
+  *effect = beta;
+  *tvalue = tv;
+  *se = sdev;
+  *pvalue = p;
+  *loglm = ll;
+  *rsquare = 1.0 - exp(-(2.0 / fc.n) * (ll - fc.logL0));  // :967
 }
 
 }  // namespace gapit
@@ -691,6 +776,63 @@ static int launch_scan(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int Q, co
   }
 }
 
+// The multi-trait form of the rotation: same main loop and scheduler, store epilogue (StoreEpi).  `g` is a view of one
+// marker block, `tiles` = eigenvector tiles + tiles of back-rotated columns in e->Vs.
+template <int S, int BN>
+static int launch_store_S(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int64_t tiles, int gsplit, const double* kscale,
+                          double* wbuf, int64_t m_ld, int nk_sq) {
+  using Epi = StoreEpi<S, BN>;
+  CUtensorMap map_a, map_b;
+  GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
+                                 static_cast<uint64_t>(g->ldn), 256));
+  const int cl = (m_ld / 256 >= 2) ? 2 : 1;
+  GAPIT_CHECK(make_tensor_map_u8(&map_b, e->Vs, static_cast<uint64_t>(e->ldn), static_cast<uint64_t>(tiles * BN),
+                                 static_cast<uint64_t>(e->ldn), BN / cl));
+  ScanSched::Params sp;
+  sp.mtiles = static_cast<int>((m_ld / 256 + cl - 1) / cl);
+  sp.cl = cl;
+  sp.gsplit = static_cast<int>(std::min<int64_t>(gsplit, tiles));
+  sp.nkq = static_cast<int>(tiles);
+  sp.kblocks = static_cast<int>(g->ldn / kBlockK);
+  sp.bn = BN;
+  sp.nchunk = 1;
+  sp.hint_a = ptx::kEvictLast;
+  sp.hint_b = ptx::kEvictNormal;
+  sp.round_ctr = nullptr;
+  sp.round_wait = 100000;   // ~50 us
+  const int pair = (65792ll * g->n < 2147483647ll) ? 1 : 0;
+  typename Epi::Params ep{kscale, wbuf, m_ld, nk_sq, pair};
+  const int nunits = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit);
+  constexpr int EPIW = 2;
+  constexpr int kThreadsEpi = 128 + 2 * 128 * EPIW;
+  if (cl == 2) {
+    const size_t rounds = size_t((sp.mtiles * sp.gsplit + nunits - 1) / nunits) + 1;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_SYNC, rounds, &sp.round_ctr));
+    GAPIT_CUDA(cudaMemsetAsync(sp.round_ctr, 0, rounds * sizeof(unsigned int), ctx->stream));
+    using PCfg = UmmaPairCfg<2, BN, 4>;
+    auto kern = umma_i8_pair_kernel<2, BN, 4, EPIW, ScanSched, Epi, 1, 1>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes + 16));
+    GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, PCfg::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
+  } else {
+    using Cfg = UmmaCfg<2, BN, 3>;
+    auto kern = umma_i8_kernel<2, BN, 3, 1, EPIW, ScanSched, Epi, 1, 1>;
+    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + 16));
+    GAPIT_CUDA(launch_umma(kern, nunits, 1, kThreadsEpi, Cfg::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
+  }
+  return GAPIT_OK;
+}
+
+static int launch_store(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int64_t tiles, int gsplit, const double* kscale,
+                        double* wbuf, int64_t m_ld, int nk_sq) {
+  switch (e->S) {
+    case 4: return launch_store_S<4, 256>(ctx, g, e, tiles, gsplit, kscale, wbuf, m_ld, nk_sq);
+    case 5: return launch_store_S<5, 240>(ctx, g, e, tiles, gsplit, kscale, wbuf, m_ld, nk_sq);
+    case 6: return launch_store_S<6, 240>(ctx, g, e, tiles, gsplit, kscale, wbuf, m_ld, nk_sq);
+    case 7: return launch_store_S<7, 224>(ctx, g, e, tiles, gsplit, kscale, wbuf, m_ld, nk_sq);
+    default: return launch_store_S<8, 256>(ctx, g, e, tiles, gsplit, kscale, wbuf, m_ld, nk_sq);
+  }
+}
+
 template <int BN>
 static int launch_glm_bn(gapit_ctx* ctx, gapit_geno* g, const int8_t* Rs_dev, int64_t rs_rows, const double* scale_dev,
                          int nc, int Q, double* part_dev, int64_t m_ld) {
@@ -732,6 +874,10 @@ static int choose_gsplit(int64_t ldn, int64_t nkq) {
   return static_cast<int>(std::min<int64_t>(g, nkq));
 }
 
+int launch_xx_contract(cudaStream_t st, const double* W2, int64_t m_ld, const double* Wt, int wt_ld, int nk, double* XX,
+                       int64_t xx_ld, int T);
+int xx_trait_tile(int T);
+int launch_v_times_cols(cudaStream_t st, const double* V, int64_t n, const double* Z, int nc, double* out, bool square);
 int launch_colstats(gapit_ctx* ctx, cudaStream_t st, const int8_t* mk, int64_t ldn, int64_t n, int64_t m, int32_t* colsum,
                     int32_t* colsumsq, int* bad_dev);
 int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
@@ -752,6 +898,13 @@ struct ScanPlan {
   int TC = 1;
   int8_t* Rs = nullptr;             // GLM: [T][128][ldn] digit planes of [X0 | y_t]
   double* Rscale = nullptr;         // GLM: [T][GAPIT_MAX_Q0+1]
+  FinalizeConsts* fc_dev = nullptr; // [T]
+  // MLM, T > 1: one rotation shared by all traits (StoreEpi + xx_contract)
+  bool shared = false;
+  int64_t lin_tiles = 0;            // tiles of back-rotated columns behind the eigenvector tiles of e->Vs
+  double* kscale = nullptr;         // [(nkq + lin_tiles) * KPB]
+  double* wt = nullptr;             // [nk][wt_ld]: w_t(k) = 1 / (lambda_k + delta_t)
+  int wt_ld = 0;
 };
 
 // one block of markers resident on the device
@@ -761,6 +914,25 @@ struct MarkerView {
   const int32_t* colsum;
   const int32_t* colsumsq;
 };
+
+// make room for `tiles` BN-row tiles in e->Vs (the eigenvector tiles are preserved)
+static int eigsys_reserve_tiles(gapit_eigsys* e, int64_t tiles) {
+  if (tiles <= e->tiles_cap) return GAPIT_OK;
+  gapit_ctx* ctx = e->ctx;
+  const int64_t cap = tiles + tiles / 16 + 1;
+  int8_t* nv = nullptr;
+  GAPIT_CUDA(cudaMalloc(&nv, size_t(cap) * e->BN * e->ldn));
+  cudaError_t err = cudaMemcpyAsync(nv, e->Vs, size_t(e->nkq) * e->BN * e->ldn, cudaMemcpyDeviceToDevice, ctx->stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+  if (err != cudaSuccess) {
+    cudaFree(nv);
+    return fail(GAPIT_ERR_CUDA, std::string("eigsys_reserve_tiles: ") + cudaGetErrorString(err));
+  }
+  cudaFree(e->Vs);
+  e->Vs = nv;
+  e->tiles_cap = cap;
+  return GAPIT_OK;
+}
 
 static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e, const double* X0, int q0, const double* Y,
                         int T, const double* delta, const double* vg, int glm, ScanPlan* plan, gapit_scan_base* base_out) {
@@ -797,9 +969,11 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
     GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
     GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
     plan->nk = e->nkq * e->KPB;
+    plan->shared = (T > 1) && !getenv("GAPIT_MULTI_CHUNKED");   // A/B switch: the trait-chunked epilogue
     plan->TC = (T > 1) ? trait_chunk(Q) : 1;
     const int nchunk = (T + plan->TC - 1) / plan->TC;
-    GAPIT_CHECK(ctx_ws_t(ctx, WS_GCONST, size_t(nchunk) * plan->nk * plan->TC * (Q + 2), &plan->gconst));
+    if (!plan->shared)
+      GAPIT_CHECK(ctx_ws_t(ctx, WS_GCONST, size_t(nchunk) * plan->nk * plan->TC * (Q + 2), &plan->gconst));
   } else {
     std::copy(X0, X0 + size_t(n) * q0, proj.begin());
     std::copy(Y, Y + size_t(n) * T, proj.begin() + size_t(n) * q0);
@@ -808,8 +982,15 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
     GAPIT_CUDA(cudaMemsetAsync(plan->Rs, 0, size_t(T) * 128 * ldn, ctx->stream));
   }
 
-  std::vector<double> w(n), gconst;
-  if (!glm) gconst.assign(size_t((T + plan->TC - 1) / plan->TC) * plan->nk * plan->TC * (Q + 2), 0.0);
+  std::vector<double> w(n), gconst, zcols, wt;
+  const int lin_nc = (q0 + 1) * T;   // back-rotated columns of the shared-rotation form: [H_t^-1 X0 | H_t^-1 r_t] per trait
+  if (plan->shared) {
+    const int tile = xx_trait_tile(T);
+    plan->wt_ld = (T + tile - 1) / tile * tile;
+    zcols.assign(size_t(lin_nc) * n, 0.0);
+    wt.assign(size_t(plan->nk) * plan->wt_ld, 0.0);
+  }
+  if (!glm && !plan->shared) gconst.assign(size_t((T + plan->TC - 1) / plan->TC) * plan->nk * plan->TC * (Q + 2), 0.0);
   const double dn = static_cast<double>(n);
   const double two_pi = 2.0 * 3.14159265358979323846;
   for (int t = 0; t < T; ++t) {
@@ -872,7 +1053,6 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
     fc.lbeta = std::lgamma(0.5 * fc.df) + std::lgamma(0.5) - std::lgamma(0.5 * fc.df + 0.5);
     fc.q0 = q0;
     fc.qpad = Q;
-    fc.gsplit = plan->gsplit;
     const double ves_glm = rss0 / static_cast<double>(n - q0);
     fc.var_scale = glm ? ves_glm : vg[t];
     if (base_out) {
@@ -887,7 +1067,20 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
       for (int j = 0; j < q0; ++j) b.beta0[j] = fc.beta0[j];
       b.singular_x0 = singular;
     }
-    if (!glm) {
+    if (plan->shared) {
+      // Z_t = diag(w_t) V'[X0 | r_t], r_t = y_t - X0 beta0_t: V Z_t = H_t^-1 [X0 | r_t].  Projecting the reduced-model
+      // residual instead of y_t gives num = x'H^-1 r directly (no xy - xa'beta0 cancellation at finalize).
+      double* zt = zcols.data() + size_t(t) * (q0 + 1) * n;
+      for (int64_t k = 0; k < n; ++k) {
+        double r = yt[k];
+        for (int j = 0; j < q0; ++j) {
+          zt[size_t(j) * n + k] = w[k] * proj[size_t(j) * n + k];
+          r -= fc.beta0[j] * proj[size_t(j) * n + k];
+        }
+        zt[size_t(q0) * n + k] = w[k] * r;
+        wt[size_t(k) * plan->wt_ld + t] = w[k];
+      }
+    } else if (!glm) {
       const int TC = plan->TC;
       double* gt = gconst.data() + size_t(t / TC) * plan->nk * TC * (Q + 2) + size_t(t % TC) * (Q + 2);
       for (int64_t k = 0; k < n; ++k) {
@@ -909,28 +1102,128 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
       GAPIT_CUDA(cudaGetLastError());
     }
   }
-  if (!glm) {
+  std::vector<FinalizeConsts> fcs(plan->fc);
+  if (plan->shared)
+    for (auto& f : fcs) std::fill(f.beta0, f.beta0 + GAPIT_MAX_Q0, 0.0);   // the xy column already is x'H^-1 (y - X0 beta0)
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_FC, size_t(T), &plan->fc_dev));
+  GAPIT_CUDA(cudaMemcpyAsync(plan->fc_dev, fcs.data(), size_t(T) * sizeof(FinalizeConsts), cudaMemcpyHostToDevice, ctx->stream));
+  if (plan->shared) {
+    // back-rotate: R = V Z (n x lin_nc), then its digit planes behind the eigenvector tiles of e->Vs
+    double *dZ = nullptr, *dRlin = nullptr;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_Z, zcols.size(), &dZ));
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_RG, zcols.size(), &dRlin));
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_WT, wt.size(), &plan->wt));
+    GAPIT_CUDA(cudaMemcpyAsync(dZ, zcols.data(), zcols.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GAPIT_CUDA(cudaMemcpyAsync(plan->wt, wt.data(), wt.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    GAPIT_CHECK(launch_v_times_cols(ctx->stream, e->V, n, dZ, lin_nc, dRlin, false));
+    plan->lin_tiles = (lin_nc + e->KPB - 1) / e->KPB;
+    GAPIT_CHECK(eigsys_reserve_tiles(e, e->nkq + plan->lin_tiles));
+    const size_t rows = size_t(e->nkq + plan->lin_tiles) * e->KPB;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_KSCALE, rows, &plan->kscale));
+    GAPIT_CUDA(cudaMemsetAsync(plan->kscale, 0, rows * 8, ctx->stream));
+    GAPIT_CUDA(cudaMemcpyAsync(plan->kscale, e->scale, size_t(plan->nk) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    int8_t* tail = e->Vs + size_t(e->nkq) * e->BN * e->ldn;
+    GAPIT_CUDA(cudaMemsetAsync(tail, 0, size_t(plan->lin_tiles) * e->BN * e->ldn, ctx->stream));
+    slice_v_kernel<<<static_cast<unsigned>(lin_nc), 256, 0, ctx->stream>>>(dRlin, n, e->S, tail, e->ldn, plan->kscale + plan->nk);
+    GAPIT_CUDA(cudaGetLastError());
+  } else if (!glm) {
     GAPIT_CUDA(cudaMemcpyAsync(plan->gconst, gconst.data(), gconst.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));  // `gconst` (pageable) must outlive the copy
+  }
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));  // the pageable host sources must outlive their copies
+  return GAPIT_OK;
+}
+
+// copy rows [k0, k0 + mc) of every trait's result arrays to the caller's SoA arrays (m_total markers per trait):
+// one strided copy per array
+static int fetch_block(cudaStream_t st, const double* out_dev, int64_t out_tstride, int64_t out_ld, int64_t k0, int64_t mc,
+                       int T, int64_t m_total, const gapit_scan_out* out) {
+  double* dsts[7] = {out->effect, out->tvalue, out->se, out->pvalue, out->rsquare, out->loglm, out->maf};
+  for (int a = 0; a < 7; ++a) {
+    if (!dsts[a]) continue;
+    GAPIT_CUDA(cudaMemcpy2DAsync(dsts[a] + k0, size_t(m_total) * 8, out_dev + size_t(a) * out_ld + k0, size_t(out_tstride) * 8,
+                                 size_t(mc) * 8, a == 6 ? 1 : size_t(T), cudaMemcpyDeviceToHost, st));
   }
   return GAPIT_OK;
 }
 
+static int launch_finalize(gapit_ctx* ctx, const ScanPlan& plan, const FinalizeSrc& src, const MarkerView& v, double* out,
+                           int64_t out_tstride, int64_t out_ld) {
+  dim3 grid(static_cast<unsigned>((v.m + 255) / 256), static_cast<unsigned>(plan.T));
+  finalize_kernel<<<grid, 256, 0, ctx->stream>>>(src, v.m, v.colsum, v.colsumsq, plan.fc_dev, out, out_tstride, out_ld);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
+// markers per pass of the shared-rotation form: whole rounds of the persistent grid, W^2 block within ~1/3 of the free
+// device memory (at most 8 GB)
+static int64_t shared_block_markers(gapit_ctx* ctx, int64_t rows) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = size_t(8) << 30;
+  size_t cap = 0;
+  if (ctx->ws_ptr[WS_WBUF]) cap = ctx->ws_cap[WS_WBUF];   // already ours: counts as available
+  const double budget = std::min(8.0e9, (double(free_b) + double(cap)) / 3.0);
+  const int64_t unit = int64_t(ctx->sm_count / 2) * 512;
+  int64_t mb = static_cast<int64_t>(budget / (double(rows) * 8.0));
+  if (const char* ev = getenv("GAPIT_SHARED_BLOCK")) mb = atoll(ev);   // tests: force several blocks
+  if (mb >= unit) return mb / unit * unit;
+  return std::max<int64_t>(512, mb / 512 * 512);
+}
+
 // scan one block of markers for every trait of the plan; results of trait t go to
-// out_dev[t * out_tstride + a * out_ld + out_off + k], a = 0..6
+// out_dev[t * out_tstride + a * out_ld + out_off + k], a = 0..6.  With host_out the finished rows are copied to the
+// caller's arrays (m_total markers per trait, rows out_off..) on the D2H stream while the next rows are computed.
 static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, double* out_dev, int64_t out_tstride,
-                    int64_t out_ld, int64_t out_off, cudaEvent_t after_reduce = nullptr) {
+                    int64_t out_ld, int64_t out_off, cudaEvent_t after_reduce = nullptr,
+                    const gapit_scan_out* host_out = nullptr, int64_t m_total = 0) {
   const int Q = plan.Q;
+  gapit_geno view;  // borrowed pointers only
+  view.ctx = ctx;
+  view.n = plan.n;
+  view.ldn = plan.ldn;
+  if (plan.shared) {
+    gapit_eigsys* e = plan.e;
+    const int64_t tiles = e->nkq + plan.lin_tiles;
+    const int64_t rows = tiles * e->KPB;
+    const int64_t mb = std::min(shared_block_markers(ctx, rows), round_up(v.m, 256));
+    double *wbuf = nullptr, *xx = nullptr;
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_WBUF, size_t(rows) * mb, &wbuf));
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_XX, size_t(plan.T) * mb, &xx));
+    for (int64_t k0 = 0; k0 < v.m; k0 += mb) {
+      const int64_t mc = std::min(mb, v.m - k0);
+      const int64_t m_ld = round_up(mc, 256);
+      view.m = mc;
+      view.mk = const_cast<int8_t*>(v.mk) + size_t(k0) * plan.ldn;
+      GAPIT_CHECK(launch_store(ctx, &view, e, tiles, plan.gsplit, plan.kscale, wbuf, m_ld, static_cast<int>(plan.nk)));
+      GAPIT_CHECK(launch_xx_contract(ctx->stream, wbuf, m_ld, plan.wt, plan.wt_ld, static_cast<int>(plan.nk), xx, m_ld, plan.T));
+      FinalizeSrc src;
+      src.xx = xx;
+      src.xx_t = m_ld;
+      src.xx_g = 0;
+      src.xa = wbuf + size_t(plan.nk) * m_ld;
+      src.xa_t = int64_t(plan.q0 + 1) * m_ld;
+      src.xa_j = m_ld;
+      src.xa_g = 0;
+      src.xy = src.xa + size_t(plan.q0) * m_ld;
+      src.xy_t = src.xa_t;
+      src.xy_g = 0;
+      src.nsplit = 1;
+      MarkerView blk{view.mk, mc, v.colsum + k0, v.colsumsq + k0};
+      GAPIT_CHECK(launch_finalize(ctx, plan, src, blk, out_dev + out_off + k0, out_tstride, out_ld));
+      if (host_out) {
+        GAPIT_CUDA(cudaEventRecord(ctx->ev_blk, ctx->stream));
+        GAPIT_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_blk, 0));
+        GAPIT_CHECK(fetch_block(ctx->d2h_stream, out_dev, out_tstride, out_ld, out_off + k0, mc, plan.T, m_total, host_out));
+      }
+    }
+    if (after_reduce) cudaEventRecord(after_reduce, ctx->stream);
+    return GAPIT_OK;
+  }
   const int64_t m_ld = round_up(v.m, 256);
   const int nsplit = plan.glm ? 1 : plan.gsplit * scan_mode(m_ld, plan.T).nhalf;   // partial sums per marker
   const int64_t part_tstride = int64_t(nsplit) * (Q + 2) * m_ld;
   double* part = nullptr;
   GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t(plan.T) * part_tstride, &part));
-  gapit_geno view;  // borrowed pointers only
-  view.ctx = ctx;
-  view.n = plan.n;
   view.m = v.m;
-  view.ldn = plan.ldn;
   view.mk = const_cast<int8_t*>(v.mk);
   view.colsum = const_cast<int32_t*>(v.colsum);
   view.colsumsq = const_cast<int32_t*>(v.colsumsq);
@@ -944,15 +1237,20 @@ static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, d
                              plan.Rscale + size_t(t) * (GAPIT_MAX_Q0 + 1), plan.q0 + 1, Q, part + t * part_tstride, m_ld));
   }
   if (after_reduce) cudaEventRecord(after_reduce, ctx->stream);
-  for (int t = 0; t < plan.T; ++t) {
-    double* o = out_dev + t * out_tstride + out_off;
-    FinalizeConsts fc = plan.fc[t];
-    fc.gsplit = nsplit;
-    finalize_kernel<<<static_cast<unsigned>((v.m + 255) / 256), 256, 0, ctx->stream>>>(
-        part + t * part_tstride, m_ld, v.m, v.colsum, v.colsumsq, fc, o, o + out_ld, o + 2 * out_ld,
-        o + 3 * out_ld, o + 4 * out_ld, o + 5 * out_ld, o + 6 * out_ld);
+  FinalizeSrc src;
+  src.xx = part;
+  src.xa = part + m_ld;
+  src.xy = part + int64_t(Q + 1) * m_ld;
+  src.xx_t = src.xa_t = src.xy_t = part_tstride;
+  src.xx_g = src.xa_g = src.xy_g = int64_t(Q + 2) * m_ld;
+  src.xa_j = m_ld;
+  src.nsplit = nsplit;
+  GAPIT_CHECK(launch_finalize(ctx, plan, src, v, out_dev + out_off, out_tstride, out_ld));
+  if (host_out) {
+    GAPIT_CUDA(cudaEventRecord(ctx->ev_blk, ctx->stream));
+    GAPIT_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_blk, 0));
+    GAPIT_CHECK(fetch_block(ctx->d2h_stream, out_dev, out_tstride, out_ld, out_off, v.m, plan.T, m_total, host_out));
   }
-  GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
 }
 
@@ -962,14 +1260,30 @@ static int check_out(const gapit_scan_out* out) {
   return GAPIT_OK;
 }
 
-// copy the 7 device result arrays of trait t (m values each, stride out_ld) to the caller's SoA arrays
-static int fetch_outputs(gapit_ctx* ctx, const double* out_dev, int64_t out_ld, int64_t m, int t, gapit_scan_out* out) {
-  double* dsts[7] = {out->effect, out->tvalue, out->se, out->pvalue, out->rsquare, out->loglm, out->maf};
-  for (int a = 0; a < 7; ++a) {
-    if (!dsts[a]) continue;
-    if (a == 6 && t > 0) continue;
-    double* dst = dsts[a] + (a == 6 ? 0 : size_t(t) * m);
-    GAPIT_CUDA(cudaMemcpyAsync(dst, out_dev + size_t(a) * out_ld, size_t(m) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+// every exit path of a scan leaves no work queued that still reads the caller's buffers (the header promises calls
+// are synchronous on return)
+struct StreamDrain {
+  gapit_ctx* c;
+  ~StreamDrain() {
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    cudaStreamSynchronize(c->d2h_stream);
+  }
+};
+
+// size the per-block workspaces of scan_run once for blocks of up to max_m markers (no regrow, hence no stream
+// synchronisation, in the middle of a pipelined call)
+static int scan_reserve(gapit_ctx* ctx, const ScanPlan& plan, int64_t max_m) {
+  void* p = nullptr;
+  const int64_t m_ld = round_up(max_m, 256);
+  if (plan.shared) {
+    const int64_t rows = (plan.e->nkq + plan.lin_tiles) * plan.e->KPB;
+    const int64_t mb = std::min(shared_block_markers(ctx, rows), m_ld);
+    GAPIT_CHECK(ctx_ws(ctx, WS_WBUF, size_t(rows) * mb * 8, &p));
+    GAPIT_CHECK(ctx_ws(ctx, WS_XX, size_t(plan.T) * mb * 8, &p));
+  } else {
+    const int nsplit = plan.glm ? 1 : plan.gsplit * scan_mode(m_ld, plan.T).nhalf;
+    GAPIT_CHECK(ctx_ws(ctx, WS_PART, size_t(plan.T) * nsplit * (plan.Q + 2) * m_ld * 8, &p));
   }
   return GAPIT_OK;
 }
@@ -985,28 +1299,31 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
     return std::chrono::duration<double, std::milli>(now() - t0).count();
   };
   auto t_start = now();
+  StreamDrain drain{ctx};
   GAPIT_CHECK(scan_prepare(ctx, g->n, g->ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
   if (trace) fprintf(stderr, "[gapit] scan_prepare %.2f ms\n", ms_since(t_start));
   const int64_t m = g->m;
   double* o = nullptr;
   GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(T) * 7 * m, &o));
+  GAPIT_CHECK(scan_reserve(ctx, plan, m));
   MarkerView v{g->mk, m, g->colsum, g->colsumsq};
   cudaEventRecord(ctx->ev0, ctx->stream);
-  GAPIT_CHECK(scan_run(ctx, plan, v, o, 7 * m, m, 0, ctx->ev3));
+  GAPIT_CHECK(scan_run(ctx, plan, v, o, 7 * m, m, 0, ctx->ev3, out, m));
   cudaEventRecord(ctx->ev1, ctx->stream);
-  for (int t = 0; t < T; ++t) GAPIT_CHECK(fetch_outputs(ctx, o + size_t(t) * 7 * m, m, m, t, out));
-  cudaEventRecord(ctx->ev2, ctx->stream);
+  GAPIT_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev1, 0));
+  cudaEventRecord(ctx->ev2, ctx->d2h_stream);
   if (trace) fprintf(stderr, "[gapit] launches enqueued at %.2f ms\n", ms_since(t_start));
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
   if (trace) fprintf(stderr, "[gapit] scan done at %.2f ms\n", ms_since(t_start));
   float ms = 0.f;
   ctx->stats = gapit_stats{};
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev3);
-  ctx->stats.kernel_ms = ms;   // rotate_reduce (MLM, all traits) or glm_reduce
+  ctx->stats.kernel_ms = ms;   // rotate_reduce or glm_reduce; shared rotation: every block's rotation + contraction + finalize
   cudaEventElapsedTime(&ms, ctx->ev3, ctx->ev1);
   ctx->stats.post_ms = ms;     // finalize
   cudaEventElapsedTime(&ms, ctx->ev1, ctx->ev2);
-  ctx->stats.d2h_ms = ms;
+  ctx->stats.d2h_ms = ms;      // result copies not hidden behind the kernels
   return GAPIT_OK;
 }
 
@@ -1021,6 +1338,7 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
   GAPIT_CHECK(check_out(out));
   const int64_t ldn = round_up(n, 128);
   ScanPlan plan;
+  StreamDrain drain{ctx};
   GAPIT_CHECK(scan_prepare(ctx, n, ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
   const size_t esz = dtype == GAPIT_F64 ? 8 : (dtype == GAPIT_I32 ? 4 : 1);
   const size_t row_bytes = dtype == GAPIT_B2 ? size_t(nb2) : size_t(n) * esz;   // dense bytes of one marker on the host
@@ -1043,6 +1361,7 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
   }
   GAPIT_CHECK(ctx_ws_t(ctx, WS_BAD, 4, &bad));
   GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(T) * 7 * m, &o));
+  GAPIT_CHECK(scan_reserve(ctx, plan, chunk));
   GAPIT_CUDA(cudaMemsetAsync(bad, 0, 4, ctx->stream));
   cudaEventRecord(ctx->ev0, ctx->stream);
   // the copy stream must not start before the workspaces are initialised
@@ -1076,16 +1395,17 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
     GAPIT_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ready[b], 0));
     GAPIT_CHECK(launch_colstats(ctx, ctx->stream, mk[b], ldn, n, mc, cs[b], cq[b], bad));
     MarkerView v{mk[b], mc, cs[b], cq[b]};
-    GAPIT_CHECK(scan_run(ctx, plan, v, o, 7 * m, m, k0));
+    GAPIT_CHECK(scan_run(ctx, plan, v, o, 7 * m, m, k0, nullptr, out, m));
     GAPIT_CUDA(cudaEventRecord(ctx->ev_free[b], ctx->stream));
   }
   cudaEventRecord(ctx->ev1, ctx->stream);
   int hbad = 0;
   GAPIT_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  for (int t = 0; t < T; ++t) GAPIT_CHECK(fetch_outputs(ctx, o + size_t(t) * 7 * m, m, m, t, out));
-  cudaEventRecord(ctx->ev2, ctx->stream);
+  GAPIT_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev1, 0));
+  cudaEventRecord(ctx->ev2, ctx->d2h_stream);
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
   GAPIT_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->d2h_stream));
   if (hbad & 2) return fail(GAPIT_ERR_DATA, "genotype matrix holds NA and no impute rule was given");
   if (hbad & 1) return fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}");
   float ms = 0.f;
@@ -1114,6 +1434,7 @@ static int eigsys_build(gapit_ctx* ctx, const double* vectors, cudaMemcpyKind ki
   e->KPB = sg.KPB;
   e->ldn = round_up(n, 128);
   e->nkq = (n + e->KPB - 1) / e->KPB;
+  e->tiles_cap = e->nkq;
   e->values.assign(values, values + n);
   const int64_t nk = e->nkq * e->KPB;
   cudaError_t err = cudaMalloc(&e->V, size_t(n) * n * 8);
@@ -1211,26 +1532,6 @@ extern "C" int gapit_p3d_scan(gapit_ctx* ctx, gapit_geno* g, const double* vecto
 // kappa_k = 1/lambda_k when solve(K) succeeds; when K is numerically singular (the usual case: centring by 2p
 // makes K 1 = 0) the reference falls back to MASS::ginv(K), i.e. kappa_k = 0 for |lambda_k| <= sqrt(eps) max|lambda|.
 // The O(n^3) inversions of the reference become O(n^2 q) products with V.
-namespace gapit {
-
-// out[c*n + j] = sum_k V[j + k n] Z[c*n + k]   (V Z, coalesced along j); optional squaring of V
-template <bool SQUARE>
-__global__ void v_times_cols_kernel(const double* __restrict__ V, int64_t n, const double* __restrict__ Z, int nc,
-                                    double* __restrict__ out) {
-  const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  for (int c = 0; c < nc; ++c) {
-    double acc = 0.0;
-    for (int64_t k = 0; k < n; ++k) {
-      const double v = V[j + k * n];
-      acc = fma(SQUARE ? v * v : v, __ldg(Z + c * n + k), acc);
-    }
-    out[c * n + j] = acc;
-  }
-}
-
-}  // namespace gapit
-
 extern "C" int gapit_blup_pev(gapit_ctx* ctx, gapit_eigsys* e, const double* X0, int q0, const double* y, double delta,
                               double vg, double* blup_out, double* pev_out, double* beta_out) {
   if (!ctx || !e || !X0 || !y || !blup_out || !pev_out || q0 < 1 || q0 > GAPIT_MAX_Q0)
@@ -1302,10 +1603,8 @@ extern "C" int gapit_blup_pev(gapit_ctx* ctx, gapit_eigsys* e, const double* X0,
   double* dZ = dR;       // reuse
   double* dOut = dProj;  // reuse
   GAPIT_CUDA(cudaMemcpyAsync(dZ, Z.data(), Z.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-  const unsigned b2 = static_cast<unsigned>((n + 127) / 128);
-  v_times_cols_kernel<false><<<b2, 128, 0, ctx->stream>>>(e->V, n, dZ, nc, dOut);
-  v_times_cols_kernel<true><<<b2, 128, 0, ctx->stream>>>(e->V, n, dZ + size_t(nc) * n, 1, dOut + size_t(nc) * n);
-  GAPIT_CUDA(cudaGetLastError());
+  GAPIT_CHECK(launch_v_times_cols(ctx->stream, e->V, n, dZ, nc, dOut, false));
+  GAPIT_CHECK(launch_v_times_cols(ctx->stream, e->V, n, dZ + size_t(nc) * n, 1, dOut + size_t(nc) * n, true));
   std::vector<double> O(size_t(n) * (nc + 1));
   GAPIT_CUDA(cudaMemcpyAsync(O.data(), dOut, O.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));

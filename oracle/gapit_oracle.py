@@ -569,3 +569,89 @@ def prcomp(X: np.ndarray):
     Xc = X - X.mean(axis=0, keepdims=True)
     u, s, _ = np.linalg.svd(Xc, full_matrices=False)
     return u * s, s * s / (X.shape[0] - 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Compression glue around the scan: GAPIT.Main.R:386-400 calls these three unconditionally
+# before GAPIT.EMMAxP3D.  Tables are held as plain lists / arrays: KI = (names, n x n matrix); Z = (row taxa,
+# column taxa, matrix) for the reference's data.frame whose first row / column carry the names; GA rows =
+# (taxon, group); GAU rows = (taxon, group, block indicator, ID).  Character sorting follows R in the C locale.
+
+def _first_appearance(labels):
+    """cutree numbers the clusters in order of first appearance of their members (stats::cutree)."""
+    seen, out = {}, []
+    for v in labels:
+        if v not in seen:
+            seen[v] = len(seen) + 1
+        out.append(seen[v])
+    return np.asarray(out, dtype=np.int64)
+
+
+def compress(line_names, KI, kinship_cluster="average", kinship_group="Mean", GN=None):
+    """GAPIT.Compress (GAPIT.Compress.R:12-112): dist() between the ROWS of the kinship (:37), hclust (:38),
+    cutree(k = GN) (:45), group kinship by Mean (:52-63) or Max / Min / Median (:72-96).
+    Returns GA (list of (name, group)) and KG (GN x GN)."""
+    from scipy.cluster.hierarchy import linkage, cut_tree
+    from scipy.spatial.distance import pdist
+    KI = np.asarray(KI, dtype=np.float64)
+    n = KI.shape[0]
+    GN = n if GN is None else int(GN)
+    if n == 1:
+        membership = np.ones(1, dtype=np.int64)
+    else:
+        method = {"average": "average", "complete": "complete", "single": "single", "ward": "ward",
+                  "mcquitty": "weighted", "median": "median", "centroid": "centroid"}[kinship_cluster]
+        tree = linkage(pdist(KI, metric="euclidean"), method=method)            # :37-38
+        membership = _first_appearance(cut_tree(tree, n_clusters=GN)[:, 0])     # :45
+    ng = int(membership.max())                                                   # :56
+    b = np.zeros((n, ng))
+    b[np.arange(n), membership - 1] = 1.0                                        # :57 diag(n)[x,]
+    if kinship_group == "Mean":
+        KG = (b.T @ KI @ b) / (b.T @ np.ones_like(KI) @ b)                       # :59-61
+    else:
+        f = {"Max": np.max, "Min": np.min, "Median": np.median}[kinship_group]   # :91-96 tapply
+        KG = np.empty((ng, ng))
+        for a in range(ng):
+            for c in range(ng):
+                KG[a, c] = f(KI[np.ix_(membership == a + 1, membership == c + 1)])
+    GA = [(str(nm), int(g)) for nm, g in zip(line_names, membership)]            # :104
+    return GA, KG
+
+
+def block(Z_col_taxa, GA, KG):
+    """GAPIT.Block (GAPIT.Block.R:14-64): split the group kinship into groups with (KW) and without (KO) a phenotyped
+    member.  Z_col_taxa = Z[1,-1].  Returns GAU rows (taxon, group, (indiv block + group block)/2, ID) in merge()'s
+    order (sorted by the group key AS CHARACTER, ties in x order), KW, KO, KWO."""
+    zset = set(str(t) for t in Z_col_taxa)
+    taxa = [t for t, _ in GA]
+    grp = [g for _, g in GA]
+    blk = [1 if t in zset else 2 for t in taxa]                                  # :19-22
+    grp12 = list(dict.fromkeys(grp))                                             # :33 unique, first appearance
+    grp1 = list(dict.fromkeys(g for g, b in zip(grp, blk) if b == 1))            # :34
+    grp2 = [g for g in grp12 if g not in set(grp1)]                              # :35 setdiff keeps x order
+    gb = {g: (1, i + 1) for i, g in enumerate(grp1)}                             # :39-42 (grp, block, ID)
+    gb.update({g: (2, i + 1) for i, g in enumerate(grp2)})
+    order_block = sorted(range(len(blk)), key=lambda i: blk[i])                  # :44 order() is stable
+    rows = [(taxa[i], grp[i], blk[i]) for i in order_block]
+    rows.sort(key=lambda r: str(r[1]))                                           # :51 merge sorts on the key column
+    GAU = [(t, g, (b + gb[g][0]) / 2.0, gb[g][1]) for t, g, b in rows]           # :53-55
+    i1 = np.asarray(grp1, dtype=np.int64) - 1
+    i2 = np.asarray(grp2, dtype=np.int64) - 1
+    KG = np.asarray(KG)
+    return GAU, KG[np.ix_(i1, i1)], KG[np.ix_(i2, i2)], KG[np.ix_(i1, i2)]       # :56-58
+
+
+def zmatrix_compress(Z_row_taxa, Z_col_taxa, Zmat, GAU):
+    """GAPIT.ZmatrixCompress (GAPIT.ZmatrixCompress.R:13-45): individual -> group incidence Z %*% DS, columns = IDs
+    of the phenotyped block, rows sorted by taxon.  Returns (row taxa sorted, matrix)."""
+    zset = set(str(t) for t in Z_col_taxa)
+    GAU0 = [r for r in GAU if r[0] in zset]                                      # :17
+    GAU1 = sorted(GAU0, key=lambda r: r[0])                                      # :18-19
+    n = max(r[3] for r in GAU1 if r[2] < 2)                                      # :21-22
+    x = np.asarray([r[3] for r in GAU1], dtype=np.int64)                         # :23
+    DS = np.eye(n)[x - 1, :]                                                     # :24
+    order_Z = sorted(range(len(Z_col_taxa)), key=lambda i: str(Z_col_taxa[i]))   # :27
+    Zs = np.asarray(Zmat, dtype=np.float64)[:, order_Z]                          # :28-33
+    out = Zs @ DS                                                                # :34
+    order_rows = sorted(range(len(Z_row_taxa)), key=lambda i: str(Z_row_taxa[i]))  # :41
+    return [str(Z_row_taxa[i]) for i in order_rows], out[order_rows, :]

@@ -11,7 +11,12 @@ function(ys,xs,K=NULL,Z=NULL,X0=NULL,CVI=NULL,CV.Inheritance=NULL,GI=NULL,GP=NUL
     SNP.P3D=TRUE,Timmer,Memory,optOnly=TRUE,SNP.effect="Add",SNP.impute="Middle", SNP.permutation=FALSE,
     ngrids=100,llim=-10,ulim=10,esp=1e-10,name.of.trait=NULL, Create.indicator = FALSE, Major.allele.zero = FALSE){
 squareZ = is.null(Z) || (ncol(Z) == nrow(Z))
-accelerated = squareZ && SNP.P3D && fullGD && !Create.indicator && !optOnly && !is.null(xs)
+# one trait without missing phenotypes / covariates and a full-rank X0: the reference drops NA phenotypes per trait
+# (vids, :113-114), loops the rows of ys (:81) and returns the REML = 0 list for singular X (GAPIT.emma.REMLE.R:16-19);
+# those calls keep the reference body
+oneTrait = is.null(dim(ys)) || ncol(ys) == 1 || nrow(ys) == 1
+cleanXY = !anyNA(ys) && (is.null(X0) || (!anyNA(X0) && det(crossprod(X0,X0)) != 0))
+accelerated = squareZ && SNP.P3D && fullGD && !Create.indicator && !optOnly && !is.null(xs) && oneTrait && cleanXY
 if(!accelerated) return(GAPIT.EMMAxP3D.reference(ys=ys,xs=xs,K=K,Z=Z,X0=X0,CVI=CVI,CV.Inheritance=CV.Inheritance,GI=GI,GP=GP,
     file.path=file.path,file.from=file.from,file.to=file.to,file.total=file.total,genoFormat=genoFormat,file.fragment=file.fragment,
     byFile=byFile,fullGD=fullGD,SNP.fraction=SNP.fraction,file.G=file.G,file.Ext.G=file.Ext.G,GTindex=GTindex,file.GD=file.GD,

@@ -802,3 +802,30 @@ def test_large_taxa_shapes(gpu_ctx):
         beta = iA @ rhs
         assert full["effect"][0, i] == pytest.approx(beta[1], rel=1e-7, abs=1e-10)
         assert full["se"][0, i] == pytest.approx(np.sqrt(iA[1, 1] * 2.0), rel=1e-8)
+
+
+def test_shared_rotation_blocks_do_not_change_results(gpu_ctx, monkeypatch):
+    """The shared-rotation form of the multi-trait scan (StoreEpi + xx_contract) works through marker blocks sized from
+    the free device memory; forcing several small blocks must give bit-identical rows (each marker's sums are formed
+    in a fixed order of the eigen index wherever its tile sits)."""
+    G, _, X0 = case(140, 1500, npc=2, seed=5)
+    T = 5
+    Yt = synth.make_phenotypes(G, ntraits=T, seed=5)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    remls = [go.emma_REMLE(Yt[:, t], X0, K) for t in range(T)]
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    kw = dict(eigsys=es, delta=[r["delta"] for r in remls], vg=[r["vg"] for r in remls], ctx=gpu_ctx)
+    whole, _ = gb().p3d_scan(geno, X0, Yt, **kw)
+    monkeypatch.setenv("GAPIT_SHARED_BLOCK", "512")
+    parts, _ = gb().p3d_scan(geno, X0, Yt, **kw)
+    for key in ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm"):
+        assert np.array_equal(whole[key], parts[key], equal_nan=True), key
+    assert np.array_equal(whole["maf"], parts["maf"])
+    for t in range(T):
+        ora = go.emmax_p3d(Yt[:, t], G.T, K, X0, eig_L=eL, reml=remls[t])
+        r, a = rel_err(parts["effect"][t], ora.effect_est, 1e-4)
+        assert r < BETA_RTOL, (t, r)
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(parts["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL

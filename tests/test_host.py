@@ -248,3 +248,70 @@ def test_synth_is_deterministic_and_thread_independent():
     c = a.astype(np.int64).sum(1)
     assert ((c == 0) | (c == 128)).sum() >= 1          # monomorphic columns are injected
     assert (np.all(a[1:] == a[:-1], axis=1)).sum() >= 1  # so are duplicated adjacent columns
+
+
+# ---- compression glue at GN = n / GN = 1 -------------------------------------------
+def _compress_case(n, seed, n_pheno):
+    rng = np.random.default_rng(seed)
+    A = rng.normal(size=(n, 3 * n))
+    K = A @ A.T / (3 * n)
+    names = [f"L{rng.integers(10**6):06d}" for _ in range(n)]
+    assert len(set(names)) == n
+    zcols = [names[i] for i in rng.permutation(n)[:n_pheno]]          # phenotyped taxa, in a shuffled order
+    zrows = list(zcols)
+    Zm = np.eye(n_pheno)
+    return names, K, zrows, zcols, Zm
+
+
+@pytest.mark.parametrize("n,n_pheno,seed", [(17, 17, 1), (23, 15, 2), (40, 40, 3)])
+def test_compress_glue_short_circuit_equals_the_clustered_route(n, n_pheno, seed):
+    """GN = n: dist + hclust + cutree(k = n) is the identity grouping (numbered by first appearance = row order) and
+    KG = KI; GN = 1: one group, KG = mean(KI).  The mirror must reproduce the oracle's restatement of
+    GAPIT.Compress / GAPIT.Block / GAPIT.ZmatrixCompress without clustering or the dense Z %*% DS."""
+    import gapit_b200.api as api
+    from oracle import gapit_oracle as go
+    names, K, zrows, zcols, Zm = _compress_case(n, seed, n_pheno)
+    for GN in (n, 1):
+        GA_o, KG_o = go.compress(names, K, GN=GN)
+        GA, KG = api.GAPIT_Compress(names, K, GN=GN)
+        assert GA == GA_o
+        assert KG.shape == KG_o.shape and np.allclose(KG, KG_o, rtol=1e-14, atol=0)
+        if GN == n:
+            assert np.array_equal(KG, K)                              # a mean of one element is that element
+        GAU_o, KW_o, KO_o, KWO_o = go.block(zcols, GA_o, KG_o)
+        GAU, KW, KO, KWO = api.GAPIT_Block(zcols, GA, KG)
+        assert GAU == GAU_o
+        for a, b in ((KW, KW_o), (KO, KO_o), (KWO, KWO_o)):
+            assert a.shape == b.shape and np.allclose(a, b, rtol=1e-14, atol=0)
+        rt_o, Z_o = go.zmatrix_compress(zrows, zcols, Zm, GAU_o)
+        rt, Z = api.GAPIT_ZmatrixCompress(zrows, zcols, Zm, GAU)
+        assert rt == rt_o and np.array_equal(Z, Z_o)
+        if GN == n:
+            # the incidence matrix is a permutation and K = KW is the kinship of the phenotyped taxa in GA order:
+            # Z KW Z' is the kinship of the sorted phenotyped taxa, i.e. nothing was compressed
+            idx = {t: i for i, t in enumerate(names)}
+            want = K[np.ix_([idx[t] for t in rt], [idx[t] for t in rt])]
+            assert np.allclose(Z @ KW @ Z.T, want, rtol=1e-14, atol=0)
+        else:
+            assert Z.shape == (n_pheno, 1) and np.all(Z == 1.0)
+
+
+def test_compress_glue_other_group_counts_stay_with_the_reference():
+    import gapit_b200.api as api
+    names, K, *_ = _compress_case(12, 5, 12)
+    with pytest.raises(NotImplementedError):
+        api.GAPIT_Compress(names, K, GN=4)
+
+
+def test_compress_oracle_general_grouping_properties():
+    """The restated clustered route at 1 < GN < n: cutree numbering by first appearance, KG = block means."""
+    from oracle import gapit_oracle as go
+    names, K, *_ = _compress_case(30, 7, 30)
+    GA, KG = go.compress(names, K, GN=6)
+    g = np.array([x for _, x in GA])
+    assert g[0] == 1 and g.max() == 6
+    firsts = [int(np.argmax(g == k)) for k in range(1, 7)]
+    assert firsts == sorted(firsts)
+    for a in range(6):
+        for b in range(6):
+            assert KG[a, b] == pytest.approx(K[np.ix_(g == a + 1, g == b + 1)].mean(), rel=1e-12)
