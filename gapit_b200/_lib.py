@@ -68,7 +68,8 @@ SIGNATURES = {
     "gapit_vanraden": (C.c_int, [_P, _P, _P, _P]),
     "gapit_gram_ld": (_I64, [_I64]),
     "gapit_vanraden_gram": (C.c_int, [_P, _P, _P, _P]),
-    "gapit_vanraden_gram_fused": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
+    "gapit_vanraden_gram_fused": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "gapit_vanraden_gram_gather": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_int]),
     "gapit_gram_owned_rows": (C.c_int, [_I64, C.c_int, C.c_int, C.POINTER(_I64), C.POINTER(_I64)]),
     "gapit_vanraden_finish": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
     "gapit_zhang": (C.c_int, [_P, _P, _P]),
@@ -93,6 +94,18 @@ SIGNATURES = {
                                       C.c_int, C.POINTER(ScanOut), C.POINTER(ScanBase)]),
     "gapit_blup_pev": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_double, C.c_double, _P, _P, _P]),
     "gapit_set_slices": (C.c_int, [_P, C.c_int]),
+    "gapit_eigsys_vectors_dev": (_P, [_P]),
+    "gapit_mctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
+    "gapit_mctx_destroy": (None, [_P]),
+    "gapit_mctx_ngpus": (C.c_int, [_P]),
+    "gapit_mctx_ctx": (_P, [_P, C.c_int]),
+    "gapit_mgeno_pack": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _I64, C.c_int, C.POINTER(_P)]),
+    "gapit_mgeno_free": (None, [_P]),
+    "gapit_mgeno_n": (_I64, [_P]),
+    "gapit_mgeno_m": (_I64, [_P]),
+    "gapit_multi_vanraden": (C.c_int, [_P, _P, _P, _P]),
+    "gapit_multi_p3d_scan": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
+                                       C.POINTER(ScanOut), C.POINTER(ScanBase)]),
 }
 
 _lib = None

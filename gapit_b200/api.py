@@ -806,3 +806,95 @@ def GAPIT_ZmatrixCompress(Z_row_taxa, Z_col_taxa, Zmat, GAU):
         np.add.at(out.T, x, Zs.T)
     order_rows = sorted(range(len(Z_row_taxa)), key=lambda i: str(Z_row_taxa[i]))
     return [str(Z_row_taxa[i]) for i in order_rows], out[order_rows, :]
+
+
+# ---------------------------------------------------------------------------
+# All GPUs of the box from one process (gapit_mctx / gapit_mgeno): what the R shim binds, mirrored for the tests.
+# ---------------------------------------------------------------------------
+class MultiContext:
+    """gapit_mctx: ``ngpus`` devices (0 = all visible) with peer access between every pair."""
+
+    def __init__(self, ngpus=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        check(self.lib.gapit_mctx_create(int(ngpus), C.byref(h)))
+        self.h = h
+        self.ngpus = int(self.lib.gapit_mctx_ngpus(h))
+
+    def context(self, gpu=0):
+        """The one-GPU context of device ``gpu`` (borrowed: for spectra / REML between the two multi-GPU calls)."""
+        c = Context.__new__(Context)
+        c.lib, c.h, c.device = self.lib, C.c_void_p(self.lib.gapit_mctx_ctx(self.h, int(gpu))), int(gpu)
+        c.close = lambda: None          # owned by the multi-context
+        return c
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.gapit_mctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MultiGenotypes:
+    """gapit_mgeno: the host matrix split into contiguous marker blocks, one per GPU."""
+
+    def __init__(self, snps, mctx, impute=None, marker_major=False):
+        self.mctx = mctx
+        if isinstance(snps, Packed2):
+            a, dtype, m, n, ld = snps.data, _lib.GAPIT_B2, snps.m, snps.n, snps.data.shape[1]
+        else:
+            a, dtype = _host_geno(snps, marker_major)
+            m, n = a.shape
+            ld = n
+        h = C.c_void_p()
+        check(mctx.lib.gapit_mgeno_pack(mctx.h, _ptr(a), dtype, n, m, ld, _lib.IMPUTE[impute], C.byref(h)))
+        self.h, self.n, self.m = h, int(n), int(m)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.mctx.lib.gapit_mgeno_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def multi_vanraden(mgeno, return_gram=False):
+    """GAPIT.kinship.VanRaden on every GPU of the multi-context (gapit_multi_vanraden)."""
+    n = mgeno.n
+    K = np.empty((n, n), dtype=np.float64, order="F")
+    G = np.empty((n, n), dtype=np.int32) if return_gram else None
+    check(mgeno.mctx.lib.gapit_multi_vanraden(mgeno.mctx.h, mgeno.h, _ptr(K), _ptr(G)))
+    return (K, G) if return_gram else K
+
+
+def multi_p3d_scan(mgeno, X0, Y, values=None, vectors=None, delta=None, vg=None, glm=False, pinned=False):
+    """The P3D scan of every marker block on its GPU (gapit_multi_p3d_scan); same returns as :func:`p3d_scan`."""
+    n, m = mgeno.n, mgeno.m
+    X0 = np.asfortranarray(X0, dtype=np.float64)
+    Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n, -1))
+    q0, T = X0.shape[1], Y.shape[1]
+    _check_scan_shapes(n, X0, T, delta, vg, glm)
+    names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
+    arrs = {k: _host_array((T, m), pinned) for k in names}
+    arrs["maf"] = _host_array((m,), pinned)
+    so = _lib.ScanOut(**{k: arrs[k].ctypes.data_as(C.POINTER(C.c_double)) for k in arrs})
+    base = (_lib.ScanBase * T)()
+    d = np.ascontiguousarray(delta, dtype=np.float64).reshape(-1) if delta is not None else None
+    v = np.ascontiguousarray(vg, dtype=np.float64).reshape(-1) if vg is not None else None
+    vec = np.asfortranarray(vectors, dtype=np.float64) if vectors is not None else None
+    val = np.ascontiguousarray(values, dtype=np.float64) if values is not None else None
+    check(mgeno.mctx.lib.gapit_multi_p3d_scan(mgeno.mctx.h, mgeno.h, _ptr(vec), _ptr(val), _ptr(X0), q0, _ptr(Y), T, _ptr(d),
+                                              _ptr(v), 1 if glm else 0, C.byref(so), base))
+    bases = [{"logL0": b.logL0, "logLM_base": b.logLM_base, "rsquare_base": b.rsquare_base, "ves": b.ves,
+              "reml": b.reml, "df": b.df, "beta0": np.array(b.beta0[:q0]), "singular_x0": bool(b.singular_x0)}
+             for b in base]
+    return arrs, bases

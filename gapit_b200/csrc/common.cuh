@@ -75,10 +75,8 @@ struct gapit_geno {
   int64_t n = 0;      // taxa
   int64_t m = 0;      // markers
   int64_t ldn = 0;    // bytes per marker row of the marker-major copy (multiple of 128)
-  int8_t* mk = nullptr;   // marker-major  [m][ldn]   : K-major operand of the rotation (contract over taxa)
-  int64_t n_rows_t = 0;   // rows of the taxa-major copy (n rounded up to 256)
-  int64_t ldm = 0;        // bytes per taxon row of the taxa-major copy (multiple of 128)
-  int8_t* tx = nullptr;   // taxa-major    [n_rows_t][ldm] : K-major operand of the kinship (contract over markers); built lazily
+  int8_t* mk = nullptr;   // marker-major  [m][ldn]: K-major operand of the rotation (contract over taxa) and MN-major
+                          // operand of the kinship cross-product (contract over markers)
   int32_t* colsum = nullptr;    // [m] sum_i x_ik
   int32_t* colsumsq = nullptr;  // [m] sum_i x_ik^2
 };

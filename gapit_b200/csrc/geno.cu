@@ -1,6 +1,5 @@
 // Genotype ingestion: host matrix (R column-major n x m, f64 / i32 / i8) ->
 // device int8 marker-major [m][ldn] with per-marker sum and sum of squares,
-// plus the taxa-major transposed copy the kinship cross-product contracts over.
 // All three kernels are HBM-bound byte shuffles (128-bit loads, coalesced rows).
 #include <algorithm>
 #include <climits>
@@ -153,54 +152,6 @@ __global__ void colstats_kernel(const int8_t* __restrict__ mk, int64_t ldn, int6
   }
 }
 
-// ---- marker-major -> taxa-major byte transpose -----------------------------
-// 128 markers x 256 taxa per block (two 128 x 128 tiles whose 8 loads per thread are all issued up front, which
-// keeps ~64 KB of reads in flight per SM); each thread owns a 4x4 byte block per tile that is transposed in
-// registers (prmt), staged through shared memory and written back as coalesced 128-byte rows.
-__global__ void __launch_bounds__(1024) transpose_kernel(const int8_t* __restrict__ mk, int64_t ldn, int64_t n,
-                                                         int64_t m, int8_t* __restrict__ tx, int64_t ldm,
-                                                         int64_t n_rows_t) {
-  __shared__ uint32_t tile[2][128][33];
-  const int txi = threadIdx.x;  // 0..31: taxa chunk (4 taxa)
-  const int tyi = threadIdx.y;  // 0..31: marker chunk (4 markers)
-  const int64_t k0 = int64_t(blockIdx.x) * 128;  // marker tile
-  const int64_t i00 = int64_t(blockIdx.y) * 256;  // first of the two taxa tiles
-  uint32_t w[2][4];
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int64_t k = k0 + tyi * 4 + r;
-      const int64_t i = i00 + h * 128 + txi * 4;
-      w[h][r] = (k < m && i < ldn) ? __ldg(reinterpret_cast<const uint32_t*>(mk + k * ldn + i)) : 0u;
-    }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    // 4x4 byte transpose: o[c] = { w[0].c, w[1].c, w[2].c, w[3].c }
-    const uint32_t t0 = __byte_perm(w[h][0], w[h][1], 0x5140);  // w0.b0 w1.b0 w0.b1 w1.b1
-    const uint32_t t1 = __byte_perm(w[h][0], w[h][1], 0x7362);  // w0.b2 w1.b2 w0.b3 w1.b3
-    const uint32_t t2 = __byte_perm(w[h][2], w[h][3], 0x5140);
-    const uint32_t t3 = __byte_perm(w[h][2], w[h][3], 0x7362);
-    tile[h][txi * 4 + 0][tyi] = __byte_perm(t0, t2, 0x5410);
-    tile[h][txi * 4 + 1][tyi] = __byte_perm(t0, t2, 0x7632);
-    tile[h][txi * 4 + 2][tyi] = __byte_perm(t1, t3, 0x5410);
-    tile[h][txi * 4 + 3][tyi] = __byte_perm(t1, t3, 0x7632);
-  }
-  __syncthreads();
-  // row `tyi + 32*j` of a tile = one taxon, 32 words = 128 markers
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int rrow = tyi + 32 * j;
-      const int64_t i = i00 + h * 128 + rrow;
-      if (i < n_rows_t) {
-        const uint32_t v = (i < n) ? tile[h][rrow][txi] : 0u;
-        *reinterpret_cast<uint32_t*>(tx + i * ldm + k0 + txi * 4) = v;
-      }
-    }
-}
-
 // asynchronous pieces shared with the streaming scan (scan.cu)
 int launch_colstats(gapit_ctx* ctx, cudaStream_t st, const int8_t* mk, int64_t ldn, int64_t n, int64_t m, int32_t* colsum,
                     int32_t* colsumsq, int* bad_dev) {
@@ -248,19 +199,6 @@ static int run_colstats(gapit_geno* g) {
   GAPIT_CUDA(cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
   if (hbad) return fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}");
-  return GAPIT_OK;
-}
-
-int geno_build_taxa_major(gapit_geno* g) {
-  if (g->tx) return GAPIT_OK;
-  gapit_ctx* ctx = g->ctx;
-  g->n_rows_t = round_up(g->n, 256);
-  g->ldm = round_up(g->m, 128);
-  GAPIT_CUDA(cudaMalloc(&g->tx, size_t(g->n_rows_t) * g->ldm));
-  dim3 block(32, 32);
-  dim3 grid(static_cast<unsigned>(g->ldm / 128), static_cast<unsigned>(g->n_rows_t / 256));   // n_rows_t is a multiple of 256
-  transpose_kernel<<<grid, block, 0, ctx->stream>>>(g->mk, g->ldn, g->n, g->m, g->tx, g->ldm, g->n_rows_t);
-  GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
 }
 
@@ -406,7 +344,6 @@ extern "C" void gapit_geno_free(gapit_geno* g) {
   if (!g) return;
   if (g->ctx) cudaSetDevice(g->ctx->device);
   cudaFree(g->mk);
-  cudaFree(g->tx);
   cudaFree(g->colsum);
   cudaFree(g->colsumsq);
   delete g;

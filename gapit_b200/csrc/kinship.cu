@@ -25,7 +25,6 @@
 
 namespace gapit {
 
-int geno_build_taxa_major(gapit_geno* g);
 
 // ------------------------------------------------------------------ K1 pieces
 struct GramSched {
@@ -109,54 +108,6 @@ struct GramSched {
   }
 };
 
-template <int MODE>   // 0: local buffer; 1 / 2: fused NVLink exchange (below) -- compile-time so the local path keeps its plain RED
-struct GramEpiT {
-  struct Params {
-    int32_t* G;   // [ldg][ldg] row-major, zero-initialised
-    int64_t ldg;
-    // Fused exchange over NVLink (sharded kinship, one process per GPU), all buffers at the same symmetric layout:
-    //   mode 1: reduce-scatter -- the tile of block-row I is added into the buffer of the rank that owns I (peer RED)
-    //   mode 2: all-reduce in the switch -- every add goes to the NVLS multicast address (multimem.red), so each
-    //           rank's buffer receives the sum of all ranks
-    int mode;
-    int world;
-    int tiles_side;
-    int root;     // >= 0: every tile goes to this rank; < 0: to the owner of its block-row
-    int32_t* peers[8];
-    int32_t* mc;
-  };
-  static constexpr int kSmemBytes = 0;
-  Params p;
-  __device__ GramEpiT(const Params& pp, uint8_t*) : p(pp) {}
-  __device__ void prepare(const Job&, int, int) {}
-  __device__ void finish() {}
-  __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int /*half*/, int /*nhalf*/) {
-    const int64_t off = (int64_t(job.a_row0) + sub * 128 + row) * p.ldg + job.b_row0;
-    int32_t* base = p.G;
-    if (MODE == 1) base = p.peers[p.root >= 0 ? p.root : min(p.world - 1, (job.tag0 * p.world) / p.tiles_side)];
-    if (MODE == 2) base = p.mc;
-    int32_t* dst = base + off;
-#pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 16) {
-      uint32_t r[16];
-      ptx::tmem_ld_x16(taddr + c0, r);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int v = static_cast<int>(r[i]);
-        if (v != 0) {
-          if (MODE == 2)
-            asm volatile("multimem.red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(dst + c0 + i), "r"(r[i]) : "memory");
-          else if (MODE == 1)   // fire-and-forget reduction on a peer-mapped address (an atom would wait for the reply)
-            asm volatile("red.relaxed.sys.global.add.s32 [%0], %1;" ::"l"(dst + c0 + i), "r"(v) : "memory");
-          else
-            atomicAdd(dst + c0 + i, v);
-        }
-      }
-    }
-  }
-};
-
 int make_tensor_map_i32_box32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_bytes);
 
 // Mode 3: the accumulator leaves through TMA.  Each epilogue warp owns 32 accumulator rows; per 32-column chunk it
@@ -210,8 +161,6 @@ struct GramEpiTma {
   }
 };
 
-using GramEpi = GramEpiT<0>;
-using GramCfg = UmmaCfg<2, 256, 3>;
 
 // ------------------------------------------------------------------ K2 pieces
 __global__ void colsum_reduce_kernel(const int32_t* __restrict__ colsum, int64_t m, int64_t two_n,
@@ -396,32 +345,20 @@ static int choose_ksplit(int ntri, int kblocks, int sms) {
   return ks;
 }
 
-// The cta_group::2 form reads the marker-major matrix directly as MN-major operands (taxa contiguous, one marker per
-// 128-byte row): no taxa-major copy, no transpose pass.  Smaller problems keep the K-major kernels on the copy.
-static bool gram_mn_major(const gapit_geno* g) {
-  if (g->n <= 256) return false;
-  if (const char* ev = getenv("GAPIT_PAIR")) if (!atoi(ev)) return false;
-  if (const char* ev = getenv("GAPIT_CLUSTER")) if (atoi(ev) < 2) return false;
-  if (const char* ev = getenv("GAPIT_GRAM_MN")) return atoi(ev) != 0;   // A/B switch for profiling
-  return true;
-}
-
-struct GramExchange {   // fused NVLink exchange of the sharded kinship (mode 0: none)
-  int mode = 0;
+struct GramExchange {   // where the tiles of this launch are reduced into (world 1: the local buffer)
   int world = 1;
-  int root = -1;
+  int root = 0;           // >= 0: every tile goes to this rank's buffer; < 0: to the owner of its block-row
   int32_t* peers[8] = {};
-  int32_t* mc = nullptr;
 };
 
-static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ldg, const GramExchange& ex = GramExchange()) {
-  const bool mn = gram_mn_major(g);
-  if (!mn) GAPIT_CHECK(geno_build_taxa_major(g));
+// One form for every shape: the cta_group::2 kernel reads the marker-major matrix directly as MN-major operands (taxa
+// contiguous, one marker per 128-byte row; no taxa-major copy, no transpose pass) and delivers each 256 x 256 tile as
+// bulk tensor reduce-adds into the Gram buffer of the rank that owns it -- the local buffer, or a peer's over NVLink.
+// A pair covers two block-rows; with a single block-row (n <= 256) the second CTA multiplies zero padding.
+static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int64_t ldg, const GramExchange& ex) {
   GramSched::Params sp;
   sp.tiles_side = static_cast<int>((g->n + 255) / 256);
-  // clusters of two CTAs take two block-rows against one block-column and multicast that column's panel
-  int cl = (sp.tiles_side >= 2) ? 2 : 1;
-  if (const char* ev = getenv("GAPIT_CLUSTER")) cl = std::max(1, std::min(cl, atoi(ev)));  // A/B switch for profiling
+  constexpr int cl = 2;
   if (int64_t(round_up(sp.tiles_side, cl)) * 256 > ldg) return fail(GAPIT_ERR_ARG, "launch_gram: Gram buffer too small");
   const int TR = (sp.tiles_side + cl - 1) / cl;
   sp.cl = cl;
@@ -429,99 +366,44 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t ld
   for (int R = 0; R < TR; ++R) sp.ntri += std::min(cl * (R + 1), sp.tiles_side);
   sp.kblocks = static_cast<int>(round_up(g->m, 128) / kBlockK);
   sp.ksplit = choose_ksplit(sp.ntri * cl, sp.kblocks, ctx->sm_count);
-  CUtensorMap map_a, map_b;
-  GramEpi::Params ep{};
-  ep.G = G_dev;
-  ep.ldg = ldg;
-  ep.mode = ex.mode;
-  ep.world = ex.world;
-  ep.tiles_side = sp.tiles_side;
-  ep.root = ex.root;
-  for (int r = 0; r < 8; ++r) ep.peers[r] = ex.peers[r];
-  ep.mc = ex.mc;
-  if (ex.mode != 0 && !mn) return fail(GAPIT_ERR_ARG, "fused kinship exchange needs the pair kernel (n > 256)");
   const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
   sp.round_ctr = nullptr;
   sp.round_wait = 100000;
-  if (const char* ev = getenv("GAPIT_ROUND_WAIT")) sp.round_wait = atoi(ev);   // 0 switches the alignment off
-  if (mn && sp.round_wait > 0) {
-    const size_t rounds = size_t((sp.ntri * sp.ksplit + nunits - 1) / nunits) + 1;
-    GAPIT_CHECK(ctx_ws_t(ctx, WS_SYNC, rounds, &sp.round_ctr));
-    GAPIT_CUDA(cudaMemsetAsync(sp.round_ctr, 0, rounds * sizeof(unsigned int), ctx->stream));
-  }
-  if (mn) {
-    // one map for both operands: [m markers][ldn bytes of taxa], boxes of 128 markers x 128 taxa
-    GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
-                                   static_cast<uint64_t>(g->ldn), 128));
-    using PCfg = UmmaPairCfg<2, 256, 4>;
-    GramExchange local = ex;
-    if (ex.mode == 0) {   // the local buffer also takes the accumulator as bulk reduce-adds (9 % faster than per-element
-      const char* ev = getenv("GAPIT_GRAM_TMA");   // RED.ADD); GAPIT_GRAM_TMA=0 is the A/B switch back to the RED epilogue
-      if (!ev || atoi(ev)) {
-        local.mode = 3;
-        local.world = 1;
-        local.root = 0;
-        local.peers[0] = G_dev;
-      }
-    }
-    if (local.mode == 3) {
-      GramEpiTma::Params et{};
-      et.world = local.world;
-      et.tiles_side = sp.tiles_side;
-      et.root = local.root;
-      for (int r = 0; r < local.world; ++r)
-        GAPIT_CHECK(make_tensor_map_i32_box32(&et.maps[r], local.peers[r], static_cast<uint64_t>(ldg), static_cast<uint64_t>(ldg),
-                                              static_cast<uint64_t>(ldg) * 4));
-      const size_t smem = PCfg::kSmemBytes + GramEpiTma::kSmemBytes + 16;
-      auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpiTma, 0, 0, true>;
-      GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-      GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, smem, ctx->stream, map_a, map_a, sp, et));
-      return GAPIT_OK;
-    }
-    if (ex.mode == 0) {
-      auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpi, 0, 0, true>;
-      GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
-      GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_a, sp, ep));
-    } else {
-      // the exchange variants share the parameter block (same layout for every MODE)
-      typename GramEpiT<1>::Params e1;
-      static_assert(sizeof(e1) == sizeof(ep), "GramEpiT<MODE>::Params must not depend on MODE");
-      memcpy(&e1, &ep, sizeof(ep));
-      if (ex.mode == 1) {
-        auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpiT<1>, 0, 0, true>;
-        GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
-        GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_a, sp, e1));
-      } else {
-        typename GramEpiT<2>::Params e2;
-        memcpy(&e2, &ep, sizeof(ep));
-        auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpiT<2>, 0, 0, true>;
-        GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
-        GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_a, sp, e2));
-      }
-    }
-    return GAPIT_OK;
-  }
-  GAPIT_CHECK(make_tensor_map_u8(&map_a, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
-                                 static_cast<uint64_t>(g->ldm), 256));
-  GAPIT_CHECK(make_tensor_map_u8(&map_b, g->tx, static_cast<uint64_t>(g->ldm), static_cast<uint64_t>(g->n),
-                                 static_cast<uint64_t>(g->ldm), 256 / cl));
-  int pair = 1;  // cta_group::2 UMMA (one M=256 instruction per CTA pair) unless switched off for A/B profiling
-  if (const char* ev = getenv("GAPIT_PAIR")) pair = atoi(ev);
-  if (cl == 2 && pair) {
-    using PCfg = UmmaPairCfg<2, 256, 4>;
-    auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpi, 0, 0>;
-    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, PCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
-  } else if (cl == 2) {
-    auto kern = umma_i8_kernel<2, 256, 3, 2, 1, GramSched, GramEpi, 0, 0>;
-    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 2, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
-  } else {
-    auto kern = umma_i8_kernel<2, 256, 3, 1, 1, GramSched, GramEpi, 0, 0>;
-    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GramCfg::kSmemBytes));
-    GAPIT_CUDA(launch_umma(kern, nunits, 1, GramCfg::kThreads, GramCfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
-  }
+  const size_t rounds = size_t((sp.ntri * sp.ksplit + nunits - 1) / nunits) + 1;
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_SYNC, rounds, &sp.round_ctr));
+  GAPIT_CUDA(cudaMemsetAsync(sp.round_ctr, 0, rounds * sizeof(unsigned int), ctx->stream));
+  // one map for both operands: [m markers][ldn bytes of taxa], boxes of 128 markers x 128 taxa
+  CUtensorMap map_a;
+  GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
+                                 static_cast<uint64_t>(g->ldn), 128));
+  using PCfg = UmmaPairCfg<2, 256, 4>;
+  GramEpiTma::Params et{};
+  et.world = ex.world;
+  et.tiles_side = sp.tiles_side;
+  et.root = ex.root;
+  for (int r = 0; r < ex.world; ++r)
+    GAPIT_CHECK(make_tensor_map_i32_box32(&et.maps[r], ex.peers[r], static_cast<uint64_t>(ldg), static_cast<uint64_t>(ldg),
+                                          static_cast<uint64_t>(ldg) * 4));
+  const size_t smem = PCfg::kSmemBytes + GramEpiTma::kSmemBytes + 16;
+  auto kern = umma_i8_pair_kernel<2, 256, 4, 1, GramSched, GramEpiTma, 0, 0, true>;
+  GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  GAPIT_CUDA(launch_umma(kern, nunits, 2, PCfg::kThreads, smem, ctx->stream, map_a, map_a, sp, et));
   return GAPIT_OK;
+}
+
+// root pulls the block-rows the other ranks own (lower-triangle part) out of their buffers over NVLink:
+// grid (row, owner-independent), 16-byte loads from the peer-mapped source
+__global__ void gram_gather_rows_kernel(int32_t* __restrict__ dst, const int32_t* const* __restrict__ peers_dev, int64_t ldg,
+                                        int tiles_side, int world, int self) {
+  const int64_t row = blockIdx.x;
+  const int I = static_cast<int>(row >> 8);
+  if (I >= tiles_side) return;
+  const int owner = min(world - 1, (I * world) / tiles_side);
+  if (owner == self) return;
+  const int64_t cols = int64_t(I + 1) * 256;   // lower triangle incl. the diagonal tile
+  const uint4* s = reinterpret_cast<const uint4*>(peers_dev[owner] + row * ldg);
+  uint4* d = reinterpret_cast<uint4*>(dst + row * ldg);
+  for (int64_t c = threadIdx.x; c < cols / 4; c += blockDim.x) d[c] = s[c];
 }
 
 }  // namespace gapit
@@ -539,43 +421,33 @@ extern "C" int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev
   colsum_reduce_kernel<<<std::min<int64_t>(1024, (g->m + 255) / 256), 256, 0, ctx->stream>>>(
       g->colsum, g->m, 2 * g->n, reinterpret_cast<unsigned long long*>(sums_dev));
   GAPIT_CUDA(cudaGetLastError());
-  cudaEvent_t evt;
-  GAPIT_CUDA(cudaEventCreate(&evt));
-  cudaEventRecord(evt, ctx->stream);
-  if (!gram_mn_major(g)) GAPIT_CHECK(geno_build_taxa_major(g));  // no-op when the taxa-major copy already exists
   cudaEventRecord(ctx->ev0, ctx->stream);
-  GAPIT_CHECK(launch_gram(ctx, g, G_dev, ldg));
+  GramExchange local;
+  local.peers[0] = G_dev;
+  GAPIT_CHECK(launch_gram(ctx, g, ldg, local));
   cudaEventRecord(ctx->ev1, ctx->stream);
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
   ctx->stats = gapit_stats{};
-  cudaEventElapsedTime(&ms, evt, ctx->ev0);
-  ctx->stats.pack_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats.kernel_ms = ms;
-  cudaEventDestroy(evt);
   return GAPIT_OK;
 }
 
-// Sharded kinship with the exchange fused into the Gram kernel's epilogue (see GramEpiT / GramEpiTma): every rank calls
-// this with the same symmetric buffers (peers[r] = rank r's buffer, mc = their NVLS multicast address or NULL), all
-// zeroed and fenced by a barrier BEFORE anyone starts; after the kernels of all ranks have completed (stream sync +
-// barrier)
-//   mode 1 (peer RED.ADD) / mode 3 (bulk tensor reduce-add through TMA): with root >= 0 rank `root` holds the complete
-//           lower triangle (reduce to root); with root < 0 rank r holds the block-rows gapit_gram_owned_rows() gives it;
-//   mode 2 (NVLS multimem.red): every rank holds the complete lower triangle, as after an all-reduce.
-extern "C" int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int32_t* mc, int world,
-                                         int rank, int mode, int root, int64_t* sums_dev) {
-  if (!ctx || !g || !peers || !sums_dev || world < 1 || world > 8 || rank < 0 || rank >= world || mode < 1 || mode > 3 ||
-      root >= world || (mode == 2 && !mc))
+// Sharded kinship with the exchange fused into the Gram kernel's epilogue (GramEpiTma): every rank calls this with the
+// same peer-mapped buffers (peers[r] = rank r's buffer), all zeroed and fenced by a barrier BEFORE anyone starts.  After
+// the kernels of all ranks have completed (stream sync + barrier): root >= 0: rank `root` holds the complete lower
+// triangle (reduce to root); root < 0: rank r holds the block-rows gapit_gram_owned_rows() gives it (reduce-scatter:
+// every rank's NVLink ingress carries 1/world of the tiles), and gapit_vanraden_gram_gather pulls them together.
+extern "C" int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int world, int rank,
+                                         int root, int64_t* sums_dev) {
+  if (!ctx || !g || !peers || !sums_dev || world < 1 || world > 8 || rank < 0 || rank >= world || root >= world)
     return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram_fused: bad argument");
   GAPIT_CUDA(cudaSetDevice(ctx->device));
   const int64_t ldg = gapit_gram_ld(g->n);
   GramExchange ex;
-  ex.mode = mode;
   ex.world = world;
   ex.root = root;
-  ex.mc = mc;
   for (int r = 0; r < world; ++r) {
     if (!peers[r]) return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram_fused: NULL peer buffer");
     ex.peers[r] = peers[r];
@@ -585,7 +457,7 @@ extern "C" int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t*
       g->colsum, g->m, 2 * g->n, reinterpret_cast<unsigned long long*>(sums_dev));
   GAPIT_CUDA(cudaGetLastError());
   cudaEventRecord(ctx->ev0, ctx->stream);
-  GAPIT_CHECK(launch_gram(ctx, g, peers[rank], ldg, ex));
+  GAPIT_CHECK(launch_gram(ctx, g, ldg, ex));
   cudaEventRecord(ctx->ev1, ctx->stream);
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0.f;
@@ -595,7 +467,32 @@ extern "C" int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t*
   return GAPIT_OK;
 }
 
-// block-rows [lo, hi) (units of 256 taxa rows) whose sums land on `rank` in mode 1
+// After a reduce-scatter (root < 0 above) and the barrier that follows it: rank `rank` copies the block-rows owned by
+// the other ranks out of their peer-mapped buffers into its own (lower triangle only), which then holds the complete
+// sums gapit_vanraden_finish starts from.  One NVLink read of (world-1)/world of the triangle.
+extern "C" int gapit_vanraden_gram_gather(gapit_ctx* ctx, int64_t n, int32_t* const* peers, int world, int rank) {
+  if (!ctx || !peers || n <= 0 || world < 1 || world > 8 || rank < 0 || rank >= world)
+    return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram_gather: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  if (world == 1) return GAPIT_OK;
+  const int64_t ldg = gapit_gram_ld(n);
+  const int tiles_side = static_cast<int>((n + 255) / 256);
+  const int32_t** pd = nullptr;
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_SYNC, 16, &pd));
+  GAPIT_CUDA(cudaMemcpyAsync(pd, peers, size_t(world) * sizeof(int32_t*), cudaMemcpyHostToDevice, ctx->stream));
+  cudaEventRecord(ctx->ev0, ctx->stream);
+  gram_gather_rows_kernel<<<static_cast<unsigned>(int64_t(tiles_side) * 256), 256, 0, ctx->stream>>>(
+      peers[rank], pd, ldg, tiles_side, world, rank);
+  GAPIT_CUDA(cudaGetLastError());
+  cudaEventRecord(ctx->ev1, ctx->stream);
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+  ctx->stats.post_ms = ms;
+  return GAPIT_OK;
+}
+
+// block-rows [lo, hi) (units of 256 taxa rows) whose sums land on `rank` after a reduce-scatter
 extern "C" int gapit_gram_owned_rows(int64_t n, int world, int rank, int64_t* row_lo, int64_t* row_hi) {
   if (n <= 0 || world < 1 || rank < 0 || rank >= world || !row_lo || !row_hi) return fail(GAPIT_ERR_ARG, "gapit_gram_owned_rows");
   const int64_t T = (n + 255) / 256;

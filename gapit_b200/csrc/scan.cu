@@ -134,7 +134,6 @@ struct ScanSched {
     int nkq;      // BN-row tiles of the sliced eigenvectors
     int kblocks;  // taxa axis in units of kBlockK
     int bn;
-    int nchunk;   // trait chunks: every chunk repeats the rotation of the tile with its own epilogue constants
     uint64_t hint_a;  // L2 eviction hints (default: marker tile evict_last -- it is re-read for every eigen tile;
     uint64_t hint_b;  //  eigen tiles evict_normal -- streamed, shared by the CTAs running together)
     unsigned int* round_ctr;  // [rounds] zeroed before the launch, or nullptr: soft alignment of the units per round
@@ -148,7 +147,7 @@ struct ScanSched {
   // cycles, so a unit that cannot be co-resident (shared GPU) only costs its peers that bounded wait, never a hang.
   __device__ void align_round() const {
     if (!p.round_ctr) return;
-    const int total = p.mtiles * p.gsplit * p.nchunk;
+    const int total = p.mtiles * p.gsplit;
     const int r = gid / stride;
     const unsigned int expect = static_cast<unsigned int>(min(stride, total - r * stride));
     volatile unsigned int* c = p.round_ctr + r;
@@ -157,19 +156,17 @@ struct ScanSched {
     while (*c < expect && clock64() - t0 < p.round_wait) __nanosleep(64);
   }
   Params p;
-  int gid, stride, kq, kq_begin, kq_end, mt, ks, tc, crank;
+  int gid, stride, kq, kq_begin, kq_end, mt, ks, crank;
   __device__ ScanSched(const Params& pp, int unit, int nunits, uint32_t cta_rank)
-      : p(pp), gid(unit - nunits), stride(nunits), kq(0), kq_begin(0), kq_end(0), mt(0), ks(0), tc(0),
+      : p(pp), gid(unit - nunits), stride(nunits), kq(0), kq_begin(0), kq_end(0), mt(0), ks(0),
         crank(static_cast<int>(cta_rank)) {}
   __device__ bool next(Job& j) {
     if (kq >= kq_end) {
       gid += stride;
-      if (gid >= p.mtiles * p.gsplit * p.nchunk) return false;
-      // split-minor, then trait chunk, then marker tile: CTAs running together share the marker tile
-      const int mc = gid / p.gsplit;
-      ks = gid - mc * p.gsplit;
-      mt = mc / p.nchunk;
-      tc = mc - mt * p.nchunk;
+      if (gid >= p.mtiles * p.gsplit) return false;
+      // split-minor, then marker tile: CTAs running together share the marker tile
+      mt = gid / p.gsplit;
+      ks = gid - mt * p.gsplit;
       kq_begin = (ks * p.nkq) / p.gsplit;
       kq_end = ((ks + 1) * p.nkq) / p.gsplit;
       kq = kq_begin;
@@ -180,7 +177,7 @@ struct ScanSched {
     j.kb_end = p.kblocks;
     j.tag0 = kq;
     j.tag1 = ks;
-    j.tag2 = tc;
+    j.tag2 = 0;
     j.group_first = (kq == kq_begin);
     j.group_last = (kq == kq_end - 1);
     ++kq;
@@ -188,41 +185,36 @@ struct ScanSched {
   }
 };
 
-template <int S, int BN, int Q, int TC>
+template <int S, int BN, int Q>
 struct ScanEpi {
   static constexpr int KPB = BN / S;
   static constexpr int GC = (S == 4 || S == 8) ? 8 : (S == 5 ? 40 : (S == 6 ? 24 : 56));  // lcm(S, 8)
   static constexpr int KG = GC / S;
   static_assert(BN % GC == 0, "accumulator columns must split into whole digit groups");
   struct Params {
-    const double* gconst;  // [chunk][nkq*KPB][TC][Q+2]: w c^2 | w c A_j ... | w c b  for the TC traits of the chunk
-    double* part;          // [T][gsplit][Q+2][m_ld]
+    const double* gconst;  // [nkq*KPB][Q+2]: w c^2 | w c A_j ... | w c b
+    double* part;          // [gsplit*nhalf][Q+2][m_ld]
     int64_t m_ld;
     int64_t m;
     int pair;              // 1: merge adjacent digit planes in int32 before converting (needs 65792 n < 2^31)
-    int T;                 // traits; chunk c of a job covers traits [c*TC, min(T, (c+1)*TC))
-    int64_t gc_tstride;    // doubles between the constants of consecutive trait chunks (= nk * TC * (Q+2))
-    int64_t part_tstride;  // doubles between the partial sums of consecutive traits
   };
-  // the constants of one job (KPB eigen indices x TC traits) are staged in shared memory while the job's MMAs run
-  static constexpr int kSmemDoubles = KPB * TC * (Q + 2);
+  // the constants of one job (KPB eigen indices) are staged in shared memory while the job's MMAs run
+  static constexpr int kSmemDoubles = KPB * (Q + 2);
   static constexpr int kSmemBytes = kSmemDoubles * 8;
   Params p;
   double* cs;
-  double acc[TC][Q + 2];
+  double acc[Q + 2];
   // exact int32 -> fp64: the bits 0x43300000:(x ^ 0x80000000) are the double 2^52 + 2^31 + x
   static __device__ __forceinline__ double i2d(int x) {
     return __hiloint2double(0x43300000, x ^ static_cast<int>(0x80000000u)) - 4503601774854144.0;
   }
   __device__ ScanEpi(const Params& pp, uint8_t* scratch) : p(pp), cs(reinterpret_cast<double*>(scratch)) {
 #pragma unroll
-    for (int t = 0; t < TC; ++t)
-#pragma unroll
-      for (int i = 0; i < Q + 2; ++i) acc[t][i] = 0.0;
+    for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
   }
   __device__ void finish() {}
   __device__ void prepare(const Job& job, int tid, int nthreads) {
-    const double* src = p.gconst + int64_t(job.tag2) * p.gc_tstride + int64_t(job.tag0) * kSmemDoubles;
+    const double* src = p.gconst + int64_t(job.tag0) * kSmemDoubles;
     for (int i = tid; i < kSmemDoubles; i += nthreads) cs[i] = __ldg(src + i);
   }
   // `half` of `nhalf` epilogue warps on this (sub-tile, quarter): column groups are dealt round-robin and every
@@ -230,12 +222,8 @@ struct ScanEpi {
   __device__ void run(const Job& job, uint32_t taddr, int sub, int row, int half, int nhalf) {
     if (job.group_first) {
 #pragma unroll
-      for (int t = 0; t < TC; ++t)
-#pragma unroll
-        for (int i = 0; i < Q + 2; ++i) acc[t][i] = 0.0;
+      for (int i = 0; i < Q + 2; ++i) acc[i] = 0.0;
     }
-    const int t0 = job.tag2 * TC;
-    const int ntr = min(TC, p.T - t0);
 #pragma unroll 1
     for (int g = half; g < BN / GC; g += nhalf) {
       uint32_t r[GC];
@@ -264,29 +252,18 @@ struct ScanEpi {
 #pragma unroll
           for (int s = S - 2; s >= 0; --s) u = fma(u, 256.0, i2d(d[s]));
         }
-        const double* c = cs + (g * KG + kk) * TC * (Q + 2);   // shared-memory broadcast reads
+        const double* c = cs + (g * KG + kk) * (Q + 2);   // shared-memory broadcast reads
+        acc[0] = fma(c[0] * u, u, acc[0]);
 #pragma unroll
-        for (int t = 0; t < TC; ++t) {
-          if (TC == 1 || t < ntr) {
-            const double* ct = c + t * (Q + 2);
-            acc[t][0] = fma(ct[0] * u, u, acc[t][0]);
-#pragma unroll
-            for (int i = 1; i < Q + 2; ++i) acc[t][i] = fma(ct[i], u, acc[t][i]);
-          }
-        }
+        for (int i = 1; i < Q + 2; ++i) acc[i] = fma(c[i], u, acc[i]);
       }
     }
     if (job.group_last) {
       const int64_t mrk = int64_t(job.a_row0) + sub * 128 + row;
       if (mrk < p.m_ld) {
+        double* dst = p.part + int64_t(job.tag1 * nhalf + half) * (Q + 2) * p.m_ld + mrk;
 #pragma unroll
-        for (int t = 0; t < TC; ++t) {
-          if (TC == 1 || t < ntr) {
-            double* dst = p.part + int64_t(t0 + t) * p.part_tstride + int64_t(job.tag1 * nhalf + half) * (Q + 2) * p.m_ld + mrk;
-#pragma unroll
-            for (int i = 0; i < Q + 2; ++i) dst[i * p.m_ld] = acc[t][i];
-          }
-        }
+        for (int i = 0; i < Q + 2; ++i) dst[i * p.m_ld] = acc[i];
       }
     }
   }
@@ -658,41 +635,29 @@ static int pad_q(int q0) {
   return 16;
 }
 
-// traits that share one rotation pass (must match the TC template arguments picked in launch_scan_S)
-static int trait_chunk(int Q) { return Q <= 1 ? 16 : (Q <= 2 ? 12 : (Q <= 4 ? 8 : (Q <= 8 ? 4 : 2))); }
+// The rotation runs as the cta_group::2 pair kernel whenever the block holds at least two 256-marker tiles, else
+// (a single tile) as the single-CTA form of the same main loop.  The single-trait epilogue runs two warps per
+// (sub-tile, lane quarter), each with its own partial sums: kScanHalves partial sums per eigen split whatever form
+// runs, so the fp64 summation order -- hence every output bit -- does not depend on the tile count.
+constexpr int kScanHalves = 2;
 
-// Which form of the rotation kernel a shape gets: clusters of two CTAs need at least two marker tiles; the
-// single-trait epilogue (few registers) runs two warps per (sub-tile, lane quarter).  Environment switches are
-// A/B knobs for profiling.
-struct ScanMode {
-  int cl;     // CTAs per cluster
-  int pair;   // 1: tcgen05 cta_group::2 UMMA
-  int nhalf;  // epilogue warps per (sub-tile, quarter) = partial sums per eigen split
-};
-static ScanMode scan_mode(int64_t m_ld, int T) {
-  ScanMode md;
-  md.cl = (m_ld / 256 >= 2) ? 2 : 1;
-  if (const char* ev = getenv("GAPIT_CLUSTER")) md.cl = std::max(1, std::min(md.cl, atoi(ev)));
-  md.pair = 1;
-  if (const char* ev = getenv("GAPIT_PAIR")) md.pair = atoi(ev) ? 1 : 0;
-  if (md.cl != 2) md.pair = 0;
-  // a single trait always keeps two partial sums per eigen split (even / odd column groups), whatever kernel form
-  // runs it, so its fp64 summation order -- hence every output bit -- does not depend on tile count or chunking
-  md.nhalf = (T == 1) ? 2 : 1;
-  return md;
+// digit planes may be merged pairwise in int32 while 257 * 256 * n < 2^31 (n <= 32,639); GAPIT_EPI_PAIR=0 forces the
+// unmerged epilogue of larger n on a small problem (test hook)
+static int epilogue_merges_planes(int64_t n) {
+  int pair = (65792ll * n < 2147483647ll) ? 1 : 0;
+  if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);
+  return pair;
 }
 
-// one launch scans traits [0, T): gconst_dev/part_dev are the arrays of trait 0, strides in doubles
-template <int S, int BN, int Q, int TC>
+// single-trait rotate + reduce: gconst_dev [nk][Q+2], part_dev [gsplit * kScanHalves][Q+2][m_ld]
+template <int S, int BN, int Q>
 static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* gconst_dev, double* part_dev,
-                          int64_t m_ld, int gsplit, int T, int64_t gc_tstride, int64_t part_tstride) {
-  using Cfg = UmmaCfg<2, BN, 3>;
-  using Epi = ScanEpi<S, BN, Q, TC>;
+                          int64_t m_ld, int gsplit) {
+  using Epi = ScanEpi<S, BN, Q>;
   CUtensorMap map_a, map_b;
   GAPIT_CHECK(make_tensor_map_u8(&map_a, g->mk, static_cast<uint64_t>(g->ldn), static_cast<uint64_t>(g->m),
                                  static_cast<uint64_t>(g->ldn), 256));
-  const ScanMode md = scan_mode(m_ld, T);
-  const int cl = md.cl;
+  const int cl = (m_ld / 256 >= 2) ? 2 : 1;
   GAPIT_CHECK(make_tensor_map_u8(&map_b, e->Vs, static_cast<uint64_t>(e->ldn), static_cast<uint64_t>(e->nkq * BN),
                                  static_cast<uint64_t>(e->ldn), BN / cl));
   ScanSched::Params sp;
@@ -702,77 +667,51 @@ static int launch_scan_SQ(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const 
   sp.nkq = static_cast<int>(e->nkq);
   sp.kblocks = static_cast<int>(g->ldn / kBlockK);
   sp.bn = BN;
-  sp.nchunk = (T + TC - 1) / TC;
-  auto hint = [](const char* name, uint64_t dflt) {   // A/B switch for profiling: 0 normal, 1 evict_first, 2 evict_last
-    const char* ev = getenv(name);
-    if (!ev) return dflt;
-    const int v = atoi(ev);
-    return v == 1 ? ptx::kEvictFirst : (v == 2 ? ptx::kEvictLast : ptx::kEvictNormal);
-  };
-  sp.hint_a = hint("GAPIT_HINT_A", ptx::kEvictLast);
-  sp.hint_b = hint("GAPIT_HINT_B", ptx::kEvictNormal);
+  sp.hint_a = ptx::kEvictLast;     // marker tile: re-read for every eigen tile
+  sp.hint_b = ptx::kEvictNormal;   // eigen tiles: streamed, shared by the CTAs running together
   sp.round_ctr = nullptr;
   sp.round_wait = 100000;   // ~50 us
-  if (const char* ev = getenv("GAPIT_ROUND_WAIT")) sp.round_wait = atoi(ev);   // 0 switches the alignment off
-  int pair = (65792ll * g->n < 2147483647ll) ? 1 : 0;
-  if (const char* ev = getenv("GAPIT_EPI_PAIR")) pair = pair && atoi(ev);  // A/B switch for profiling
-  typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, pair, T, gc_tstride, part_tstride};
-  const int nunits = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit * sp.nchunk);
-  constexpr int EPIW = (TC == 1) ? 2 : 1;
+  typename Epi::Params ep{gconst_dev, part_dev, m_ld, g->m, epilogue_merges_planes(g->n)};
+  const int nunits = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit);
+  constexpr int EPIW = kScanHalves;
   constexpr int kThreadsEpi = 128 + 2 * 128 * EPIW;
-  if (md.pair && sp.round_wait > 0) {
-    const int nun = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit * sp.nchunk);
-    const size_t rounds = size_t((sp.mtiles * sp.gsplit * sp.nchunk + nun - 1) / nun) + 1;
+  if (cl == 2) {
+    const size_t rounds = size_t((sp.mtiles * sp.gsplit + nunits - 1) / nunits) + 1;
     GAPIT_CHECK(ctx_ws_t(ctx, WS_SYNC, rounds, &sp.round_ctr));
     GAPIT_CUDA(cudaMemsetAsync(sp.round_ctr, 0, rounds * sizeof(unsigned int), ctx->stream));
-  }
-  if (md.pair) {
     using PCfg = UmmaPairCfg<2, BN, 4>;
     auto kern = umma_i8_pair_kernel<2, BN, 4, EPIW, ScanSched, Epi, 1, 1>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PCfg::kSmemBytes + Epi::kSmemBytes + 16));
     GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, PCfg::kSmemBytes + Epi::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
-  } else if (cl == 2) {
-    auto kern = umma_i8_kernel<2, BN, 3, 2, EPIW, ScanSched, Epi, 1, 1>;
-    GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + Epi::kSmemBytes + 16));
-    GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, Cfg::kSmemBytes + Epi::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
   } else {
-    auto kern = umma_i8_kernel<2, BN, 3, 1, EPIW, ScanSched, Epi, 1, 1>;
+    using Cfg = UmmaCfg<2, BN, 3>;
+    auto kern = umma_i8_kernel<2, BN, 3, EPIW, ScanSched, Epi, 1, 1>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + Epi::kSmemBytes + 16));
     GAPIT_CUDA(launch_umma(kern, nunits, 1, kThreadsEpi, Cfg::kSmemBytes + Epi::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
   }
   return GAPIT_OK;
 }
 
-#define GAPIT_SCAN_ARGS ctx, g, e, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride
 template <int S, int BN>
 static int launch_scan_S(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int Q, const double* gconst_dev,
-                         double* part_dev, int64_t m_ld, int gsplit, int T, int64_t gc_tstride, int64_t part_tstride) {
-  if (T > 1) {  // trait-chunked epilogue: TC traits share one rotation pass (TC * (Q+2) register accumulators)
-    switch (Q) {
-      case 1: return launch_scan_SQ<S, BN, 1, 16>(GAPIT_SCAN_ARGS);
-      case 2: return launch_scan_SQ<S, BN, 2, 12>(GAPIT_SCAN_ARGS);
-      case 4: return launch_scan_SQ<S, BN, 4, 8>(GAPIT_SCAN_ARGS);
-      case 8: return launch_scan_SQ<S, BN, 8, 4>(GAPIT_SCAN_ARGS);
-      default: return launch_scan_SQ<S, BN, 16, 2>(GAPIT_SCAN_ARGS);
-    }
-  }
+                         double* part_dev, int64_t m_ld, int gsplit) {
   switch (Q) {
-    case 1: return launch_scan_SQ<S, BN, 1, 1>(GAPIT_SCAN_ARGS);
-    case 2: return launch_scan_SQ<S, BN, 2, 1>(GAPIT_SCAN_ARGS);
-    case 4: return launch_scan_SQ<S, BN, 4, 1>(GAPIT_SCAN_ARGS);
-    case 8: return launch_scan_SQ<S, BN, 8, 1>(GAPIT_SCAN_ARGS);
-    default: return launch_scan_SQ<S, BN, 16, 1>(GAPIT_SCAN_ARGS);
+    case 1: return launch_scan_SQ<S, BN, 1>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    case 2: return launch_scan_SQ<S, BN, 2>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    case 4: return launch_scan_SQ<S, BN, 4>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    case 8: return launch_scan_SQ<S, BN, 8>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
+    default: return launch_scan_SQ<S, BN, 16>(ctx, g, e, gconst_dev, part_dev, m_ld, gsplit);
   }
 }
 
 static int launch_scan(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int Q, const double* gconst_dev, double* part_dev,
-                       int64_t m_ld, int gsplit, int T, int64_t gc_tstride, int64_t part_tstride) {
+                       int64_t m_ld, int gsplit) {
   switch (e->S) {
-    case 4: return launch_scan_S<4, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
-    case 5: return launch_scan_S<5, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
-    case 6: return launch_scan_S<6, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
-    case 7: return launch_scan_S<7, 224>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
-    default: return launch_scan_S<8, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit, T, gc_tstride, part_tstride);
+    case 4: return launch_scan_S<4, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    case 5: return launch_scan_S<5, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    case 6: return launch_scan_S<6, 240>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    case 7: return launch_scan_S<7, 224>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
+    default: return launch_scan_S<8, 256>(ctx, g, e, Q, gconst_dev, part_dev, m_ld, gsplit);
   }
 }
 
@@ -795,13 +734,11 @@ static int launch_store_S(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int64_
   sp.nkq = static_cast<int>(tiles);
   sp.kblocks = static_cast<int>(g->ldn / kBlockK);
   sp.bn = BN;
-  sp.nchunk = 1;
   sp.hint_a = ptx::kEvictLast;
   sp.hint_b = ptx::kEvictNormal;
   sp.round_ctr = nullptr;
   sp.round_wait = 100000;   // ~50 us
-  const int pair = (65792ll * g->n < 2147483647ll) ? 1 : 0;
-  typename Epi::Params ep{kscale, wbuf, m_ld, nk_sq, pair};
+  typename Epi::Params ep{kscale, wbuf, m_ld, nk_sq, epilogue_merges_planes(g->n)};
   const int nunits = std::min(ctx->sm_count / cl, sp.mtiles * sp.gsplit);
   constexpr int EPIW = 2;
   constexpr int kThreadsEpi = 128 + 2 * 128 * EPIW;
@@ -815,7 +752,7 @@ static int launch_store_S(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, int64_
     GAPIT_CUDA(launch_umma(kern, nunits, 2, kThreadsEpi, PCfg::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
   } else {
     using Cfg = UmmaCfg<2, BN, 3>;
-    auto kern = umma_i8_kernel<2, BN, 3, 1, EPIW, ScanSched, Epi, 1, 1>;
+    auto kern = umma_i8_kernel<2, BN, 3, EPIW, ScanSched, Epi, 1, 1>;
     GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes + 16));
     GAPIT_CUDA(launch_umma(kern, nunits, 1, kThreadsEpi, Cfg::kSmemBytes + 16, ctx->stream, map_a, map_b, sp, ep));
   }
@@ -846,7 +783,7 @@ static int launch_glm_bn(gapit_ctx* ctx, gapit_geno* g, const int8_t* Rs_dev, in
                                  static_cast<uint64_t>(g->ldn), BN));
   GlmSched::Params sp{static_cast<int>(m_ld / 256), static_cast<int>(g->ldn / kBlockK)};
   typename Epi::Params ep{scale_dev, g->colsumsq, part_dev, m_ld, g->m, nc, Q};
-  auto kern = umma_i8_kernel<2, BN, 4, 1, 1, GlmSched, Epi, 1, 1>;
+  auto kern = umma_i8_kernel<2, BN, 4, 1, GlmSched, Epi, 1, 1>;
   GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   const int grid = std::min(ctx->sm_count, sp.mtiles);
   GAPIT_CUDA(launch_umma(kern, grid, 1, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream, map_a, map_b, sp, ep));
@@ -867,8 +804,7 @@ static int launch_glm(gapit_ctx* ctx, gapit_geno* g, const int8_t* Rs_dev, int64
 // inside ~48 MB of L2.  Depends on n only, so results do not change with the marker shard or SM count.
 static int choose_gsplit(int64_t ldn, int64_t nkq) {
   const double bytes = 148.0 * 256.0 * static_cast<double>(ldn);
-  double budget = 48.0e6;
-  if (const char* ev = getenv("GAPIT_GSPLIT_MB")) budget = std::max(1.0, atof(ev)) * 1.0e6;   // A/B switch for profiling
+  const double budget = 48.0e6;
   int g = static_cast<int>(std::ceil(bytes / budget));
   g = std::max(1, g);
   return static_cast<int>(std::min<int64_t>(g, nkq));
@@ -893,9 +829,8 @@ struct ScanPlan {
   int q0 = 0, Q = 0, T = 0, glm = 0, gsplit = 1;
   gapit_eigsys* e = nullptr;
   std::vector<FinalizeConsts> fc;   // per trait
-  double* gconst = nullptr;         // MLM: [chunk][nk][TC][Q+2], TC traits per chunk share one rotation pass
+  double* gconst = nullptr;         // MLM, T = 1: [nk][Q+2] epilogue constants of the fused rotate + reduce
   int64_t nk = 0;
-  int TC = 1;
   int8_t* Rs = nullptr;             // GLM: [T][128][ldn] digit planes of [X0 | y_t]
   double* Rscale = nullptr;         // GLM: [T][GAPIT_MAX_Q0+1]
   FinalizeConsts* fc_dev = nullptr; // [T]
@@ -969,11 +904,8 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
     GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
     GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
     plan->nk = e->nkq * e->KPB;
-    plan->shared = (T > 1) && !getenv("GAPIT_MULTI_CHUNKED");   // A/B switch: the trait-chunked epilogue
-    plan->TC = (T > 1) ? trait_chunk(Q) : 1;
-    const int nchunk = (T + plan->TC - 1) / plan->TC;
-    if (!plan->shared)
-      GAPIT_CHECK(ctx_ws_t(ctx, WS_GCONST, size_t(nchunk) * plan->nk * plan->TC * (Q + 2), &plan->gconst));
+    plan->shared = (T > 1);   // several traits: one rotation for all of them (StoreEpi + xx_contract)
+    if (!plan->shared) GAPIT_CHECK(ctx_ws_t(ctx, WS_GCONST, size_t(plan->nk) * (Q + 2), &plan->gconst));
   } else {
     std::copy(X0, X0 + size_t(n) * q0, proj.begin());
     std::copy(Y, Y + size_t(n) * T, proj.begin() + size_t(n) * q0);
@@ -990,7 +922,7 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
     zcols.assign(size_t(lin_nc) * n, 0.0);
     wt.assign(size_t(plan->nk) * plan->wt_ld, 0.0);
   }
-  if (!glm && !plan->shared) gconst.assign(size_t((T + plan->TC - 1) / plan->TC) * plan->nk * plan->TC * (Q + 2), 0.0);
+  if (!glm && !plan->shared) gconst.assign(size_t(plan->nk) * (Q + 2), 0.0);
   const double dn = static_cast<double>(n);
   const double two_pi = 2.0 * 3.14159265358979323846;
   for (int t = 0; t < T; ++t) {
@@ -1081,11 +1013,10 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
         wt[size_t(k) * plan->wt_ld + t] = w[k];
       }
     } else if (!glm) {
-      const int TC = plan->TC;
-      double* gt = gconst.data() + size_t(t / TC) * plan->nk * TC * (Q + 2) + size_t(t % TC) * (Q + 2);
+      double* gt = gconst.data();
       for (int64_t k = 0; k < n; ++k) {
         const double c = e->h_scale[k];
-        double* gk = gt + size_t(k) * TC * (Q + 2);
+        double* gk = gt + size_t(k) * (Q + 2);
         gk[0] = w[k] * c * c;
         for (int j = 0; j < q0; ++j) gk[1 + j] = w[k] * c * proj[size_t(j) * n + k];
         gk[Q + 1] = w[k] * c * yt[k];
@@ -1136,11 +1067,11 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
 // copy rows [k0, k0 + mc) of every trait's result arrays to the caller's SoA arrays (m_total markers per trait):
 // one strided copy per array
 static int fetch_block(cudaStream_t st, const double* out_dev, int64_t out_tstride, int64_t out_ld, int64_t k0, int64_t mc,
-                       int T, int64_t m_total, const gapit_scan_out* out) {
+                       int T, int64_t m_total, const gapit_scan_out* out, int64_t host_off) {
   double* dsts[7] = {out->effect, out->tvalue, out->se, out->pvalue, out->rsquare, out->loglm, out->maf};
   for (int a = 0; a < 7; ++a) {
     if (!dsts[a]) continue;
-    GAPIT_CUDA(cudaMemcpy2DAsync(dsts[a] + k0, size_t(m_total) * 8, out_dev + size_t(a) * out_ld + k0, size_t(out_tstride) * 8,
+    GAPIT_CUDA(cudaMemcpy2DAsync(dsts[a] + host_off + k0, size_t(m_total) * 8, out_dev + size_t(a) * out_ld + k0, size_t(out_tstride) * 8,
                                  size_t(mc) * 8, a == 6 ? 1 : size_t(T), cudaMemcpyDeviceToHost, st));
   }
   return GAPIT_OK;
@@ -1174,7 +1105,7 @@ static int64_t shared_block_markers(gapit_ctx* ctx, int64_t rows) {
 // caller's arrays (m_total markers per trait, rows out_off..) on the D2H stream while the next rows are computed.
 static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, double* out_dev, int64_t out_tstride,
                     int64_t out_ld, int64_t out_off, cudaEvent_t after_reduce = nullptr,
-                    const gapit_scan_out* host_out = nullptr, int64_t m_total = 0) {
+                    const gapit_scan_out* host_out = nullptr, int64_t m_total = 0, int64_t host_off = 0) {
   const int Q = plan.Q;
   gapit_geno view;  // borrowed pointers only
   view.ctx = ctx;
@@ -1212,14 +1143,14 @@ static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, d
       if (host_out) {
         GAPIT_CUDA(cudaEventRecord(ctx->ev_blk, ctx->stream));
         GAPIT_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_blk, 0));
-        GAPIT_CHECK(fetch_block(ctx->d2h_stream, out_dev, out_tstride, out_ld, out_off + k0, mc, plan.T, m_total, host_out));
+        GAPIT_CHECK(fetch_block(ctx->d2h_stream, out_dev, out_tstride, out_ld, out_off + k0, mc, plan.T, m_total, host_out, host_off));
       }
     }
     if (after_reduce) cudaEventRecord(after_reduce, ctx->stream);
     return GAPIT_OK;
   }
   const int64_t m_ld = round_up(v.m, 256);
-  const int nsplit = plan.glm ? 1 : plan.gsplit * scan_mode(m_ld, plan.T).nhalf;   // partial sums per marker
+  const int nsplit = plan.glm ? 1 : plan.gsplit * kScanHalves;   // partial sums per marker
   const int64_t part_tstride = int64_t(nsplit) * (Q + 2) * m_ld;
   double* part = nullptr;
   GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t(plan.T) * part_tstride, &part));
@@ -1228,9 +1159,7 @@ static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, d
   view.colsum = const_cast<int32_t*>(v.colsum);
   view.colsumsq = const_cast<int32_t*>(v.colsumsq);
   if (!plan.glm) {
-    // one launch for all traits: the rotation of a marker tile is shared by a chunk of traits
-    GAPIT_CHECK(launch_scan(ctx, &view, plan.e, Q, plan.gconst, part, m_ld, plan.gsplit, plan.T,
-                            plan.nk * plan.TC * (Q + 2), part_tstride));
+    GAPIT_CHECK(launch_scan(ctx, &view, plan.e, Q, plan.gconst, part, m_ld, plan.gsplit));   // single trait
   } else {
     for (int t = 0; t < plan.T; ++t)
       GAPIT_CHECK(launch_glm(ctx, &view, plan.Rs + size_t(t) * 128 * plan.ldn, 128,
@@ -1249,7 +1178,7 @@ static int scan_run(gapit_ctx* ctx, const ScanPlan& plan, const MarkerView& v, d
   if (host_out) {
     GAPIT_CUDA(cudaEventRecord(ctx->ev_blk, ctx->stream));
     GAPIT_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_blk, 0));
-    GAPIT_CHECK(fetch_block(ctx->d2h_stream, out_dev, out_tstride, out_ld, out_off, v.m, plan.T, m_total, host_out));
+    GAPIT_CHECK(fetch_block(ctx->d2h_stream, out_dev, out_tstride, out_ld, out_off, v.m, plan.T, m_total, host_out, host_off));
   }
   return GAPIT_OK;
 }
@@ -1282,14 +1211,17 @@ static int scan_reserve(gapit_ctx* ctx, const ScanPlan& plan, int64_t max_m) {
     GAPIT_CHECK(ctx_ws(ctx, WS_WBUF, size_t(rows) * mb * 8, &p));
     GAPIT_CHECK(ctx_ws(ctx, WS_XX, size_t(plan.T) * mb * 8, &p));
   } else {
-    const int nsplit = plan.glm ? 1 : plan.gsplit * scan_mode(m_ld, plan.T).nhalf;
+    const int nsplit = plan.glm ? 1 : plan.gsplit * kScanHalves;
     GAPIT_CHECK(ctx_ws(ctx, WS_PART, size_t(plan.T) * nsplit * (plan.Q + 2) * m_ld * 8, &p));
   }
   return GAPIT_OK;
 }
 
-static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
-                     const double* delta, const double* vg, int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
+// m_total / m_off: the caller's result arrays hold m_total markers per trait and this handle's markers start at m_off
+// (a marker shard of a table scanned by several GPUs); m_total = 0: the arrays hold exactly g->m markers
+int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
+              const double* delta, const double* vg, int glm, gapit_scan_out* out, gapit_scan_base* base_out,
+              int64_t m_total = 0, int64_t m_off = 0) {
   if (!g) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL genotype handle");
   GAPIT_CHECK(check_out(out));
   ScanPlan plan;
@@ -1308,7 +1240,7 @@ static int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const doubl
   GAPIT_CHECK(scan_reserve(ctx, plan, m));
   MarkerView v{g->mk, m, g->colsum, g->colsumsq};
   cudaEventRecord(ctx->ev0, ctx->stream);
-  GAPIT_CHECK(scan_run(ctx, plan, v, o, 7 * m, m, 0, ctx->ev3, out, m));
+  GAPIT_CHECK(scan_run(ctx, plan, v, o, 7 * m, m, 0, ctx->ev3, out, m_total > 0 ? m_total : m, m_off));
   cudaEventRecord(ctx->ev1, ctx->stream);
   GAPIT_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev1, 0));
   cudaEventRecord(ctx->ev2, ctx->d2h_stream);
@@ -1484,6 +1416,8 @@ extern "C" int gapit_eigsys_project(gapit_ctx* ctx, gapit_eigsys* e, const doubl
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
   return GAPIT_OK;
 }
+
+extern "C" const double* gapit_eigsys_vectors_dev(const gapit_eigsys* e) { return e ? e->V : nullptr; }
 
 extern "C" void gapit_eigsys_free(gapit_eigsys* e) {
   if (!e) return;

@@ -58,23 +58,14 @@ struct UmmaCfg {
 //        run(job, taddr, sub, row, half, nhalf), finish() (after the last job, before the CTA may exit).
 //        The parameter block is a __grid_constant__, so an epilogue may hand tensor maps inside it to TMA.
 //
-// CL == 2 runs the kernel as thread-block clusters of two CTAs that work on the same B tile with different
-// A tiles: each CTA fetches half of the B box and TMA-multicasts it into both CTAs' shared memory, so the
-// L2 -> SM operand traffic of a pair drops from 2(A+B) to 2A+B bytes.  A ring slot is released when the UMMAs of
-// BOTH CTAs have consumed it (tcgen05.commit multicast onto both `empty` barriers, arrival count 2).
-// map_b must then be encoded with boxes of BN/CL rows.
-template <int MSUB, int BN, int STAGES, int CL, int EPIW, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
+template <int MSUB, int BN, int STAGES, int EPIW, class Sched, class Epi, uint32_t A_SIGNED, uint32_t B_SIGNED>
 __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
     umma_i8_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const typename Sched::Params sp, const __grid_constant__ typename Epi::Params ep) {
   using Cfg = UmmaCfg<MSUB, BN, STAGES>;
-  static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
-  static_assert((BN / CL) % 8 == 0, "each CTA's share of the B box must keep the 8-row swizzle groups whole");
-  constexpr uint32_t kBShare = (BN / CL) * kBlockK;
-  constexpr uint16_t kClusterMask = (1u << CL) - 1u;
-  const uint32_t crank = (CL > 1) ? ptx::cluster_ctarank() : 0u;
-  const int unit = blockIdx.x / CL;
-  const int nunits = gridDim.x / CL;
+  const uint32_t crank = 0u;
+  const int unit = blockIdx.x;
+  const int nunits = gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -97,7 +88,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full[i], 1);
-      ptx::mbar_init(&empty[i], CL);
+      ptx::mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < Cfg::kAccStages; ++i) {
       ptx::mbar_init(&tfull[i], 1);
@@ -107,8 +98,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
   }
   if (warp == 2) ptx::tmem_alloc(tmem_ptr, kTmemCols);
   ptx::tc_fence_before_sync();
-  if (CL > 1) ptx::cluster_sync();  // peers' barriers must be initialised before any remote arrive / multicast
-  else __syncthreads();
+  __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -125,11 +115,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
           uint8_t* sb = sa + Cfg::kABytes;
           ptx::mbar_arrive_expect_tx(&full[st], Cfg::kStageBytes);
           ptx::tma_load_2d(&map_a, &full[st], sa, kb * kBlockK, job.a_row0, sch.hint_a());
-          if (CL > 1)
-            ptx::tma_load_2d_multicast(&map_b, &full[st], sb + crank * kBShare, kb * kBlockK,
-                                       job.b_row0 + static_cast<int>(crank) * (BN / CL), kClusterMask, sch.hint_b());
-          else
-            ptx::tma_load_2d(&map_b, &full[st], sb, kb * kBlockK, job.b_row0, sch.hint_b());
+          ptx::tma_load_2d(&map_b, &full[st], sb, kb * kBlockK, job.b_row0, sch.hint_b());
           if (++st == STAGES) {
             st = 0;
             ph ^= 1;
@@ -164,8 +150,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
               ptx::umma_i8_ss(d_col, da, db, idesc, (kb > job.kb_begin || k > 0) ? 1u : 0u);
             }
           }
-          if (CL > 1) ptx::umma_commit_multicast(&empty[st], kClusterMask);
-          else ptx::umma_commit(&empty[st]);
+          ptx::umma_commit(&empty[st]);
           if (kb == job.kb_end - 1) ptx::umma_commit(&tfull[acc]);
         }
         __syncwarp();
@@ -208,8 +193,7 @@ __global__ void __launch_bounds__(128 + MSUB * 128 * EPIW, 1)
   }
 
   ptx::tc_fence_before_sync();
-  if (CL > 1) ptx::cluster_sync();  // no CTA may exit while its peer can still multicast into it or arrive on its barriers
-  else __syncthreads();
+  __syncthreads();
   if (warp == 2) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 

@@ -127,17 +127,18 @@ int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t* 
 int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, const int64_t* sums_dev, double* K_dev_out,
                           double* K_host_out, int32_t* G_host_out);
 /* The same partial cross-product with the exchange FUSED into the kernel's epilogue over NVLink peer memory, instead of
- * a collective after it.  peers[r] = rank r's Gram buffer (gapit_gram_ld(n)^2 int32 each, same layout everywhere,
- * peer-mapped into this process: e.g. torch symmetric memory or cudaIpc handles), mc = the NVLS multicast address of
- * the same buffers (mode 2 only).  Protocol: every rank zeroes its buffer, all ranks pass a barrier, every rank calls
- * this, all ranks synchronise their streams and pass a barrier again.  Then
- *   mode 3 (bulk tensor reduce-adds through TMA, 32 x 32 int32 boxes; the fast one) and mode 1 (4-byte RED.ADD on peer
- *          pointers): root >= 0: rank `root` holds the complete lower triangle (reduce to root); root < 0: rank r holds
- *          the complete block-rows gapit_gram_owned_rows(n, world, r) (reduce-scatter);
- *   mode 2 (NVLS multimem.red): every rank holds the complete lower triangle (all-reduce in the switch).
- * gapit_vanraden_finish then runs on a complete buffer.  Integer adds: bit-identical to the NCCL route. */
-int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int32_t* mc, int world, int rank,
-                              int mode, int root, int64_t* sums_dev);
+ * a collective after it: every 256 x 256 tile leaves the kernel as bulk tensor reduce-adds (TMA, 32 x 32 int32 boxes)
+ * into the Gram buffer of the rank that owns it.  peers[r] = rank r's Gram buffer (gapit_gram_ld(n)^2 int32 each, same
+ * layout everywhere, peer-mapped into this process: cudaDeviceEnablePeerAccess pointers, torch symmetric memory or
+ * cudaIpc handles).  Protocol: every rank zeroes its buffer, all ranks pass a barrier, every rank calls this, all ranks
+ * synchronise their streams and pass a barrier again.  Then, with root >= 0, rank `root` holds the complete lower
+ * triangle (reduce to root); with root < 0 rank r holds the complete block-rows gapit_gram_owned_rows(n, world, r)
+ * (reduce-scatter: each rank's NVLink ingress carries 1/world of the tiles) and the rank that goes on calls
+ * gapit_vanraden_gram_gather to pull the other ranks' block-rows into its own buffer.  gapit_vanraden_finish then runs
+ * on a complete buffer.  Integer adds: bit-identical to the all-reduce route for any rank count. */
+int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int world, int rank, int root,
+                              int64_t* sums_dev);
+int gapit_vanraden_gram_gather(gapit_ctx* ctx, int64_t n, int32_t* const* peers, int world, int rank);
 int gapit_gram_owned_rows(int64_t n, int world, int rank, int64_t* row_lo, int64_t* row_hi);
 
 /* ---- ZHANG kinship and PCA covariates from the same integer cross-product ----------------------------
@@ -223,6 +224,8 @@ int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const double* val
 int gapit_eigsys_from_device(gapit_ctx* ctx, const double* vectors_dev, const double* values, int64_t n, gapit_eigsys** out);
 int gapit_eigsys_project(gapit_ctx* ctx, gapit_eigsys* e, const double* R, int nc, double* out);
 void gapit_eigsys_free(gapit_eigsys* e);
+/* device address of the n x n column-major eigenvectors held by the handle (valid until gapit_eigsys_free) */
+const double* gapit_eigsys_vectors_dev(const gapit_eigsys* e);
 int gapit_p3d_scan_dev(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
                        const double* delta, const double* vg, int glm, gapit_scan_out* out,
                        gapit_scan_base* base_out);
@@ -241,6 +244,32 @@ int gapit_p3d_scan_host(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int
  * from the spectrum (|lambda|min / |lambda|max < DBL_EPSILON => pseudo-inverse with tolerance sqrt(eps)). */
 int gapit_blup_pev(gapit_ctx* ctx, gapit_eigsys* e, const double* X0, int q0, const double* y, double delta, double vg,
                    double* blup_out, double* pev_out, double* beta_out);
+
+/* ---- all GPUs of one box from ONE process -----------------------------------
+ * What an R session binds: no launcher, no torch.distributed.  gapit_mctx_create(ngpus, ...) opens `ngpus` devices
+ * (0 = every visible one, at most 8) and enables peer access between every pair; it fails with GAPIT_ERR_NO_DEVICE when
+ * a pair has none.  gapit_mgeno_pack splits the host genotype matrix (layout and dtypes of gapit_geno_pack) into
+ * contiguous marker blocks, one per GPU, uploaded concurrently on one host thread per GPU.  gapit_multi_vanraden:
+ * every GPU's cross-product kernel reduce-scatters its tiles to the block-row owners over NVLink (bulk tensor
+ * reduce-adds), GPU 0 gathers the rows and runs the exact epilogue; the result is bit-identical to gapit_vanraden for
+ * any GPU count.  gapit_multi_p3d_scan: the eigen-system is uploaded once and copied GPU to GPU, every GPU scans its
+ * block, rows land in the caller's arrays (m markers per trait) in marker order.  Arguments as in gapit_vanraden /
+ * gapit_p3d_scan.  The worker threads never call back into the host runtime. */
+typedef struct gapit_mctx gapit_mctx;
+typedef struct gapit_mgeno gapit_mgeno;
+int gapit_mctx_create(int ngpus, gapit_mctx** out);
+void gapit_mctx_destroy(gapit_mctx* mc);
+int gapit_mctx_ngpus(const gapit_mctx* mc);
+gapit_ctx* gapit_mctx_ctx(gapit_mctx* mc, int gpu); /* the one-GPU context of device `gpu` (spectra, REML inputs ...) */
+int gapit_mgeno_pack(gapit_mctx* mc, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
+                     gapit_impute impute, gapit_mgeno** out);
+void gapit_mgeno_free(gapit_mgeno* g);
+int64_t gapit_mgeno_n(const gapit_mgeno* g);
+int64_t gapit_mgeno_m(const gapit_mgeno* g);
+int gapit_multi_vanraden(gapit_mctx* mc, gapit_mgeno* g, double* K_out, int32_t* G_out);
+int gapit_multi_p3d_scan(gapit_mctx* mc, gapit_mgeno* g, const double* vectors, const double* values, const double* X0,
+                         int q0, const double* Y, int T, const double* delta, const double* vg, int glm,
+                         gapit_scan_out* out, gapit_scan_base* base_out /* T entries */);
 
 /* tuning knobs (0 = default): number of int8 slices of V (4..8) */
 int gapit_set_slices(gapit_ctx* ctx, int slices);

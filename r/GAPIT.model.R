@@ -7,3 +7,7 @@ GAPIT <- function(..., model=NULL){
   grp <- switch(model, GLM=1, MLM=1000000, stop("model must be \"GLM\" or \"MLM\""))
   GAPIT.reference(..., group.from=grp, group.to=grp)
 }
+
+# GPUs: the library opens every visible GPU of the box at its first call and shards markers across them
+# (gapit_mctx_create / gapit_mgeno_pack).  gapit.gpus(k) re-opens it on the first k devices; returns the count in use.
+`gapit.gpus` <- function(ngpus = getOption("gapit.gpus", 0L)) .Call("gapit_R_init", as.integer(ngpus))

@@ -15,11 +15,25 @@
 
 #include "gapitcuda.h"
 
-static gapit_ctx* g_ctx = NULL;
+/* Every visible GPU of the box (at most 8) behind one multi-context; options(gapit.gpus = k) is read by the R
+ * wrappers and passed to gapit_R_init before the first call to use fewer.  ctx() is GPU 0's one-GPU context. */
+static gapit_mctx* g_mctx = NULL;
 
-static gapit_ctx* ctx(void) {
-  if (!g_ctx && gapit_ctx_create(0, &g_ctx) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
-  return g_ctx;
+static gapit_mctx* mctx(void) {
+  if (!g_mctx && gapit_mctx_create(0, &g_mctx) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  return g_mctx;
+}
+
+static gapit_ctx* ctx(void) { return gapit_mctx_ctx(mctx(), 0); }
+
+/* .Call("gapit_R_init", ngpus): (re)open the library on `ngpus` devices (0 = all); returns the count in use */
+SEXP gapit_R_init(SEXP ngpus) {
+  if (g_mctx) {
+    gapit_mctx_destroy(g_mctx);
+    g_mctx = NULL;
+  }
+  if (gapit_mctx_create(Rf_asInteger(ngpus), &g_mctx) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  return Rf_ScalarInteger(gapit_mctx_ngpus(g_mctx));
 }
 
 static gapit_dtype sexp_dtype(SEXP x) {
@@ -42,24 +56,23 @@ static uint8_t* pack_matrix(SEXP x, int64_t n, int64_t m, int64_t* nb_out) {
   return packed;
 }
 
-/* GAPIT.kinship.VanRaden(snps): n x m matrix -> n x n double matrix (GAPIT.kinship.VanRaden.R:1-37) */
+/* GAPIT.kinship.VanRaden(snps): n x m matrix -> n x n double matrix (GAPIT.kinship.VanRaden.R:1-37).
+ * Markers are split across every GPU of the multi-context; the partial cross-products are exchanged inside the kernel. */
 SEXP gapit_R_vanraden(SEXP snps) {
   SEXP dim = Rf_getAttrib(snps, R_DimSymbol);
   const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
-  gapit_geno* g = NULL;
+  /* everything that can longjmp (context creation, R allocations) happens before a device handle exists */
+  gapit_mctx* mc = mctx();
   int64_t nb = 0;
   const uint8_t* packed = pack_matrix(snps, n, m, &nb);
-  /* the reference does not impute here: NA propagates to a NaN matrix, so NA is an error for us */
-  int rc = gapit_geno_pack(ctx(), packed, GAPIT_B2, n, m, nb, GAPIT_IMPUTE_NONE, &g);
-  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
   SEXP K = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
-  rc = gapit_vanraden(ctx(), g, REAL(K), NULL);
-  gapit_geno_free(g);
-  if (rc != GAPIT_OK) {
-    UNPROTECT(1);
-    Rf_error("gapitcuda: %s", gapit_last_error());
-  }
+  gapit_mgeno* g = NULL;
+  /* the reference does not impute here: NA propagates to a NaN matrix, so NA is an error for us */
+  int rc = gapit_mgeno_pack(mc, packed, GAPIT_B2, n, m, nb, GAPIT_IMPUTE_NONE, &g);
+  if (rc == GAPIT_OK) rc = gapit_multi_vanraden(mc, g, REAL(K), NULL);
+  gapit_mgeno_free(g);
   UNPROTECT(1);
+  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
   return K;
 }
 
@@ -131,24 +144,38 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP 
   const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
   const int q0 = INTEGER(Rf_getAttrib(X0, R_DimSymbol))[1];
   const int is_glm = Rf_asLogical(glm);
+  /* everything that can longjmp happens before a device handle exists */
+  gapit_mctx* mc = mctx();
   int64_t nb = 0;
-  const uint8_t* packed = pack_matrix(xs, n, m, &nb);   /* may Rf_error: before any device resource is held */
-  gapit_eigsys* e = NULL;
-  if (!is_glm && gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e) != GAPIT_OK)
-    Rf_error("gapitcuda: %s", gapit_last_error());
+  const uint8_t* packed = pack_matrix(xs, n, m, &nb);
   SEXP res = PROTECT(Rf_allocMatrix(REALSXP, (int)m, 7));
+  SEXP b = PROTECT(Rf_allocVector(REALSXP, 7 + q0));
   double* r = REAL(res);
   gapit_scan_out out = {r, r + m, r + 2 * m, r + 3 * m, r + 4 * m, r + 5 * m, r + 6 * m};
   gapit_scan_base base;
   double d = is_glm ? 0.0 : Rf_asReal(delta), v = is_glm ? 0.0 : Rf_asReal(vg);
-  int rc = gapit_p3d_scan_host(ctx(), packed, GAPIT_B2, n, m, nb, (gapit_impute)Rf_asInteger(impute), e,
-                               REAL(X0), q0, REAL(y), 1, &d, &v, is_glm, &out, &base);
-  gapit_eigsys_free(e);
+  const gapit_impute imp = (gapit_impute)Rf_asInteger(impute);
+  int rc;
+  if (gapit_mctx_ngpus(mc) == 1) {
+    /* one GPU: stream the packed rows (upload overlapped with the scan) */
+    gapit_eigsys* e = NULL;
+    rc = is_glm ? GAPIT_OK : gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e);
+    if (rc == GAPIT_OK)
+      rc = gapit_p3d_scan_host(ctx(), packed, GAPIT_B2, n, m, nb, imp, e, REAL(X0), q0, REAL(y), 1, &d, &v, is_glm, &out, &base);
+    gapit_eigsys_free(e);
+  } else {
+    /* several GPUs: one marker block per GPU, results in marker order */
+    gapit_mgeno* g = NULL;
+    rc = gapit_mgeno_pack(mc, packed, GAPIT_B2, n, m, nb, imp, &g);
+    if (rc == GAPIT_OK)
+      rc = gapit_multi_p3d_scan(mc, g, is_glm ? NULL : REAL(vectors), is_glm ? NULL : REAL(values), REAL(X0), q0, REAL(y), 1,
+                                &d, &v, is_glm, &out, &base);
+    gapit_mgeno_free(g);
+  }
   if (rc != GAPIT_OK) {
-    UNPROTECT(1);
+    UNPROTECT(2);
     Rf_error("gapitcuda: %s", gapit_last_error());
   }
-  SEXP b = PROTECT(Rf_allocVector(REALSXP, 7 + q0));
   REAL(b)[0] = base.logL0;
   REAL(b)[1] = base.logLM_base;
   REAL(b)[2] = base.rsquare_base;
@@ -167,18 +194,20 @@ SEXP gapit_R_blup_pev(SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP delta, SE
   SEXP dim = Rf_getAttrib(X0, R_DimSymbol);
   const int64_t n = INTEGER(dim)[0];
   const int q0 = INTEGER(dim)[1];
-  gapit_eigsys* e = NULL;
-  if (gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  gapit_ctx* c = ctx();
   SEXP blup = PROTECT(Rf_allocMatrix(REALSXP, (int)n, 1));
   SEXP pev = PROTECT(Rf_allocMatrix(REALSXP, (int)n, 1));
   SEXP beta = PROTECT(Rf_allocVector(REALSXP, q0));
-  int rc = gapit_blup_pev(ctx(), e, REAL(X0), q0, REAL(y), Rf_asReal(delta), Rf_asReal(vg), REAL(blup), REAL(pev), REAL(beta));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  const double dl = Rf_asReal(delta), vgv = Rf_asReal(vg);
+  gapit_eigsys* e = NULL;   /* from here on nothing can longjmp until the handle is released */
+  int rc = gapit_eigsys_upload(c, REAL(vectors), REAL(values), n, &e);
+  if (rc == GAPIT_OK) rc = gapit_blup_pev(c, e, REAL(X0), q0, REAL(y), dl, vgv, REAL(blup), REAL(pev), REAL(beta));
   gapit_eigsys_free(e);
   if (rc != GAPIT_OK) {
-    UNPROTECT(3);
+    UNPROTECT(4);
     Rf_error("gapitcuda: %s", gapit_last_error());
   }
-  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
   SET_VECTOR_ELT(out, 0, blup);
   SET_VECTOR_ELT(out, 1, pev);
   SET_VECTOR_ELT(out, 2, beta);
@@ -208,11 +237,12 @@ SEXP gapit_R_reml_eigL(SEXP values, SEXP Vty, SEXP VtX, SEXP ngrids, SEXP llim, 
 SEXP gapit_R_zhang(SEXP snps) {
   SEXP dim = Rf_getAttrib(snps, R_DimSymbol);
   const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
-  gapit_geno* g = NULL;
-  if (gapit_geno_pack(ctx(), sexp_data(snps), sexp_dtype(snps), n, m, n, GAPIT_IMPUTE_NONE, &g) != GAPIT_OK)
-    Rf_error("gapitcuda: %s", gapit_last_error());   /* :27 "Missing data is not allowed for numerical genotype data" */
+  gapit_ctx* c = ctx();
+  const gapit_dtype dt = sexp_dtype(snps);
   SEXP K = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
-  int rc = gapit_zhang(ctx(), g, REAL(K));
+  gapit_geno* g = NULL;   /* nothing below can longjmp while the handle is held */
+  int rc = gapit_geno_pack(c, sexp_data(snps), dt, n, m, n, GAPIT_IMPUTE_NONE, &g);   /* :27 "Missing data is not allowed ..." */
+  if (rc == GAPIT_OK) rc = gapit_zhang(c, g, REAL(K));
   gapit_geno_free(g);
   UNPROTECT(1);
   if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
@@ -223,18 +253,19 @@ SEXP gapit_R_zhang(SEXP snps) {
 SEXP gapit_R_pca(SEXP X, SEXP ncomp) {
   SEXP dim = Rf_getAttrib(X, R_DimSymbol);
   const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1], k = Rf_asInteger(ncomp), rank = n < m ? n : m;
-  gapit_geno* g = NULL;
-  if (gapit_geno_pack(ctx(), sexp_data(X), sexp_dtype(X), n, m, n, GAPIT_IMPUTE_NONE, &g) != GAPIT_OK)
-    Rf_error("gapitcuda: %s", gapit_last_error());
+  gapit_ctx* c = ctx();
+  const gapit_dtype dt = sexp_dtype(X);
   SEXP x = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)k));
   SEXP ev = PROTECT(Rf_allocVector(REALSXP, rank));
-  int rc = gapit_pca(ctx(), g, k, REAL(x), REAL(ev));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  gapit_geno* g = NULL;   /* nothing below can longjmp while the handle is held */
+  int rc = gapit_geno_pack(c, sexp_data(X), dt, n, m, n, GAPIT_IMPUTE_NONE, &g);
+  if (rc == GAPIT_OK) rc = gapit_pca(c, g, k, REAL(x), REAL(ev));
   gapit_geno_free(g);
   if (rc != GAPIT_OK) {
-    UNPROTECT(2);
+    UNPROTECT(3);
     Rf_error("gapitcuda: %s", gapit_last_error());
   }
-  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
   SET_VECTOR_ELT(out, 0, x);
   SET_VECTOR_ELT(out, 1, ev);
   UNPROTECT(3);

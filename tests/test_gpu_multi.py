@@ -31,3 +31,46 @@ def test_sharded_pipeline_matches_one_gpu():
     line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
     rep = json.loads(line)
     assert rep["ok"] and rep["gram_bit_identical"] and rep["kinship_bit_identical"] and rep["scan_max_rel_diff"] <= 1e-13
+
+
+@pytest.mark.parametrize("ngpus", [1, 2, 4])
+def test_one_process_drives_every_gpu_through_the_c_abi(ngpus):
+    """gapit_mctx / gapit_mgeno (what the R shim binds): one process, one host thread per GPU, no torch.distributed.
+    Kinship bit-identical to the one-GPU call (integer sums), scan rows identical wherever a marker sits."""
+    import numpy as np
+    import torch
+    import gapit_b200 as gb
+    from gapit_b200 import synth
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    n, m = 600, 5003
+    G = synth.make_genotypes(n, m, seed=29, threads=4)
+    Y = synth.make_phenotypes(G, ntraits=3, seed=29)
+    X0 = synth.make_covariates(G, npc=1)
+    ctx = gb.Context(0)
+    one = gb.Genotypes(G, ctx=ctx, marker_major=True)
+    K1, G1 = gb.GAPIT_kinship_VanRaden(one, ctx=ctx, return_gram=True, verbose=False)
+    eL = gb.emma_eigen_L_wo_Z(K1, ctx=ctx)
+    remls = [gb.GAPIT_emma_REMLE(Y[:, t], X0, K1, eig_L=eL, ctx=ctx) for t in range(3)]
+    delta, vg = [r["delta"] for r in remls], [r["vg"] for r in remls]
+    es = gb.EigenSystem(eL["values"], eL["vectors"], ctx=ctx)
+    ref, refb = gb.p3d_scan(one, X0, Y, eigsys=es, delta=delta, vg=vg, ctx=ctx)
+    ref1, _ = gb.p3d_scan(one, X0, Y[:, :1], eigsys=es, delta=delta[:1], vg=vg[:1], ctx=ctx)
+    refg, _ = gb.p3d_scan(one, X0, Y, glm=True, ctx=ctx)
+
+    mctx = gb.MultiContext(ngpus)
+    assert mctx.ngpus == ngpus
+    for src in (G, gb.Packed2.from_dosages(G, marker_major=True)):
+        mg = gb.MultiGenotypes(src, mctx, marker_major=True)
+        K, Gm = gb.multi_vanraden(mg, return_gram=True)
+        assert np.array_equal(Gm, G1) and np.array_equal(K, K1)
+        got, gotb = gb.multi_p3d_scan(mg, X0, Y, values=eL["values"], vectors=eL["vectors"], delta=delta, vg=vg)
+        got1, _ = gb.multi_p3d_scan(mg, X0, Y[:, :1], values=eL["values"], vectors=eL["vectors"], delta=delta[:1], vg=vg[:1])
+        gotg, _ = gb.multi_p3d_scan(mg, X0, Y, glm=True)
+        for key in ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm", "maf"):
+            assert np.array_equal(got[key], ref[key], equal_nan=True), key
+            assert np.array_equal(got1[key], ref1[key], equal_nan=True), key
+            assert np.array_equal(gotg[key], refg[key], equal_nan=True), key
+        assert gotb[0]["logL0"] == refb[0]["logL0"] and gotb[2]["rsquare_base"] == refb[2]["rsquare_base"]
+        mg.close()
+    mctx.close()

@@ -38,7 +38,7 @@ dist.all_reduce(s_t)
 K = np.empty((n, n), order="F")
 Gi = np.empty((n, n), dtype=np.int32)
 _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_t.data_ptr(), s_t.data_ptr(), None, K.ctypes.data, Gi.ctypes.data))
-# ---- the same sums with the exchange fused into the Gram kernel (peer RED / NVLS multimem.red), no collective --------
+# ---- the same sums with the exchange fused into the Gram kernel (bulk tensor reduce-adds over NVLink), no collective ----
 fused = {}
 try:
     import ctypes
@@ -47,40 +47,40 @@ try:
     G_sym = symm_mem.empty((ldg, ldg), dtype=torch.int32, device=dev)
     hdl = symm_mem.rendezvous(G_sym, dist.group.WORLD)
     peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
-    mc = int(hdl.multicast_ptr) if hdl.has_multicast_support else 0
     s_f = torch.empty(3, dtype=torch.int64, device=dev)
-    # the product path is mode 3 (bulk tensor reduce-adds); CHK_ALL_MODES=1 also runs the 4-byte transports
-    variants = [(3, -1), (3, 0)]
-    if os.environ.get("CHK_ALL_MODES"):
-        variants = [(1, -1)] + ([(2, -1)] if mc else []) + variants
-    for mode, root in variants:
+    ref_t = torch.tril(G_t[:n, :n])
+    # root = -1: reduce-scatter by block-row owner, then the finishing rank (every rank in turn here) gathers the rows
+    # the others own; root = 0: reduce to one rank
+    for root in (-1, 0):
         G_sym.zero_()
         torch.cuda.synchronize()
         hdl.barrier()
         t0 = time.perf_counter()
-        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, ctypes.c_void_p(mc), world, rank, mode, root,
-                                                 s_f.data_ptr()))
+        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, root, s_f.data_ptr()))
         torch.cuda.synchronize()
         hdl.barrier()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        full = G_sym.clone()
-        if root >= 0:   # reduce to root: only that rank holds the sums; hand them to the others for the comparison
+        same = True
+        if root >= 0:
             full = hdl.get_buffer(root, (ldg, ldg), torch.int32).clone()
             torch.cuda.synchronize()
-        elif mode != 2:   # reduce-scatter modes: every rank pulls the block-rows the others own (the finishing rank would do only this)
-            for r in range(world):
-                lo, hi = ctypes.c_int64(), ctypes.c_int64()
-                _lib.check(lib.gapit_gram_owned_rows(n, world, r, ctypes.byref(lo), ctypes.byref(hi)))
-                if r != rank and hi.value > lo.value:
-                    full[lo.value:hi.value].copy_(hdl.get_buffer(r, (ldg, ldg), torch.int32)[lo.value:hi.value])
-            torch.cuda.synchronize()
-        hdl.barrier()
-        # compare the lower triangle (by 256-tiles) with the all-reduced one
-        ref_t = torch.tril(G_t[:n, :n])
-        got_t = torch.tril(full[:n, :n])
-        fused[f"mode{mode}_root{root}"] = {"bit_identical": bool(torch.equal(ref_t, got_t)), "call_ms": dt * 1e3}
-except Exception as exc:   # no peer access / symmetric memory on this box: the NCCL route stays the product path
+            same = bool(torch.equal(ref_t, torch.tril(full[:n, :n])))
+            hdl.barrier()
+        else:
+            for gatherer in range(world):     # one rank at a time pulls the others' block-rows into its own buffer
+                if rank == gatherer:
+                    keep = G_sym.clone()
+                    _lib.check(lib.gapit_vanraden_gram_gather(ctx.h, n, peers, world, rank))
+                    torch.cuda.synchronize()
+                    same = same and bool(torch.equal(ref_t, torch.tril(G_sym[:n, :n])))
+                    G_sym.copy_(keep)         # leave only the owned rows for the next gatherer
+                    torch.cuda.synchronize()
+                hdl.barrier()
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        fused[f"root{root}"] = {"bit_identical": bool(flag.item()), "call_ms": dt * 1e3}
+except Exception as exc:   # no peer access / symmetric memory on this box: the NCCL route stays available
     fused = {"unavailable": repr(exc)[:200]}
 vec = torch.empty((n, n), dtype=torch.float64, device=dev)
 val = torch.empty(n, dtype=torch.float64, device=dev)
