@@ -4,15 +4,18 @@
     python bench.py --gpus N --steps K --warmup W            # this repo (libgapitcuda)
     python bench.py --impl reference --gpus N --steps K ...  # CPU reference arm (oracle restatement)
 
-Workload (BASELINE.json configs[1]): 5,000 taxa x 500,000 SNPs per GPU, one trait,
-intercept-only covariates, VanRaden kinship + MLM/P3D scan (GLM scan reported beside it).
-A "step" is one P3D scan of every marker resident on the GPU.  Under torchrun each rank
-holds its own 500,000-marker shard (weak scaling); the kinship partial cross-products are
-summed with one NCCL all-reduce, the eigen-system is broadcast once, the scan needs no
-collective and rank 0 gathers the p-values.
+Headline workload (BASELINE.json configs[1]): 5,000 taxa x 500,000 SNPs per GPU, one trait, intercept-only covariates,
+VanRaden kinship + MLM/P3D scan (GLM scan reported beside it).  A "step" is one P3D scan of every marker resident on
+the GPU.  Under torchrun each rank holds its own 500,000-marker shard (weak scaling); the kinship partial
+cross-products are exchanged inside the Gram kernel over NVLink (reduce-scatter + one row gather), the eigen-system is
+broadcast once, the scan needs no collective and rank 0 gathers the p-values.
 `e2e` is the same scan through the public host-buffer call (`gapit_p3d_scan_host`) from pinned host memory in the
 library's packed host format (2 bits per genotype call), results back to the host every step; `e2e.int8` is the same
-call fed one byte per call.  One JSON line is printed by rank 0 (see the task contract for the keys).
+call fed one byte per call.
+Beside the headline the same line carries: `parity` (the oracle run on the very markers the GPU scanned, in this run),
+the other BASELINE configs as `legs` (N = 1: configs[4], 100 traits; N >= 2: configs[2] and configs[3], STRONG scaling:
+total work fixed, sharded over the N ranks), and the int8 / fp64 tensor ceilings calibrated on this box.
+One JSON line is printed by rank 0 (see the task contract for the keys).
 """
 from __future__ import annotations
 
@@ -31,11 +34,24 @@ sys.path.insert(0, ROOT)
 
 METRIC = "SNPs tested/sec (MLM P3D)"
 UNIT = "SNPs/s"
-# (taxa, markers per GPU, slices) -> dram__bytes_read.sum + dram__bytes_write.sum of one rotate_reduce launch
-# (`ncu --set full`, profiles/r1c_ncu_full_pair_kernels_c2.csv).  The digit planes (154 MB) do not fit L2 beside the
-# marker tiles, so each wave of marker tiles streams them once: 66 waves x 154 MB + the genotypes once = 12.7 GB is the
-# floor of this tiling; the soft round alignment of the scheduler keeps the measured figure at it (83 GB without).
-NCU_TRAFFIC_BYTES = {(5000, 500000, 6): 13.3e9}
+
+
+def workload_name(n, m):
+    """The `config.workload` string -- identical in both arms."""
+    return f"MLM P3D scan, {n} taxa x {m} SNPs per GPU, 1 trait, q0=1 (BASELINE configs[1] per GPU)"
+
+
+def ncu_traffic(n, m, S):
+    """DRAM bytes (read + write) of one rotate_reduce launch from the committed `ncu --set full` capture of this exact
+    shape (profiles/traffic.json, written by tools/ncu_traffic.py from the capture it names); None for other shapes."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            for e in json.load(f)["rotate_reduce"]:
+                if (e["n"], e["m"], e["slices"]) == (n, m, S):
+                    return e["dram_bytes"], e["source"]
+    except Exception:
+        pass
+    return None, None
 
 
 def parse():
@@ -52,6 +68,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--kinship-exchange", default="fused", choices=["fused", "nccl"],
                     help="N > 1: exchange of the Gram partials fused into the kernel over NVLink peer memory, or ncclAllReduce")
+    ap.add_argument("--no-legs", action="store_true", help="skip the other BASELINE configs (configs[2..4])")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--reml-route", default="eigL", choices=["eigL", "eigR"],
                     help="eigL: REML from the spectrum of K alone (one eigendecomposition); eigR: the reference's "
                          "second decomposition of S(K+I)S (emma.txt:82-89)")
@@ -140,6 +158,49 @@ def calibrate_int8_tops(dev):
         return None
 
 
+def calibrate_fp64_tflops(dev):
+    """cuBLAS DGEMM (torch.matmul float64, 8192^3) on this box: the measured fp64 ceiling the rotation would have as
+    a plain fp64 GEMM."""
+    import torch
+    try:
+        a = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
+        b = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            a @ b
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            a @ b
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+    except Exception:
+        return None
+
+
+def count_launches(fn):
+    """Kernels of libgapitcuda launched by one call of `fn`, counted by CUPTI through torch.profiler (names in
+    namespace gapit::).  Returns (count, {kernel name: launches}) or (None, reason)."""
+    import torch
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        names = {}
+        for ev in prof.events():
+            nm = ev.name
+            if "gapit::" in nm or nm.startswith("gapit"):
+                key = nm.split("(")[0][:96]
+                names[key] = names.get(key, 0) + 1
+        return sum(names.values()), names
+    except Exception as exc:
+        return None, repr(exc)[:160]
+
+
 def cpu_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -148,14 +209,53 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
-def cpu_scan_sample(n, ns, seed, eig_L, reml, G=None, Y=None, X0=None):
+def cpu_scan_sample(n, ns, seed, eig_L, reml, G=None, Y=None, X0=None, keep=None):
     """Time the oracle's per-marker loop (two n x n GEMVs per marker, GAPIT.EMMAxP3D.R:634,957)
-    on `ns` markers.  Returns SNPs/s."""
+    on `ns` markers.  Returns SNPs/s; the oracle's rows are left in keep["ora"] for the in-run parity check."""
     from oracle import gapit_oracle as go
     t0 = time.perf_counter()
-    go.emmax_p3d(Y, G[:ns].T, K=np.zeros((2, 2)), X0=X0, eig_L=eig_L, reml=reml)
+    ora = go.emmax_p3d(Y, G[:ns].T, K=np.zeros((2, 2)), X0=X0, eig_L=eig_L, reml=reml)
     dt = time.perf_counter() - t0
+    if keep is not None:
+        keep["ora"] = ora
     return ns / dt, dt
+
+
+def parity_report(arrs, G_host, Y, X0, eig_L, reml_d, ora, ns_loop, block=2048):
+    """Correctness on the same inputs in the same run: (1) the oracle's per-marker loop (the restated reference path)
+    on the first `ns_loop` markers, (2) the batched fp64 derivation (oracle/batched.py: V'X by dgemm + closed-form
+    bordered solve, independent of the loop and of the int8 split) on three blocks -- first, middle, last -- of the
+    shard, against the rows the GPU produced for those markers."""
+    from oracle import batched
+    m = G_host.shape[0]
+    rep = {}
+    if ora is not None:
+        ref = {"effect": ora.effect_est, "se": ora.se_clean, "tvalue": ora.stats, "pvalue": ora.ps}
+        with np.errstate(divide="ignore"):
+            ref["log10p"] = np.log10(ora.ps)
+        one = {k: arrs[k][0] for k in ("effect", "se", "tvalue", "pvalue")}
+        rep["per_marker_loop"] = batched.compare(one, ref, rows=slice(0, ns_loop))
+    worst = None
+    nb = 0
+    for k0 in sorted({0, max(0, (m // 2) // block * block), max(0, m - block)}):
+        k1 = min(m, k0 + block)
+        ref = batched.p3d_block(Y, G_host[k0:k1].T, X0, eig_L["values"], eig_L["vectors"], reml_d["delta"], reml_d["vg"])
+        one = {k: arrs[k][0] for k in ("effect", "se", "tvalue", "pvalue")}
+        c = batched.compare(one, ref, rows=slice(k0, k1))
+        nb += c["n_markers"]
+        if worst is None:
+            worst = c
+        else:
+            for key in ("beta_rel_max", "se_rel_max", "beta_err_in_se_units_max", "dlog10p_max"):
+                worst[key] = max(worst[key], c[key])
+            worst["nan_rows_identical"] = worst["nan_rows_identical"] and c["nan_rows_identical"]
+            worst["n_tested"] += c["n_tested"]
+    worst["n_markers"] = nb
+    rep["batched_fp64"] = worst
+    rep["tolerance"] = {"beta_se_rel": 1e-8, "dlog10p_abs": 1e-6}
+    rep["pass"] = bool(all(v["nan_rows_identical"] and v["se_rel_max"] < 1e-8 and v["beta_rel_max"] < 1e-8 and
+                           v["dlog10p_max"] < 1e-6 for v in (rep.get("per_marker_loop"), rep["batched_fp64"]) if v))
+    return rep
 
 
 def run_reference(args):
@@ -196,8 +296,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"MLM P3D scan, {n} taxa x {args.m} SNPs per GPU, 1 trait, q0=1",
-                       "sample": f"{ns} markers per step, per-marker loop with two n x n GEMVs"},
+            "config": {"workload": workload_name(n, args.m)},
+            "sample": f"{ns} markers per step, per-marker loop with two n x n GEMVs",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{ns} of {args.m} markers per step (cost is exactly linear in markers); "
                                        f"numpy/OpenBLAS oracle restatement of GAPIT.EMMAxP3D.R:397-979, K from {m_kin} markers"},
@@ -270,8 +370,10 @@ def main():
         return float(ms.item()) / steps, float(np.mean(kms))
 
     # ---------------- kinship: gram (+ exchange) + epilogue ----------------
-    # N > 1: the exchange is fused into the Gram kernel -- every rank's epilogue adds its tiles into rank 0's buffer over
-    # NVLink as bulk tensor reduce-adds (gapit_vanraden_gram_fused, mode 3, root 0; buffers from torch symmetric memory).
+    # N > 1: the exchange is fused into the Gram kernel -- every rank's epilogue adds its tiles into the buffer of the
+    # rank that owns the block-row, over NVLink, as bulk tensor reduce-adds (gapit_vanraden_gram_fused, root = -1:
+    # reduce-scatter, each rank's ingress carries 1/N of the tiles; buffers from torch symmetric memory); rank 0 then
+    # pulls the rows it does not own (gapit_vanraden_gram_gather) and runs the epilogue.
     # `--kinship-exchange nccl` (or a box without peer access) runs Gram -> ncclAllReduce instead.
     import ctypes
     ldg = lib.gapit_gram_ld(n)
@@ -285,7 +387,7 @@ def main():
             G_t = symm_mem.empty((ldg, ldg), dtype=torch.int32, device=dev)
             hdl = symm_mem.rendezvous(G_t, dist.group.WORLD)
             peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
-            exchange = "fused: bulk tensor reduce-add into rank 0 over NVLink (TMA), no collective"
+            exchange = "fused: tiles reduce-scattered over NVLink inside the Gram kernel (TMA bulk reduce-add), rank 0 gathers the rows"
         except Exception as exc:
             hdl = None
             exchange = f"nccl (symmetric memory unavailable: {exc!r})"[:160]
@@ -294,14 +396,14 @@ def main():
 
     def kinship_step():
         if hdl is not None:
-            if rank == 0:
-                G_t.zero_()
+            G_t.zero_()
             hdl.barrier()
-            _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, None, world, rank, 3, 0, sums_t.data_ptr()))
+            _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, -1, sums_t.data_ptr()))
             st = ctx.stats()
             hdl.barrier()
             dist.all_reduce(sums_t)
             if rank == 0:
+                _lib.check(lib.gapit_vanraden_gram_gather(ctx.h, n, peers, world, 0))
                 _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_t.data_ptr(), sums_t.data_ptr(), K_dev.data_ptr(), None, None))
         else:
             _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_t.data_ptr(), sums_t.data_ptr()))
@@ -373,25 +475,33 @@ def main():
     del K_dev
 
     # ---------------- the timed hot path: MLM P3D scan ----------------
+    # N > 1: rank 0 gathers every shard's p-values.  The rows come back in page-locked memory (reused across steps), so
+    # the gather's send buffer is filled by one asynchronous H2D copy on the shared stream, with no staging allocation.
     gather_buf = [torch.empty(m, dtype=torch.float64, device=dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+    p_dev = torch.empty(m, dtype=torch.float64, device=dev) if world > 1 else None
+    out_arrs = gb.alloc_scan_out(1, m, pinned=True)
     last = {}
 
     def scan_step():
-        arrs, bases = gb.p3d_scan(geno, X0, Y[:, :1], eigsys=es, delta=[delta], vg=[vg], ctx=ctx, pinned=True)
+        arrs, bases = gb.p3d_scan(geno, X0, Y[:, :1], eigsys=es, delta=[delta], vg=[vg], ctx=ctx, pinned=True, out=out_arrs)
         last["arrs"] = arrs
         if world > 1:
-            p = torch.from_numpy(arrs["pvalue"][0]).to(dev)
-            dist.gather(p, gather_buf, dst=0)
+            p_dev.copy_(torch.from_numpy(arrs["pvalue"][0]), non_blocking=True)
+            dist.gather(p_dev, gather_buf, dst=0)
 
     sampler = ClockSampler(local)
     sampler.start()
     scan_ms, scan_kernel_ms = timed(scan_step, args.steps, args.warmup)
     clocks = sampler.stop()
     value = m_total / (scan_ms * 1e-3)
+    # kernels of this library launched by ONE scan step, counted by CUPTI on an extra untimed step
+    launches_per_step, launch_names = count_launches(scan_step)
 
     # GLM scan (K = NULL branch), HBM-bound
+    glm_arrs = gb.alloc_scan_out(1, m, pinned=True)
+
     def glm_step():
-        gb.p3d_scan(geno, X0, Y[:, :1], glm=True, ctx=ctx, pinned=True)
+        gb.p3d_scan(geno, X0, Y[:, :1], glm=True, ctx=ctx, pinned=True, out=glm_arrs)
 
     glm_ms, glm_kernel_ms = timed(glm_step, max(2, args.steps), args.warmup)
 
@@ -405,13 +515,13 @@ def main():
         P2 = gb.Packed2.from_dosages(G_host, marker_major=True, pinned=True)
 
         def e2e_packed_step():
-            arrs, _ = gb.p3d_scan_host(P2, X0, Y[:, :1], eigsys=es, delta=[delta], vg=[vg], ctx=ctx, pinned=True)
+            arrs, _ = gb.p3d_scan_host(P2, X0, Y[:, :1], eigsys=es, delta=[delta], vg=[vg], ctx=ctx, pinned=True, out=glm_arrs)
             last["e2e_min_p"] = float(np.nanmin(arrs["pvalue"]))
         e2p_ms, _ = timed(e2e_packed_step, args.steps, 1)
 
         def e2e_int8_step():
             arrs, _ = gb.p3d_scan_host(G_host, X0, Y[:, :1], eigsys=es, delta=[delta], vg=[vg], ctx=ctx,
-                                       marker_major=True, pinned=True)
+                                       marker_major=True, pinned=True, out=glm_arrs)
             last["e2e_int8_min_p"] = float(np.nanmin(arrs["pvalue"]))
         e2e_ms, _ = timed(e2e_int8_step, args.steps, 1)
         assert last["e2e_int8_min_p"] == last["e2e_min_p"]
@@ -427,6 +537,7 @@ def main():
 
     # ---------------- CPU baseline beside it (rank 0, N=1) ----------------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         eig_L = {"values": values, "vectors": vectors}
         reml_d = {"delta": delta, "vg": vg, "ve": delta * vg, "REML": 0.0}
@@ -434,37 +545,65 @@ def main():
         if not ns:   # pilot, then size the sample for ~15 s of CPU work
             v0, _ = cpu_scan_sample(n, min(m, 16), 0, eig_L, reml_d, G_host, Y[:, 0], X0)
             ns = int(max(16, min(m, 40.0 * v0)))
-        v, dt = cpu_scan_sample(n, ns, 0, eig_L, reml_d, G_host, Y[:, 0], X0)
+        kept = {}
+        v, dt = cpu_scan_sample(n, ns, 0, eig_L, reml_d, G_host, Y[:, 0], X0, keep=kept)
         cpu = {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
                "sample": f"first {ns} of {m} markers ({dt:.1f} s); oracle restatement of GAPIT.EMMAxP3D.R:397-979 "
                          f"(two n x n GEMVs per marker) on numpy/OpenBLAS, eigen-system and delta injected"}
+        if not args.no_parity:
+            # the same markers, the same eigen-system and delta, the same run: GPU rows against the oracle's
+            parity = parity_report(last["arrs"], G_host, Y[:, 0], X0, eig_L, reml_d, kept.get("ora"), ns)
+        del kept
+    del vectors
 
     # ---------------- roofline of the dominant kernel (rotate_reduce) ----------------
     int8_ops = 2.0 * n * n * m * S                     # int8-native: S digit planes of V
     fp64_flops = 2.0 * n * n * m                       # algorithmic fp64 flops of the rotation
     achieved = int8_ops / (scan_kernel_ms * 1e-3) / 1e12
     int8_meas = calibrate_int8_tops(dev)
+    fp64_meas = calibrate_fp64_tflops(dev)
     int8_peak = int8_meas if int8_meas else 2.0 * pk["bf16_tflops"]
-    # DRAM bytes (read + write) of one rotate_reduce launch from `ncu --set full` on this exact configuration
-    # (profiles/r1c_ncu_full_pair_kernels_c2.csv); null for other shapes
-    traffic = NCU_TRAFFIC_BYTES.get((n, m, S))
+    # DRAM bytes (read + write) of one rotate_reduce launch: from the committed `ncu --set full` capture of this exact
+    # shape (profiles/traffic.json names the capture); null for any other shape -- it is not measurable inside this run
+    traffic, traffic_src = ncu_traffic(n, m, S)
     roofline = {"bound": "tensor", "kernel": "umma_i8_pair_kernel<ScanSched,ScanEpi> (rotate_reduce, tcgen05 cta_group::2)",
                 "achieved": achieved, "peak": int8_peak, "unit": "TFLOP/s", "frac": achieved / int8_peak,
-                "traffic": traffic, "algorithmic_bytes": float(n) * m + float(n) * n * S,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": float(n) * m + float(n) * n * S,
                 "peak_note": ("int8 dense ceiling measured in this run: cuBLASLt int8 GEMM 8192^3 via torch._int_mm, best of 10 "
                               "(MEASURED_PEAKS.json holds no int8 figure)" if int8_meas else
                               f"2 x bf16_tflops of MEASURED_PEAKS.json ({pk['source']}); int8 calibration unavailable"),
                 "peak_2x_bf16_measured": 2.0 * pk["bf16_tflops"], "peak_nominal": 4500.0,
                 "kernel_ms": scan_kernel_ms, "slices": S,
-                "fp64_equivalent_tflops": fp64_flops / (scan_kernel_ms * 1e-3) / 1e12}
+                "fp64_equivalent_tflops": fp64_flops / (scan_kernel_ms * 1e-3) / 1e12,
+                # the same rotation as a plain fp64 GEMM would be bounded by cuBLAS DGEMM, measured here
+                "fp64_dgemm_tflops_measured": fp64_meas,
+                "fp64_equiv_frac": (fp64_flops / (scan_kernel_ms * 1e-3) / 1e12 / fp64_meas) if fp64_meas else None}
     glm_bytes = float(n) * m
+    # ---------------- the other BASELINE configs, full size, on this box (outside the timed region above) -------------
+    min_p = float(np.nanmin(last["arrs"]["pvalue"]))
+    legs = None
+    if not args.no_legs:
+        from gapit_b200 import fullsize
+        es.close()
+        geno.close()
+        es = geno = None
+        del out_arrs, glm_arrs, last["arrs"], G_pin, G_host
+        torch.cuda.empty_cache()
+        legs = {}
+        for name in (["c5"] if world == 1 else ["c3", "c4"]):
+            try:
+                legs[name] = fullsize.run_config(name, ctx, dev, rank, world, slices=S, exchange=args.kinship_exchange)
+            except Exception as exc:   # a leg must not take the headline down with it
+                legs[name] = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
+        legs["scaling"] = "strong: total work of the named config fixed, markers sharded over the N ranks" if world > 1 \
+            else "one GPU"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": scan_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int8 x int8 -> int32 rotation (6 digit planes of fp64 V), fp64 epilogue",
         "data": "synthetic",
-        "config": {"workload": f"MLM P3D scan, {n} taxa x {m} SNPs per GPU ({m_total} total), 1 trait, q0=1 "
-                               f"(BASELINE configs[1] per GPU)", "kinship": "VanRaden", "slices": S,
+        "config": {"workload": workload_name(n, m), "markers_total": m_total, "kinship": "VanRaden", "slices": S,
                    "l2": "inputs larger than L2 (genotypes 2.5 GB per GPU)", "parallelism": f"marker-shard x{world}"},
         "kinship": {"tops": kin_tops, "ms": kin_ms, "gram_kernel_ms": gram_ms, "gram_kernel_tops_per_gpu": gram_tops_local,
                     "ops": "n(n+1)m integer multiply-adds counted once per lower-triangle pair",
@@ -478,16 +617,21 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": e2e,
-        "gpu_launches": args.steps * 3,
-        "gpu_launches_note": "per scan step: vt_project + umma_i8_pair rotate_reduce + finalize",
+        "gpu_launches": (launches_per_step * args.steps) if launches_per_step else args.steps * 3,
+        "gpu_launches_note": ({"per_step": launches_per_step, "counted_by": "CUPTI (torch.profiler) on one extra untimed step",
+                               "kernels": launch_names} if launches_per_step else
+                              f"CUPTI unavailable ({launch_names}); per scan step: vt_project + rotate_reduce + finalize"),
+        "parity": parity,
+        "legs": legs,
         "clocks": clocks,
         "reml": {"delta": delta, "vg": vg},
-        "min_p": float(np.nanmin(last["arrs"]["pvalue"])),
+        "min_p": min_p,
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
-    es.close()
-    geno.close()
+    if es is not None:
+        es.close()
+        geno.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgapitcuda.so")
 
 GAPIT_MAX_Q0 = 16
-GAPIT_F64, GAPIT_I32, GAPIT_I8, GAPIT_B2 = 0, 1, 2, 3
+GAPIT_F64, GAPIT_I32, GAPIT_I8, GAPIT_B2, GAPIT_BED_A1, GAPIT_BED_A2 = 0, 1, 2, 3, 4, 5
 IMPUTE = {None: -1, "None": -1, "Minor": 0, "Middle": 1, "Major": 2}
 EFFECT = {"Add": 0, "Dom": 1, "Left": 2, "Right": 3}
 
@@ -95,6 +95,10 @@ SIGNATURES = {
     "gapit_blup_pev": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_double, C.c_double, _P, _P, _P]),
     "gapit_set_slices": (C.c_int, [_P, C.c_int]),
     "gapit_eigsys_vectors_dev": (_P, [_P]),
+    "gapit_bed_header": (C.c_int, [_P, _I64, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
+    "gapit_text_index_lines": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I64)]),
+    "gapit_numtext_shape": (C.c_int, [_P, _I64, _P, _I64, C.c_int, C.POINTER(_I64), C.POINTER(_I64)]),
+    "gapit_numtext_numericalize": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _I64, C.c_int, _P, C.POINTER(_P)]),
     "gapit_mctx_create": (C.c_int, [C.c_int, C.POINTER(_P)]),
     "gapit_mctx_destroy": (None, [_P]),
     "gapit_mctx_ngpus": (C.c_int, [_P]),

@@ -14,6 +14,7 @@ All arithmetic happens in libgapitcuda.so; this module only marshals buffers.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 
 import numpy as np
@@ -82,11 +83,25 @@ class Packed2:
     byte i//4 at bits 2(i%4).. (PLINK .bed bit order); code 0/1/2 = dosage, 3 = NA.  A quarter of the int8 bytes
     over PCIe; the device expands it to the int8 operand layout."""
 
-    def __init__(self, data, n):
-        self.data = np.ascontiguousarray(data, dtype=np.uint8)
+    def __init__(self, data, n, dtype=_lib.GAPIT_B2):
+        self.data = data if (isinstance(data, np.ndarray) and data.dtype == np.uint8 and data.flags.c_contiguous) \
+            else np.ascontiguousarray(data, dtype=np.uint8)
         self.n = int(n)
         assert self.data.ndim == 2 and self.data.shape[1] >= (self.n + 3) // 4
         self.m = int(self.data.shape[0])
+        self.dtype = int(dtype)      # GAPIT_B2, or GAPIT_BED_A1 / GAPIT_BED_A2: the rows of a PLINK .bed as they are
+
+    @staticmethod
+    def from_bed(bed, n, count="A1"):
+        """The variant rows of a PLINK .bed (bytes, bytearray, numpy uint8 array or np.memmap of the whole file) for n
+        samples: header checked by the library, rows used in place (no copy, no host-side recoding); dosage = copies
+        of ``count`` ("A1", PLINK's --recode A convention, or "A2")."""
+        buf = np.frombuffer(bed, dtype=np.uint8) if not isinstance(bed, np.ndarray) else bed.reshape(-1)
+        m, off = C.c_int64(), C.c_int64()
+        check(_lib.load().gapit_bed_header(_ptr(buf), buf.shape[0], int(n), C.byref(m), C.byref(off)))
+        nb = (int(n) + 3) // 4
+        rows = buf[off.value:off.value + m.value * nb].reshape(m.value, nb)
+        return Packed2(rows, n, dtype=_lib.GAPIT_BED_A1 if count == "A1" else _lib.GAPIT_BED_A2)
 
     @staticmethod
     def from_dosages(a, marker_major=False, pinned=False, threads=0):
@@ -127,7 +142,7 @@ class Genotypes:
         lib = self.ctx.lib
         if isinstance(snps, Packed2):
             h = C.c_void_p()
-            check(lib.gapit_geno_pack(self.ctx.h, _ptr(snps.data), _lib.GAPIT_B2, snps.n, snps.m, snps.data.shape[1],
+            check(lib.gapit_geno_pack(self.ctx.h, _ptr(snps.data), snps.dtype, snps.n, snps.m, snps.data.shape[1],
                                       _lib.IMPUTE[impute], C.byref(h)))
             self.h = h
             self.n, self.m = snps.n, snps.m
@@ -342,6 +357,79 @@ def p3d_scan_hapmap(G, X0, Y, eigsys=None, delta=None, vg=None, glm=False, file_
         f = G[start:off[k]].split(b"\t", 4)
         GI.append((f[0].decode(), f[2].decode(), f[3].decode()))
     return arrs, bases, GT, GI
+
+
+# ---------------------------------------------------------------------------
+# Genotype files either side of the path: PLINK .bed / .bim / .fam and GAPIT's numeric text
+# (genoFormat = "EMMA": file.GD / file.GM, GAPIT.Fragment.R:94-136).  The bulk bytes go to the GPU as they are.
+# ---------------------------------------------------------------------------
+def read_plink(prefix, count="A1", mmap=True):
+    """``prefix``.bed/.bim/.fam -> (Packed2 rows of the .bed used in place, taxa names GT, GI columns SNP / Chromosome
+    / Position, alleles (A1, A2)).  .fam and .bim are small whitespace tables parsed here; the .bed is memory-mapped,
+    so a scan streams it from disk in marker blocks (gapit_p3d_scan_host: upload overlapped with the scan)."""
+    with open(prefix + ".fam") as f:
+        fam = [ln.split() for ln in f if ln.strip()]
+    with open(prefix + ".bim") as f:
+        bim = [ln.split() for ln in f if ln.strip()]
+    GT = [r[1] for r in fam]                                   # within-family ID
+    bed = np.memmap(prefix + ".bed", dtype=np.uint8, mode="r") if mmap else np.fromfile(prefix + ".bed", dtype=np.uint8)
+    rows = Packed2.from_bed(bed, len(GT), count=count)
+    if rows.m != len(bim):
+        raise ValueError(f"{prefix}.bed holds {rows.m} variants, {prefix}.bim {len(bim)}")
+    GI = {"SNP": [r[1] for r in bim], "Chromosome": [r[0] for r in bim], "Position": [int(r[3]) for r in bim]}
+    return rows, GT, GI, [(r[4], r[5]) for r in bim]
+
+
+def GAPIT_numeric_text(GD, heading=True, SNP_impute=None, ctx=None, want_gd=True, want_geno=False):
+    """GAPIT's numeric genotype table (``file.GD``: heading row, then one row per taxon: name, one dosage per marker) ->
+    (GD as int8 (n, m) or None, taxa names GT, marker names of the heading or None, Genotypes handle or None).
+    ``GD``: the bytes of the table or a path.  Tokenising and parsing happen on the GPU (gapit_numtext_numericalize)."""
+    ctx = ctx or default_context()
+    if isinstance(GD, str):
+        with open(GD, "rb") as f:
+            GD = f.read()
+    buf = np.frombuffer(GD, dtype=np.uint8)
+    lib = ctx.lib
+    nl = C.c_int64()
+    check(lib.gapit_text_index_lines(_ptr(buf), buf.shape[0], None, 0, C.byref(nl)))
+    off = np.empty(nl.value + 1, dtype=np.int64)
+    check(lib.gapit_text_index_lines(_ptr(buf), buf.shape[0], _ptr(off), off.shape[0], C.byref(nl)))
+    n, m = C.c_int64(), C.c_int64()
+    check(lib.gapit_numtext_shape(_ptr(buf), buf.shape[0], _ptr(off), nl.value, 1 if heading else 0, C.byref(n), C.byref(m)))
+    n, m = n.value, m.value
+    first = 1 if heading else 0
+    gd = np.empty((m, n), dtype=np.int8) if want_gd else None
+    h = C.c_void_p()
+    check(lib.gapit_numtext_numericalize(ctx.h, _ptr(buf), buf.shape[0], _ptr(off), first, n, m, _lib.IMPUTE[SNP_impute],
+                                         _ptr(gd), C.byref(h) if want_geno else None))
+    geno = None
+    if want_geno:
+        geno = Genotypes.__new__(Genotypes)
+        geno.ctx, geno.h, geno.n, geno.m = ctx, h, int(n), int(m)
+    text = bytes(GD)
+    names = text[off[0]:off[1]].split()[1:] if heading else None
+    GT = [text[off[first + i]:off[first + i + 1]].replace(b",", b" ").split(None, 1)[0].decode() for i in range(n)]
+    return (gd.T if gd is not None else None), GT, ([x.decode() for x in names] if names else None), geno
+
+
+def p3d_scan_file(genotypes, X0, Y, eigsys=None, delta=None, vg=None, glm=False, SNP_impute="Middle", ctx=None,
+                  genoFormat=None, count="A1"):
+    """The by-file branch of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:259-331 over GAPIT.Fragment.R) for the two file formats
+    beside HapMap: a PLINK prefix (``genoFormat="bed"``: the memory-mapped .bed streams through the scan in marker
+    blocks, file bytes uploaded as they are, upload overlapped with the scan) or GAPIT's numeric text
+    (``genoFormat="EMMA"``: parsed on the GPU, then scanned resident).  Taxa must be in the order of ``Y`` (the
+    reference's GTindex re-ordering is the caller's).  Returns (arrays (T, m), per-trait bases, GT, GI or marker names)."""
+    ctx = ctx or default_context()
+    if genoFormat is None:
+        genoFormat = "bed" if isinstance(genotypes, str) and os.path.exists(genotypes + ".bed") else "EMMA"
+    if genoFormat == "bed":
+        rows, GT, GI, _ = read_plink(genotypes, count=count)
+        arrs, bases = p3d_scan_host(rows, X0, Y, eigsys=eigsys, delta=delta, vg=vg, glm=glm, ctx=ctx, impute=SNP_impute)
+        return arrs, bases, GT, GI
+    _, GT, names, geno = GAPIT_numeric_text(genotypes, SNP_impute=SNP_impute, ctx=ctx, want_gd=False, want_geno=True)
+    arrs, bases = p3d_scan(geno, X0, Y, eigsys=eigsys, delta=delta, vg=vg, glm=glm, ctx=ctx)
+    geno.close()
+    return arrs, bases, GT, names
 
 
 def _as_geno(snps, ctx, impute=None):
@@ -581,12 +669,12 @@ def _host_geno(snps, marker_major):
 
 
 def p3d_scan_host(snps, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=None, impute=None, marker_major=False,
-                  pinned=False):
+                  pinned=False, out=None):
     """Streaming scan straight from a host genotype matrix (H2D overlapped with the scan).  Same returns as
     :func:`p3d_scan`."""
     ctx = ctx or default_context()
     if isinstance(snps, Packed2):
-        a, dtype, m, n, ld = snps.data, _lib.GAPIT_B2, snps.m, snps.n, snps.data.shape[1]
+        a, dtype, m, n, ld = snps.data, snps.dtype, snps.m, snps.n, snps.data.shape[1]
     else:
         a, dtype = _host_geno(snps, marker_major)
         m, n = a.shape
@@ -595,9 +683,10 @@ def p3d_scan_host(snps, X0, Y, eigsys=None, delta=None, vg=None, glm=False, ctx=
     Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n, -1))
     q0, T = X0.shape[1], Y.shape[1]
     _check_scan_shapes(n, X0, T, delta, vg, glm)
-    names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
-    arrs = {k: _host_array((T, m), pinned) for k in names}
-    arrs["maf"] = _host_array((m,), pinned)
+    if out is not None and out["effect"].shape == (T, m) and out["maf"].shape == (m,):
+        arrs = out
+    else:
+        arrs = alloc_scan_out(T, m, pinned)
     so = _lib.ScanOut(**{k: arrs[k].ctypes.data_as(C.POINTER(C.c_double)) for k in arrs})
     base = (_lib.ScanBase * T)()
     d = np.ascontiguousarray(delta, dtype=np.float64).reshape(-1) if delta is not None else None
@@ -846,7 +935,7 @@ class MultiGenotypes:
     def __init__(self, snps, mctx, impute=None, marker_major=False):
         self.mctx = mctx
         if isinstance(snps, Packed2):
-            a, dtype, m, n, ld = snps.data, _lib.GAPIT_B2, snps.m, snps.n, snps.data.shape[1]
+            a, dtype, m, n, ld = snps.data, snps.dtype, snps.m, snps.n, snps.data.shape[1]
         else:
             a, dtype = _host_geno(snps, marker_major)
             m, n = a.shape

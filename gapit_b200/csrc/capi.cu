@@ -140,6 +140,7 @@ extern "C" int gapit_ctx_create(int device, gapit_ctx** out) {
 extern "C" void gapit_ctx_destroy(gapit_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  scan_plan_cache_drop(ctx);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);

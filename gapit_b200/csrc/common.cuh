@@ -31,8 +31,15 @@ int fail(int code, const std::string& msg);
   } while (0)
 
 inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+// host dtypes that hold 2 bits per genotype call (rows of ceil(n/4) bytes), and the device recode each needs
+inline bool is_packed2(gapit_dtype d) { return d == GAPIT_B2 || d == GAPIT_BED_A1 || d == GAPIT_BED_A2; }
+inline int packed2_recode(gapit_dtype d) { return d == GAPIT_BED_A1 ? 1 : (d == GAPIT_BED_A2 ? 2 : 0); }
 
 }  // namespace gapit
+
+namespace gapit {
+struct ScanPlan;
+}
 
 // Opaque handles of the C ABI.
 struct gapit_ctx {
@@ -52,6 +59,10 @@ struct gapit_ctx {
   cudaStream_t copy_stream = nullptr;   // H2D of the next genotype chunk while the current one is scanned
   cudaEvent_t ev2 = nullptr, ev3 = nullptr;
   cudaEvent_t ev_ready[2] = {}, ev_free[2] = {};
+  // the marker-free part of the last scan (reduced models, epilogue constants, back-rotated columns), kept so that
+  // scanning block after block / fragment after fragment with the same traits does not redo it (scan.cu)
+  gapit::ScanPlan* plan_cache = nullptr;
+  uint64_t plan_key = 0;
   cudaStream_t d2h_stream = nullptr;   // finished result rows go to the host while the next marker block is computed
   cudaEvent_t ev_blk = nullptr;        // results of a marker block are final
 };
@@ -61,6 +72,7 @@ enum WsSlot { WS_R = 0, WS_PROJ, WS_GCONST, WS_PART, WS_OUT, WS_RG, WS_RS, WS_RS
               WS_CS0, WS_CS1, WS_CQ0, WS_CQ1, WS_STAGE0, WS_STAGE1, WS_SYNC, WS_FC, WS_WBUF, WS_WT, WS_XX, WS_KSCALE, WS_Z };
 // device workspace of at least `bytes` in `slot` (contents are not preserved when it grows)
 int ctx_ws(gapit_ctx* ctx, int slot, size_t bytes, void** out);
+void scan_plan_cache_drop(gapit_ctx* ctx, const void* eigsys = nullptr);   // scan.cu
 template <class T>
 inline int ctx_ws_t(gapit_ctx* ctx, int slot, size_t count, T** out) {
   void* p = nullptr;

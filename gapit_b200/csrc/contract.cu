@@ -151,6 +151,116 @@ int launch_xx_contract(cudaStream_t st, const double* W2, int64_t m_ld, const do
   }
 }
 
+// ------------------------------------------------------------------ V'R
+// out[c*n + k] = sum_j V[j + k n] R[j + c n]  (the projections V'[X0 | Y] the reduced model, REML and the back-rotation
+// start from): the same DMMA tiling with both operands contiguous along the contracted index j.  CTA = 128 eigenvectors
+// x (8 NT8) columns, ring stages of 16 taxa; 8-byte cp.async so that odd n needs no alignment.  j ascending in chunks of
+// 4 => fixed summation order.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, int src_bytes) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+
+constexpr int kVtLd = 20;   // padded row of 16 taxa: stride = 4 (mod 16) doubles => conflict-free fragment reads
+__host__ __device__ constexpr int vt_smem_bytes(int nt8) { return kXxStages * (128 + 8 * nt8) * kVtLd * 8; }
+
+template <int NT8>
+__global__ void __launch_bounds__(256, (NT8 <= 8) ? 2 : 1)
+    vt_project_kernel(const double* __restrict__ V, int64_t n, const double* __restrict__ R, int nc, double* __restrict__ out) {
+  constexpr int TN = 8 * NT8, KT = kXxKT, STAGES = kXxStages, LD = kVtLd;
+  extern __shared__ double xsm[];
+  double* As = xsm;                       // [STAGES][128][LD]
+  double* Bs = xsm + STAGES * 128 * LD;   // [STAGES][TN][LD]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t k0 = int64_t(blockIdx.x) * 128;
+  const int cb = blockIdx.y * TN;
+  const int nkt = static_cast<int>((n + KT - 1) / KT);
+
+  auto load_stage = [&](int st, int kt) {
+    const int64_t j0 = int64_t(kt) * KT;
+    for (int c = tid; c < 128 * KT; c += 256) {
+      const int r = c >> 4, jj = c & 15;
+      const bool ok = (k0 + r < n) && (j0 + jj < n);
+      cp_async8(&As[(st * 128 + r) * LD + jj], V + (ok ? (k0 + r) * n + j0 + jj : 0), ok ? 8 : 0);
+    }
+    for (int c = tid; c < TN * KT; c += 256) {
+      const int r = c >> 4, jj = c & 15;
+      const bool ok = (cb + r < nc) && (j0 + jj < n);
+      cp_async8(&Bs[(st * TN + r) * LD + jj], R + (ok ? int64_t(cb + r) * n + j0 + jj : 0), ok ? 8 : 0);
+    }
+  };
+
+  double acc[2][NT8][2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < NT8; ++j) acc[h][j][0] = acc[h][j][1] = 0.0;
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) {
+    if (s < nkt) load_stage(s, s);
+    cp_async_commit();
+  }
+  const int ar = lane & 3, ac = lane >> 2;
+  for (int kt = 0; kt < nkt; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    if (kt + STAGES - 1 < nkt) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
+    cp_async_commit();
+    const double* a_st = As + ((kt % STAGES) * 128 + warp * 16 + ac) * LD + ar;
+    const double* b_st = Bs + ((kt % STAGES) * TN + ac) * LD + ar;
+#pragma unroll
+    for (int k4 = 0; k4 < KT / 4; ++k4) {
+      const double a0 = a_st[k4 * 4];
+      const double a1 = a_st[8 * LD + k4 * 4];
+      double b[NT8];
+#pragma unroll
+      for (int j = 0; j < NT8; ++j) b[j] = b_st[j * 8 * LD + k4 * 4];
+#pragma unroll
+      for (int j = 0; j < NT8; ++j) {
+        dmma884(acc[0][j][0], acc[0][j][1], a0, b[j]);
+        dmma884(acc[1][j][0], acc[1][j][1], a1, b[j]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int64_t k = k0 + warp * 16 + h * 8 + ac;
+    if (k >= n) continue;
+#pragma unroll
+    for (int j = 0; j < NT8; ++j) {
+      const int c = cb + j * 8 + 2 * ar;
+      if (c < nc) out[int64_t(c) * n + k] = acc[h][j][0];
+      if (c + 1 < nc) out[int64_t(c + 1) * n + k] = acc[h][j][1];
+    }
+  }
+}
+
+template <int NT8>
+static int launch_vt_nt(cudaStream_t st, const double* V, int64_t n, const double* R, int nc, double* out, int ytiles) {
+  auto kern = vt_project_kernel<NT8>;
+  constexpr int smem = vt_smem_bytes(NT8);
+  GAPIT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  dim3 grid(static_cast<unsigned>((n + 127) / 128), static_cast<unsigned>(ytiles));
+  kern<<<grid, 256, smem, st>>>(V, n, R, nc, out);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
+// V (n x n column-major), R (n x nc column-major) -> out (n x nc column-major) = V'R; all device pointers
+int launch_vt_project(cudaStream_t st, const double* V, int64_t n, const double* R, int nc, double* out) {
+  const int tile = xx_trait_tile(nc);
+  const int ytiles = (nc + tile - 1) / tile;
+  switch (tile) {
+    case 8: return launch_vt_nt<1>(st, V, n, R, nc, out, ytiles);
+    case 16: return launch_vt_nt<2>(st, V, n, R, nc, out, ytiles);
+    case 32: return launch_vt_nt<4>(st, V, n, R, nc, out, ytiles);
+    case 64: return launch_vt_nt<8>(st, V, n, R, nc, out, ytiles);
+    case 104: return launch_vt_nt<13>(st, V, n, R, nc, out, ytiles);
+    default: return launch_vt_nt<16>(st, V, n, R, nc, out, ytiles);
+  }
+}
+
 // ------------------------------------------------------------------ V Z
 // out[j + c n] = sum_k (SQUARE ? V_jk^2 : V_jk) Z[k + c n]: one thread per row j (coalesced along j), NC columns per
 // thread so V is streamed once per NC columns, Z chunks broadcast from shared memory; k ascending => fixed order.

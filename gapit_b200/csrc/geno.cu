@@ -80,8 +80,12 @@ __device__ __forceinline__ uint32_t spread2(uint32_t b) {   // 4 x 2-bit fields 
   return (v | (v << 6)) & 0x03030303u;
 }
 
+// recode: 0 = GAPIT_B2 codes (0/1/2 dosage, 3 NA); 1 / 2 = the codes of a PLINK .bed row (00 hom A1, 01 missing, 10 het,
+// 11 hom A2) counted as copies of A1 / of A2.  With (h, l) the two bits of a code the B2 code is
+//   copies of A2: (l, h ^ l)      copies of A1: (~h, h ^ l)        (01 -> 11 = NA either way)
+// applied to all 16 codes of a word at once.
 __global__ void __launch_bounds__(256) unpack2_kernel(const uint8_t* __restrict__ src, int64_t nb, int64_t n, int64_t mc,
-                                                      int8_t* __restrict__ dst, int64_t ldn, int impute,
+                                                      int8_t* __restrict__ dst, int64_t ldn, int impute, int recode,
                                                       int* __restrict__ bad) {
   const int groups = static_cast<int>(ldn >> 4);  // ldn is a multiple of 128
   const uint32_t na = impute < 0 ? 0u : static_cast<uint32_t>(impute);
@@ -98,6 +102,10 @@ __global__ void __launch_bounds__(256) unpack2_kernel(const uint8_t* __restrict_
         const uint32_t lo = __ldg(src32 + (off >> 2));
         const uint32_t hi = __ldg(src32 + (off >> 2) + 1);
         pk = __funnelshift_r(lo, hi, static_cast<uint32_t>(off & 3) * 8u);
+        if (recode) {
+          const uint32_t l = pk & 0x55555555u, h = (pk >> 1) & 0x55555555u;
+          pk = ((recode == 1 ? (~h & 0x55555555u) : l) << 1) | (h ^ l);
+        }
         const int64_t left = n - byte0 * 4;              // genotypes of this row from byte0 on
         if (left < 16) pk &= (1u << (2 * static_cast<int>(left))) - 1u;   // bits past the last taxon are ignored
       }
@@ -178,13 +186,13 @@ int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_
 
 // stage: `mc` dense rows of ceil(n/4) packed bytes already on the device
 int launch_unpack2(gapit_ctx* ctx, cudaStream_t st, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
-                   int impute, int* bad_dev) {
+                   int impute, int* bad_dev, int recode) {
   const int64_t groups = ldn / 16;
   int threads = 64;   // CTA width with the fewest idle threads in a row's last CTA
   for (int t : {128, 256})
     if ((groups + t - 1) / t * t <= (groups + threads - 1) / threads * threads) threads = t;
   dim3 grid(static_cast<unsigned>((groups + threads - 1) / threads), static_cast<unsigned>(std::min<int64_t>(mc, 65535)));
-  unpack2_kernel<<<grid, threads, 0, st>>>(static_cast<const uint8_t*>(stage), (n + 3) / 4, n, mc, dst, ldn, impute, bad_dev);
+  unpack2_kernel<<<grid, threads, 0, st>>>(static_cast<const uint8_t*>(stage), (n + 3) / 4, n, mc, dst, ldn, impute, recode, bad_dev);
   GAPIT_CUDA(cudaGetLastError());
   return GAPIT_OK;
 }
@@ -208,7 +216,7 @@ using namespace gapit;
 
 extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, int64_t n, int64_t m, int64_t ld,
                                gapit_impute impute, gapit_geno** out) {
-  if (!ctx || !snps || !out || n <= 0 || m <= 0 || ld < (dtype == GAPIT_B2 ? (n + 3) / 4 : n))
+  if (!ctx || !snps || !out || n <= 0 || m <= 0 || ld < (is_packed2(dtype) ? (n + 3) / 4 : n))
     return fail(GAPIT_ERR_ARG, "gapit_geno_pack: bad argument");
   GAPIT_CUDA(cudaSetDevice(ctx->device));
   gapit_geno* g = new gapit_geno();
@@ -278,7 +286,7 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
     if (e != cudaSuccess) return cleanup(fail(GAPIT_ERR_CUDA, std::string("genotype conversion: ") + cudaGetErrorString(e)));
     if (hbad & 2) return cleanup(fail(GAPIT_ERR_DATA, "genotype matrix holds NA and no impute rule was given"));
     if (hbad & 1) return cleanup(fail(GAPIT_ERR_DATA, "genotype matrix holds a value outside {0,1,2}"));
-  } else if (dtype == GAPIT_B2) {
+  } else if (is_packed2(dtype)) {
     const int64_t nb = (n + 3) / 4;
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(m, (int64_t(256) << 20) / nb));
     void* stage = nullptr;
@@ -292,7 +300,7 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
       const char* src = static_cast<const char*>(snps) + size_t(k0) * ld;
       if (ld == nb) e = cudaMemcpyAsync(stage, src, size_t(mc) * nb, cudaMemcpyHostToDevice, ctx->stream);
       else e = cudaMemcpy2DAsync(stage, nb, src, ld, nb, mc, cudaMemcpyHostToDevice, ctx->stream);
-      if (e == cudaSuccess && launch_unpack2(ctx, ctx->stream, stage, n, mc, g->mk + k0 * g->ldn, g->ldn, int(impute), bad) != GAPIT_OK)
+      if (e == cudaSuccess && launch_unpack2(ctx, ctx->stream, stage, n, mc, g->mk + k0 * g->ldn, g->ldn, int(impute), bad, packed2_recode(dtype)) != GAPIT_OK)
         return cleanup(GAPIT_ERR_CUDA);
     }
     int hbad = 0;

@@ -19,9 +19,11 @@
 //   K4  finalize         per marker: Schur complement of [X0t xst]'[X0t xst] (:736-748), beta (:772),
 //                        t (:936-937), p = 2 pt(|t|, df) (:939), logLM and R^2 (:955-967).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -58,6 +60,7 @@ struct gapit_eigsys {
   double* scale = nullptr;   // [nkq*KPB] c_k = max_j |V_jk| / (126 * 256^(S-1)), 0 beyond n
   std::vector<double> values;  // host, descending
   std::vector<double> h_scale;
+  uint64_t serial = 0;         // unique per handle (a cached scan plan must not outlive the handle it was built for)
 };
 
 namespace gapit {
@@ -95,33 +98,6 @@ __global__ void slice_v_kernel(const double* __restrict__ V, int64_t n, int S, i
       Vs[(k * S + s) * ldn + j] = static_cast<int8_t>(d);
       q = (q - d) >> 8;
     }
-  }
-}
-
-// ------------------------------------------------------------------ projections V'R
-// out[c*n + k] = sum_j V[j + k n] R[j + c n]; one warp per k, fixed summation order
-template <int NC>
-__global__ void vt_project_kernel(const double* __restrict__ V, int64_t n, const double* __restrict__ R, int nc,
-                                  int c0, double* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t k = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  if (k >= n) return;
-  const double* v = V + k * n;
-  double acc[NC];
-#pragma unroll
-  for (int c = 0; c < NC; ++c) acc[c] = 0.0;
-  for (int64_t j = lane; j < n; j += 32) {
-    const double vj = v[j];
-#pragma unroll
-    for (int c = 0; c < NC; ++c)
-      if (c0 + c < nc) acc[c] = fma(vj, __ldg(R + (c0 + c) * n + j), acc[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    double a = acc[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0 && c0 + c < nc) out[(c0 + c) * n + k] = a;
   }
 }
 
@@ -455,6 +431,9 @@ __device__ double betacf(double a, double b, double x) {
   return h;
 }
 
+// 1 / (1.5 + k): the term ratios of the series below without a division
+__device__ const double kInvHalfPlus[64] = {0.6666666666666666, 0.4, 0.2857142857142857, 0.2222222222222222, 0.18181818181818182, 0.15384615384615385, 0.13333333333333333, 0.11764705882352941, 0.10526315789473684, 0.09523809523809523, 0.08695652173913043, 0.08, 0.07407407407407407, 0.06896551724137931, 0.06451612903225806, 0.06060606060606061, 0.05714285714285714, 0.05405405405405406, 0.05128205128205128, 0.04878048780487805, 0.046511627906976744, 0.044444444444444446, 0.0425531914893617, 0.04081632653061224, 0.0392156862745098, 0.03773584905660377, 0.03636363636363636, 0.03508771929824561, 0.03389830508474576, 0.03278688524590164, 0.031746031746031744, 0.03076923076923077, 0.029850746268656716, 0.028985507246376812, 0.028169014084507043, 0.0273972602739726, 0.02666666666666667, 0.025974025974025976, 0.02531645569620253, 0.024691358024691357, 0.024096385542168676, 0.023529411764705882, 0.022988505747126436, 0.02247191011235955, 0.02197802197802198, 0.021505376344086023, 0.021052631578947368, 0.020618556701030927, 0.020202020202020204, 0.019801980198019802, 0.019417475728155338, 0.01904761904761905, 0.018691588785046728, 0.01834862385321101, 0.018018018018018018, 0.017699115044247787, 0.017391304347826087, 0.017094017094017096, 0.01680672268907563, 0.01652892561983471, 0.016260162601626018, 0.016, 0.015748031496062992, 0.015503875968992248};
+
 // 2 * pt(|t|, df, lower.tail = FALSE) = I_{df/(df+t^2)}(df/2, 1/2)
 __device__ double two_sided_t_pvalue(double t, double df, double lbeta) {
   if (t != t) return t;
@@ -463,12 +442,27 @@ __device__ double two_sided_t_pvalue(double t, double df, double lbeta) {
   const double a = 0.5 * df, b = 0.5;
   const double x = df / (df + t2);
   const double y = t2 / (df + t2);
+  if (y <= 0.0) return 1.0;
   const double ln_x = -log1p(t2 / df);
   const double ln_y = log(y);
-  if (x < (a + 1.0) / (a + b + 2.0)) {
-    return exp(a * ln_x + b * ln_y - lbeta - log(a)) * betacf(a, b, x);
+  // Nearly every marker (t^2 below ~20): the lower part 1 - p = I_y(1/2, df/2) = y^(1/2) (1-y)^(df/2) / (1/2 B) * S with
+  // the hypergeometric series S = sum_k [(1/2 + df/2)_k / (3/2)_k] y^k, whose terms behave like (t^2/2)^k / (3/2)_k:
+  // 20-60 multiply-adds, against ~sqrt(df) continued-fraction steps with two divisions each.  This test comes FIRST: one
+  // lane on the continued fraction holds its whole warp there, and with the customary switch at t^2 ~ 3 that is 94 % of
+  // the warps.  1 - (.) costs 1e-16 / p of relative accuracy -- 1e-11 at the switch-over (p ~ 1e-5), far inside the
+  // 1e-6 tolerance on log10 p (log B is formed in extended precision for the same reason).
+  if (a * y < 10.0) {
+    const double ay = (a + b) * y;
+    double term = 1.0, S = 1.0;
+    int k = 0;
+    for (; k < 64; ++k) {
+      term *= fma(static_cast<double>(k), y, ay) * kInvHalfPlus[k];
+      S += term;
+      if (term < 1e-17 * S) break;
+    }
+    if (k < 64) return 1.0 - exp(b * ln_y + a * ln_x - lbeta - log(b)) * S;
   }
-  if (y <= 0.0) return 1.0;
+  if (x < (a + 1.0) / (a + b + 2.0)) return exp(a * ln_x + b * ln_y - lbeta - log(a)) * betacf(a, b, x);
   return 1.0 - exp(b * ln_y + a * ln_x - lbeta - log(b)) * betacf(b, a, y);
 }
 
@@ -813,13 +807,14 @@ static int choose_gsplit(int64_t ldn, int64_t nkq) {
 int launch_xx_contract(cudaStream_t st, const double* W2, int64_t m_ld, const double* Wt, int wt_ld, int nk, double* XX,
                        int64_t xx_ld, int T);
 int xx_trait_tile(int T);
+int launch_vt_project(cudaStream_t st, const double* V, int64_t n, const double* R, int nc, double* out);
 int launch_v_times_cols(cudaStream_t st, const double* V, int64_t n, const double* Z, int nc, double* out, bool square);
 int launch_colstats(gapit_ctx* ctx, cudaStream_t st, const int8_t* mk, int64_t ldn, int64_t n, int64_t m, int32_t* colsum,
                     int32_t* colsumsq, int* bad_dev);
 int launch_convert(cudaStream_t st, gapit_dtype dtype, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
                    int impute, int* bad_dev);
 int launch_unpack2(gapit_ctx* ctx, cudaStream_t st, const void* stage, int64_t n, int64_t mc, int8_t* dst, int64_t ldn,
-                   int impute, int* bad_dev);
+                   int impute, int* bad_dev, int recode);
 
 // Everything about a scan that does not depend on the markers: the marker-free model of every trait
 // (i = 0 of the reference loop), the per-eigenvalue constants of the rotation epilogue (MLM) or the digit
@@ -834,6 +829,7 @@ struct ScanPlan {
   int8_t* Rs = nullptr;             // GLM: [T][128][ldn] digit planes of [X0 | y_t]
   double* Rscale = nullptr;         // GLM: [T][GAPIT_MAX_Q0+1]
   FinalizeConsts* fc_dev = nullptr; // [T]
+  std::vector<gapit_scan_base> bases;
   // MLM, T > 1: one rotation shared by all traits (StoreEpi + xx_contract)
   bool shared = false;
   int64_t lin_tiles = 0;            // tiles of back-rotated columns behind the eigenvector tiles of e->Vs
@@ -869,8 +865,8 @@ static int eigsys_reserve_tiles(gapit_eigsys* e, int64_t tiles) {
   return GAPIT_OK;
 }
 
-static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e, const double* X0, int q0, const double* Y,
-                        int T, const double* delta, const double* vg, int glm, ScanPlan* plan, gapit_scan_base* base_out) {
+static int scan_plan_build(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e, const double* X0, int q0, const double* Y,
+                           int T, const double* delta, const double* vg, int glm, ScanPlan* plan) {
   if (!ctx || !X0 || !Y || T < 1) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL argument");
   if (q0 < 1 || q0 > GAPIT_MAX_Q0) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: q0 must be 1.." + std::to_string(GAPIT_MAX_Q0));
   if (!glm && (!e || !delta || !vg)) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: MLM needs an eigen-system, delta and vg");
@@ -886,6 +882,8 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
   plan->e = e;
   plan->gsplit = glm ? 1 : choose_gsplit(ldn, e->nkq);
   plan->fc.resize(T);
+  plan->bases.assign(T, gapit_scan_base{});
+  gapit_scan_base* base_out = plan->bases.data();
   const int Q = plan->Q;
   const int nc = q0 + T;
 
@@ -898,9 +896,7 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
   if (!glm) {
     double* dProj = nullptr;
     GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(n) * nc, &dProj));
-    const unsigned blocks = static_cast<unsigned>((n * 32 + 255) / 256);
-    for (int c0 = 0; c0 < nc; c0 += 8) vt_project_kernel<8><<<blocks, 256, 0, ctx->stream>>>(e->V, n, dR, nc, c0, dProj);
-    GAPIT_CUDA(cudaGetLastError());
+    GAPIT_CHECK(launch_vt_project(ctx->stream, e->V, n, dR, nc, dProj));
     GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
     GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
     plan->nk = e->nkq * e->KPB;
@@ -982,7 +978,9 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
     fc.sumlog = sumlog;
     fc.n = dn;
     fc.df = static_cast<double>(n - q0 - 1);
-    fc.lbeta = std::lgamma(0.5 * fc.df) + std::lgamma(0.5) - std::lgamma(0.5 * fc.df + 0.5);
+    // log B(df/2, 1/2) in extended precision: the two lgamma terms (~1e5 at n = 20,000) cancel to O(log n), and the
+    // p-values of the bulk of the markers are 1 - (lower part), which magnifies an absolute error here by 1 / p
+    fc.lbeta = static_cast<double>(lgammal(0.5L * (long double)fc.df) + lgammal(0.5L) - lgammal(0.5L * (long double)fc.df + 0.5L));
     fc.q0 = q0;
     fc.qpad = Q;
     const double ves_glm = rss0 / static_cast<double>(n - q0);
@@ -1061,6 +1059,56 @@ static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e,
     GAPIT_CUDA(cudaMemcpyAsync(plan->gconst, gconst.data(), gconst.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));  // the pageable host sources must outlive their copies
+  return GAPIT_OK;
+}
+
+// 64-bit mix of a byte range (word-wise multiply-xorshift); keys the plan cache
+static uint64_t mix_bytes(const void* p, size_t nbytes, uint64_t h) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  size_t i = 0;
+  for (; i + 8 <= nbytes; i += 8) {
+    uint64_t w;
+    memcpy(&w, b + i, 8);
+    h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+  }
+  uint64_t w = 0;
+  if (i < nbytes) memcpy(&w, b + i, nbytes - i);
+  h = (h ^ w ^ (uint64_t(nbytes) << 32)) * 0xC2B2AE3D27D4EB4Full;
+  return h ^ (h >> 32);
+}
+
+// The plan of a scan depends on the traits, covariates, variance components and the eigen-system, not on the markers:
+// GAPIT's by-file loop (GAPIT.EMMAxP3D.R:259-331) and any block-by-block driver call the scan again and again with the
+// same ones, so the last plan stays on the context, keyed by a hash of every input it was built from.
+static int scan_prepare(gapit_ctx* ctx, int64_t n, int64_t ldn, gapit_eigsys* e, const double* X0, int q0, const double* Y,
+                        int T, const double* delta, const double* vg, int glm, ScanPlan** plan_out, gapit_scan_base* base_out) {
+  if (!ctx || !X0 || !Y || T < 1) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL argument");
+  if (q0 < 1 || q0 > GAPIT_MAX_Q0) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: q0 must be 1.." + std::to_string(GAPIT_MAX_Q0));
+  if (!glm && (!e || !delta || !vg)) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: MLM needs an eigen-system, delta and vg");
+  uint64_t key = 0x243F6A8885A308D3ull;
+  const int64_t dims[6] = {n, ldn, q0, T, glm, (!glm && e) ? int64_t(e->serial) * 16 + e->S : 0};
+  key = mix_bytes(dims, sizeof(dims), key);
+  key = mix_bytes(X0, size_t(n) * q0 * 8, key);
+  key = mix_bytes(Y, size_t(n) * T * 8, key);
+  if (!glm) {
+    key = mix_bytes(delta, size_t(T) * 8, key);
+    key = mix_bytes(vg, size_t(T) * 8, key);
+  }
+  if (key == 0) key = 1;
+  if (!ctx->plan_cache || ctx->plan_key != key) {
+    scan_plan_cache_drop(ctx);
+    ScanPlan* p = new ScanPlan();
+    const int rc = scan_plan_build(ctx, n, ldn, e, X0, q0, Y, T, delta, vg, glm, p);
+    if (rc != GAPIT_OK) {
+      delete p;
+      return rc;
+    }
+    ctx->plan_cache = p;
+    ctx->plan_key = key;
+  }
+  *plan_out = ctx->plan_cache;
+  if (base_out) std::copy(ctx->plan_cache->bases.begin(), ctx->plan_cache->bases.end(), base_out);
   return GAPIT_OK;
 }
 
@@ -1224,7 +1272,7 @@ int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, 
               int64_t m_total = 0, int64_t m_off = 0) {
   if (!g) return fail(GAPIT_ERR_ARG, "gapit_p3d_scan: NULL genotype handle");
   GAPIT_CHECK(check_out(out));
-  ScanPlan plan;
+  ScanPlan* planp = nullptr;
   const bool trace = getenv("GAPIT_TRACE") != nullptr;   // host-side phase times on stderr
   auto now = [] { return std::chrono::steady_clock::now(); };
   auto ms_since = [&](std::chrono::steady_clock::time_point t0) {
@@ -1232,7 +1280,8 @@ int scan_impl(gapit_ctx* ctx, gapit_geno* g, gapit_eigsys* e, const double* X0, 
   };
   auto t_start = now();
   StreamDrain drain{ctx};
-  GAPIT_CHECK(scan_prepare(ctx, g->n, g->ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
+  GAPIT_CHECK(scan_prepare(ctx, g->n, g->ldn, e, X0, q0, Y, T, delta, vg, glm, &planp, base_out));
+  const ScanPlan& plan = *planp;
   if (trace) fprintf(stderr, "[gapit] scan_prepare %.2f ms\n", ms_since(t_start));
   const int64_t m = g->m;
   double* o = nullptr;
@@ -1265,15 +1314,16 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
                           gapit_impute impute, gapit_eigsys* e, const double* X0, int q0, const double* Y, int T,
                           const double* delta, const double* vg, int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
   const int64_t nb2 = (n + 3) / 4;   // bytes per marker of the 2-bit packed form
-  if (!snps || n <= 0 || m <= 0 || ld < (dtype == GAPIT_B2 ? nb2 : n))
+  if (!snps || n <= 0 || m <= 0 || ld < (is_packed2(dtype) ? nb2 : n))
     return fail(GAPIT_ERR_ARG, "gapit_p3d_scan_host: bad genotype argument");
   GAPIT_CHECK(check_out(out));
   const int64_t ldn = round_up(n, 128);
-  ScanPlan plan;
+  ScanPlan* planp = nullptr;
   StreamDrain drain{ctx};
-  GAPIT_CHECK(scan_prepare(ctx, n, ldn, e, X0, q0, Y, T, delta, vg, glm, &plan, base_out));
+  GAPIT_CHECK(scan_prepare(ctx, n, ldn, e, X0, q0, Y, T, delta, vg, glm, &planp, base_out));
+  const ScanPlan& plan = *planp;
   const size_t esz = dtype == GAPIT_F64 ? 8 : (dtype == GAPIT_I32 ? 4 : 1);
-  const size_t row_bytes = dtype == GAPIT_B2 ? size_t(nb2) : size_t(n) * esz;   // dense bytes of one marker on the host
+  const size_t row_bytes = is_packed2(dtype) ? size_t(nb2) : size_t(n) * esz;   // dense bytes of one marker on the host
   // marker block: ~320 MB of int8 (multiple of 256 markers), at most 65535 for the convert grid
   int64_t chunk = std::max<int64_t>(256, (int64_t(320) << 20) / ldn / 256 * 256);
   if (const char* ev = getenv("GAPIT_STREAM_CHUNK")) chunk = std::max<int64_t>(256, atoll(ev) / 256 * 256);  // tests
@@ -1289,7 +1339,7 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
     GAPIT_CHECK(ctx_ws_t(ctx, WS_CS0 + b, size_t(chunk), &cs[b]));
     GAPIT_CHECK(ctx_ws_t(ctx, WS_CQ0 + b, size_t(chunk), &cq[b]));
     if (dtype != GAPIT_I8 || (ld == n && ldn != n)) GAPIT_CHECK(ctx_ws(ctx, WS_STAGE0 + b, size_t(chunk) * row_bytes + 8, &stage[b]));
-    if (ldn != n && dtype != GAPIT_B2) GAPIT_CUDA(cudaMemsetAsync(mk[b], 0, size_t(chunk) * ldn, ctx->stream));
+    if (ldn != n && !is_packed2(dtype)) GAPIT_CUDA(cudaMemsetAsync(mk[b], 0, size_t(chunk) * ldn, ctx->stream));
   }
   GAPIT_CHECK(ctx_ws_t(ctx, WS_BAD, 4, &bad));
   GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(T) * 7 * m, &o));
@@ -1313,11 +1363,11 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
       GAPIT_CUDA(cudaMemcpy2DAsync(mk[b], ldn, stage[b], n, n, mc, cudaMemcpyDeviceToDevice, ctx->copy_stream));
     } else if (dtype == GAPIT_I8) {
       GAPIT_CUDA(cudaMemcpy2DAsync(mk[b], ldn, src, ld, n, mc, cudaMemcpyHostToDevice, ctx->copy_stream));
-    } else if (dtype == GAPIT_B2) {
+    } else if (is_packed2(dtype)) {
       // a quarter of the int8 bytes over PCIe, expanded to the int8 operand layout on the device
       if (ld == nb2) GAPIT_CUDA(cudaMemcpyAsync(stage[b], src, size_t(mc) * nb2, cudaMemcpyHostToDevice, ctx->copy_stream));
       else GAPIT_CUDA(cudaMemcpy2DAsync(stage[b], nb2, src, ld, nb2, mc, cudaMemcpyHostToDevice, ctx->copy_stream));
-      GAPIT_CHECK(launch_unpack2(ctx, ctx->copy_stream, stage[b], n, mc, mk[b], ldn, int(impute), bad));
+      GAPIT_CHECK(launch_unpack2(ctx, ctx->copy_stream, stage[b], n, mc, mk[b], ldn, int(impute), bad, packed2_recode(dtype)));
     } else {
       GAPIT_CUDA(cudaMemcpy2DAsync(stage[b], size_t(n) * esz, src, size_t(ld) * esz, size_t(n) * esz, mc,
                                    cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -1351,6 +1401,16 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
 
 }  // namespace gapit
 
+namespace gapit {
+void scan_plan_cache_drop(gapit_ctx* ctx, const void* eigsys) {
+  if (!ctx || !ctx->plan_cache) return;
+  if (eigsys && ctx->plan_cache->e != eigsys) return;
+  delete ctx->plan_cache;
+  ctx->plan_cache = nullptr;
+  ctx->plan_key = 0;
+}
+}  // namespace gapit
+
 using namespace gapit;
 
 static int eigsys_build(gapit_ctx* ctx, const double* vectors, cudaMemcpyKind kind, const double* values, int64_t n,
@@ -1358,6 +1418,8 @@ static int eigsys_build(gapit_ctx* ctx, const double* vectors, cudaMemcpyKind ki
   if (!ctx || !vectors || !values || !out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_eigsys_upload: bad argument");
   GAPIT_CUDA(cudaSetDevice(ctx->device));
   gapit_eigsys* e = new gapit_eigsys();
+  static std::atomic<uint64_t> next_serial{1};
+  e->serial = next_serial.fetch_add(1);
   e->ctx = ctx;
   e->n = n;
   const SliceGeom sg = slice_geom(ctx->slices);
@@ -1409,9 +1471,7 @@ extern "C" int gapit_eigsys_project(gapit_ctx* ctx, gapit_eigsys* e, const doubl
   GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n) * nc, &dR));
   GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(n) * nc, &dP));
   GAPIT_CUDA(cudaMemcpyAsync(dR, R, size_t(n) * nc * 8, cudaMemcpyHostToDevice, ctx->stream));
-  const unsigned blocks = static_cast<unsigned>((n * 32 + 255) / 256);
-  for (int c0 = 0; c0 < nc; c0 += 8) vt_project_kernel<8><<<blocks, 256, 0, ctx->stream>>>(e->V, n, dR, nc, c0, dP);
-  GAPIT_CUDA(cudaGetLastError());
+  GAPIT_CHECK(launch_vt_project(ctx->stream, e->V, n, dR, nc, dP));
   GAPIT_CUDA(cudaMemcpyAsync(out, dP, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
   return GAPIT_OK;
@@ -1422,6 +1482,7 @@ extern "C" const double* gapit_eigsys_vectors_dev(const gapit_eigsys* e) { retur
 extern "C" void gapit_eigsys_free(gapit_eigsys* e) {
   if (!e) return;
   if (e->ctx) cudaSetDevice(e->ctx->device);
+  scan_plan_cache_drop(e->ctx, e);
   cudaFree(e->V);
   cudaFree(e->Vs);
   cudaFree(e->scale);
@@ -1480,9 +1541,7 @@ extern "C" int gapit_blup_pev(gapit_ctx* ctx, gapit_eigsys* e, const double* X0,
   GAPIT_CHECK(ctx_ws_t(ctx, WS_PROJ, size_t(n) * (nc + 2), &dProj));
   GAPIT_CUDA(cudaMemcpyAsync(dR, X0, size_t(n) * q0 * 8, cudaMemcpyHostToDevice, ctx->stream));
   GAPIT_CUDA(cudaMemcpyAsync(dR + size_t(n) * q0, y, size_t(n) * 8, cudaMemcpyHostToDevice, ctx->stream));
-  const unsigned blocks = static_cast<unsigned>((n * 32 + 255) / 256);
-  for (int c0 = 0; c0 < nc; c0 += 8) vt_project_kernel<8><<<blocks, 256, 0, ctx->stream>>>(e->V, n, dR, nc, c0, dProj);
-  GAPIT_CUDA(cudaGetLastError());
+  GAPIT_CHECK(launch_vt_project(ctx->stream, e->V, n, dR, nc, dProj));
   std::vector<double> proj(size_t(n) * nc);
   GAPIT_CUDA(cudaMemcpyAsync(proj.data(), dProj, size_t(n) * nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
   GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));

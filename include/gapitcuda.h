@@ -43,7 +43,9 @@ typedef struct gapit_geno gapit_geno;
 /* element type of a host genotype matrix.  GAPIT_B2: 2 bits per genotype, marker-major: marker k starts at byte
  * k*ld (ld >= ceil(n/4) BYTES), taxon i in byte i/4 at bits 2(i%4)..2(i%4)+1 (the bit order of a PLINK .bed row);
  * code 0/1/2 = dosage, 3 = NA (imputed by the gapit_impute rule, rejected with GAPIT_IMPUTE_NONE). */
-typedef enum { GAPIT_F64 = 0, GAPIT_I32 = 1, GAPIT_I8 = 2, GAPIT_B2 = 3 } gapit_dtype;
+/* GAPIT_BED_A1 / GAPIT_BED_A2: the rows of a PLINK .bed file as they are (same bit order; codes 00 = homozygous A1,
+ * 01 = missing, 10 = heterozygous, 11 = homozygous A2), dosage = copies of A1 / of A2; recoded on the device. */
+typedef enum { GAPIT_F64 = 0, GAPIT_I32 = 1, GAPIT_I8 = 2, GAPIT_B2 = 3, GAPIT_BED_A1 = 4, GAPIT_BED_A2 = 5 } gapit_dtype;
 /* NA rule for GAPIT_F64 input (GAPIT.EMMAxP3D.R:20-24, SNP.impute): NaN -> value; NONE rejects NaN */
 typedef enum { GAPIT_IMPUTE_NONE = -1, GAPIT_IMPUTE_MINOR = 0, GAPIT_IMPUTE_MIDDLE = 1, GAPIT_IMPUTE_MAJOR = 2 } gapit_impute;
 
@@ -109,6 +111,29 @@ int gapit_hapmap_index(const char* text, int64_t bytes, int heading, int64_t* n_
 int gapit_hapmap_numericalize(gapit_ctx* ctx, const char* text, int64_t bytes, const int64_t* row_off, int bit, int stride,
                               int64_t n, int64_t m, int effect, gapit_impute impute, int major_allele_zero,
                               int8_t* gd_out, gapit_geno** geno_out);
+
+/* ---- PLINK .bed (the reference itself only reads HapMap and numeric text) ------------
+ * gapit_bed_header checks the magic bytes (6C 1B) and the variant-major mode byte (01), and returns the number of
+ * variants m for n samples (.fam rows) and the offset of the first variant row (3).  The rows then go to
+ * gapit_geno_pack / gapit_p3d_scan_host / gapit_mgeno_pack as GAPIT_BED_A1 or GAPIT_BED_A2 with ld = ceil(n/4): the
+ * file bytes cross PCIe as they are (a memory-mapped .bed streams through gapit_p3d_scan_host in marker blocks, upload
+ * overlapped with the scan) and the PLINK codes are mapped to dosages by the unpack kernel.  .bim / .fam are small
+ * text tables parsed by the host language (r/GAPIT.Bed.R, gapit_b200.read_plink). */
+int gapit_bed_header(const void* bytes, int64_t len, int64_t n, int64_t* m_out, int64_t* data_off_out);
+
+/* ---- numeric text genotypes, genoFormat = "EMMA" (GAPIT.Fragment.R:94-136: `file.GD`, heading row, one row per TAXON:
+ * name then one dosage per marker, blank / tab / comma separated; 0 1 2 (also 1.0 ...), NA NaN . for missing) ------
+ * gapit_text_index_lines (host): offsets of the line starts, off_out[nlines] = bytes; off_out = NULL sizes the array.
+ * gapit_numtext_shape (host): taxa n (non-blank rows after the heading) and markers m (tokens of the first data row - 1).
+ * gapit_numtext_numericalize (device): the text goes to the GPU in row blocks (upload overlapped with parsing); every
+ * row is tokenised and parsed by one CTA, then one byte transpose gives the marker-major operand layout.  gd_out (may
+ * be NULL): n x m int8, R's column-major layout; geno_out (may be NULL): the handle the kinship and scan calls take.
+ * A value that is not a dosage, a ragged row, or NA with GAPIT_IMPUTE_NONE is GAPIT_ERR_DATA. */
+int gapit_text_index_lines(const char* text, int64_t bytes, int64_t* off_out, int64_t cap, int64_t* nlines_out);
+int gapit_numtext_shape(const char* text, int64_t bytes, const int64_t* line_off, int64_t nlines, int heading,
+                        int64_t* n_out, int64_t* m_out);
+int gapit_numtext_numericalize(gapit_ctx* ctx, const char* text, int64_t bytes, const int64_t* line_off, int64_t first_row,
+                               int64_t n, int64_t m, gapit_impute impute, int8_t* gd_out, gapit_geno** geno_out);
 
 /* ---- VanRaden kinship (GAPIT.kinship.VanRaden.R:11-32) -------------------
  * K_out: n x n fp64 column-major (symmetric).  G_out (optional, may be NULL):

@@ -655,3 +655,34 @@ def zmatrix_compress(Z_row_taxa, Z_col_taxa, Zmat, GAU):
     out = Zs @ DS                                                                # :34
     order_rows = sorted(range(len(Z_row_taxa)), key=lambda i: str(Z_row_taxa[i]))  # :41
     return [str(Z_row_taxa[i]) for i in order_rows], out[order_rows, :]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Genotype file formats beside HapMap.  The reference has no .bed reader; the restatement
+# follows the PLINK 1 binary specification (variant-major: magic 6C 1B 01, then per variant ceil(n/4) bytes, sample i
+# in bits 2(i%4).. of byte i/4; 00 = homozygous A1, 01 = missing, 10 = heterozygous, 11 = homozygous A2).
+def read_bed(bed, n, count="A1"):
+    """-> int8 (n, m) dosages (copies of `count`), -1 for missing."""
+    b = np.frombuffer(bytes(bed), dtype=np.uint8)
+    assert b[0] == 0x6C and b[1] == 0x1B and b[2] == 0x01, "not a variant-major PLINK .bed"
+    nb = (n + 3) // 4
+    m = (b.size - 3) // nb
+    rows = b[3:3 + m * nb].reshape(m, nb)
+    codes = np.stack([(rows >> (2 * j)) & 3 for j in range(4)], axis=2).reshape(m, nb * 4)[:, :n]
+    a1 = np.array([2, -1, 1, 0], dtype=np.int8)
+    a2 = np.array([0, -1, 1, 2], dtype=np.int8)
+    return (a1 if count == "A1" else a2)[codes].T
+
+
+def read_numeric_text(text, heading=True):
+    """GAPIT's numeric genotype table (GAPIT.Fragment.R:100-128: read.table(head = TRUE), GT = first column, GD = the
+    rest): -> (GD float (n, m) with NaN for NA, GT, marker names)."""
+    lines = [ln for ln in bytes(text).decode().replace(",", " ").splitlines() if ln.strip()]
+    names = lines[0].split()[1:] if heading else None
+    rows = [ln.split() for ln in lines[1 if heading else 0:]]
+    GT = [r[0] for r in rows]
+
+    def val(tok):
+        return float("nan") if tok in ("NA", "NaN", "nan", ".", "-") else float(tok)
+    GD = np.array([[val(t) for t in r[1:]] for r in rows], dtype=np.float64)
+    return GD, GT, names

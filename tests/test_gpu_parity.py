@@ -716,7 +716,15 @@ def test_full_size_c2_properties(gpu_ctx):
     # the streaming host path too
     host, _ = gb().p3d_scan_host(G, X0, Y, marker_major=True, **kw)
     assert np.array_equal(host["pvalue"], full["pvalue"], equal_nan=True)
-    # spot rows against the dense GLS solve (Cholesky of K + delta I)
+    # three blocks of 1,024 markers (first, middle, last tiles) against the batched fp64 derivation (oracle/batched.py:
+    # one dgemm V'X + the closed-form bordered solve -- independent of the per-marker loop and of the int8 split) at
+    # north_star's tolerances, plus spot rows against the dense Cholesky GLS that never touches the eigen route
+    from oracle import batched
+    for k0 in (0, 249856, m - 1024):
+        ref = batched.p3d_block(Y, G[k0:k0 + 1024].T, X0, eL["values"], eL["vectors"], reml["delta"], reml["vg"])
+        c = batched.compare({k: full[k][0] for k in ("effect", "se", "tvalue", "pvalue")}, ref, rows=slice(k0, k0 + 1024))
+        assert c["nan_rows_identical"] and c["n_tested"] > 1000, c
+        assert c["beta_rel_max"] < BETA_RTOL and c["se_rel_max"] < BETA_RTOL and c["dlog10p_max"] < LOGP_ATOL, c
     L = np.linalg.cholesky(K + reml["delta"] * np.eye(n))
     yw = np.linalg.solve(L, Y)
     x0w = np.linalg.solve(L, X0[:, 0])
@@ -729,10 +737,13 @@ def test_full_size_c2_properties(gpu_ctx):
         se = np.sqrt(iXX[1, 1] * reml["vg"])
         assert full["effect"][0, i] == pytest.approx(b[1], rel=1e-7, abs=1e-10)
         assert full["se"][0, i] == pytest.approx(se, rel=1e-8)
+    gref = batched.p3d_block(Y, G[:2048].T, X0, glm=True)
     # GLM rows against OLS with the reduced-model variance (:937)
     glm, gbase = gb().p3d_scan(geno, X0, Y, glm=True, ctx=gpu_ctx)
     ves = float(((Y - Y.mean()) ** 2).sum() / (n - 1))
     assert gbase[0]["ves"] == pytest.approx(ves, rel=1e-10)
+    c = batched.compare({k: glm[k][0] for k in ("effect", "se", "tvalue", "pvalue")}, gref, rows=slice(0, 2048))
+    assert c["nan_rows_identical"] and c["beta_rel_max"] < BETA_RTOL and c["se_rel_max"] < BETA_RTOL and c["dlog10p_max"] < LOGP_ATOL, c
     for i in (5, 400000):
         x = G[i].astype(np.float64)
         if x.min() == x.max():
@@ -781,27 +792,66 @@ def test_large_taxa_shapes(gpu_ctx):
     Y = synth.make_phenotypes(G[:2048], seed=4)[:, 0]
     X0 = np.ones((n, 1))
     geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
-    K = gb().GAPIT_kinship_VanRaden(geno, ctx=gpu_ctx, verbose=False) + 0.5 * np.eye(n)   # few markers: keep K well posed
+    K = gb().GAPIT_kinship_VanRaden(geno, ctx=gpu_ctx, verbose=False)   # undoctored: rank <= 8,192, K 1 = 0
     eL = gb().emma_eigen_L_wo_Z(K, ctx=gpu_ctx)
     assert np.all(np.diff(eL["values"]) <= 1e-9)
+    reml = gb().GAPIT_emma_REMLE(Y, X0, K, eig_L=eL, ctx=gpu_ctx)        # the REML delta of this very kinship
+    assert reml["delta"] > 0 and np.isfinite(reml["vg"])
     es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
-    kw = dict(eigsys=es, delta=[1.3], vg=[2.0], ctx=gpu_ctx)
+    kw = dict(eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]], ctx=gpu_ctx)
     full, _ = gb().p3d_scan(geno, X0, Y, **kw)
     assert full["pvalue"][0, 8000] == full["pvalue"][0, 77] and full["effect"][0, 8000] == full["effect"][0, 77]
     part, _ = gb().p3d_scan(gb().Genotypes(G[3000:5000], ctx=gpu_ctx, marker_major=True), X0, Y, **kw)
     assert np.array_equal(part["pvalue"][0], full["pvalue"][0, 3000:5000], equal_nan=True)
-    # spot rows against the eigen-space GLS computed on the host in fp64
-    lam, V = eL["values"], eL["vectors"]
-    w = 1.0 / (lam + 1.3)
-    yt, x0t = V.T @ Y, V.T @ X0[:, 0]
-    for i in (0, 77, 8191):
-        xt = V.T @ G[i].astype(np.float64)
-        A = np.array([[np.sum(w * x0t * x0t), np.sum(w * x0t * xt)], [np.sum(w * x0t * xt), np.sum(w * xt * xt)]])
-        rhs = np.array([np.sum(w * x0t * yt), np.sum(w * xt * yt)])
-        iA = np.linalg.inv(A)
-        beta = iA @ rhs
-        assert full["effect"][0, i] == pytest.approx(beta[1], rel=1e-7, abs=1e-10)
-        assert full["se"][0, i] == pytest.approx(np.sqrt(iA[1, 1] * 2.0), rel=1e-8)
+    # 2 x 1,024 markers against the batched fp64 derivation at north_star's tolerances (beta / SE 1e-8, -log10 p 1e-6)
+    from oracle import batched
+    for k0 in (0, m - 1024):
+        ref = batched.p3d_block(Y, G[k0:k0 + 1024].T, X0, eL["values"], eL["vectors"], reml["delta"], reml["vg"])
+        c = batched.compare({k: full[k][0] for k in ("effect", "se", "tvalue", "pvalue")}, ref, rows=slice(k0, k0 + 1024))
+        assert c["nan_rows_identical"] and c["n_tested"] > 1000, c
+        assert c["beta_rel_max"] < BETA_RTOL and c["se_rel_max"] < BETA_RTOL and c["dlog10p_max"] < LOGP_ATOL, c
+    # three traits through the shared rotation at this taxa count: every trait against its own single-trait launch
+    Y3 = synth.make_phenotypes(G[:2048], ntraits=3, seed=4)
+    r3 = [gb().GAPIT_emma_REMLE(Y3[:, t], X0, K, eig_L=eL, ctx=gpu_ctx) for t in range(3)]
+    multi, _ = gb().p3d_scan(geno, X0, Y3, eigsys=es, delta=[r["delta"] for r in r3], vg=[r["vg"] for r in r3], ctx=gpu_ctx)
+    for t in (0, 2):
+        one, _ = gb().p3d_scan(geno, X0, Y3[:, t], eigsys=es, delta=[r3[t]["delta"]], vg=[r3[t]["vg"]], ctx=gpu_ctx)
+        ok = ~np.isnan(one["tvalue"][0])
+        assert np.array_equal(np.isnan(multi["tvalue"][t]), ~ok)
+        assert np.max(np.abs(multi["se"][t][ok] - one["se"][0][ok]) / one["se"][0][ok]) < 1e-10
+        assert np.max(np.abs(multi["effect"][t][ok] - one["effect"][0][ok]) / one["se"][0][ok]) < 1e-9   # in SE units
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(multi["pvalue"][t][ok]) - np.log10(one["pvalue"][0][ok]))) < 1e-7
+
+
+@pytest.mark.parametrize("T", [1, 4])
+def test_unmerged_digit_epilogue_of_large_taxa_counts(gpu_ctx, monkeypatch, T):
+    """n >= 32,640 cannot merge adjacent digit planes in int32 (257 * 256 * n overflows) and takes the unmerged
+    epilogue; GAPIT_EPI_PAIR=0 forces that path at a size the oracle handles, for the fused single-trait epilogue
+    (T = 1) and the store epilogue of the shared rotation (T = 4)."""
+    G, _, X0 = case(333, 900, npc=2, seed=17)
+    Yt = synth.make_phenotypes(G, ntraits=T, seed=17)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    remls = [go.emma_REMLE(Yt[:, t], X0, K) for t in range(T)]
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    kw = dict(eigsys=es, delta=[r["delta"] for r in remls], vg=[r["vg"] for r in remls], ctx=gpu_ctx)
+    merged, _ = gb().p3d_scan(geno, X0, Yt, **kw)
+    monkeypatch.setenv("GAPIT_EPI_PAIR", "0")
+    plain, _ = gb().p3d_scan(geno, X0, Yt, **kw)
+    for t in range(T):
+        ora = go.emmax_p3d(Yt[:, t], G.T, K, X0, eig_L=eL, reml=remls[t])
+        ok = ~np.isnan(ora.stats)
+        assert np.array_equal(np.isnan(plain["tvalue"][t]), ~ok)
+        r, a = rel_err(plain["effect"][t], ora.effect_est, 1e-4)
+        assert r < BETA_RTOL, (t, r)
+        r, a = rel_err(plain["se"][t], ora.se_clean, 0.0)
+        assert r < SE_RTOL, (t, r)
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(plain["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
+        # the integer digit sums are exact either way: merging only changes how they are converted
+        assert np.allclose(plain["effect"][t], merged["effect"][t], rtol=1e-12, atol=0, equal_nan=True)
 
 
 def test_shared_rotation_blocks_do_not_change_results(gpu_ctx, monkeypatch):
@@ -829,3 +879,100 @@ def test_shared_rotation_blocks_do_not_change_results(gpu_ctx, monkeypatch):
         assert r < BETA_RTOL, (t, r)
         with np.errstate(divide="ignore"):
             assert np.nanmax(np.abs(np.log10(parts["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
+
+
+# ------------------------------------------------------------------ PLINK .bed and numeric text
+def _write_bed(G_na, count="A1"):
+    """Independent encoder: (n, m) dosages of `count` (-1 = missing) -> bytes of a variant-major .bed."""
+    n, m = G_na.shape
+    code = {"A1": {2: 0, -1: 1, 1: 2, 0: 3}, "A2": {0: 0, -1: 1, 1: 2, 2: 3}}[count]
+    nb = (n + 3) // 4
+    out = bytearray([0x6C, 0x1B, 0x01])
+    for k in range(m):
+        row = bytearray(nb)
+        for i in range(n):
+            row[i // 4] |= code[int(G_na[i, k])] << (2 * (i % 4))
+        out += row
+    return bytes(out)
+
+
+@pytest.mark.parametrize("n,m,count", [(5, 7, "A1"), (131, 97, "A2"), (600, 350, "A1")])
+def test_plink_bed_rows_go_to_the_gpu_as_they_are(gpu_ctx, tmp_path, n, m, count):
+    rng = np.random.default_rng(n + m)
+    G = rng.integers(0, 3, size=(n, m)).astype(np.int8)
+    G_na = G.copy()
+    G_na[rng.random((n, m)) < 0.02] = -1
+    bed = _write_bed(G_na, count)
+    assert np.array_equal(go.read_bed(bed, n, count), G_na)                     # the oracle against the encoder
+    rows = gb().Packed2.from_bed(bed, n, count=count)
+    assert rows.m == m
+    with pytest.raises(gb().GapitCudaError):                                     # missing calls, no impute rule
+        gb().Genotypes(rows, ctx=gpu_ctx)
+    for rule, val in (("Middle", 1), ("Major", 2), ("Minor", 0)):
+        g = gb().Genotypes(rows, ctx=gpu_ctx, impute=rule)
+        want = np.where(G_na < 0, val, G_na).astype(np.int64)
+        cs, cq = g.colsums()
+        assert np.array_equal(cs, want.sum(0)) and np.array_equal(cq, (want * want).sum(0))
+        K, gram = gb().GAPIT_kinship_VanRaden(g, ctx=gpu_ctx, return_gram=True, verbose=False)
+        assert np.array_equal(gram, want @ want.T)
+    with pytest.raises(gb().GapitCudaError):
+        gb().Packed2.from_bed(b"\x6c\x1b\x00" + bed[3:], n)                     # sample-major mode byte
+    with pytest.raises(gb().GapitCudaError):
+        gb().Packed2.from_bed(b"\x00\x1b\x01" + bed[3:], n)                     # wrong magic
+    # files on disk: .fam / .bim parsed on the host, the .bed memory-mapped and streamed through the scan
+    prefix = str(tmp_path / "geno")
+    open(prefix + ".bed", "wb").write(bed)
+    open(prefix + ".fam", "w").write("".join(f"F{i} T{i} 0 0 0 -9\n" for i in range(n)))
+    open(prefix + ".bim", "w").write("".join(f"1\tS{k}\t0\t{100 + k}\tA\tG\n" for k in range(m)))
+    rows2, GT, GI, alleles = gb().read_plink(prefix, count=count)
+    assert GT[:2] == ["T0", "T1"] and GI["SNP"][-1] == f"S{m - 1}" and GI["Position"][0] == 100 and alleles[0] == ("A", "G")
+    if n > 100:
+        Y = np.random.default_rng(1).normal(size=n)
+        X0 = np.ones((n, 1))
+        want = np.where(G_na < 0, 1, G_na).astype(np.int8)
+        ref, _ = gb().p3d_scan_host(want.T.copy(), X0, Y, glm=True, ctx=gpu_ctx, marker_major=True)
+        got, _, _, _ = gb().p3d_scan_file(prefix, X0, Y, glm=True, ctx=gpu_ctx, count=count)
+        for key in ("effect", "pvalue", "maf"):
+            assert np.array_equal(got[key], ref[key], equal_nan=True), key
+
+
+@pytest.mark.parametrize("n,m", [(3, 5), (70, 333), (300, 5000)])
+def test_numeric_text_table_is_parsed_on_the_gpu(gpu_ctx, n, m):
+    """genoFormat = "EMMA" (GAPIT.Fragment.R:94-136): file.GD with a heading row and one row per taxon."""
+    rng = np.random.default_rng(7 * n + m)
+    G = rng.integers(0, 3, size=(n, m))
+    na = rng.random((n, m)) < 0.01
+    seps = ["\t", " ", ",", "  "]
+    lines = ["taxa\t" + "\t".join(f"m{k}" for k in range(m))]
+    for i in range(n):
+        sep = seps[i % 4]
+        toks = []
+        for k in range(m):
+            if na[i, k]:
+                toks.append(["NA", "NaN", "."][k % 3])
+            else:
+                toks.append(str(G[i, k]) if (i + k) % 5 else f"{G[i, k]}.0")
+        lines.append(f"line_{i:04d}{sep}" + sep.join(toks))
+    text = ("\r\n" if n % 2 else "\n").join(lines).encode() + (b"\n" if n % 3 else b"")
+    GD_o, GT_o, names_o = go.read_numeric_text(text)
+    assert np.array_equal(np.isnan(GD_o), na)
+    gd, GT, names, _ = gb().GAPIT_numeric_text(text, SNP_impute="Middle", ctx=gpu_ctx)
+    assert GT == GT_o and names == names_o
+    assert np.array_equal(gd, np.where(na, 1, G))
+    if na.any():
+        with pytest.raises(gb().GapitCudaError):                                 # NA and no impute rule
+            gb().GAPIT_numeric_text(text, SNP_impute=None, ctx=gpu_ctx)
+    bad = text.replace(b"line_0001", b"line_0001 2", 1) if n > 1 else text + b"x 1\n"
+    with pytest.raises(gb().GapitCudaError):                                     # ragged row
+        gb().GAPIT_numeric_text(bad, SNP_impute="Middle", ctx=gpu_ctx)
+    with pytest.raises(gb().GapitCudaError):                                     # a value that is no dosage
+        gb().GAPIT_numeric_text(text.rstrip(b"\r\n") + b"\nextra" + b"\t7" * m + b"\n", SNP_impute="Middle", ctx=gpu_ctx)
+    if n >= 70:   # the parsed table as a device handle: scan it, compare with the scan of the same dosages from int8
+        Y = rng.normal(size=n)
+        X0 = np.ones((n, 1))
+        want = np.where(na, 1, G).astype(np.int8)
+        ref, _ = gb().p3d_scan_host(want.T.copy(), X0, Y, glm=True, ctx=gpu_ctx, marker_major=True)
+        got, _, GT2, names2 = gb().p3d_scan_file(text, X0, Y, glm=True, ctx=gpu_ctx, genoFormat="EMMA")
+        assert GT2 == GT_o and names2 == names_o
+        for key in ("effect", "pvalue", "maf"):
+            assert np.array_equal(got[key], ref[key], equal_nan=True), key

@@ -53,7 +53,7 @@ def test_product_path_never_imports_the_oracle():
                 if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".R")):
                     txt = open(os.path.join(dirpath, f)).read()
                     assert "import oracle" not in txt and "from oracle" not in txt, f
-    # bench.py: the oracle appears only inside the two CPU legs
+    # bench.py: the oracle appears only inside the two CPU legs and the in-run parity check (as the checker)
     import ast
     tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
     users = set()
@@ -61,7 +61,7 @@ def test_product_path_never_imports_the_oracle():
         for n in ast.walk(fn):
             if isinstance(n, ast.ImportFrom) and n.module and n.module.startswith("oracle"):
                 users.add(fn.name)
-    assert users <= {"cpu_scan_sample", "run_reference"}, users
+    assert users <= {"cpu_scan_sample", "run_reference", "parity_report"}, users
 
 
 def test_reml_host_code_matches_oracle():
