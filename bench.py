@@ -62,7 +62,7 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--n", type=int, default=5000, help="taxa (default: BASELINE configs[1])")
     ap.add_argument("--m", type=int, default=500000, help="markers per GPU")
-    ap.add_argument("--slices", type=int, default=6)
+    ap.add_argument("--slices", type=int, default=0, help="digit planes of the rotation (0 = the library default)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="markers of the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -323,7 +323,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n, m = args.n, args.m
-    S = args.slices
     pk = peaks()
 
     # ---------------- synthetic inputs (host, pinned) ----------------
@@ -339,7 +338,8 @@ def main():
         Y = yt.cpu().numpy()
     X0 = np.ones((n, 1))
 
-    ctx = gb.Context(local, slices=S)
+    ctx = gb.Context(local, slices=args.slices or None)
+    S = ctx.slices
     stream = torch.cuda.Stream(device=dev)      # one non-default stream for torch, NCCL and libgapitcuda alike
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
@@ -601,7 +601,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": scan_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "int8 x int8 -> int32 rotation (6 digit planes of fp64 V), fp64 epilogue",
+        "dtype": f"int8 x int8 -> int32 rotation ({S} digit planes of fp64 V), fp64 epilogue",
         "data": "synthetic",
         "config": {"workload": workload_name(n, m), "markers_total": m_total, "kinship": "VanRaden", "slices": S,
                    "l2": "inputs larger than L2 (genotypes 2.5 GB per GPU)", "parallelism": f"marker-shard x{world}"},

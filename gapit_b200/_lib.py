@@ -76,6 +76,8 @@ SIGNATURES = {
     "gapit_pca": (C.c_int, [_P, _P, _I64, _P, _P]),
     "gapit_eigh": (C.c_int, [_P, _P, _I64, _P, _P]),
     "gapit_eigh_dev": (C.c_int, [_P, _P, _I64, _P]),
+    "gapit_eigh_dev_mg": (C.c_int, [_P, _P, _I64, _P, C.c_int]),
+    "gapit_eigh_mg": (C.c_int, [_P, _P, _I64, _P, _P, C.c_int]),
     "gapit_eigen_R": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P]),
     "gapit_reml": (C.c_int, [_P, _P, _I64, C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(RemlOut)]),
     "gapit_reml_eigL": (C.c_int, [_P, _P, _P, _I64, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
@@ -94,6 +96,7 @@ SIGNATURES = {
                                       C.c_int, C.POINTER(ScanOut), C.POINTER(ScanBase)]),
     "gapit_blup_pev": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_double, C.c_double, _P, _P, _P]),
     "gapit_set_slices": (C.c_int, [_P, C.c_int]),
+    "gapit_get_slices": (C.c_int, [_P]),
     "gapit_eigsys_vectors_dev": (_P, [_P]),
     "gapit_bed_header": (C.c_int, [_P, _I64, _I64, C.POINTER(_I64), C.POINTER(_I64)]),
     "gapit_text_index_lines": (C.c_int, [_P, _I64, _P, _I64, C.POINTER(_I64)]),

@@ -49,7 +49,12 @@ class Context:
             check(self.lib.gapit_ctx_set_stream(self.h, C.c_void_p(int(cuda_stream) or 1)))
 
     def set_slices(self, slices):
+        """Digit planes of the rotation (4..8); 0 restores the library default."""
         check(self.lib.gapit_set_slices(self.h, int(slices)))
+
+    @property
+    def slices(self):
+        return int(self.lib.gapit_get_slices(self.h))
 
     def stats(self):
         s = _lib.Stats()

@@ -172,9 +172,11 @@ extern "C" int gapit_ctx_set_stream(gapit_ctx* ctx, void* cuda_stream) {
   return GAPIT_OK;
 }
 
+extern "C" int gapit_get_slices(const gapit_ctx* ctx) { return ctx ? ctx->slices : 0; }
+
 extern "C" int gapit_set_slices(gapit_ctx* ctx, int slices) {
   if (!ctx) return fail(GAPIT_ERR_ARG, "gapit_set_slices: NULL ctx");
-  if (slices == 0) slices = 6;
+  if (slices == 0) slices = GAPIT_DEFAULT_SLICES;
   if (slices < 4 || slices > 8) return fail(GAPIT_ERR_ARG, "gapit_set_slices: slices must be 4..8");
   ctx->slices = slices;
   return GAPIT_OK;

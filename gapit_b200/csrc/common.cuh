@@ -51,7 +51,7 @@ struct gapit_ctx {
   // timings of the last call, ms (CUDA events on `stream`)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   gapit_stats stats = {};
-  int slices = 6;  // int8 slices of V used by the rotation (Ozaki split)
+  int slices = GAPIT_DEFAULT_SLICES;  // int8 digit planes of V used by the rotation (Ozaki split)
   // grow-only device workspaces reused across calls (no cudaMalloc/cudaFree on the hot path)
   static constexpr int kWsSlots = 32;
   void* ws_ptr[kWsSlots] = {};
@@ -72,7 +72,7 @@ enum WsSlot { WS_R = 0, WS_PROJ, WS_GCONST, WS_PART, WS_OUT, WS_RG, WS_RS, WS_RS
               WS_CS0, WS_CS1, WS_CQ0, WS_CQ1, WS_STAGE0, WS_STAGE1, WS_SYNC, WS_FC, WS_WBUF, WS_WT, WS_XX, WS_KSCALE, WS_Z };
 // device workspace of at least `bytes` in `slot` (contents are not preserved when it grows)
 int ctx_ws(gapit_ctx* ctx, int slot, size_t bytes, void** out);
-void scan_plan_cache_drop(gapit_ctx* ctx, const void* eigsys = nullptr);   // scan.cu
+void scan_plan_cache_drop(gapit_ctx* ctx);   // scan.cu
 template <class T>
 inline int ctx_ws_t(gapit_ctx* ctx, int slot, size_t count, T** out) {
   void* p = nullptr;
@@ -84,6 +84,7 @@ inline int ctx_ws_t(gapit_ctx* ctx, int slot, size_t count, T** out) {
 
 struct gapit_geno {
   gapit_ctx* ctx = nullptr;
+  int device = 0;         // for the free path: the handle may outlive its context
   int64_t n = 0;      // taxa
   int64_t m = 0;      // markers
   int64_t ldn = 0;    // bytes per marker row of the marker-major copy (multiple of 128)

@@ -221,6 +221,7 @@ extern "C" int gapit_geno_pack(gapit_ctx* ctx, const void* snps, gapit_dtype dty
   GAPIT_CUDA(cudaSetDevice(ctx->device));
   gapit_geno* g = new gapit_geno();
   g->ctx = ctx;
+  g->device = ctx->device;
   g->n = n;
   g->m = m;
   g->ldn = round_up(n, 128);
@@ -324,6 +325,7 @@ extern "C" int gapit_geno_from_device(gapit_ctx* ctx, const int8_t* mk_dev, int6
   GAPIT_CUDA(cudaSetDevice(ctx->device));
   gapit_geno* g = new gapit_geno();
   g->ctx = ctx;
+  g->device = ctx->device;
   g->n = n;
   g->m = m;
   g->ldn = round_up(n, 128);
@@ -350,7 +352,7 @@ extern "C" int gapit_geno_from_device(gapit_ctx* ctx, const int8_t* mk_dev, int6
 
 extern "C" void gapit_geno_free(gapit_geno* g) {
   if (!g) return;
-  if (g->ctx) cudaSetDevice(g->ctx->device);
+  cudaSetDevice(g->device);   // never through g->ctx: host languages may destroy the context first
   cudaFree(g->mk);
   cudaFree(g->colsum);
   cudaFree(g->colsumsq);
@@ -362,7 +364,7 @@ extern "C" int64_t gapit_geno_m(const gapit_geno* g) { return g ? g->m : 0; }
 
 extern "C" int gapit_geno_colsums(const gapit_geno* g, int32_t* colsum_out, int32_t* colsumsq_out) {
   if (!g) return fail(GAPIT_ERR_ARG, "gapit_geno_colsums: NULL handle");
-  GAPIT_CUDA(cudaSetDevice(g->ctx->device));
+  GAPIT_CUDA(cudaSetDevice(g->device));
   if (colsum_out) GAPIT_CUDA(cudaMemcpy(colsum_out, g->colsum, size_t(g->m) * 4, cudaMemcpyDeviceToHost));
   if (colsumsq_out) GAPIT_CUDA(cudaMemcpy(colsumsq_out, g->colsumsq, size_t(g->m) * 4, cudaMemcpyDeviceToHost));
   return GAPIT_OK;

@@ -314,6 +314,7 @@ extern "C" int gapit_hapmap_numericalize(gapit_ctx* ctx, const char* text, int64
   const int64_t ldn = round_up(n, 128);
   gapit_geno* g = new gapit_geno();
   g->ctx = ctx;
+  g->device = ctx->device;
   g->n = n;
   g->m = m;
   g->ldn = ldn;

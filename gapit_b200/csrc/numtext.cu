@@ -210,6 +210,7 @@ extern "C" int gapit_numtext_numericalize(gapit_ctx* ctx, const char* text, int6
   const int64_t ldm = round_up(m, 128), ldn = round_up(n, 128);
   gapit_geno* g = new gapit_geno();
   g->ctx = ctx;
+  g->device = ctx->device;
   g->n = n;
   g->m = m;
   g->ldn = ldn;

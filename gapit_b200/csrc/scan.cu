@@ -60,7 +60,9 @@ struct gapit_eigsys {
   double* scale = nullptr;   // [nkq*KPB] c_k = max_j |V_jk| / (126 * 256^(S-1)), 0 beyond n
   std::vector<double> values;  // host, descending
   std::vector<double> h_scale;
-  uint64_t serial = 0;         // unique per handle (a cached scan plan must not outlive the handle it was built for)
+  uint64_t serial = 0;         // unique per handle: part of the scan-plan cache key, so a plan built for a freed handle
+                               // can never be matched again (the handle may outlive its context at interpreter exit)
+  int device = 0;
 };
 
 namespace gapit {
@@ -1402,9 +1404,8 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
 }  // namespace gapit
 
 namespace gapit {
-void scan_plan_cache_drop(gapit_ctx* ctx, const void* eigsys) {
+void scan_plan_cache_drop(gapit_ctx* ctx) {
   if (!ctx || !ctx->plan_cache) return;
-  if (eigsys && ctx->plan_cache->e != eigsys) return;
   delete ctx->plan_cache;
   ctx->plan_cache = nullptr;
   ctx->plan_key = 0;
@@ -1421,6 +1422,7 @@ static int eigsys_build(gapit_ctx* ctx, const double* vectors, cudaMemcpyKind ki
   static std::atomic<uint64_t> next_serial{1};
   e->serial = next_serial.fetch_add(1);
   e->ctx = ctx;
+  e->device = ctx->device;
   e->n = n;
   const SliceGeom sg = slice_geom(ctx->slices);
   e->S = sg.S;
@@ -1481,8 +1483,7 @@ extern "C" const double* gapit_eigsys_vectors_dev(const gapit_eigsys* e) { retur
 
 extern "C" void gapit_eigsys_free(gapit_eigsys* e) {
   if (!e) return;
-  if (e->ctx) cudaSetDevice(e->ctx->device);
-  scan_plan_cache_drop(e->ctx, e);
+  cudaSetDevice(e->device);   // never through e->ctx: host languages may destroy the context first
   cudaFree(e->V);
   cudaFree(e->Vs);
   cudaFree(e->scale);

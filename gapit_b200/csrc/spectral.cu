@@ -7,6 +7,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "common.cuh"
 
 namespace gapit {
@@ -121,6 +123,15 @@ int syevd_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* w_dev) {
   return GAPIT_OK;
 }
 
+// ascending -> descending order of the eigenvectors, in place (also used by spectral_mg.cu)
+int launch_swap_cols(cudaStream_t st, double* A_dev, int64_t n) {
+  if (n < 2) return GAPIT_OK;
+  dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(std::min<int64_t>(n / 2, 65535)));
+  swap_cols_kernel<<<grid, 256, 0, st>>>(A_dev, n);
+  GAPIT_CUDA(cudaGetLastError());
+  return GAPIT_OK;
+}
+
 // shared tail: A_dev holds eigenvectors (ascending); emit the first `keep` in descending order
 static int emit_desc(gapit_ctx* ctx, double* A_dev, double* w_dev, int64_t n, int64_t keep, double shift,
                      double* values_out, double* vectors_out) {
@@ -180,6 +191,74 @@ extern "C" int gapit_eigh_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* 
   if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("gapit_eigh_dev: ") + cudaGetErrorString(e));
   for (int64_t c = 0; c < n; ++c) values_out[c] = w[n - 1 - c];
   return GAPIT_OK;
+}
+
+// Multi-GPU eigensolver: cusolverMgSyevd lives in libgapitcuda_mg.so next to this library and is loaded on first use.
+// (libcusolverMg binds the CUDA toolkit's own libcublas; a host process that already carries another libcublas -- a
+// PyTorch wheel's -- cannot load it, and then this call reports that and the caller keeps the one-GPU solver.)
+typedef int (*MgSyevdFn)(int, void*, double*, int64_t, double*, int, char*, int);
+static MgSyevdFn mg_syevd_fn(std::string* why) {
+  static MgSyevdFn fn = nullptr;
+  static std::string err;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    Dl_info info;
+    std::string dir = ".";
+    if (dladdr(reinterpret_cast<void*>(&gapit_eigh_dev), &info) && info.dli_fname) {
+      dir = info.dli_fname;
+      const size_t slash = dir.find_last_of('/');
+      dir = slash == std::string::npos ? "." : dir.substr(0, slash);
+    }
+    void* h = dlopen((dir + "/libgapitcuda_mg.so").c_str(), RTLD_NOW | RTLD_LOCAL);
+    if (!h) err = dlerror();
+    else if (!(fn = reinterpret_cast<MgSyevdFn>(dlsym(h, "gapit_mg_syevd")))) err = "gapit_mg_syevd missing in libgapitcuda_mg.so";
+  }
+  if (!fn && why) *why = err;
+  return fn;
+}
+
+extern "C" int gapit_eigh_dev_mg(gapit_ctx* ctx, double* A_dev, int64_t n, double* values_out, int ngpus) {
+  if (!ctx || !A_dev || !values_out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_eigh_dev_mg: bad argument");
+  int ndev = gapit_device_count();
+  if (ngpus <= 0) ngpus = ndev;
+  ngpus = std::min(ngpus, ndev);
+  if (ngpus < 2 || n < 2048) return gapit_eigh_dev(ctx, A_dev, n, values_out);
+  std::string why;
+  MgSyevdFn fn = mg_syevd_fn(&why);
+  if (!fn) return fail(GAPIT_ERR_NO_DEVICE, "multi-GPU eigensolver unavailable in this process: " + why);
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  std::vector<double> w(n);
+  char msg[512] = {0};
+  const int rc = fn(ctx->device, ctx->stream, A_dev, n, w.data(), ngpus, msg, sizeof(msg));
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  if (rc != 0) return fail(rc, msg);
+  GAPIT_CHECK(launch_swap_cols(ctx->stream, A_dev, n));   // ascending -> R's descending order
+  GAPIT_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int64_t c = 0; c < n; ++c) values_out[c] = w[n - 1 - c];
+  return GAPIT_OK;
+}
+
+// host-buffer form of the above (what the R shim calls for eigen(K)): falls back to the one-GPU solver when the
+// multi-GPU one cannot be used in this process
+extern "C" int gapit_eigh_mg(gapit_ctx* ctx, const double* A, int64_t n, double* values_out, double* vectors_out, int ngpus) {
+  if (!ctx || !A || !values_out || !vectors_out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_eigh_mg: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  double* A_dev = nullptr;
+  GAPIT_CUDA(cudaMalloc(&A_dev, size_t(n) * n * 8));
+  cudaError_t e = cudaMemcpyAsync(A_dev, A, size_t(n) * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  int rc = (e == cudaSuccess) ? GAPIT_OK : fail(GAPIT_ERR_CUDA, std::string("gapit_eigh_mg: ") + cudaGetErrorString(e));
+  if (rc == GAPIT_OK) {
+    rc = gapit_eigh_dev_mg(ctx, A_dev, n, values_out, ngpus);
+    if (rc == GAPIT_ERR_NO_DEVICE) rc = gapit_eigh_dev(ctx, A_dev, n, values_out);
+  }
+  if (rc == GAPIT_OK) {
+    e = cudaMemcpyAsync(vectors_out, A_dev, size_t(n) * n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(GAPIT_ERR_CUDA, std::string("gapit_eigh_mg: ") + cudaGetErrorString(e));
+  }
+  cudaFree(A_dev);
+  return rc;
 }
 
 extern "C" int gapit_eigen_R(gapit_ctx* ctx, const double* K, const double* X, int64_t n, int64_t q, double* values_out,

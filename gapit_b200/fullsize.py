@@ -42,7 +42,7 @@ def gen_block(n, mb, seed, dev, pop):
     return out
 
 
-def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8, slices=6, exchange="fused"):
+def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8, slices=None, exchange="fused"):
     """Run one full-size configuration; returns the report dict (meaningful on rank 0).  ``ctx`` must already share the
     current torch stream (``ctx.set_stream``)."""
     import torch
@@ -243,7 +243,7 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
         dist.all_reduce(sk, op=dist.ReduceOp.MAX)
     T_["scan_kernels_s_max_rank"] = float(sk[0]) * 1e-3
     T_["scan_d2h_tail_s"] = scan_d2h_ms * 1e-3
-    S = slices
+    S = slices or ctx.slices
     # the rotation is counted ONCE whatever the number of traits (int8-native 2 n^2 m S)
     out.update({
         "snps_per_s": m / T_["scan_total_s"], "snp_trait_tests_per_s": m * max(T, 1) / T_["scan_total_s"],

@@ -182,6 +182,14 @@ int gapit_eigh(gapit_ctx* ctx, const double* A, int64_t n, double* values_out, d
 /* Device-resident form: A_dev (n x n column-major, e.g. K_dev_out of gapit_vanraden_finish) is overwritten by the
  * eigenvectors in descending order of the eigenvalues (values_out: host, n) -- no n^2 host round trip. */
 int gapit_eigh_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* values_out);
+/* The same on `ngpus` GPUs of this process (0 = every visible one): cuSOLVER's multi-GPU solver cusolverMgSyevd on a
+ * 1-D block-cyclic copy of A dealt out over NVLink, eigenvectors gathered back into A_dev.  Needs peer access; falls
+ * through to gapit_eigh_dev for ngpus < 2 or n < 2048.  The solver sits in libgapitcuda_mg.so (loaded on first use);
+ * GAPIT_ERR_NO_DEVICE when it cannot be loaded into this process (libcusolverMg needs the CUDA toolkit's libcublas: a
+ * host process carrying another copy, e.g. a PyTorch wheel's, cannot use it).  gapit_eigh_mg is the host-buffer form
+ * (eigen(K) of the R shim) and falls back to the one-GPU solver by itself. */
+int gapit_eigh_dev_mg(gapit_ctx* ctx, double* A_dev, int64_t n, double* values_out, int ngpus);
+int gapit_eigh_mg(gapit_ctx* ctx, const double* A, int64_t n, double* values_out, double* vectors_out, int ngpus);
 /* gapit_eigen_R: eigen(S (K+I) S) with S = I - X (X'X)^-1 X'; returns the first
  * n-q values minus 1 and the first n-q vectors (n x (n-q) column-major). */
 int gapit_eigen_R(gapit_ctx* ctx, const double* K, const double* X, int64_t n, int64_t q, double* values_out,
@@ -296,8 +304,14 @@ int gapit_multi_p3d_scan(gapit_mctx* mc, gapit_mgeno* g, const double* vectors, 
                          int q0, const double* Y, int T, const double* delta, const double* vg, int glm,
                          gapit_scan_out* out, gapit_scan_base* base_out /* T entries */);
 
-/* tuning knobs (0 = default): number of int8 slices of V (4..8) */
+/* Number of int8 digit planes each eigenvector is split into for the rotation (4..8; 0 = the default).  Each plane is 8
+ * bits of the eigenvector relative to its largest element: S planes reproduce the fp64 product to ~2^-(8S) per element.
+ * Default 5: measured against the fp64 oracle (bench.py `parity`, tests) beta holds 5e-10 relative, SE 2e-13, -log10 p
+ * 1e-11 -- 20x inside the 1e-8 / 1e-6 tolerances -- and the scan is 21 % faster than with 6 planes (which reach the
+ * oracle's own rounding, 3e-11). */
+#define GAPIT_DEFAULT_SLICES 5
 int gapit_set_slices(gapit_ctx* ctx, int slices);
+int gapit_get_slices(const gapit_ctx* ctx);
 
 #ifdef __cplusplus
 }

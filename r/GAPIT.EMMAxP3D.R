@@ -29,7 +29,8 @@ Memory=GAPIT.Memory(Memory=Memory,Infor="P3D Start")
 if(is.null(dim(ys)) || ncol(ys) == 1)  ys <- matrix(ys, 1, length(ys))        # :29
 if(is.null(X0)) X0 <- matrix(1, ncol(ys), 1)                                  # :30
 if(!is.null(K)) {if(length(K)<= 1) K = NULL}                                  # :34
-n <- ncol(ys); q0 <- ncol(X0); q1 <- q0 + 1; m <- ncol(xs)
+n <- ncol(ys); q0 <- ncol(X0); q1 <- q0 + 1
+xs.arg <- if(is.raw(xs)) xs else as.matrix(xs)        # a raw vector is the content of a PLINK .bed (r/GAPIT.Bed.R)
 y <- as.numeric(ys[1,])
 impute <- switch(SNP.impute, Minor=0L, Middle=1L, Major=2L, -1L)
 glm <- is.null(K)
@@ -57,12 +58,13 @@ if(!glm){
   bp <- .Call("gapit_R_blup_pev", eig.L$vectors, eig.L$values, X0, y, REMLE_delta, vgs)      # :779-839
   BLUP <- bp[[1]]; PEV <- bp[[2]]; BLUP_Plus_Mean <- bp[[3]][1] + BLUP                        # :818-819
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="PEV"); Memory=GAPIT.Memory(Memory=Memory,Infor="PEV")
-  res <- .Call("gapit_R_p3d_scan", as.matrix(xs), eig.L$vectors, eig.L$values, X0, y, REMLE_delta, vgs, FALSE, impute)
+  res <- .Call("gapit_R_p3d_scan", xs.arg, eig.L$vectors, eig.L$values, X0, y, REMLE_delta, vgs, FALSE, impute)
 } else {
-  res <- .Call("gapit_R_p3d_scan", as.matrix(xs), NULL, NULL, X0, y, 0, 0, TRUE, impute)
+  res <- .Call("gapit_R_p3d_scan", xs.arg, NULL, NULL, X0, y, 0, 0, TRUE, impute)
 }
 Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="Screening SNPs"); Memory=GAPIT.Memory(Memory=Memory,Infor="Screening SNPs")
 base <- attr(res, "base")
+m <- nrow(res)
 if(glm){ ves <- base[4]; REMLs <- base[5]; vgs <- 0; BLUP <- 0; BLUP_Plus_Mean <- NaN; PEV <- ves }   # :868-875
 if(base[7] != 0) print("At least two of your covariates are linearly dependent. Please reconsider the covariates you are using for GWAS and GPS")   # :711
 beta.cv <- base[8:(7+q0)]

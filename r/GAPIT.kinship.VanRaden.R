@@ -7,7 +7,7 @@ function(snps,hasInbred=TRUE) {
 print("Calculating kinship with VanRaden method...")
 print("substracting P...")
 print("Getting X'X...")
-K=.Call("gapit_R_vanraden", as.matrix(snps))
+K=.Call("gapit_R_vanraden", if(is.raw(snps)) snps else as.matrix(snps))   # raw = a PLINK .bed (r/GAPIT.Bed.R)
 print("Adjusting...")
 print("Calculating kinship with VanRaden method: done")
 return(K)

@@ -45,30 +45,54 @@ static gapit_dtype sexp_dtype(SEXP x) {
 
 static const void* sexp_data(SEXP x) { return TYPEOF(x) == REALSXP ? (const void*)REAL(x) : (const void*)INTEGER(x); }
 
-/* An R matrix holds 8 (numeric) or 4 (integer) bytes per genotype call: pack it to 2 bits per call on the host's
- * threads (gapit_pack2_host) so that 1/32 (1/16) of the bytes cross PCIe.  R_alloc memory is freed by R at the end of
- * the .Call, also on error.  NA becomes code 3 and meets the impute rule on the device, as in GAPIT.EMMAxP3D.R:20-24. */
-static uint8_t* pack_matrix(SEXP x, int64_t n, int64_t m, int64_t* nb_out) {
-  const int64_t nb = (n + 3) / 4;
-  uint8_t* packed = (uint8_t*)R_alloc((size_t)m * (size_t)nb, 1);
-  if (gapit_pack2_host(sexp_data(x), sexp_dtype(x), n, m, n, packed, 0) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
-  *nb_out = nb;
-  return packed;
+/* Genotype argument of the .Call targets: either an R matrix (n x m numeric / integer), or the raw bytes of a PLINK
+ * .bed file (readBin(path, "raw", file.size(path))) carrying attributes "n" (rows of the .fam) and "count" (1 = copies
+ * of A1, 2 = copies of A2) -- see r/GAPIT.Bed.R.
+ * An R matrix holds 8 (numeric) or 4 (integer) bytes per genotype call: it is packed to 2 bits per call on the host's
+ * threads (gapit_pack2_host) so that 1/32 (1/16) of the bytes cross PCIe; R_alloc memory is freed by R at the end of
+ * the .Call, also on error.  A .bed is used in place.  NA / missing becomes code 3 and meets the impute rule on the
+ * device, as in GAPIT.EMMAxP3D.R:20-24.  May Rf_error: call before any device handle exists. */
+typedef struct {
+  const uint8_t* rows;
+  int64_t n, m, nb;
+  gapit_dtype dtype;
+} geno_src;
+
+static geno_src geno_source(SEXP x) {
+  geno_src g;
+  if (TYPEOF(x) == RAWSXP) {
+    SEXP an = Rf_getAttrib(x, Rf_install("n")), ac = Rf_getAttrib(x, Rf_install("count"));
+    if (an == R_NilValue) Rf_error("gapitcuda: a raw .bed vector needs attribute \"n\" (samples in the .fam)");
+    int64_t off = 0;
+    g.n = (int64_t)Rf_asInteger(an);
+    if (gapit_bed_header(RAW(x), XLENGTH(x), g.n, &g.m, &off) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+    g.rows = (const uint8_t*)RAW(x) + off;
+    g.nb = (g.n + 3) / 4;
+    g.dtype = (ac != R_NilValue && Rf_asInteger(ac) == 2) ? GAPIT_BED_A2 : GAPIT_BED_A1;
+    return g;
+  }
+  SEXP dim = Rf_getAttrib(x, R_DimSymbol);
+  g.n = INTEGER(dim)[0];
+  g.m = INTEGER(dim)[1];
+  g.nb = (g.n + 3) / 4;
+  g.dtype = GAPIT_B2;
+  uint8_t* packed = (uint8_t*)R_alloc((size_t)g.m * (size_t)g.nb, 1);
+  if (gapit_pack2_host(sexp_data(x), sexp_dtype(x), g.n, g.m, g.n, packed, 0) != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  g.rows = packed;
+  return g;
 }
 
 /* GAPIT.kinship.VanRaden(snps): n x m matrix -> n x n double matrix (GAPIT.kinship.VanRaden.R:1-37).
  * Markers are split across every GPU of the multi-context; the partial cross-products are exchanged inside the kernel. */
 SEXP gapit_R_vanraden(SEXP snps) {
-  SEXP dim = Rf_getAttrib(snps, R_DimSymbol);
-  const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
   /* everything that can longjmp (context creation, R allocations) happens before a device handle exists */
   gapit_mctx* mc = mctx();
-  int64_t nb = 0;
-  const uint8_t* packed = pack_matrix(snps, n, m, &nb);
+  const geno_src src = geno_source(snps);
+  const int64_t n = src.n;
   SEXP K = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
   gapit_mgeno* g = NULL;
   /* the reference does not impute here: NA propagates to a NaN matrix, so NA is an error for us */
-  int rc = gapit_mgeno_pack(mc, packed, GAPIT_B2, n, m, nb, GAPIT_IMPUTE_NONE, &g);
+  int rc = gapit_mgeno_pack(mc, src.rows, src.dtype, n, src.m, src.nb, GAPIT_IMPUTE_NONE, &g);
   if (rc == GAPIT_OK) rc = gapit_multi_vanraden(mc, g, REAL(K), NULL);
   gapit_mgeno_free(g);
   UNPROTECT(1);
@@ -76,12 +100,15 @@ SEXP gapit_R_vanraden(SEXP snps) {
   return K;
 }
 
-/* eigen(K, symmetric=TRUE) in R's order: list(values, vectors)   (emma.txt:58-61) */
+/* eigen(K, symmetric=TRUE) in R's order: list(values, vectors)   (emma.txt:58-61).  On a multi-GPU box the
+ * decomposition runs on every GPU of the multi-context (cusolverMgSyevd); one GPU, or a process that cannot load the
+ * multi-GPU solver, uses cusolverDn syevd. */
 SEXP gapit_R_eigen_L(SEXP K) {
   const int64_t n = INTEGER(Rf_getAttrib(K, R_DimSymbol))[0];
+  gapit_mctx* mc = mctx();
   SEXP values = PROTECT(Rf_allocVector(REALSXP, n));
   SEXP vectors = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
-  int rc = gapit_eigh(ctx(), REAL(K), n, REAL(values), REAL(vectors));
+  int rc = gapit_eigh_mg(ctx(), REAL(K), n, REAL(values), REAL(vectors), gapit_mctx_ngpus(mc));
   if (rc != GAPIT_OK) {
     UNPROTECT(2);
     Rf_error("gapitcuda: %s", gapit_last_error());
@@ -135,19 +162,19 @@ SEXP gapit_R_reml(SEXP lambda, SEXP etas, SEXP ngrids, SEXP llim, SEXP ulim, SEX
 }
 
 /* The marker loop of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:397-979), one trait.
- * xs n x m (numeric/integer), vectors/values = eig.L (ignored when glm), X0 n x q0, y length n.
+ * xs n x m (numeric/integer) or the raw bytes of a .bed (see geno_source), vectors/values = eig.L (ignored when glm),
+ * X0 n x q0, y length n.
  * impute: -1 none, 0 Minor, 1 Middle, 2 Major.  Returns an m x 7 matrix
  * (effect, t, se, p, rsquare, logLM, maf) with attribute "base" =
  * c(logL0, logLM_base, rsquare_base, ves, reml, df, singular_x0, beta0[1..q0]). */
 SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP delta, SEXP vg, SEXP glm, SEXP impute) {
-  SEXP dim = Rf_getAttrib(xs, R_DimSymbol);
-  const int64_t n = INTEGER(dim)[0], m = INTEGER(dim)[1];
   const int q0 = INTEGER(Rf_getAttrib(X0, R_DimSymbol))[1];
   const int is_glm = Rf_asLogical(glm);
   /* everything that can longjmp happens before a device handle exists */
   gapit_mctx* mc = mctx();
-  int64_t nb = 0;
-  const uint8_t* packed = pack_matrix(xs, n, m, &nb);
+  const geno_src src = geno_source(xs);
+  const int64_t n = src.n, m = src.m, nb = src.nb;
+  const uint8_t* packed = src.rows;
   SEXP res = PROTECT(Rf_allocMatrix(REALSXP, (int)m, 7));
   SEXP b = PROTECT(Rf_allocVector(REALSXP, 7 + q0));
   double* r = REAL(res);
@@ -161,12 +188,12 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP 
     gapit_eigsys* e = NULL;
     rc = is_glm ? GAPIT_OK : gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e);
     if (rc == GAPIT_OK)
-      rc = gapit_p3d_scan_host(ctx(), packed, GAPIT_B2, n, m, nb, imp, e, REAL(X0), q0, REAL(y), 1, &d, &v, is_glm, &out, &base);
+      rc = gapit_p3d_scan_host(ctx(), packed, src.dtype, n, m, nb, imp, e, REAL(X0), q0, REAL(y), 1, &d, &v, is_glm, &out, &base);
     gapit_eigsys_free(e);
   } else {
     /* several GPUs: one marker block per GPU, results in marker order */
     gapit_mgeno* g = NULL;
-    rc = gapit_mgeno_pack(mc, packed, GAPIT_B2, n, m, nb, imp, &g);
+    rc = gapit_mgeno_pack(mc, packed, src.dtype, n, m, nb, imp, &g);
     if (rc == GAPIT_OK)
       rc = gapit_multi_p3d_scan(mc, g, is_glm ? NULL : REAL(vectors), is_glm ? NULL : REAL(values), REAL(X0), q0, REAL(y), 1,
                                 &d, &v, is_glm, &out, &base);

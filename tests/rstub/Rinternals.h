@@ -3,7 +3,8 @@
 typedef struct SEXPREC* SEXP;
 typedef ptrdiff_t R_xlen_t;
 typedef unsigned char Rbyte;
-extern SEXP R_DimSymbol, R_NamesSymbol;
+extern SEXP R_DimSymbol, R_NamesSymbol, R_NilValue;
+#define RAWSXP 24
 #define REALSXP 14
 #define INTSXP 13
 #define VECSXP 19

@@ -464,7 +464,7 @@ def test_mlm_scan_slice_counts(gpu_ctx, slices):
     try:
         res = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0, ctx=gpu_ctx, eig_L=eL, reml=reml)
     finally:
-        gpu_ctx.set_slices(6)
+        gpu_ctx.set_slices(0)
     r, a = rel_err(res["effect.est"][:, 0], ora.effect_est, 1e-3)
     assert r < BETA_RTOL   # 5 planes: ~1e-9 (tools/slice_accuracy.py); 6 and up: the oracle's own rounding
     with np.errstate(divide="ignore"):
@@ -570,8 +570,9 @@ def test_multi_trait_matches_single_trait_calls(gpu_ctx):
                                 ctx=gpu_ctx)
     for t in range(3):
         one, b1 = gb().p3d_scan(geno, X0, Yt[:, t], eigsys=es, delta=[remls[t]["delta"]], vg=[remls[t]["vg"]], ctx=gpu_ctx)
-        # a single trait keeps two partial sums per eigen split, a trait chunk one: same numbers to rounding
-        assert np.allclose(arrs["pvalue"][t], one["pvalue"][0], rtol=1e-11, atol=0, equal_nan=True)
+        # the single-trait launch reduces in registers, several traits go through the shared rotation (W^2 + back-rotated
+        # columns): two evaluations of the same sums whose digit-plane rounding differs -- far below the oracle tolerance
+        assert np.allclose(arrs["pvalue"][t], one["pvalue"][0], rtol=1e-8, atol=0, equal_nan=True)
         ora = go.emmax_p3d(Yt[:, t], G.T, K, X0, eig_L=eL, reml=remls[t])
         with np.errstate(divide="ignore"):
             assert np.nanmax(np.abs(np.log10(arrs["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
@@ -902,6 +903,7 @@ def test_plink_bed_rows_go_to_the_gpu_as_they_are(gpu_ctx, tmp_path, n, m, count
     G = rng.integers(0, 3, size=(n, m)).astype(np.int8)
     G_na = G.copy()
     G_na[rng.random((n, m)) < 0.02] = -1
+    G_na[n // 2, m // 2] = -1                                                    # at least one missing call
     bed = _write_bed(G_na, count)
     assert np.array_equal(go.read_bed(bed, n, count), G_na)                     # the oracle against the encoder
     rows = gb().Packed2.from_bed(bed, n, count=count)

@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--m", type=int, default=0)
     ap.add_argument("--traits", type=int, default=-1)
     ap.add_argument("--blocks", type=int, default=8, help="marker blocks (the 8-GPU layout's shards)")
-    ap.add_argument("--slices", type=int, default=6)
+    ap.add_argument("--slices", type=int, default=0)
     ap.add_argument("--exchange", default="fused", choices=["fused", "nccl"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -31,12 +31,12 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    ctx = gb.Context(local, slices=args.slices)
+    ctx = gb.Context(local, slices=args.slices or None)
     stream = torch.cuda.Stream(device=dev)      # one non-default stream for torch, NCCL and libgapitcuda alike
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     out = fullsize.run_config(args.config, ctx, dev, rank, world, n=args.n or None, m=args.m or None,
-                              T=None if args.traits < 0 else args.traits, blocks=args.blocks, slices=args.slices,
+                              T=None if args.traits < 0 else args.traits, blocks=args.blocks, slices=ctx.slices,
                               exchange=args.exchange)
     if rank == 0:
         print(json.dumps(out), flush=True)
