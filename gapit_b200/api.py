@@ -737,7 +737,8 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
     """The accelerated branch of GAPIT.EMMAxP3D: Z NULL or square, SNP.P3D, fullGD, no indicators, !optOnly.
 
     Returns the reference's named list (GAPIT.EMMAxP3D.R:1018-1020) as a dict; per-marker
-    entries are (m, 1) arrays like the reference's m x g matrices with g = 1.  ``eig_L`` /
+    entries are (m, g) arrays like the reference's m x g matrices (g traits = rows of ``ys``; the scalars vgs / ves /
+    REMLs / BLUP / effect.cv are those of the last trait, as the reference's loop leaves them).  ``eig_L`` /
     ``reml`` may be injected (tests feed both sides identical spectra); they are otherwise
     computed where the reference computes them (:48, :58, :202).  ``reml_route="eigL"`` (default) evaluates the REML
     likelihood from eig.L alone (``gapit_reml_eigL``: same function of delta, measured agreement 1e-13 in delta), so
@@ -750,8 +751,15 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
     if not SNP_P3D or not fullGD or Create_indicator or optOnly:
         raise NotImplementedError("only the P3D / fullGD / additive scan is accelerated (SURVEY.md section 8b)")
     Timmer = _timmer(Timmer, "P3D Start")
-    ys = np.asarray(ys, dtype=np.float64).reshape(-1)                     # :29
-    n = ys.shape[0]
+    # :29  ys is a g x n matrix of g traits (a vector is one trait).  The reference loops the traits (:81) and repeats the
+    # rotation for each; here all g traits share one eigendecomposition and ONE rotation (BASELINE configs[4]).
+    # Missing phenotypes (per-trait subsetting, :113-114) keep the reference body.
+    ys = np.asarray(ys, dtype=np.float64)
+    ys = ys.reshape(1, -1) if (ys.ndim == 1 or 1 in ys.shape) else ys
+    if np.isnan(ys).any():
+        raise NotImplementedError("missing phenotypes are subset per trait by the reference body (GAPIT.EMMAxP3D.R:113-114)")
+    g, n = ys.shape
+    Y = np.asfortranarray(ys.T)                                           # n x g
     if X0 is None:                                                        # :30
         X0 = np.ones((n, 1))
     X0 = np.asarray(X0, dtype=np.float64)
@@ -765,56 +773,64 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
 
     def run_scan(**kw):
         if resident:
-            return p3d_scan(xs, X0, ys, ctx=ctx, **kw)
-        return p3d_scan_host(xs, X0, ys, ctx=ctx, impute=SNP_impute, **kw)
+            return p3d_scan(xs, X0, Y, ctx=ctx, **kw)
+        return p3d_scan_host(xs, X0, Y, ctx=ctx, impute=SNP_impute, **kw)
     glm = K is None
+    y_last = np.ascontiguousarray(Y[:, g - 1])
     if not glm:
         if eig_L is None:
             eig_L = emma_eigen_L_wo_Z(K, ctx=ctx)                         # :48
         Timmer = _timmer(Timmer, "eig.L")
-        if reml is None and reml_route == "eigL":
-            reml = GAPIT_emma_REMLE(ys, X0, K, None, ngrids, llim, ulim, esp, eig_L=eig_L, ctx=ctx)    # :202
-        if reml is None:
+        es = EigenSystem(eig_L["values"], eig_L["vectors"], ctx=ctx)      # :224 folded into the kernel weights
+        if reml is not None:
+            remls = [reml] if isinstance(reml, dict) else list(reml)
+        elif reml_route == "eigL":                                        # :202 for every trait, from eig.L alone
+            proj = es.project(np.column_stack([X0, Y]))
+            remls = reml_from_projections_multi(eig_L["values"], proj[:, q0:], proj[:, :q0], ngrids, llim, ulim, esp)
+        else:
             try:
                 eig_R = emma_eigen_R_wo_Z(K, X0, ctx=ctx)                 # :58
             except GapitCudaError:
                 # :70-74 early return when eig.R fails
+                es.close()
                 return {"ps": None, "REMLs": np.nan, "stats": None, "effect.est": None, "dfs": None, "maf": None,
                         "nobs": None, "Timmer": Timmer, "Memory": Memory, "vgs": np.nan, "ves": np.nan,
                         "BLUP": None, "BLUP_Plus_Mean": None, "PEV": None, "BLUE": None}
             Timmer = _timmer(Timmer, "eig.R")
-            reml = GAPIT_emma_REMLE(ys, X0, K, None, ngrids, llim, ulim, esp, eig_R=eig_R, ctx=ctx)   # :202
+            remls = [GAPIT_emma_REMLE(Y[:, t], X0, K, None, ngrids, llim, ulim, esp, eig_R=eig_R, ctx=ctx) for t in range(g)]
+        if len(remls) != g:
+            raise ValueError(f"{g} traits need {g} REML results, got {len(remls)}")
         Timmer = _timmer(Timmer, "REML")
-        es = EigenSystem(eig_L["values"], eig_L["vectors"], ctx=ctx)      # :224 folded into the kernel weights
         Timmer = _timmer(Timmer, "U Matrix")
-        # i = 0: BLUP / PEV of the marker-free model (:779-839), then the marker loop
-        BLUP, PEV, beta0 = blup_pev(es, X0, ys, reml["delta"], reml["vg"], ctx=ctx)
+        # i = 0: BLUP / PEV of the marker-free model (:779-839) -- of the LAST trait, which is what the reference's
+        # loop leaves in its scalars -- then the marker loop of all traits
+        last = remls[-1]
+        BLUP, PEV, beta0 = blup_pev(es, X0, y_last, last["delta"], last["vg"], ctx=ctx)
         Timmer = _timmer(Timmer, "PEV")
-        arrs, bases = run_scan(eigsys=es, delta=[reml["delta"]], vg=[reml["vg"]])
+        arrs, bases = run_scan(eigsys=es, delta=[r["delta"] for r in remls], vg=[r["vg"] for r in remls])
         es.close()
-        vgs, ves, REMLs = reml["vg"], reml["ve"], reml["REML"]
+        vgs, ves, REMLs = last["vg"], last["ve"], last["REML"]
     else:
         arrs, bases = run_scan(glm=True)
-        vgs, ves, REMLs = 0.0, bases[0]["ves"], bases[0]["reml"]           # :868-872
+        vgs, ves, REMLs = 0.0, bases[-1]["ves"], bases[-1]["reml"]         # :868-872
         BLUP, PEV = 0.0, ves                                              # :873-875
-        beta0 = bases[0]["beta0"]
+        beta0 = bases[-1]["beta0"]
     Timmer = _timmer(Timmer, "Screening SNPs")
     if bases[0]["singular_x0"]:                                           # :711
         print("At least two of your covariates are linearly dependent. Please reconsider the covariates you are using for GWAS and GPS")
-    b = bases[0]
-    col = lambda a: a.reshape(m, 1)
-    stats = arrs["tvalue"][0]
+    mat = lambda a: np.ascontiguousarray(np.asarray(a).T)                 # (g, m) -> the reference's m x g
+    stats = arrs["tvalue"]
     normal = ~np.isnan(stats)
-    dfs = np.where(normal, b["df"], np.nan)
+    dfs = np.where(normal, np.array([b["df"] for b in bases])[:, None], np.nan)
     # :972 stderr = beta[ncol(CVI)+1] / t -- an index into the (q0+1)-vector of the full model that only
     # lands on the marker effect when ncol(CVI) == q0; past the end R yields NA.
-    stderr = np.full(m, np.nan)
+    stderr = np.full((g, m), np.nan)
     if CVI is not None:
         idx = np.asarray(CVI).shape[1]                                    # 0-based position ncol(CVI)
         if idx == q0:
-            stderr = arrs["effect"][0] / stats
+            stderr = arrs["effect"] / stats
         # idx < q0 would need the per-marker covariate effects the scan does not return
-    rsq_base = np.where(normal, b["rsquare_base"], np.nan)
+    rsq_base = np.where(normal, np.array([b["rsquare_base"] for b in bases])[:, None], np.nan)
     # :841-861 / :877-889  BLUE = XCV %*% beta.Inheritance with XCV = cbind(1, CVI[,-1]) (X itself for an intercept-only fit)
     BLUE = None
     if q0 == 1:
@@ -828,17 +844,17 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
             BLUE = (XCV @ b_inh).reshape(n, 1)
     Timmer = _timmer(Timmer, "GWAS done for this Trait")
     return {
-        "ps": col(arrs["pvalue"][0]), "REMLs": -2.0 * REMLs, "stats": col(stats),
-        "effect.est": col(arrs["effect"][0]), "rsquare_base": col(rsq_base), "rsquare": col(arrs["rsquare"][0]),
-        "dfs": col(dfs), "df": col(dfs.copy()), "tvalue": col(stats.copy()), "stderr": col(stderr),
-        "maf": col(arrs["maf"]), "nobs": col(np.full(m, float(n))), "Timmer": Timmer, "Memory": Memory,
-        "vgs": vgs, "ves": ves,
+        "ps": mat(arrs["pvalue"]), "REMLs": -2.0 * REMLs, "stats": mat(stats),
+        "effect.est": mat(arrs["effect"]), "rsquare_base": mat(rsq_base), "rsquare": mat(arrs["rsquare"]),
+        "dfs": mat(dfs), "df": mat(dfs), "tvalue": mat(stats), "stderr": mat(stderr),
+        "maf": np.repeat(arrs["maf"].reshape(m, 1), g, axis=1), "nobs": np.full((m, g), float(n)), "Timmer": Timmer,
+        "Memory": Memory, "vgs": vgs, "ves": ves,
         # i = 0 block (:779-861): BLUP = K H^-1 (y - X beta), PEV = diag(C22), BLUE = XCV beta
         "BLUP": BLUP if glm else BLUP.reshape(n, 1),
         "BLUP_Plus_Mean": (np.nan if glm else (beta0[0] + BLUP).reshape(n, 1)),           # :818-819, :874
         "PEV": PEV if glm else PEV.reshape(n, 1), "BLUE": BLUE,
-        "logLM": col(arrs["loglm"][0]), "effect.snp": col(arrs["effect"][0]), "effect.cv": b["beta0"],
-        "se": col(arrs["se"][0]), "delta": (None if glm else reml["delta"]),
+        "logLM": mat(arrs["loglm"]), "effect.snp": mat(arrs["effect"]), "effect.cv": bases[-1]["beta0"],
+        "se": mat(arrs["se"]), "delta": (None if glm else [r["delta"] for r in remls] if g > 1 else remls[0]["delta"]),
     }
 
 

@@ -161,13 +161,13 @@ SEXP gapit_R_reml(SEXP lambda, SEXP etas, SEXP ngrids, SEXP llim, SEXP ulim, SEX
   return out;
 }
 
-/* The marker loop of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:397-979), one trait.
+/* The marker loop of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:397-979) for T traits that share X0 and the eigen-system: the
+ * reference loops the rows of ys (:81) and repeats the rotation for each; here one rotation serves them all.
  * xs n x m (numeric/integer) or the raw bytes of a .bed (see geno_source), vectors/values = eig.L (ignored when glm),
- * X0 n x q0, y length n.
- * impute: -1 none, 0 Minor, 1 Middle, 2 Major.  Returns an m x 7 matrix
- * (effect, t, se, p, rsquare, logLM, maf) with attribute "base" =
- * c(logL0, logLM_base, rsquare_base, ves, reml, df, singular_x0, beta0[1..q0]). */
-SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP delta, SEXP vg, SEXP glm, SEXP impute) {
+ * X0 n x q0, Y n x T (a vector is one trait), delta / vg length T.  impute: -1 none, 0 Minor, 1 Middle, 2 Major.
+ * Returns list(effect, tvalue, se, pvalue, rsquare, loglm) of m x T matrices, maf (length m) and base, a
+ * (7 + q0) x T matrix with rows logL0, logLM_base, rsquare_base, ves, reml, df, singular_x0, beta0[1..q0]. */
+SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP Y, SEXP delta, SEXP vg, SEXP glm, SEXP impute) {
   const int q0 = INTEGER(Rf_getAttrib(X0, R_DimSymbol))[1];
   const int is_glm = Rf_asLogical(glm);
   /* everything that can longjmp happens before a device handle exists */
@@ -175,12 +175,22 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP 
   const geno_src src = geno_source(xs);
   const int64_t n = src.n, m = src.m, nb = src.nb;
   const uint8_t* packed = src.rows;
-  SEXP res = PROTECT(Rf_allocMatrix(REALSXP, (int)m, 7));
-  SEXP b = PROTECT(Rf_allocVector(REALSXP, 7 + q0));
-  double* r = REAL(res);
-  gapit_scan_out out = {r, r + m, r + 2 * m, r + 3 * m, r + 4 * m, r + 5 * m, r + 6 * m};
-  gapit_scan_base base;
-  double d = is_glm ? 0.0 : Rf_asReal(delta), v = is_glm ? 0.0 : Rf_asReal(vg);
+  const int T = (int)(XLENGTH(Y) / n);
+  if ((int64_t)T * n != XLENGTH(Y) || T < 1) Rf_error("gapitcuda: Y must hold n values per trait");
+  if (!is_glm && (XLENGTH(delta) != T || XLENGTH(vg) != T)) Rf_error("gapitcuda: delta and vg need one value per trait");
+  SEXP res = PROTECT(Rf_allocVector(VECSXP, 8));
+  for (int a = 0; a < 6; ++a) SET_VECTOR_ELT(res, a, Rf_allocMatrix(REALSXP, (int)m, T));
+  SET_VECTOR_ELT(res, 6, Rf_allocVector(REALSXP, m));
+  SET_VECTOR_ELT(res, 7, Rf_allocMatrix(REALSXP, 7 + q0, T));
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 8));
+  const char* names[8] = {"effect", "tvalue", "se", "pvalue", "rsquare", "loglm", "maf", "base"};
+  for (int a = 0; a < 8; ++a) SET_STRING_ELT(nm, a, Rf_mkChar(names[a]));
+  Rf_setAttrib(res, R_NamesSymbol, nm);
+  gapit_scan_base* base = (gapit_scan_base*)R_alloc((size_t)T, sizeof(gapit_scan_base));
+  gapit_scan_out out = {REAL(VECTOR_ELT(res, 0)), REAL(VECTOR_ELT(res, 1)), REAL(VECTOR_ELT(res, 2)), REAL(VECTOR_ELT(res, 3)),
+                        REAL(VECTOR_ELT(res, 4)), REAL(VECTOR_ELT(res, 5)), REAL(VECTOR_ELT(res, 6))};
+  const double* d = is_glm ? NULL : REAL(delta);
+  const double* v = is_glm ? NULL : REAL(vg);
   const gapit_impute imp = (gapit_impute)Rf_asInteger(impute);
   int rc;
   if (gapit_mctx_ngpus(mc) == 1) {
@@ -188,30 +198,32 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP y, SEXP 
     gapit_eigsys* e = NULL;
     rc = is_glm ? GAPIT_OK : gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e);
     if (rc == GAPIT_OK)
-      rc = gapit_p3d_scan_host(ctx(), packed, src.dtype, n, m, nb, imp, e, REAL(X0), q0, REAL(y), 1, &d, &v, is_glm, &out, &base);
+      rc = gapit_p3d_scan_host(ctx(), packed, src.dtype, n, m, nb, imp, e, REAL(X0), q0, REAL(Y), T, d, v, is_glm, &out, base);
     gapit_eigsys_free(e);
   } else {
     /* several GPUs: one marker block per GPU, results in marker order */
     gapit_mgeno* g = NULL;
     rc = gapit_mgeno_pack(mc, packed, src.dtype, n, m, nb, imp, &g);
     if (rc == GAPIT_OK)
-      rc = gapit_multi_p3d_scan(mc, g, is_glm ? NULL : REAL(vectors), is_glm ? NULL : REAL(values), REAL(X0), q0, REAL(y), 1,
-                                &d, &v, is_glm, &out, &base);
+      rc = gapit_multi_p3d_scan(mc, g, is_glm ? NULL : REAL(vectors), is_glm ? NULL : REAL(values), REAL(X0), q0, REAL(Y), T, d, v,
+                                is_glm, &out, base);
     gapit_mgeno_free(g);
   }
   if (rc != GAPIT_OK) {
     UNPROTECT(2);
     Rf_error("gapitcuda: %s", gapit_last_error());
   }
-  REAL(b)[0] = base.logL0;
-  REAL(b)[1] = base.logLM_base;
-  REAL(b)[2] = base.rsquare_base;
-  REAL(b)[3] = base.ves;
-  REAL(b)[4] = base.reml;
-  REAL(b)[5] = base.df;
-  REAL(b)[6] = (double)base.singular_x0;
-  memcpy(REAL(b) + 7, base.beta0, sizeof(double) * q0);
-  Rf_setAttrib(res, Rf_install("base"), b);
+  double* b = REAL(VECTOR_ELT(res, 7));
+  for (int t = 0; t < T; ++t, b += 7 + q0) {
+    b[0] = base[t].logL0;
+    b[1] = base[t].logLM_base;
+    b[2] = base[t].rsquare_base;
+    b[3] = base[t].ves;
+    b[4] = base[t].reml;
+    b[5] = base[t].df;
+    b[6] = (double)base[t].singular_x0;
+    memcpy(b + 7, base[t].beta0, sizeof(double) * q0);
+  }
   UNPROTECT(2);
   return res;
 }
@@ -256,6 +268,26 @@ SEXP gapit_R_reml_eigL(SEXP values, SEXP Vty, SEXP VtX, SEXP ngrids, SEXP llim, 
   REAL(out)[1] = r.delta;
   REAL(out)[2] = r.ve;
   REAL(out)[3] = r.vg;
+  UNPROTECT(1);
+  return out;
+}
+
+/* REML of T traits from eig.L alone (gapit_R_reml_eigL for every column of VtY, on the host's threads): 4 x T matrix with
+ * rows REML, delta, ve, vg. */
+SEXP gapit_R_reml_eigL_multi(SEXP values, SEXP VtY, SEXP VtX, SEXP ngrids, SEXP llim, SEXP ulim, SEXP esp) {
+  const int64_t n = XLENGTH(values);
+  const int q = (int)(XLENGTH(VtX) / n), T = (int)(XLENGTH(VtY) / n);
+  gapit_reml_out* r = (gapit_reml_out*)R_alloc((size_t)T, sizeof(gapit_reml_out));
+  int rc = gapit_reml_eigL_multi(REAL(values), REAL(VtY), REAL(VtX), n, q, T, Rf_asInteger(ngrids), Rf_asReal(llim),
+                                 Rf_asReal(ulim), Rf_asReal(esp), r, NULL);
+  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, 4, T));
+  for (int t = 0; t < T; ++t) {
+    REAL(out)[4 * t + 0] = r[t].REML;
+    REAL(out)[4 * t + 1] = r[t].delta;
+    REAL(out)[4 * t + 2] = r[t].ve;
+    REAL(out)[4 * t + 3] = r[t].vg;
+  }
   UNPROTECT(1);
   return out;
 }

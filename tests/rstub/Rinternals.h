@@ -13,5 +13,5 @@ extern SEXP R_DimSymbol, R_NamesSymbol, R_NilValue;
 int TYPEOF(SEXP); double* REAL(SEXP); int* INTEGER(SEXP); Rbyte* RAW(SEXP);
 SEXP Rf_getAttrib(SEXP, SEXP); SEXP Rf_setAttrib(SEXP, SEXP, SEXP); SEXP Rf_allocMatrix(int, int, int); SEXP Rf_allocVector(int, R_xlen_t);
 SEXP PROTECT(SEXP); void UNPROTECT(int); void Rf_error(const char*, ...); int Rf_asInteger(SEXP); double Rf_asReal(SEXP); int Rf_asLogical(SEXP);
-R_xlen_t XLENGTH(SEXP); SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP); void SET_STRING_ELT(SEXP, R_xlen_t, SEXP); SEXP Rf_mkChar(const char*); SEXP Rf_install(const char*); SEXP Rf_ScalarInteger(int);
+R_xlen_t XLENGTH(SEXP); SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP); SEXP VECTOR_ELT(SEXP, R_xlen_t); void SET_STRING_ELT(SEXP, R_xlen_t, SEXP); SEXP Rf_mkChar(const char*); SEXP Rf_install(const char*); SEXP Rf_ScalarInteger(int);
 char* R_alloc(size_t, int);

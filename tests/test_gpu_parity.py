@@ -978,3 +978,33 @@ def test_numeric_text_table_is_parsed_on_the_gpu(gpu_ctx, n, m):
         assert GT2 == GT_o and names2 == names_o
         for key in ("effect", "pvalue", "maf"):
             assert np.array_equal(got[key], ref[key], equal_nan=True), key
+
+
+def test_emmaxp3d_with_several_rows_of_ys_shares_one_rotation(gpu_ctx):
+    """GAPIT.EMMAxP3D loops the rows of ys (`for (j in 1:g)`, :81) and fills m x g matrices; the drop-in runs all g traits
+    through one eigendecomposition and one rotation.  Every column must equal the one-trait call of that row (and the
+    oracle), the scalar entries are those of the last trait (what the reference's loop leaves behind)."""
+    G, _, X0 = case(170, 700, npc=2, seed=41)
+    g = 4
+    Yt = synth.make_phenotypes(G, ntraits=g, seed=41)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    CVI = np.column_stack([np.zeros(170), X0[:, 1:]])
+    many = gb().GAPIT_EMMAxP3D(Yt.T, G.T, K, X0=X0, CVI=CVI, ctx=gpu_ctx, eig_L=eL)
+    assert many["ps"].shape == (700, g) and many["maf"].shape == (700, g)
+    for t in range(g):
+        one = gb().GAPIT_EMMAxP3D(Yt[:, t], G.T, K, X0=X0, CVI=CVI, ctx=gpu_ctx, eig_L=eL)
+        ok = ~np.isnan(one["stats"][:, 0])
+        assert np.array_equal(np.isnan(many["stats"][:, t]), ~ok)
+        assert np.allclose(many["effect.est"][ok, t], one["effect.est"][ok, 0], rtol=0, atol=1e-9 * np.abs(one["se"][ok, 0]).max())
+        assert np.allclose(many["se"][ok, t], one["se"][ok, 0], rtol=1e-10, atol=0)
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(many["ps"][:, t]) - np.log10(one["ps"][:, 0]))) < 1e-7
+        assert np.allclose(many["rsquare_base"][ok, t], one["rsquare_base"][ok, 0], rtol=0, atol=1e-12)
+        reml = go.emma_REMLE(Yt[:, t], X0, K)
+        ora = go.emmax_p3d(Yt[:, t], G.T, K, X0, eig_L=eL, reml=reml)
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(many["ps"][:, t]) - np.log10(ora.ps))) < 1e-4   # own REML vs the oracle's
+    last = gb().GAPIT_EMMAxP3D(Yt[:, g - 1], G.T, K, X0=X0, CVI=CVI, ctx=gpu_ctx, eig_L=eL)
+    assert many["vgs"] == pytest.approx(last["vgs"], rel=1e-12) and many["REMLs"] == pytest.approx(last["REMLs"], rel=1e-12)
+    assert np.allclose(many["BLUP"], last["BLUP"], rtol=1e-9, atol=1e-12) and np.allclose(many["effect.cv"], last["effect.cv"])
