@@ -208,12 +208,51 @@ __global__ void gram_rowsum_kernel(const int32_t* __restrict__ G, int64_t ldg, i
   if (lane == 0) s[row] = acc;
 }
 
-// K (column-major n x n) from the mirrored G; exact int64 numerator, one fp64 division.
-__global__ void vanraden_epilogue_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n,
-                                         const long long* __restrict__ s, const unsigned long long* __restrict__ sums,
-                                         double* __restrict__ K) {
-  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// ---- K (column-major n x n) from the LOWER triangle of G alone (no mirror pass): 32 x 32 tiles with bi >= bj --------
+// s_i = sum_j G_ij over the full symmetric row = row sums of the lower 32 x 32 tiles (bj <= bi; a diagonal tile holds
+// both triangles) + column sums of the strictly lower ones (bi > bj).  One CTA owns a block of 32 rows (pass 0) or of 32
+// columns (pass 1) and walks its tiles, so every s_i has a single writer per pass: no atomics, fixed order.
+__global__ void gram_sums_lower_kernel(const int32_t* __restrict__ G, int64_t ldg, int tiles32, int pass,
+                                       long long* __restrict__ s) {
+  const int b = blockIdx.x;
+  const int x = threadIdx.x, y0 = threadIdx.y;
+  __shared__ long long red[8][32];
+  if (pass == 0) {
+    long long r[4] = {0, 0, 0, 0};
+    for (int bj = 0; bj <= b; ++bj)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) r[q] += G[(int64_t(b) * 32 + y0 + 8 * q) * ldg + int64_t(bj) * 32 + x];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      long long v = r[q];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (x == 0) s[int64_t(b) * 32 + y0 + 8 * q] = v;
+    }
+  } else {
+    long long c = 0;
+    for (int bi = b + 1; bi < tiles32; ++bi)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) c += G[(int64_t(bi) * 32 + y0 + 8 * q) * ldg + int64_t(b) * 32 + x];
+    red[y0][x] = c;
+    __syncthreads();
+    if (y0 == 0) {
+      long long t = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += red[q][x];
+      s[int64_t(b) * 32 + x] += t;   // after pass 0 on the same stream
+    }
+  }
+}
+
+// K_ij and K_ji from the lower tile (i in block-row bi, j in block-column bj): exact int64 numerator, one fp64 division;
+// the (j, i) entry is written as read (contiguous along j), the (i, j) entry through a shared-memory transpose.
+__global__ void vanraden_epilogue_lower_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n,
+                                               const long long* __restrict__ s, const unsigned long long* __restrict__ sums,
+                                               double* __restrict__ K) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bj > bi) return;
+  __shared__ double tile[32][33];
   const long long sum_c = static_cast<long long>(sums[0]);
   const long long sum_c2 = static_cast<long long>(sums[1]);
   const long long n2 = static_cast<long long>(sums[2]);
@@ -221,13 +260,28 @@ __global__ void vanraden_epilogue_kernel(const int32_t* __restrict__ G, int64_t 
   // remove the all-2 columns (GAPIT.kinship.VanRaden.R:11-13)
   const long long c2 = sum_c2 - n2 * 4 * nn * nn;
   const long long c1 = sum_c - n2 * 2 * nn;
-  const long long D = 2 * nn * c1 - c2;
-  const long long si = s[i] - 4 * n2 * nn;
-  for (int64_t j = blockIdx.y; j < n; j += gridDim.y) {
-    const long long g = static_cast<long long>(G[j * ldg + i]) - 4 * n2;  // symmetric: read along the row
-    const long long sj = s[j] - 4 * n2 * nn;
-    const long long num = nn * nn * g - nn * (si + sj) + c2;
-    K[i + j * n] = 2.0 * static_cast<double>(num) / static_cast<double>(D);
+  const double D = static_cast<double>(2 * nn * c1 - c2);
+  const int x = threadIdx.x, y0 = threadIdx.y;
+  const int64_t j = int64_t(bj) * 32 + x;
+  const long long sj = (j < n) ? s[j] - 4 * n2 * nn : 0;
+  for (int y = y0; y < 32; y += 8) {
+    const int64_t i = int64_t(bi) * 32 + y;
+    double v = 0.0;
+    if (i < n && j < n) {
+      const long long g = static_cast<long long>(G[i * ldg + j]) - 4 * n2;
+      const long long si = s[i] - 4 * n2 * nn;
+      const long long num = nn * nn * g - nn * (si + sj) + c2;
+      v = 2.0 * static_cast<double>(num) / D;
+      K[j + i * n] = v;                                  // element (j, i): contiguous along j
+    }
+    tile[y][x] = v;
+  }
+  if (bi == bj) return;                                  // the diagonal tile wrote both orientations already
+  __syncthreads();
+  const int64_t i2 = int64_t(bi) * 32 + x;               // now x runs along i
+  for (int y = y0; y < 32; y += 8) {
+    const int64_t j2 = int64_t(bj) * 32 + y;
+    if (i2 < n && j2 < n) K[i2 + j2 * n] = tile[x][y];   // element (i, j): contiguous along i
   }
 }
 
@@ -517,15 +571,21 @@ extern "C" int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, 
   const int64_t ldg = gapit_gram_ld(n);
   long long* s = nullptr;
   double* K_dev = K_dev_out;
-  GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n), &s));                       // arena: no leak on the error paths below
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n) + 32, &s));                  // arena: no leak on the error paths below
   if (!K_dev) GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(n) * n, &K_dev));
   {
-    dim3 grid(static_cast<unsigned>(ldg / 32), static_cast<unsigned>(ldg / 32));
-    gram_mirror_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg);
-    gram_rowsum_kernel<<<static_cast<unsigned>((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(G_dev, ldg, n, s);
-    dim3 g2(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(std::min<int64_t>(n, 65535)));
-    vanraden_epilogue_kernel<<<g2, 256, 0, ctx->stream>>>(G_dev, ldg, n, s,
-                                                           reinterpret_cast<const unsigned long long*>(sums_dev), K_dev);
+    // everything from the lower triangle the Gram kernel (and the row gather of the sharded form) left: the row sums,
+    // then both orientations of every K entry; the int32 matrix itself is mirrored only when the caller asks for it
+    const unsigned t32 = static_cast<unsigned>((n + 31) / 32);
+    dim3 grid(t32, t32);
+    gram_sums_lower_kernel<<<t32, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg, static_cast<int>(t32), 0, s);
+    gram_sums_lower_kernel<<<t32, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg, static_cast<int>(t32), 1, s);
+    vanraden_epilogue_lower_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(
+        G_dev, ldg, n, s, reinterpret_cast<const unsigned long long*>(sums_dev), K_dev);
+    if (G_host_out) {
+      dim3 gm(static_cast<unsigned>(ldg / 32), static_cast<unsigned>(ldg / 32));
+      gram_mirror_kernel<<<gm, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg);
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess && K_host_out)

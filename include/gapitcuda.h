@@ -146,7 +146,9 @@ int gapit_vanraden(gapit_ctx* ctx, gapit_geno* g, double* K_out, int32_t* G_out)
  * (gapit_gram_ld(n)^2 int32, zeroed by the call) and 3 int64 partial scalars
  * {sum c, sum c^2, #all-2 columns} into sums_dev (device); the caller sums both
  * across ranks (ncclAllReduce, integer => bit-identical for any rank count)
- * and any rank finishes. */
+ * and any rank finishes.  Only the LOWER triangle of G_dev (by 256 x 256 tiles) is computed and read; the finish call
+ * writes K to K_dev_out (device, may be NULL) and / or K_host_out, and mirrors G_dev into a full symmetric matrix only
+ * when G_host_out is asked for. */
 int64_t gapit_gram_ld(int64_t n);
 int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev, int64_t* sums_dev);
 int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, const int64_t* sums_dev, double* K_dev_out,

@@ -774,15 +774,19 @@ def test_large_taxa_shapes(gpu_ctx):
     _lib.check(lib.gapit_vanraden_finish(gpu_ctx.h, n, G_t.data_ptr(), sums.data_ptr(), K_t.data_ptr(), None, None))
     cs, cq = geno.colsums()
     c = cs.astype(np.int64)
-    assert int(G_t[:n, :n].to(torch.int64).sum().item()) == int((c * c).sum())
-    assert int(torch.diagonal(G_t[:n, :n]).to(torch.int64).sum().item()) == int(cq.astype(np.int64).sum())
+    Gl = torch.tril(G_t[:n, :n]).to(torch.int64)
+    dg = torch.diagonal(G_t[:n, :n]).to(torch.int64).sum().item()
+    assert 2 * int(Gl.sum().item()) - int(dg) == int((c * c).sum())               # sum over the full symmetric matrix
+    del Gl
+    assert int(dg) == int(cq.astype(np.int64).sum())
     for lo in (0, 24900, 49700):                     # first, middle and last tile bands
         sub = G[:, lo:lo + 300].astype(np.int64)
-        assert np.array_equal(G_t[lo:lo + 300, lo:lo + 300].cpu().numpy(), sub.T @ sub)
+        assert np.array_equal(np.tril(G_t[lo:lo + 300, lo:lo + 300].cpu().numpy()), np.tril(sub.T @ sub))
     a = G[:, 100:200].astype(np.int64)
     b = G[:, 49000:49100].astype(np.int64)
-    assert np.array_equal(G_t[49000:49100, 100:200].cpu().numpy(), b.T @ a)
-    assert np.array_equal(G_t[100:200, 49000:49100].cpu().numpy(), a.T @ b)      # mirrored upper part
+    assert np.array_equal(G_t[49000:49100, 100:200].cpu().numpy(), b.T @ a)      # lower triangle (the upper one is not formed)
+    Ksub = K_t[49000:49100, 100:200].cpu().numpy()                                # K is written in both orientations
+    assert np.array_equal(Ksub, K_t[100:200, 49000:49100].cpu().numpy().T)
     assert K_t.sum(dim=1).abs().max().item() < 1e-7
     del G_t, K_t, geno
     torch.cuda.empty_cache()
@@ -1008,3 +1012,22 @@ def test_emmaxp3d_with_several_rows_of_ys_shares_one_rotation(gpu_ctx):
     last = gb().GAPIT_EMMAxP3D(Yt[:, g - 1], G.T, K, X0=X0, CVI=CVI, ctx=gpu_ctx, eig_L=eL)
     assert many["vgs"] == pytest.approx(last["vgs"], rel=1e-12) and many["REMLs"] == pytest.approx(last["REMLs"], rel=1e-12)
     assert np.allclose(many["BLUP"], last["BLUP"], rtol=1e-9, atol=1e-12) and np.allclose(many["effect.cv"], last["effect.cv"])
+
+
+def test_eigh_mg_entry_agrees_with_the_one_gpu_solver(gpu_ctx):
+    """gapit_eigh_mg (eigen(K) of the R shim): on one GPU -- or in a process that cannot load the multi-GPU solver, like
+    this one, which carries PyTorch's libcublas -- it must fall through to the one-GPU syevd and give the same answer."""
+    import ctypes as C
+    from gapit_b200 import _lib
+    rng = np.random.default_rng(3)
+    n = 2500                                     # above the 2,048 threshold of the multi-GPU route
+    A = rng.normal(size=(n, n + 50))
+    K = np.asfortranarray(A @ A.T / (n + 50))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    v1, V1 = np.empty(n), np.empty((n, n), order="F")
+    v2, V2 = np.empty(n), np.empty((n, n), order="F")
+    _lib.check(gpu_ctx.lib.gapit_eigh(gpu_ctx.h, P(K), n, P(v1), P(V1)))
+    _lib.check(gpu_ctx.lib.gapit_eigh_mg(gpu_ctx.h, P(K), n, P(v2), P(V2), 0))
+    assert np.all(np.diff(v2) <= 1e-12) and np.allclose(v1, v2, rtol=0, atol=1e-11 * v1[0])
+    idx = [0, 1, n // 2, n - 1]
+    assert np.abs(K @ V2[:, idx] - V2[:, idx] * v2[idx]).max() < 1e-10 * v1[0]

@@ -315,3 +315,46 @@ def test_compress_oracle_general_grouping_properties():
     for a in range(6):
         for b in range(6):
             assert KG[a, b] == pytest.approx(K[np.ix_(g == a + 1, g == b + 1)].mean(), rel=1e-12)
+
+
+# ---- host-side pieces of the file formats: no GPU needed -------------------------------
+def test_bed_header_and_text_indexing_on_the_host():
+    import ctypes as C
+    from gapit_b200 import _lib
+    lib = _lib.load()
+    m, off = C.c_int64(), C.c_int64()
+    bed = bytes([0x6C, 0x1B, 0x01]) + bytes(3 * 7)                  # n = 10 samples -> 3 bytes per variant, 7 variants
+    assert lib.gapit_bed_header(bed, len(bed), 10, C.byref(m), C.byref(off)) == 0 and (m.value, off.value) == (7, 3)
+    assert lib.gapit_bed_header(bed, len(bed), 9, C.byref(m), C.byref(off)) == 0 and m.value == 7     # ceil(9/4) = 3 too
+    assert lib.gapit_bed_header(bed, len(bed), 16, C.byref(m), C.byref(off)) != 0                     # 21 is no multiple of 4
+    assert b"whole number" in lib.gapit_last_error()
+    assert lib.gapit_bed_header(bytes([0x6C, 0x1B, 0x00]) + bytes(21), 24, 10, C.byref(m), None) != 0
+    assert b"sample-major" in lib.gapit_last_error()
+    assert lib.gapit_bed_header(b"abc" + bytes(21), 24, 10, C.byref(m), None) != 0
+    assert b"magic" in lib.gapit_last_error()
+    text = b"taxa m1 m2 m3\nA 0 1 2\r\nB\t2\t1\tNA\n\nC,1,1,0"       # final line without newline, one blank line
+    nl = C.c_int64()
+    assert lib.gapit_text_index_lines(text, len(text), None, 0, C.byref(nl)) == 0 and nl.value == 5
+    offs = (C.c_int64 * (nl.value + 1))()
+    assert lib.gapit_text_index_lines(text, len(text), offs, nl.value + 1, C.byref(nl)) == 0
+    assert list(offs) == [0, 14, 23, 32, 33, len(text)]
+    assert lib.gapit_text_index_lines(text, len(text), offs, 3, C.byref(nl)) != 0                      # array too small
+    n, mm = C.c_int64(), C.c_int64()
+    assert lib.gapit_numtext_shape(text, len(text), offs, nl.value, 1, C.byref(n), C.byref(mm)) == 0
+    assert (n.value, mm.value) == (4, 3)      # the blank line in the middle is a row (and will be rejected as ragged)
+    t2 = b"taxa m1 m2\nA 0 1\nB 2 2\n\n\n"
+    assert lib.gapit_text_index_lines(t2, len(t2), None, 0, C.byref(nl)) == 0
+    offs2 = (C.c_int64 * (nl.value + 1))()
+    lib.gapit_text_index_lines(t2, len(t2), offs2, nl.value + 1, C.byref(nl))
+    assert lib.gapit_numtext_shape(t2, len(t2), offs2, nl.value, 1, C.byref(n), C.byref(mm)) == 0
+    assert (n.value, mm.value) == (2, 2)      # trailing blank lines are not taxa
+
+
+def test_oracle_file_format_readers():
+    from oracle import gapit_oracle as go
+    n, rows = 6, [0b11_10_01_00, 0b00_11]      # sample 0: 00 (hom A1), 1: 01 (missing), 2: 10 (het), 3: 11 (hom A2), 4: 11, 5: 00
+    bed = bytes([0x6C, 0x1B, 0x01] + rows)
+    assert go.read_bed(bed, n, "A1").T.tolist() == [[2, -1, 1, 0, 0, 2]]
+    assert go.read_bed(bed, n, "A2").T.tolist() == [[0, -1, 1, 2, 2, 0]]
+    GD, GT, names = go.read_numeric_text(b"taxa\tm1\tm2\nA 0 1.0\nB,NA,2\n")
+    assert GT == ["A", "B"] and names == ["m1", "m2"] and GD[0].tolist() == [0.0, 1.0] and np.isnan(GD[1, 0]) and GD[1, 1] == 2.0

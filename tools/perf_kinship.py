@@ -31,13 +31,13 @@ for rep in range(3):
           f"gram call {1e3*(t1-t0):.1f} ms, epilogue {1e3*(t2-t1):.1f} ms", flush=True)
 cs, cq = geno.colsums()
 c = cs.astype(np.int64)
-tot = int(G_t[:n, :n].to(torch.int64).sum().item())
 tr = int(torch.diagonal(G_t[:n, :n]).to(torch.int64).sum().item())
+tot = 2 * int(torch.tril(G_t[:n, :n]).sum(dtype=torch.int64).item()) - tr      # only the lower triangle is formed
 print("sum G == sum c^2:", tot == int((c * c).sum()), " trace G == sum x^2:", tr == int(cq.astype(np.int64).sum()))
-sym = bool(torch.equal(G_t[:4096, :4096], G_t[:4096, :4096].T))
+sym = bool(torch.equal(K_t[:4096, :4096], K_t[:4096, :4096].T))
 sub = G[:, -300:].astype(np.float64)   # last taxa: exercises the last tile band (fp64 BLAS: exact below 2^53)
 ref = (sub.T @ sub).astype(np.int64)
 got = G_t[n - 300:n, n - 300:n].cpu().numpy()
-print("symmetric block:", sym, " last 300x300 block exact:", np.array_equal(got, ref))
+print("K symmetric block:", sym, " last 300x300 block (lower) exact:", np.array_equal(np.tril(got), np.tril(ref)))
 rs = K_t.sum(dim=1).abs().max().item()
 print("max |K 1| =", rs, " K[0,0] =", K_t[0, 0].item())
