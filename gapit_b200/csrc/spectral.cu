@@ -74,42 +74,25 @@ __global__ void swap_cols_kernel(double* __restrict__ A, int64_t n) {
 }
 
 // in-place syevd on a device matrix; eigenvalues (ascending) into w_dev.  The 64-bit API (cusolverDnXsyevd) has no
-// 32-bit workspace limit; GAPIT_SYEVD=legacy selects the int-indexed cusolverDnDsyevd (n <= 46,000) for A/B timing.
+// 32-bit workspace limit on n.
 int syevd_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* w_dev) {
   GAPIT_CHECK(ensure_solver(ctx));
-  const char* ev = getenv("GAPIT_SYEVD");
-  const bool legacy = ev && std::string(ev) == "legacy";
   int* info = nullptr;
   void* work = nullptr;
   std::vector<char> hwork;
-  cusolverStatus_t st;
   cusolverDnParams_t params = nullptr;
   GAPIT_CUDA(cudaMalloc(&info, 4));
-  if (legacy) {
-    if (n > 46000) {
-      cudaFree(info);
-      return fail(GAPIT_ERR_ARG, "eigh: n above the 32-bit cuSOLVER workspace limit");
-    }
-    int lwork = 0;
-    st = cusolverDnDsyevd_bufferSize(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, int(n), A_dev, int(n),
-                                     w_dev, &lwork);
-    if (st == CUSOLVER_STATUS_SUCCESS && cudaMalloc(&work, size_t(lwork) * 8) != cudaSuccess) st = CUSOLVER_STATUS_ALLOC_FAILED;
-    if (st == CUSOLVER_STATUS_SUCCESS)
-      st = cusolverDnDsyevd(ctx->solver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, int(n), A_dev, int(n), w_dev,
-                            static_cast<double*>(work), lwork, info);
-  } else {
-    size_t dbytes = 0, hbytes = 0;
-    st = cusolverDnCreateParams(&params);
-    if (st == CUSOLVER_STATUS_SUCCESS)
-      st = cusolverDnXsyevd_bufferSize(ctx->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F,
-                                       A_dev, n, CUDA_R_64F, w_dev, CUDA_R_64F, &dbytes, &hbytes);
-    if (st == CUSOLVER_STATUS_SUCCESS && cudaMalloc(&work, std::max<size_t>(dbytes, 16)) != cudaSuccess)
-      st = CUSOLVER_STATUS_ALLOC_FAILED;
-    if (st == CUSOLVER_STATUS_SUCCESS) {
-      hwork.resize(std::max<size_t>(hbytes, 16));
-      st = cusolverDnXsyevd(ctx->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A_dev, n,
-                            CUDA_R_64F, w_dev, CUDA_R_64F, work, dbytes, hwork.data(), hbytes, info);
-    }
+  size_t dbytes = 0, hbytes = 0;
+  cusolverStatus_t st = cusolverDnCreateParams(&params);
+  if (st == CUSOLVER_STATUS_SUCCESS)
+    st = cusolverDnXsyevd_bufferSize(ctx->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F,
+                                     A_dev, n, CUDA_R_64F, w_dev, CUDA_R_64F, &dbytes, &hbytes);
+  if (st == CUSOLVER_STATUS_SUCCESS && cudaMalloc(&work, std::max<size_t>(dbytes, 16)) != cudaSuccess)
+    st = CUSOLVER_STATUS_ALLOC_FAILED;
+  if (st == CUSOLVER_STATUS_SUCCESS) {
+    hwork.resize(std::max<size_t>(hbytes, 16));
+    st = cusolverDnXsyevd(ctx->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F, A_dev, n,
+                          CUDA_R_64F, w_dev, CUDA_R_64F, work, dbytes, hwork.data(), hbytes, info);
   }
   int hinfo = -1;
   cudaError_t e = cudaMemcpyAsync(&hinfo, info, 4, cudaMemcpyDeviceToHost, ctx->stream);

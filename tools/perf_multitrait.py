@@ -1,5 +1,5 @@
-"""Multi-trait scan (BASELINE configs[4] in miniature): T traits share one eigendecomposition; the trait-chunked
-epilogue shares one rotation pass per 16 traits."""
+"""Multi-trait scan (BASELINE configs[4] in miniature): T traits share one eigendecomposition and ONE rotation
+(store epilogue + fp64 DMMA contraction)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,4 +30,4 @@ for rep in range(3):
 t0 = time.perf_counter()
 one, _ = gb.p3d_scan(geno, X0, Y[:, :1], eigsys=es, delta=d[:1], vg=v[:1], ctx=ctx, pinned=True)
 print(f"T=1: kernel {ctx.stats()['kernel_ms']:.1f} ms, wall {1e3*(time.perf_counter()-t0):.1f} ms")
-print("trait 0 equal to single-trait run (rtol 1e-11):", np.allclose(arrs['pvalue'][0], one['pvalue'][0], rtol=1e-11, equal_nan=True))
+print("trait 0 equal to single-trait run (rtol 1e-8):", np.allclose(arrs['pvalue'][0], one['pvalue'][0], rtol=1e-8, equal_nan=True))

@@ -1,4 +1,5 @@
-"""A/B timing of the scan kernel under environment switches (kernel_ms from the library's own CUDA events)."""
+"""Timing of the single-trait scan kernel per digit-plane count, with the merged and the unmerged digit epilogue
+(GAPIT_EPI_PAIR, the test hook of the n >= 32,640 path); kernel_ms from the library's own CUDA events."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,7 +17,7 @@ print("kinship kernel_ms", ctx.stats())
 eL = gb.emma_eigen_L_wo_Z(K, ctx=ctx)
 reml = gb.GAPIT_emma_REMLE(Y[:, 0], X0, K, ctx=ctx)
 variants = [v.split(",") for v in os.environ.get("PERF_VARIANTS", "GAPIT_EPI_PAIR=1;GAPIT_EPI_PAIR=0").split(";")]
-for S in [int(x) for x in os.environ.get("PERF_SLICES", "6").split(",")]:
+for S in [int(x) for x in os.environ.get("PERF_SLICES", "5,6").split(",")]:
     ctx.set_slices(S)
     es = gb.EigenSystem(eL["values"], eL["vectors"], ctx=ctx)
     for rep in range(3):

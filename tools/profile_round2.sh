@@ -1,7 +1,7 @@
 #!/bin/bash
-# round-2 profile evidence on one GPU (each capture only after the plain command exited 0)
+# Round-2 profile evidence on one GPU (run through gpurun; each capture only after the plain command exited 0).
+# Outputs land in gpurun_out/; tools/ncu_traffic.py and the summaries under profiles/ are made from the raw CSVs.
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q > gpurun_out/r2i_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2i_pytest.log; tail -6 gpurun_out/r2i_pytest.log
 CMD="python bench.py --steps 2 --warmup 3 --no-legs --no-cpu-baseline --no-e2e"
 $CMD > gpurun_out/r2i_bench_plain.json.log 2>&1 || { echo "plain bench failed"; tail -5 gpurun_out/r2i_bench_plain.json.log; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(?!.*(sytrd|syherk|transpose|stedc|steqr|lansy|copy_info|xx_set|laed|larf|ormtr|gemm|cutlass|elementwise|reduce_kernel)).*$" -c 200 --csv --log-file gpurun_out/r2_launches_c2.csv $CMD > gpurun_out/r2i_ncu1.log 2>&1
