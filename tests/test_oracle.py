@@ -243,3 +243,31 @@ def test_golden_ingest_reproduces(ingest_golden):
     X = g["GD2_Major_0"].astype(np.float64)
     assert np.array_equal(go.kinship_zhang(X), g["zhang"])
     assert np.allclose(go.prcomp(X)[1], g["pca_ev"], rtol=1e-12, atol=1e-12)
+
+
+def test_batched_derivation_agrees_with_the_per_marker_loop():
+    """oracle/batched.py (one dgemm V'X + closed-form bordered solve) against the restated per-marker loop, MLM and GLM:
+    two independent routes to the same table -- the batched one is what checks thousands of markers at n = 5,000 and
+    20,000 in the GPU tests and in bench.py's in-run parity block."""
+    from oracle import batched
+    from gapit_b200 import synth
+    n, m = 240, 400
+    G = synth.make_genotypes(n, m, seed=3)
+    G[7] = 2                                    # a constant marker
+    Y = synth.make_phenotypes(G)[:, 0]
+    X0 = synth.make_covariates(G, npc=2)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    reml = go.emma_REMLE(Y, X0, K)
+    ora = go.emmax_p3d(Y, G.T, K, X0, eig_L=eL, reml=reml)
+    blk = batched.p3d_block(Y, G.T, X0, eL["values"], eL["vectors"], reml["delta"], reml["vg"])
+    c = batched.compare({"effect": ora.effect_est, "se": ora.se_clean, "tvalue": ora.stats, "pvalue": ora.ps}, blk)
+    assert c["nan_rows_identical"] and c["n_tested"] == m - 1
+    assert c["beta_rel_max"] < 1e-10 and c["se_rel_max"] < 1e-13 and c["dlog10p_max"] < 1e-10
+    ok = ~np.isnan(ora.stats)
+    assert np.max(np.abs(ora.rsquare[ok] - blk["rsquare"][ok])) < 1e-13
+    assert np.max(np.abs(ora.logLM[ok] - blk["loglm"][ok])) < 1e-9
+    og = go.emmax_p3d(Y, G.T, None, X0)
+    bg = batched.p3d_block(Y, G.T, X0, glm=True)
+    c = batched.compare({"effect": og.effect_est, "se": og.se_clean, "tvalue": og.stats, "pvalue": og.ps}, bg)
+    assert c["nan_rows_identical"] and c["beta_rel_max"] < 1e-10 and c["se_rel_max"] < 1e-13 and c["dlog10p_max"] < 1e-10
