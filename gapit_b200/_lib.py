@@ -57,6 +57,8 @@ SIGNATURES = {
     "gapit_geno_pack": (C.c_int, [_P, _P, C.c_int, _I64, _I64, _I64, C.c_int, C.POINTER(_P)]),
     "gapit_pack2_host": (C.c_int, [_P, C.c_int, _I64, _I64, _I64, _P, C.c_int]),
     "gapit_geno_from_device": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(_P)]),
+    "gapit_geno_wrap_device": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(_P)]),
+    "gapit_geno_select_taxa": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),
     "gapit_geno_free": (None, [_P]),
     "gapit_geno_n": (_I64, [_P]),
     "gapit_geno_m": (_I64, [_P]),

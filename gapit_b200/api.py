@@ -182,6 +182,28 @@ class Genotypes:
         self.h, self.n, self.m = h, int(n), int(m)
         return self
 
+    @classmethod
+    def wrap_device(cls, data_ptr, n, m, ctx=None, keepalive=None):
+        """Zero-copy: int8 dosages already on the device in the library's own layout -- marker k at data_ptr + k*ld with
+        ld = n rounded up to 128, e.g. a contiguous (m, ld) torch.int8 CUDA tensor whose first n columns hold the data.
+        The memory stays the caller's; ``keepalive`` (the tensor) is held by the handle."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        ld = (int(n) + 127) // 128 * 128
+        h = C.c_void_p()
+        check(self.ctx.lib.gapit_geno_wrap_device(self.ctx.h, C.c_void_p(int(data_ptr)), int(n), int(m), ld, C.byref(h)))
+        self.h, self.n, self.m, self._keepalive = h, int(n), int(m), keepalive
+        return self
+
+    def select_taxa(self, GTindex):
+        """``GD[GTindex,]`` (GAPIT.EMMAxP3D.R:315): a new handle with the taxa ``GTindex`` (0-based) in that order."""
+        idx = np.ascontiguousarray(GTindex, dtype=np.int64).reshape(-1)
+        out = Genotypes.__new__(Genotypes)
+        h = C.c_void_p()
+        check(self.ctx.lib.gapit_geno_select_taxa(self.ctx.h, self.h, _ptr(idx), idx.shape[0], C.byref(h)))
+        out.ctx, out.h, out.n, out.m = self.ctx, h, int(idx.shape[0]), self.m
+        return out
+
     def colsums(self):
         cs = np.empty(self.m, dtype=np.int32)
         cq = np.empty(self.m, dtype=np.int32)
@@ -318,12 +340,13 @@ def GAPIT_HapMap(G, SNP_effect="Add", SNP_impute="Middle", heading=True, Create_
 
 
 def p3d_scan_hapmap(G, X0, Y, eigsys=None, delta=None, vg=None, glm=False, file_fragment=65536, SNP_effect="Add",
-                    SNP_impute="Middle", Major_allele_zero=False, heading=True, ctx=None):
+                    SNP_impute="Middle", Major_allele_zero=False, heading=True, ctx=None, GTindex=None):
     """The by-file branch of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:262-330) on a HapMap file: fragments of
     ``file_fragment`` markers (GAPIT.Fragment.R:14-77) are numericalized on the GPU straight from the text
     (GAPIT.HapMap.R:34-38) and scanned with the shared eigen-system and variance components; nothing but the file text
-    crosses PCIe.  ``G``: bytes of the table or a path.  Taxa must be in the order of ``Y`` (the reference's
-    ``GTindex`` re-ordering is the caller's).  Returns (arrays (T, m), per-trait bases, GT, GI)."""
+    crosses PCIe.  ``G``: bytes of the table or a path.  ``GTindex`` (0-based taxa of the file, in phenotype order) is the
+    reference's ``xs = myFRG$GD[GTindex,]`` (:315), applied on the device; without it the file's taxa must already be in
+    the order of ``Y``.  Returns (arrays (T, m), per-trait bases, GT, GI)."""
     ctx = ctx or default_context()
     if isinstance(G, str):
         with open(G, "rb") as f:
@@ -337,7 +360,8 @@ def p3d_scan_hapmap(G, X0, Y, eigsys=None, delta=None, vg=None, glm=False, file_
     check(lib.gapit_hapmap_index(_ptr(buf), buf.shape[0], 1 if heading else 0, C.byref(n), C.byref(m), C.byref(bit),
                                  _ptr(off), m.value, C.byref(hoff)))
     n, m, bit = n.value, m.value, bit.value
-    Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n, -1))
+    n_scan = n if GTindex is None else len(GTindex)
+    Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n_scan, -1))
     T = Y.shape[1]
     names = ("effect", "tvalue", "se", "pvalue", "rsquare", "loglm")
     arrs = {k: np.empty((T, m)) for k in names}
@@ -347,6 +371,10 @@ def p3d_scan_hapmap(G, X0, Y, eigsys=None, delta=None, vg=None, glm=False, file_
         k1 = min(m, k0 + int(file_fragment))
         _, geno = _numericalize(ctx, G, off[k0:k1], bit, bit + 1, n, k1 - k0, SNP_effect, SNP_impute, Major_allele_zero,
                                 False, True)
+        if GTindex is not None:
+            sel = geno.select_taxa(GTindex)
+            geno.close()
+            geno = sel
         part, bases = p3d_scan(geno, X0, Y, eigsys=eigsys, delta=delta, vg=vg, glm=glm, ctx=ctx)
         geno.close()
         for k in names:
@@ -418,20 +446,42 @@ def GAPIT_numeric_text(GD, heading=True, SNP_impute=None, ctx=None, want_gd=True
 
 
 def p3d_scan_file(genotypes, X0, Y, eigsys=None, delta=None, vg=None, glm=False, SNP_impute="Middle", ctx=None,
-                  genoFormat=None, count="A1"):
+                  genoFormat=None, count="A1", GTindex=None):
     """The by-file branch of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:259-331 over GAPIT.Fragment.R) for the two file formats
     beside HapMap: a PLINK prefix (``genoFormat="bed"``: the memory-mapped .bed streams through the scan in marker
     blocks, file bytes uploaded as they are, upload overlapped with the scan) or GAPIT's numeric text
-    (``genoFormat="EMMA"``: parsed on the GPU, then scanned resident).  Taxa must be in the order of ``Y`` (the
-    reference's GTindex re-ordering is the caller's).  Returns (arrays (T, m), per-trait bases, GT, GI or marker names)."""
+    (``genoFormat="EMMA"``: parsed on the GPU, then scanned resident).  ``GTindex`` (0-based taxa of the file in
+    phenotype order) applies the reference's ``GD[GTindex,]`` (:315) on the device (the .bed is then packed resident in
+    marker blocks instead of streamed).  Returns (arrays (T, m), per-trait bases, GT, GI or marker names)."""
     ctx = ctx or default_context()
     if genoFormat is None:
         genoFormat = "bed" if isinstance(genotypes, str) and os.path.exists(genotypes + ".bed") else "EMMA"
     if genoFormat == "bed":
         rows, GT, GI, _ = read_plink(genotypes, count=count)
-        arrs, bases = p3d_scan_host(rows, X0, Y, eigsys=eigsys, delta=delta, vg=vg, glm=glm, ctx=ctx, impute=SNP_impute)
+        if GTindex is None:
+            arrs, bases = p3d_scan_host(rows, X0, Y, eigsys=eigsys, delta=delta, vg=vg, glm=glm, ctx=ctx, impute=SNP_impute)
+            return arrs, bases, GT, GI
+        Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(len(GTindex), -1))
+        arrs, bases = alloc_scan_out(Y.shape[1], rows.m, pinned=False), None
+        frag = 65536                                              # marker blocks, as GAPIT.Fragment reads them
+        for k0 in range(0, rows.m, frag):
+            k1 = min(rows.m, k0 + frag)
+            full = Genotypes(Packed2(rows.data[k0:k1], rows.n, dtype=rows.dtype), ctx=ctx, impute=SNP_impute)
+            geno = full.select_taxa(GTindex)
+            full.close()
+            part, bases = p3d_scan(geno, X0, Y, eigsys=eigsys, delta=delta, vg=vg, glm=glm, ctx=ctx)
+            geno.close()
+            for k in part:
+                if k == "maf":
+                    arrs[k][k0:k1] = part[k]
+                else:
+                    arrs[k][:, k0:k1] = part[k]
         return arrs, bases, GT, GI
     _, GT, names, geno = GAPIT_numeric_text(genotypes, SNP_impute=SNP_impute, ctx=ctx, want_gd=False, want_geno=True)
+    if GTindex is not None:
+        sel = geno.select_taxa(GTindex)
+        geno.close()
+        geno = sel
     arrs, bases = p3d_scan(geno, X0, Y, eigsys=eigsys, delta=delta, vg=vg, glm=glm, ctx=ctx)
     geno.close()
     return arrs, bases, GT, names

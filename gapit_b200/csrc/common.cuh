@@ -85,6 +85,7 @@ inline int ctx_ws_t(gapit_ctx* ctx, int slot, size_t count, T** out) {
 struct gapit_geno {
   gapit_ctx* ctx = nullptr;
   int device = 0;         // for the free path: the handle may outlive its context
+  bool borrowed = false;  // mk belongs to the caller (gapit_geno_wrap_device)
   int64_t n = 0;      // taxa
   int64_t m = 0;      // markers
   int64_t ldn = 0;    // bytes per marker row of the marker-major copy (multiple of 128)

@@ -350,10 +350,81 @@ extern "C" int gapit_geno_from_device(gapit_ctx* ctx, const int8_t* mk_dev, int6
   return GAPIT_OK;
 }
 
+// Zero-copy form: the caller already holds the dosages in the device layout (marker k at mk_dev + k*ld, ld = n rounded up
+// to 128, 128-byte aligned) and keeps ownership; the bytes n..ld of every row are zeroed here, the statistics computed.
+extern "C" int gapit_geno_wrap_device(gapit_ctx* ctx, int8_t* mk_dev, int64_t n, int64_t m, int64_t ld, gapit_geno** out) {
+  if (!ctx || !mk_dev || !out || n <= 0 || m <= 0 || ld != round_up(n, 128) || (reinterpret_cast<uintptr_t>(mk_dev) & 127))
+    return fail(GAPIT_ERR_ARG, "gapit_geno_wrap_device: needs ld = n rounded up to 128 and a 128-byte aligned pointer");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  gapit_geno* g = new gapit_geno();
+  g->ctx = ctx;
+  g->device = ctx->device;
+  g->n = n;
+  g->m = m;
+  g->ldn = ld;
+  g->mk = mk_dev;
+  g->borrowed = true;
+  cudaError_t e = cudaMalloc(&g->colsum, size_t(m) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&g->colsumsq, size_t(m) * 4);
+  if (e == cudaSuccess && ld != n) e = cudaMemset2DAsync(mk_dev + n, size_t(ld), 0, size_t(ld - n), size_t(m), ctx->stream);
+  const int rc = (e == cudaSuccess) ? run_colstats(g)
+                                    : fail(GAPIT_ERR_CUDA, std::string("gapit_geno_wrap_device: ") + cudaGetErrorString(e));
+  if (rc != GAPIT_OK) {
+    gapit_geno_free(g);
+    return rc;
+  }
+  *out = g;
+  return GAPIT_OK;
+}
+
+// out[k][i] = in[k][index[i]]: the `GD[GTindex,]` row selection of the reference's by-file loop
+// (GAPIT.EMMAxP3D.R:315), on the marker-major device matrix.  grid (taxa chunks, markers)
+__global__ void select_taxa_kernel(const int8_t* __restrict__ src, int64_t ld_src, const int64_t* __restrict__ index,
+                                   int64_t n_new, int64_t m, int8_t* __restrict__ dst, int64_t ld_dst) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= ld_dst) return;
+  const int64_t from = i < n_new ? index[i] : -1;
+  for (int64_t k = blockIdx.y; k < m; k += gridDim.y) dst[k * ld_dst + i] = from >= 0 ? src[k * ld_src + from] : int8_t(0);
+}
+
+extern "C" int gapit_geno_select_taxa(gapit_ctx* ctx, const gapit_geno* g, const int64_t* index, int64_t n_new,
+                                      gapit_geno** out) {
+  if (!ctx || !g || !index || !out || n_new <= 0) return fail(GAPIT_ERR_ARG, "gapit_geno_select_taxa: bad argument");
+  for (int64_t i = 0; i < n_new; ++i)
+    if (index[i] < 0 || index[i] >= g->n) return fail(GAPIT_ERR_ARG, "gapit_geno_select_taxa: taxon index out of range");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  gapit_geno* h = new gapit_geno();
+  h->ctx = ctx;
+  h->device = ctx->device;
+  h->n = n_new;
+  h->m = g->m;
+  h->ldn = round_up(n_new, 128);
+  int64_t* idx_dev = nullptr;
+  cudaError_t e = cudaMalloc(&h->mk, size_t(h->m) * h->ldn);
+  if (e == cudaSuccess) e = cudaMalloc(&h->colsum, size_t(h->m) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&h->colsumsq, size_t(h->m) * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&idx_dev, size_t(n_new) * 8);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(idx_dev, index, size_t(n_new) * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    dim3 grid(static_cast<unsigned>((h->ldn + 255) / 256), static_cast<unsigned>(std::min<int64_t>(h->m, 65535)));
+    select_taxa_kernel<<<grid, 256, 0, ctx->stream>>>(g->mk, g->ldn, idx_dev, n_new, h->m, h->mk, h->ldn);
+    e = cudaGetLastError();
+  }
+  int rc = (e == cudaSuccess) ? run_colstats(h) : fail(GAPIT_ERR_CUDA, std::string("gapit_geno_select_taxa: ") + cudaGetErrorString(e));
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(idx_dev);
+  if (rc != GAPIT_OK) {
+    gapit_geno_free(h);
+    return rc;
+  }
+  *out = h;
+  return GAPIT_OK;
+}
+
 extern "C" void gapit_geno_free(gapit_geno* g) {
   if (!g) return;
   cudaSetDevice(g->device);   // never through g->ctx: host languages may destroy the context first
-  cudaFree(g->mk);
+  if (!g->borrowed) cudaFree(g->mk);
   cudaFree(g->colsum);
   cudaFree(g->colsumsq);
   delete g;

@@ -6,7 +6,8 @@ genotypes are generated on the device block by block, so no 20-50 GB host matrix
     C4  50,000 taxa x 1,000,000 SNPs:           VanRaden kinship only
     C5  10,000 taxa x 2,000,000 SNPs x 100 traits sharing one eigendecomposition (one rotation for all traits)
 
-Markers are split into contiguous blocks; rank r owns blocks r, r+N, ...  Kinship: every block's cross-product kernel
+Markers are split into contiguous blocks; rank r owns blocks r, r+N, ... and holds them in ONE resident handle, generated
+straight into the library's device layout (zero-copy `gapit_geno_wrap_device`).  Kinship: every rank's cross-product kernel
 reduce-scatters its tiles straight into the block-row owners' Gram buffers over NVLink (bulk tensor reduce-adds,
 ``gapit_vanraden_gram_fused`` with root = -1; buffers from torch symmetric memory), rank 0 gathers the rows it does not
 own (``gapit_vanraden_gram_gather``) and runs the exact epilogue.  Rank 0 runs the eigendecomposition (cuSOLVER, timed
@@ -69,10 +70,24 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
             torch.cuda.synchronize()
 
     T_ = {}
+    # ---------------- genotypes: every block of this rank, generated straight into the library's device layout ----------
+    # (one resident handle per rank: one cross-product launch and one scan call, however many blocks the rank owns;
+    # block b is generated from its own seed, so the data -- and every checksum -- do not depend on the rank count)
+    t_g = time.perf_counter()
+    ldn = (n + 127) // 128 * 128
+    m_rank = sum(bounds[b + 1] - bounds[b] for b in mine)
+    big = torch.zeros((m_rank, ldn), dtype=torch.int8, device=dev)
+    off = 0
+    for b in mine:
+        mb = bounds[b + 1] - bounds[b]
+        big[off:off + mb, :n] = gen_block(n, mb, 1000 + b, dev, pop)
+        off += mb
+    geno = gb.Genotypes.wrap_device(big.data_ptr(), n, m_rank, ctx=ctx, keepalive=big)
+    torch.cuda.synchronize()
+    T_["generate_s"] = time.perf_counter() - t_g
     # ---------------- kinship ----------------
     ldg = lib.gapit_gram_ld(n)
-    s_acc = torch.zeros(3, dtype=torch.int64, device=dev)
-    s_t = torch.empty(3, dtype=torch.int64, device=dev)
+    s_t = torch.zeros(3, dtype=torch.int64, device=dev)
     hdl = None
     if world > 1 and exchange == "fused":
         try:
@@ -85,62 +100,40 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
             hdl = None
     if hdl is None:
         G_acc = torch.zeros((ldg, ldg), dtype=torch.int32, device=dev)
-        peers = (ctypes.c_void_p * 1)(G_acc.data_ptr())
-    fused = hdl is not None or world == 1
-    G_t = None if fused else torch.empty((ldg, ldg), dtype=torch.int32, device=dev)
-    gram_ms = 0.0
-    keep = {}
     K_dev = torch.empty((n, n), dtype=torch.float64, device=dev)     # the result buffer exists before the clock starts
     sync()
-    t_gen = 0.0
     t0 = time.perf_counter()
-    if fused:
+    if hdl is not None:   # tiles go to their block-row owners inside the kernel, rank 0 gathers the rows
         G_acc.zero_()
-        if hdl is not None:
-            hdl.barrier()
-    for b in mine:
-        tg = time.perf_counter()
-        blk = gen_block(n, bounds[b + 1] - bounds[b], 1000 + b, dev, pop)
-        torch.cuda.synchronize()
-        t_gen += time.perf_counter() - tg
-        geno = gb.Genotypes.from_device(blk.data_ptr(), n, blk.shape[0], ctx=ctx)
-        del blk
-        if fused:   # blocks of one rank accumulate in place; across ranks the tiles go to their block-row owners
-            _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world if hdl is not None else 1,
-                                                     rank if hdl is not None else 0, -1 if hdl is not None else 0,
-                                                     s_t.data_ptr()))
-        else:
-            _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_t.data_ptr(), s_t.data_ptr()))
-            G_acc += G_t
-        gram_ms += ctx.stats()["kernel_ms"]
-        s_acc += s_t
-        if cfg["scan"] and len(mine) == 1:
-            keep[b] = geno           # one block per rank: keep it resident for the scan
-        else:
-            geno.close()
-    if world > 1:
+        hdl.barrier()
+        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, -1, s_t.data_ptr()))
+        gram_ms = ctx.stats()["kernel_ms"]
         ta = time.perf_counter()
-        if hdl is not None:
-            hdl.barrier()
-            if rank == 0:
-                _lib.check(lib.gapit_vanraden_gram_gather(ctx.h, n, peers, world, 0))
-                T_["gather_rows_ms"] = ctx.stats()["post_ms"]
-        else:
-            dist.all_reduce(G_acc)
-        dist.all_reduce(s_acc)
+        hdl.barrier()
+        if rank == 0:
+            _lib.check(lib.gapit_vanraden_gram_gather(ctx.h, n, peers, world, 0))
+            T_["gather_rows_ms"] = ctx.stats()["post_ms"]
+        dist.all_reduce(s_t)
         torch.cuda.synchronize()
         T_["exchange_tail_s"] = time.perf_counter() - ta
+    else:
+        _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_acc.data_ptr(), s_t.data_ptr()))
+        gram_ms = ctx.stats()["kernel_ms"]
+        if world > 1:
+            ta = time.perf_counter()
+            dist.all_reduce(G_acc)
+            dist.all_reduce(s_t)
+            torch.cuda.synchronize()
+            T_["exchange_tail_s"] = time.perf_counter() - ta
     T_["exchange"] = ("fused: tiles reduce-scattered over NVLink inside the Gram kernel, rank 0 gathers the rows"
                       if hdl is not None else ("nccl all-reduce" if world > 1 else "none"))
-    del G_t
     tf = time.perf_counter()
     if rank == 0 or hdl is None:
-        _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_acc.data_ptr(), s_acc.data_ptr(), K_dev.data_ptr(), None, None))
+        _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_acc.data_ptr(), s_t.data_ptr(), K_dev.data_ptr(), None, None))
     torch.cuda.synchronize()
     T_["kinship_epilogue_s"] = time.perf_counter() - tf
     sync()
-    T_["kinship_total_s"] = time.perf_counter() - t0 - t_gen
-    T_["generate_s"] = t_gen
+    T_["kinship_total_s"] = time.perf_counter() - t0
     gram_ms_t = torch.tensor([gram_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(gram_ms_t, op=dist.ReduceOp.MAX)
@@ -157,7 +150,8 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
     if not cfg["scan"]:
         out["timings_s"] = T_
         out["end_to_end_s"] = T_["kinship_total_s"]
-        del K_dev
+        geno.close()
+        del K_dev, big
         torch.cuda.empty_cache()
         return out
     # ---------------- spectra + REML on rank 0, broadcast (everything stays on the device) ----------------
@@ -203,41 +197,28 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
     if world > 1:
         dist.broadcast(dv_t, 0)
     delta, vg = dv_t[0].cpu().numpy(), dv_t[1].cpu().numpy()
-    # ---------------- the scan ----------------
-    scan_kernel_ms = scan_d2h_ms = 0.0
-    minp = 1.0
-    # result arrays are page-locked once, before the clock starts (1.2 GB per 250k-marker block at 100 traits)
-    sizes = {bounds[b + 1] - bounds[b] for b in mine}
-    arrs = gb.alloc_scan_out(T, sizes.pop(), pinned=True) if len(sizes) == 1 else None
+    # ---------------- the scan: one call per rank over its resident markers ----------------
+    # result arrays are page-locked once, before the clock starts (9.6 GB for 100 traits x 2,000,000 markers)
+    arrs = gb.alloc_scan_out(T, m_rank, pinned=True)
     if world > 1:   # first use of a collective sets up its NCCL channels (~1 s): not part of the scan
         w = torch.zeros(8, device=dev, dtype=torch.float64)
         dist.gather(w, [torch.empty_like(w) for _ in range(world)] if rank == 0 else None, dst=0)
     sync()
-    t_gen = 0.0
     t1 = time.perf_counter()
-    for b in mine:
-        if b in keep:
-            geno = keep[b]
-        else:
-            tg = time.perf_counter()
-            blk = gen_block(n, bounds[b + 1] - bounds[b], 1000 + b, dev, pop)
-            geno = gb.Genotypes.from_device(blk.data_ptr(), n, blk.shape[0], ctx=ctx)
-            del blk
-            torch.cuda.synchronize()
-            t_gen += time.perf_counter() - tg
-        arrs, _ = gb.p3d_scan(geno, X0, Y, eigsys=es, delta=delta, vg=vg, ctx=ctx, pinned=True, out=arrs)
-        st = ctx.stats()
-        scan_kernel_ms += st["kernel_ms"]
-        scan_d2h_ms += st["d2h_ms"]
-        geno.close()
-    if world > 1:   # rank 0 gathers every shard's p-values of trait 0 (marker order = block order): device to device
-        p = torch.from_numpy(np.ascontiguousarray(arrs["pvalue"][0])).to(dev, non_blocking=True)
+    arrs, _ = gb.p3d_scan(geno, X0, Y, eigsys=es, delta=delta, vg=vg, ctx=ctx, pinned=True, out=arrs)
+    st = ctx.stats()
+    scan_kernel_ms, scan_d2h_ms = st["kernel_ms"] + st["post_ms"], st["d2h_ms"]
+    if world > 1:   # rank 0 gathers every shard's p-values of trait 0 (marker order = rank order within a block round)
+        mx = max((bounds[b + 1] - bounds[b]) for b in range(nblocks)) * ((nblocks + world - 1) // world)
+        p = torch.zeros(mx, dtype=torch.float64, device=dev)
+        p[:m_rank].copy_(torch.from_numpy(arrs["pvalue"][0]), non_blocking=True)
         bufs = [torch.empty_like(p) for _ in range(world)] if rank == 0 else None
         dist.gather(p, bufs, dst=0)
     sync()
-    T_["scan_total_s"] = time.perf_counter() - t1 - t_gen
-    minp = float(np.nanmin(arrs["pvalue"]))      # of the last block scanned (a consumer's read, outside the clock)
-    T_["generate_scan_blocks_s"] = t_gen
+    T_["scan_total_s"] = time.perf_counter() - t1
+    minp = float(np.nanmin(arrs["pvalue"][0]))    # a consumer's read, outside the clock
+    geno.close()
+    del big
     sk = torch.tensor([scan_kernel_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(sk, op=dist.ReduceOp.MAX)
@@ -248,7 +229,7 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
     out.update({
         "snps_per_s": m / T_["scan_total_s"], "snp_trait_tests_per_s": m * max(T, 1) / T_["scan_total_s"],
         "scan_int8_tops_per_gpu_rotation_once": 2.0 * n * n * (m / world) * S / T_["scan_kernels_s_max_rank"] / 1e12,
-        "min_p_last_block": minp, "delta_first": float(delta[0]),
+        "min_p_trait0_this_rank": minp, "delta_first": float(delta[0]),
         "end_to_end_s": T_["kinship_total_s"] + T_.get("eigh_s", 0.0) + T_.get("reml_all_traits_s", 0.0) +
                         T_["broadcast_s"] + T_["eigsys_slice_s"] + T_["scan_total_s"],
         "timings_s": T_})

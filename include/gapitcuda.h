@@ -87,6 +87,12 @@ int gapit_pack2_host(const void* snps, gapit_dtype dtype, int64_t n, int64_t m, 
  * the context's stream: either share that stream with the producer of mk_dev (gapit_ctx_set_stream) or
  * synchronise the producer first. */
 int gapit_geno_from_device(gapit_ctx* ctx, const int8_t* mk_dev, int64_t n, int64_t m, int64_t ld, gapit_geno** out);
+/* Zero-copy form of the same: mk_dev already has the library's layout (ld = n rounded up to 128, 128-byte aligned) and
+ * stays the caller's (it must outlive the handle); the padding bytes n..ld of every row are zeroed by the call. */
+int gapit_geno_wrap_device(gapit_ctx* ctx, int8_t* mk_dev, int64_t n, int64_t m, int64_t ld, gapit_geno** out);
+/* A new handle holding taxa index[0..n_new) of `g` (0-based, repeats allowed), every marker: the `GD[GTindex,]` of the
+ * reference's by-file loop (GAPIT.EMMAxP3D.R:315), which brings the taxa of a genotype file into phenotype order. */
+int gapit_geno_select_taxa(gapit_ctx* ctx, const gapit_geno* g, const int64_t* index, int64_t n_new, gapit_geno** out);
 void gapit_geno_free(gapit_geno* g);
 int64_t gapit_geno_n(const gapit_geno* g);
 int64_t gapit_geno_m(const gapit_geno* g);

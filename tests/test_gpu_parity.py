@@ -1031,3 +1031,43 @@ def test_eigh_mg_entry_agrees_with_the_one_gpu_solver(gpu_ctx):
     assert np.all(np.diff(v2) <= 1e-12) and np.allclose(v1, v2, rtol=0, atol=1e-11 * v1[0])
     idx = [0, 1, n // 2, n - 1]
     assert np.abs(K @ V2[:, idx] - V2[:, idx] * v2[idx]).max() < 1e-10 * v1[0]
+
+
+def test_by_file_scans_reorder_taxa_with_gtindex(gpu_ctx, tmp_path):
+    """`xs = myFRG$GD[GTindex,]` (GAPIT.EMMAxP3D.R:315): the genotype file holds more taxa than were phenotyped, in its
+    own order; GTindex brings them into phenotype order.  Applied on the device for HapMap text, numeric text and .bed."""
+    rng = np.random.default_rng(77)
+    G, _, _ = case(150, 500, npc=0, edge=False)                  # the file: 150 taxa
+    idx = rng.permutation(150)[:110]                              # 110 phenotyped taxa, shuffled
+    Y = rng.normal(size=110)
+    X0 = np.column_stack([np.ones(110), rng.normal(size=110)])
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    sel = geno.select_taxa(idx)
+    cs, cq = sel.colsums()
+    want = G[:, idx].astype(np.int64)
+    assert sel.n == 110 and np.array_equal(cs, want.sum(1)) and np.array_equal(cq, (want * want).sum(1))
+    with pytest.raises(gb().GapitCudaError):
+        geno.select_taxa([0, 150])
+    ref, _ = gb().p3d_scan(sel, X0, Y, glm=True, ctx=gpu_ctx)
+    # HapMap text without missing calls: the file's dosages are G up to the per-marker allele orientation, so compare
+    # against the same text scanned through a host-side reordering of its own numericalization
+    text = synth.make_hapmap_text(G, bit=2, missing=0.0)
+    GD = go.hapmap(synth.hapmap_rows(text), SNP_impute="Middle")["GD"]           # 150 x 500
+    href, _ = gb().p3d_scan_host(np.ascontiguousarray(GD[idx].T.astype(np.int8)), X0, Y, glm=True, ctx=gpu_ctx, marker_major=True)
+    hgot, _, GT, _ = gb().p3d_scan_hapmap(text, X0, Y, glm=True, file_fragment=128, ctx=gpu_ctx, GTindex=idx)
+    assert len(GT) == 150
+    for key in ("effect", "pvalue", "maf"):
+        assert np.array_equal(hgot[key], href[key], equal_nan=True), key
+    # numeric text and .bed carry G itself
+    lines = ["taxa " + " ".join(f"m{k}" for k in range(500))] + [f"t{i} " + " ".join(map(str, G[:, i])) for i in range(150)]
+    ngot, _, GT2, _ = gb().p3d_scan_file("\n".join(lines).encode(), X0, Y, glm=True, ctx=gpu_ctx, genoFormat="EMMA", GTindex=idx)
+    bed = _write_bed(G.T.astype(np.int8), "A1")
+    prefix = str(tmp_path / "g")
+    open(prefix + ".bed", "wb").write(bed)
+    open(prefix + ".fam", "w").write("".join(f"F t{i} 0 0 0 -9\n" for i in range(150)))
+    open(prefix + ".bim", "w").write("".join(f"1 m{k} 0 {k + 1} A C\n" for k in range(500)))
+    bgot, _, GT3, _ = gb().p3d_scan_file(prefix, X0, Y, glm=True, ctx=gpu_ctx, GTindex=idx)
+    assert GT2[:3] == ["t0", "t1", "t2"] and GT3 == GT2
+    for key in ("effect", "pvalue", "maf"):
+        assert np.array_equal(ngot[key], ref[key], equal_nan=True), key
+        assert np.array_equal(bgot[key], ref[key], equal_nan=True), key
