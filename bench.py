@@ -596,6 +596,12 @@ def main():
             except Exception as exc:   # a leg must not take the headline down with it
                 legs[name] = {"error": repr(exc)[:300]}
             torch.cuda.empty_cache()
+            leg = legs[name]
+            # the same denominator as `roofline.peak`: the cuBLASLt int8 ceiling measured in this run, per GPU
+            if "kinship_tops_kernel" in leg:
+                leg["kinship_kernel_frac_of_int8_ceiling"] = leg["kinship_tops_kernel"] / world / int8_peak
+            if "scan_int8_tops_per_gpu_rotation_once" in leg:
+                leg["scan_frac_of_int8_ceiling"] = leg["scan_int8_tops_per_gpu_rotation_once"] / int8_peak
         legs["scaling"] = "strong: total work of the named config fixed, markers sharded over the N ranks" if world > 1 \
             else "one GPU"
     line = {

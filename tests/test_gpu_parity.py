@@ -1071,3 +1071,33 @@ def test_by_file_scans_reorder_taxa_with_gtindex(gpu_ctx, tmp_path):
     for key in ("effect", "pvalue", "maf"):
         assert np.array_equal(ngot[key], ref[key], equal_nan=True), key
         assert np.array_equal(bgot[key], ref[key], equal_nan=True), key
+
+
+@pytest.mark.parametrize("n,m,npc,T", [(60, 200, 0, 3), (90, 256, 5, 2), (120, 700, 1, 130), (64, 300, 15, 9)])
+def test_shared_rotation_edge_shapes(gpu_ctx, n, m, npc, T):
+    """Corners of the multi-trait path: a single 256-marker tile (the one-CTA form of the main loop with the store
+    epilogue), more than 128 traits (two trait tiles of the DMMA contraction), the maximum of 16 covariate columns
+    (many back-rotated columns), n below one operand tile."""
+    G, _, X0 = case(n, m, npc=npc, seed=100 + T)
+    Yt = synth.make_phenotypes(G, ntraits=T, seed=100 + T)
+    K = go.kinship_vanraden(G.T)
+    eL = go.emma_eigen_L_wo_Z(K)
+    eR = go.emma_eigen_R_wo_Z(K, X0)
+    check_t = sorted({0, T // 2, T - 1})
+    remls = [go.emma_REMLE(Yt[:, t], X0, K, eig_R=eR) for t in range(T)]
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    es = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    arrs, bases = gb().p3d_scan(geno, X0, Yt, eigsys=es, delta=[r["delta"] for r in remls], vg=[r["vg"] for r in remls],
+                                ctx=gpu_ctx)
+    for t in check_t:
+        ora = go.emmax_p3d(Yt[:, t], G.T, K, X0, eig_L=eL, reml=remls[t])
+        ok = ~np.isnan(ora.stats)
+        assert np.array_equal(np.isnan(arrs["tvalue"][t]), ~ok)
+        r, a = rel_err(arrs["effect"][t], ora.effect_est, 1e-4)
+        assert r < BETA_RTOL, (t, r)
+        r, a = rel_err(arrs["se"][t], ora.se_clean, 0.0)
+        assert r < SE_RTOL, (t, r)
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(arrs["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
+        assert np.max(np.abs(arrs["rsquare"][t][ok] - ora.rsquare[ok])) < 1e-9
+        assert bases[t]["beta0"] == pytest.approx(ora.effect_cv, rel=1e-8, abs=1e-10)
