@@ -384,9 +384,12 @@ def main():
     if world > 1 and args.kinship_exchange == "fused":
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            G_t = symm_mem.empty((ldg, ldg), dtype=torch.int32, device=dev)
-            hdl = symm_mem.rendezvous(G_t, dist.group.WORLD)
+            flat = symm_mem.empty(ldg * ldg + 8, dtype=torch.int32, device=dev)   # Gram buffer + mailbox of the 3 scalar sums
+            hdl = symm_mem.rendezvous(flat, dist.group.WORLD)
+            G_t = flat[:ldg * ldg].view(ldg, ldg)
+            box = flat[ldg * ldg:].view(torch.int64)
             peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            boxes = (ctypes.c_void_p * world)(*[int(p) + ldg * ldg * 4 for p in hdl.buffer_ptrs])
             exchange = "fused: tiles reduce-scattered over NVLink inside the Gram kernel (TMA bulk reduce-add), rank 0 gathers the rows"
         except Exception as exc:
             hdl = None
@@ -396,15 +399,14 @@ def main():
 
     def kinship_step():
         if hdl is not None:
-            G_t.zero_()
+            flat.zero_()
             hdl.barrier()
-            _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, -1, sums_t.data_ptr()))
+            _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, -1, sums_t.data_ptr(), boxes))
             st = ctx.stats()
-            hdl.barrier()
-            dist.all_reduce(sums_t)
+            hdl.barrier()              # after it every rank's mailbox holds the scalar sums of all ranks: no all-reduce
             if rank == 0:
                 _lib.check(lib.gapit_vanraden_gram_gather(ctx.h, n, peers, world, 0))
-                _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_t.data_ptr(), sums_t.data_ptr(), K_dev.data_ptr(), None, None))
+                _lib.check(lib.gapit_vanraden_finish(ctx.h, n, G_t.data_ptr(), box.data_ptr(), K_dev.data_ptr(), None, None))
         else:
             _lib.check(lib.gapit_vanraden_gram(ctx.h, geno.h, G_t.data_ptr(), sums_t.data_ptr()))
             if world > 1:

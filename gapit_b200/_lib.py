@@ -70,7 +70,7 @@ SIGNATURES = {
     "gapit_vanraden": (C.c_int, [_P, _P, _P, _P]),
     "gapit_gram_ld": (_I64, [_I64]),
     "gapit_vanraden_gram": (C.c_int, [_P, _P, _P, _P]),
-    "gapit_vanraden_gram_fused": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "gapit_vanraden_gram_fused": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gapit_vanraden_gram_gather": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_int]),
     "gapit_gram_owned_rows": (C.c_int, [_I64, C.c_int, C.c_int, C.POINTER(_I64), C.POINTER(_I64)]),
     "gapit_vanraden_finish": (C.c_int, [_P, _I64, _P, _P, _P, _P, _P]),
@@ -78,6 +78,7 @@ SIGNATURES = {
     "gapit_pca": (C.c_int, [_P, _P, _I64, _P, _P]),
     "gapit_eigh": (C.c_int, [_P, _P, _I64, _P, _P]),
     "gapit_eigh_dev": (C.c_int, [_P, _P, _I64, _P]),
+    "gapit_eigh_dev_range": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P]),
     "gapit_eigh_dev_mg": (C.c_int, [_P, _P, _I64, _P, C.c_int]),
     "gapit_eigh_mg": (C.c_int, [_P, _P, _I64, _P, _P, C.c_int]),
     "gapit_eigen_R": (C.c_int, [_P, _P, _P, _I64, _I64, _P, _P]),
@@ -113,6 +114,7 @@ SIGNATURES = {
     "gapit_mgeno_n": (_I64, [_P]),
     "gapit_mgeno_m": (_I64, [_P]),
     "gapit_multi_vanraden": (C.c_int, [_P, _P, _P, _P]),
+    "gapit_multi_eigh": (C.c_int, [_P, _P, _I64, _P, _P]),
     "gapit_multi_p3d_scan": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
                                        C.POINTER(ScanOut), C.POINTER(ScanBase)]),
 }

@@ -581,6 +581,18 @@ def eigh_dev(K_ptr, n, ctx=None):
     return values
 
 
+def eigh_dev_range(K_ptr, n, first, count, out_ptr, ctx=None):
+    """Eigenpairs [first, first + count) of the descending order of a device-resident symmetric matrix
+    (gapit_eigh_dev_range, cuSOLVER syevdx by index): the n x count column-major vectors go to the device buffer
+    ``out_ptr``, the matrix at ``K_ptr`` is destroyed; returns the ``count`` eigenvalues.  Several GPUs holding the
+    same matrix each take one slice of the spectrum (gapit_b200/fullsize.py)."""
+    ctx = ctx or default_context()
+    values = np.empty(int(count))
+    check(ctx.lib.gapit_eigh_dev_range(ctx.h, C.c_void_p(int(K_ptr)), int(n), int(first), int(count), _ptr(values),
+                                       C.c_void_p(int(out_ptr))))
+    return values
+
+
 def reml_from_projections(values, Vty, VtX, ngrids=100, llim=-10, ulim=10, esp=1e-10):
     """gapit_reml_eigL on rotated inputs (EigenSystem.project): {"REML", "delta", "ve", "vg"}."""
     lam = np.ascontiguousarray(values, dtype=np.float64)
@@ -1034,6 +1046,16 @@ def multi_vanraden(mgeno, return_gram=False):
     G = np.empty((n, n), dtype=np.int32) if return_gram else None
     check(mgeno.mctx.lib.gapit_multi_vanraden(mgeno.mctx.h, mgeno.h, _ptr(K), _ptr(G)))
     return (K, G) if return_gram else K
+
+
+def multi_eigh(K, mctx):
+    """emma.eigen.L.wo.Z (emma.txt:58-61) with the spectrum sliced over the GPUs of the multi-context (gapit_multi_eigh)."""
+    K = np.asfortranarray(K, dtype=np.float64)
+    n = K.shape[0]
+    values = np.empty(n)
+    vectors = np.empty((n, n), order="F")
+    check(mctx.lib.gapit_multi_eigh(mctx.h, _ptr(K), n, _ptr(values), _ptr(vectors)))
+    return {"values": values, "vectors": vectors}
 
 
 def multi_p3d_scan(mgeno, X0, Y, values=None, vectors=None, delta=None, vg=None, glm=False, pinned=False):

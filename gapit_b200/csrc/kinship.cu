@@ -185,6 +185,16 @@ __global__ void colsum_reduce_kernel(const int32_t* __restrict__ colsum, int64_t
   }
 }
 
+// the three scalar sums of this rank's markers added into every rank's mailbox (peer-mapped memory, system-scope atomics):
+// after the exchange's closing barrier each mailbox holds the totals, no collective needed for them
+struct SumPeers {
+  unsigned long long* p[8];
+};
+__global__ void push_sums_kernel(const unsigned long long* __restrict__ local, SumPeers peers, int world) {
+  const int r = threadIdx.x / 3, i = threadIdx.x % 3;
+  if (r < world) atomicAdd_system(peers.p[r] + i, local[i]);
+}
+
 // upper tile (I < J in 256-blocks) <- transpose of lower tile; 32x32 sub-tiles through shared memory
 __global__ void gram_mirror_kernel(int32_t* __restrict__ G, int64_t ldg) {
   __shared__ int32_t t[32][33];
@@ -493,8 +503,10 @@ extern "C" int gapit_vanraden_gram(gapit_ctx* ctx, gapit_geno* g, int32_t* G_dev
 // the kernels of all ranks have completed (stream sync + barrier): root >= 0: rank `root` holds the complete lower
 // triangle (reduce to root); root < 0: rank r holds the block-rows gapit_gram_owned_rows() gives it (reduce-scatter:
 // every rank's NVLink ingress carries 1/world of the tiles), and gapit_vanraden_gram_gather pulls them together.
+// sum_peers (may be NULL): sum_peers[r] = 3 int64 on rank r, peer-mapped and zeroed with the Gram buffers; this rank's
+// scalar sums are added into every one of them, so after the closing barrier each holds the totals for gapit_vanraden_finish.
 extern "C" int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int world, int rank,
-                                         int root, int64_t* sums_dev) {
+                                         int root, int64_t* sums_dev, int64_t* const* sum_peers) {
   if (!ctx || !g || !peers || !sums_dev || world < 1 || world > 8 || rank < 0 || rank >= world || root >= world)
     return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram_fused: bad argument");
   GAPIT_CUDA(cudaSetDevice(ctx->device));
@@ -510,6 +522,16 @@ extern "C" int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t*
   colsum_reduce_kernel<<<std::min<int64_t>(1024, (g->m + 255) / 256), 256, 0, ctx->stream>>>(
       g->colsum, g->m, 2 * g->n, reinterpret_cast<unsigned long long*>(sums_dev));
   GAPIT_CUDA(cudaGetLastError());
+  if (sum_peers) {
+    SumPeers sp;
+    for (int r = 0; r < 8; ++r) sp.p[r] = nullptr;
+    for (int r = 0; r < world; ++r) {
+      if (!sum_peers[r]) return fail(GAPIT_ERR_ARG, "gapit_vanraden_gram_fused: NULL sums mailbox");
+      sp.p[r] = reinterpret_cast<unsigned long long*>(sum_peers[r]);
+    }
+    push_sums_kernel<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<const unsigned long long*>(sums_dev), sp, world);
+    GAPIT_CUDA(cudaGetLastError());
+  }
   cudaEventRecord(ctx->ev0, ctx->stream);
   GAPIT_CHECK(launch_gram(ctx, g, ldg, ex));
   cudaEventRecord(ctx->ev1, ctx->stream);

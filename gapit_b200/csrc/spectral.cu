@@ -62,6 +62,13 @@ __global__ void reverse_cols_kernel(const double* __restrict__ src, int64_t n, i
   for (int64_t c = blockIdx.y; c < ncols; c += gridDim.y) dst[i + c * n] = src[i + (n - 1 - c) * n];
 }
 
+// column c of dst <- column (k-1-c) of src, for c < k (the first k columns, reversed)
+__global__ void reverse_first_cols_kernel(const double* __restrict__ src, int64_t n, int64_t k, double* __restrict__ dst) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int64_t c = blockIdx.y; c < k; c += gridDim.y) dst[i + c * n] = src[i + (k - 1 - c) * n];
+}
+
 // column c <-> column n-1-c, in place (ascending -> descending order of the eigenvectors)
 __global__ void swap_cols_kernel(double* __restrict__ A, int64_t n) {
   const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -173,6 +180,61 @@ extern "C" int gapit_eigh_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* 
   if (rc != GAPIT_OK) return rc;
   if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("gapit_eigh_dev: ") + cudaGetErrorString(e));
   for (int64_t c = 0; c < n; ++c) values_out[c] = w[n - 1 - c];
+  return GAPIT_OK;
+}
+
+// Eigenpairs [first, first + count) of R's descending order, by index range (cusolverDnXsyevdx).  profiles/
+// r2_syevd_breakdown.log: at n = 20,000 the tridiagonalisation is 3.9 s of syevd's 4.5 s and a range call costs 4.1 s
+// whatever the range, so several GPUs each taking a slice of the spectrum (gapit_multi_eigh, gapit_b200/fullsize.py)
+// share the divide-and-conquer back-transformation and the output traffic, not the tridiagonalisation.
+extern "C" int gapit_eigh_dev_range(gapit_ctx* ctx, double* A_dev, int64_t n, int64_t first, int64_t count,
+                                    double* values_out, double* vectors_dev_out) {
+  if (!ctx || !A_dev || !values_out || !vectors_dev_out || n <= 0 || first < 0 || count < 1 || first + count > n)
+    return fail(GAPIT_ERR_ARG, "gapit_eigh_dev_range: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  GAPIT_CHECK(ensure_solver(ctx));
+  const int64_t il = n - (first + count) + 1, iu = n - first;      // 1-based, ascending
+  double* w_dev = nullptr;
+  int* info = nullptr;
+  void* work = nullptr;
+  std::vector<char> hwork;
+  cusolverDnParams_t params = nullptr;
+  GAPIT_CUDA(cudaMalloc(&w_dev, size_t(n) * 8));
+  cudaError_t e = cudaMalloc(&info, 4);
+  size_t dbytes = 0, hbytes = 0;
+  int64_t meig = 0;
+  double vl = 0.0, vu = 0.0;
+  cusolverStatus_t st = e == cudaSuccess ? cusolverDnCreateParams(&params) : CUSOLVER_STATUS_ALLOC_FAILED;
+  if (st == CUSOLVER_STATUS_SUCCESS)
+    st = cusolverDnXsyevdx_bufferSize(ctx->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_LOWER, n,
+                                      CUDA_R_64F, A_dev, n, &vl, &vu, il, iu, &meig, CUDA_R_64F, w_dev, CUDA_R_64F, &dbytes, &hbytes);
+  if (st == CUSOLVER_STATUS_SUCCESS && cudaMalloc(&work, std::max<size_t>(dbytes, 16)) != cudaSuccess)
+    st = CUSOLVER_STATUS_ALLOC_FAILED;
+  if (st == CUSOLVER_STATUS_SUCCESS) {
+    hwork.resize(std::max<size_t>(hbytes, 16));
+    st = cusolverDnXsyevdx(ctx->solver, params, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_LOWER, n, CUDA_R_64F,
+                           A_dev, n, &vl, &vu, il, iu, &meig, CUDA_R_64F, w_dev, CUDA_R_64F, work, dbytes, hwork.data(), hbytes, info);
+  }
+  int hinfo = -1;
+  std::vector<double> w(count);
+  if (st == CUSOLVER_STATUS_SUCCESS && meig == count) {
+    // the slice comes back ascending in the first `count` columns of A_dev and entries of w_dev
+    dim3 grid(static_cast<unsigned>((n + 255) / 256), static_cast<unsigned>(std::min<int64_t>(count, 65535)));
+    reverse_first_cols_kernel<<<grid, 256, 0, ctx->stream>>>(A_dev, n, count, vectors_dev_out);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(w.data(), w_dev, size_t(count) * 8, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&hinfo, info, 4, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(work);
+  cudaFree(info);
+  cudaFree(w_dev);
+  if (params) cusolverDnDestroyParams(params);
+  if (st != CUSOLVER_STATUS_SUCCESS) return fail(GAPIT_ERR_CUDA, "cuSOLVER syevdx failed, status " + std::to_string(int(st)));
+  if (e != cudaSuccess) return fail(GAPIT_ERR_CUDA, std::string("gapit_eigh_dev_range: ") + cudaGetErrorString(e));
+  if (hinfo != 0) return fail(GAPIT_ERR_NUMERIC, "syevdx did not converge, info " + std::to_string(hinfo));
+  if (meig != count) return fail(GAPIT_ERR_NUMERIC, "syevdx returned " + std::to_string(meig) + " eigenpairs, expected " + std::to_string(count));
+  for (int64_t c = 0; c < count; ++c) values_out[c] = w[count - 1 - c];
   return GAPIT_OK;
 }
 

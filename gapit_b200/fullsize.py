@@ -92,9 +92,12 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
     if world > 1 and exchange == "fused":
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            G_acc = symm_mem.empty((ldg, ldg), dtype=torch.int32, device=dev)
-            hdl = symm_mem.rendezvous(G_acc, dist.group.WORLD)
+            flat = symm_mem.empty(ldg * ldg + 8, dtype=torch.int32, device=dev)   # Gram buffer + mailbox of the 3 scalar sums
+            hdl = symm_mem.rendezvous(flat, dist.group.WORLD)
+            G_acc = flat[:ldg * ldg].view(ldg, ldg)
+            box = flat[ldg * ldg:].view(torch.int64)
             peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+            boxes = (ctypes.c_void_p * world)(*[int(p) + ldg * ldg * 4 for p in hdl.buffer_ptrs])
         except Exception as exc:   # no peer access on this box
             print("symmetric memory unavailable, using ncclAllReduce:", repr(exc)[:200], flush=True)
             hdl = None
@@ -104,16 +107,16 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
     sync()
     t0 = time.perf_counter()
     if hdl is not None:   # tiles go to their block-row owners inside the kernel, rank 0 gathers the rows
-        G_acc.zero_()
+        flat.zero_()
         hdl.barrier()
-        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, -1, s_t.data_ptr()))
+        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, -1, s_t.data_ptr(), boxes))
         gram_ms = ctx.stats()["kernel_ms"]
         ta = time.perf_counter()
         hdl.barrier()
+        s_t = box[:3]                 # the scalar sums of all ranks, added into every rank's mailbox by the same call
         if rank == 0:
             _lib.check(lib.gapit_vanraden_gram_gather(ctx.h, n, peers, world, 0))
             T_["gather_rows_ms"] = ctx.stats()["post_ms"]
-        dist.all_reduce(s_t)
         torch.cuda.synchronize()
         T_["exchange_tail_s"] = time.perf_counter() - ta
     else:
@@ -170,18 +173,44 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
     Y = np.asfortranarray(Yt.cpu().numpy().T)
     X0 = np.ones((n, 1))
     sync()
-    if rank == 0:
+    sliced = world > 1 and n >= 2048 * world
+    if sliced:
+        # every rank solves for its own slice of the spectrum (cuSOLVER syevdx by index range): the tridiagonalisation
+        # -- 87 % of syevd at n = 20,000 and bound by HBM, profiles/r2_syevd_breakdown.log -- is repeated on every
+        # GPU, the divide-and-conquer back-transformation and the eigenvector traffic are split
         t1 = time.perf_counter()
-        lam = gb.eigh_dev(K_dev.data_ptr(), n, ctx=ctx)      # K_dev now holds the eigenvectors (row r = vector r)
-        T_["eigh_s"] = time.perf_counter() - t1
-        val_t.copy_(torch.from_numpy(lam))
-    sync()
-    t1 = time.perf_counter()
-    if world > 1:
         dist.broadcast(K_dev, 0)
-        dist.broadcast(val_t, 0)
+        lo_r = [n * r // world for r in range(world + 1)]
+        V_t = torch.empty((n, n), dtype=torch.float64, device=dev)      # row r = eigenvector r (descending)
+        lam = gb.eigh_dev_range(K_dev.data_ptr(), n, lo_r[rank], lo_r[rank + 1] - lo_r[rank],
+                                V_t[lo_r[rank]:lo_r[rank + 1]].data_ptr(), ctx=ctx)
+        val_t[lo_r[rank]:lo_r[rank + 1]].copy_(torch.from_numpy(lam))
+        sync()
+        T_["eigh_s"] = time.perf_counter() - t1
+        T_["eigh_route"] = f"spectrum sliced over {world} GPUs (K broadcast + syevdx per rank)"
+        t1 = time.perf_counter()
+        for r in range(world):
+            dist.broadcast(V_t[lo_r[r]:lo_r[r + 1]], r)
+            dist.broadcast(val_t[lo_r[r]:lo_r[r + 1]], r)
+        K_dev = V_t
+        del V_t
+    else:
+        if rank == 0:
+            t1 = time.perf_counter()
+            lam = gb.eigh_dev(K_dev.data_ptr(), n, ctx=ctx)      # K_dev now holds the eigenvectors (row r = vector r)
+            T_["eigh_s"] = time.perf_counter() - t1
+            val_t.copy_(torch.from_numpy(lam))
+        sync()
+        t1 = time.perf_counter()
+        if world > 1:
+            dist.broadcast(K_dev, 0)
+            dist.broadcast(val_t, 0)
     sync()
     T_["broadcast_s"] = time.perf_counter() - t1
+    if rank == 0:   # 64 eigenvectors spread over the spectrum (and over the ranks' slices): orthonormal?
+        pick = K_dev[torch.linspace(0, n - 1, 64, device=dev).long()]
+        out["eigvec_orthonormality_err_sample"] = float((pick @ pick.T - torch.eye(64, dtype=torch.float64, device=dev)).abs().max())
+        del pick
     t1 = time.perf_counter()
     es = gb.EigenSystem.from_device(val_t.cpu().numpy(), K_dev.data_ptr(), ctx=ctx)
     del K_dev

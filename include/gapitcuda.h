@@ -168,9 +168,14 @@ int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, const int64
  * triangle (reduce to root); with root < 0 rank r holds the complete block-rows gapit_gram_owned_rows(n, world, r)
  * (reduce-scatter: each rank's NVLink ingress carries 1/world of the tiles) and the rank that goes on calls
  * gapit_vanraden_gram_gather to pull the other ranks' block-rows into its own buffer.  gapit_vanraden_finish then runs
- * on a complete buffer.  Integer adds: bit-identical to the all-reduce route for any rank count. */
+ * on a complete buffer.  Integer adds: bit-identical to the all-reduce route for any rank count.
+ * sums_dev receives this rank's 3 partial scalars as in gapit_vanraden_gram.  sum_peers (may be NULL): sum_peers[r] = 3
+ * int64 on rank r, peer-mapped like the Gram buffers and zeroed with them before the opening barrier (e.g. the tail of
+ * the same allocation); every rank adds its scalars into all of them, so after the closing barrier each rank's own
+ * mailbox holds the totals gapit_vanraden_finish wants -- no collective for them either.  With NULL the caller sums the
+ * partial scalars over the ranks itself. */
 int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* peers, int world, int rank, int root,
-                              int64_t* sums_dev);
+                              int64_t* sums_dev, int64_t* const* sum_peers);
 int gapit_vanraden_gram_gather(gapit_ctx* ctx, int64_t n, int32_t* const* peers, int world, int rank);
 int gapit_gram_owned_rows(int64_t n, int world, int rank, int64_t* row_lo, int64_t* row_hi);
 
@@ -190,6 +195,12 @@ int gapit_eigh(gapit_ctx* ctx, const double* A, int64_t n, double* values_out, d
 /* Device-resident form: A_dev (n x n column-major, e.g. K_dev_out of gapit_vanraden_finish) is overwritten by the
  * eigenvectors in descending order of the eigenvalues (values_out: host, n) -- no n^2 host round trip. */
 int gapit_eigh_dev(gapit_ctx* ctx, double* A_dev, int64_t n, double* values_out);
+/* Eigenpairs [first, first + count) of the descending order only (cusolverDnXsyevdx by index range): values_out host
+ * (count), vectors_dev_out device n x count column-major; A_dev (lower triangle read) is destroyed.  A range call costs
+ * the tridiagonalisation whatever the range (3.9 s of syevd's 4.5 s at n = 20,000, profiles/r2_syevd_breakdown.log), so
+ * giving each GPU one slice of the spectrum splits the back-transformation and the output, not the whole solve. */
+int gapit_eigh_dev_range(gapit_ctx* ctx, double* A_dev, int64_t n, int64_t first, int64_t count, double* values_out,
+                         double* vectors_dev_out);
 /* The same on `ngpus` GPUs of this process (0 = every visible one): cuSOLVER's multi-GPU solver cusolverMgSyevd on a
  * 1-D block-cyclic copy of A dealt out over NVLink, eigenvectors gathered back into A_dev.  Needs peer access; falls
  * through to gapit_eigh_dev for ngpus < 2 or n < 2048.  The solver sits in libgapitcuda_mg.so (loaded on first use);
@@ -308,6 +319,9 @@ void gapit_mgeno_free(gapit_mgeno* g);
 int64_t gapit_mgeno_n(const gapit_mgeno* g);
 int64_t gapit_mgeno_m(const gapit_mgeno* g);
 int gapit_multi_vanraden(gapit_mctx* mc, gapit_mgeno* g, double* K_out, int32_t* G_out);
+/* eigen(A) as gapit_eigh (values descending, vectors n x n column-major, both host), the spectrum sliced over the
+ * GPUs of the context: each one runs gapit_eigh_dev_range for n/ngpus eigenpairs.  One GPU (or n < 2048): gapit_eigh. */
+int gapit_multi_eigh(gapit_mctx* mc, const double* A, int64_t n, double* values_out, double* vectors_out);
 int gapit_multi_p3d_scan(gapit_mctx* mc, gapit_mgeno* g, const double* vectors, const double* values, const double* X0,
                          int q0, const double* Y, int T, const double* delta, const double* vg, int glm,
                          gapit_scan_out* out, gapit_scan_base* base_out /* T entries */);

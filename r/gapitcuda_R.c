@@ -100,15 +100,16 @@ SEXP gapit_R_vanraden(SEXP snps) {
   return K;
 }
 
-/* eigen(K, symmetric=TRUE) in R's order: list(values, vectors)   (emma.txt:58-61).  On a multi-GPU box the
- * decomposition runs on every GPU of the multi-context (cusolverMgSyevd); one GPU, or a process that cannot load the
- * multi-GPU solver, uses cusolverDn syevd. */
+/* eigen(K, symmetric=TRUE) in R's order: list(values, vectors)   (emma.txt:58-61).  On a multi-GPU box every GPU of
+ * the multi-context solves for its own slice of the spectrum (gapit_multi_eigh: cusolverDn syevdx by index range, ~10 %
+ * faster than one GPU at n = 20,000; cusolverMgSyevd, gapit_eigh_mg, measured 2-3x SLOWER and is not used); one GPU
+ * uses cusolverDn syevd. */
 SEXP gapit_R_eigen_L(SEXP K) {
   const int64_t n = INTEGER(Rf_getAttrib(K, R_DimSymbol))[0];
   gapit_mctx* mc = mctx();
   SEXP values = PROTECT(Rf_allocVector(REALSXP, n));
   SEXP vectors = PROTECT(Rf_allocMatrix(REALSXP, (int)n, (int)n));
-  int rc = gapit_eigh_mg(ctx(), REAL(K), n, REAL(values), REAL(vectors), gapit_mctx_ngpus(mc));
+  int rc = gapit_multi_eigh(mc, REAL(K), n, REAL(values), REAL(vectors));
   if (rc != GAPIT_OK) {
     UNPROTECT(2);
     Rf_error("gapitcuda: %s", gapit_last_error());

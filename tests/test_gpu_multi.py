@@ -74,3 +74,27 @@ def test_one_process_drives_every_gpu_through_the_c_abi(ngpus):
         assert gotb[0]["logL0"] == refb[0]["logL0"] and gotb[2]["rsquare_base"] == refb[2]["rsquare_base"]
         mg.close()
     mctx.close()
+
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_eigen_decomposition_sliced_over_the_gpus(ngpus):
+    """gapit_multi_eigh (eigen(K) of the R shim): every GPU solves for n/ngpus eigenpairs by index range; side by side
+    they are one orthonormal eigen-system with the one-GPU solver's values."""
+    import numpy as np
+    import torch
+    import gapit_b200 as gb
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    rng = np.random.default_rng(9)
+    n = 1024 * ngpus + 77                         # the route needs >= 1,024 eigenpairs per GPU
+    A = rng.normal(size=(n, n + 30))
+    K = A @ A.T / (n + 30)
+    mctx = gb.MultiContext(ngpus)
+    got = gb.multi_eigh(K, mctx)
+    ref = gb.emma_eigen_L_wo_Z(K, ctx=mctx.context(0))
+    vals, V = got["values"], got["vectors"]
+    assert np.all(np.diff(vals) <= 1e-12) and np.allclose(vals, ref["values"], rtol=0, atol=1e-12 * vals[0])
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-11
+    assert np.abs(K @ V - V * vals).max() < 1e-11 * vals[0]
+    mctx.close()
+

@@ -1101,3 +1101,26 @@ def test_shared_rotation_edge_shapes(gpu_ctx, n, m, npc, T):
             assert np.nanmax(np.abs(np.log10(arrs["pvalue"][t]) - np.log10(ora.ps))) < LOGP_ATOL
         assert np.max(np.abs(arrs["rsquare"][t][ok] - ora.rsquare[ok])) < 1e-9
         assert bases[t]["beta0"] == pytest.approx(ora.effect_cv, rel=1e-8, abs=1e-10)
+
+
+def test_eigh_by_index_range_assembles_the_full_decomposition(gpu_ctx):
+    """gapit_eigh_dev_range: three uneven slices of the spectrum, each solved from its own copy of K, put side by side
+    are one eigendecomposition -- values equal to the full solve, V orthonormal ACROSS the slices, K V = V diag(values)."""
+    import torch
+    rng = np.random.default_rng(5)
+    n = 700
+    A = rng.normal(size=(n, n + 40))
+    K = A @ A.T / (n + 40)
+    ref = gb().emma_eigen_L_wo_Z(K, ctx=gpu_ctx)
+    dev = torch.device("cuda", gpu_ctx.device)
+    V_t = torch.empty((n, n), dtype=torch.float64, device=dev)          # row r = eigenvector r
+    vals = np.empty(n)
+    for lo, hi in ((0, 1), (1, 450), (450, n)):
+        K_t = torch.from_numpy(K).to(dev)                               # symmetric: row- and column-major agree
+        vals[lo:hi] = gb().eigh_dev_range(K_t.data_ptr(), n, lo, hi - lo, V_t[lo:hi].data_ptr(), ctx=gpu_ctx)
+    V = V_t.cpu().numpy().T
+    assert np.all(np.diff(vals) <= 1e-12) and np.allclose(vals, ref["values"], rtol=0, atol=1e-12 * vals[0])
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-11
+    assert np.abs(K @ V - V * vals).max() < 1e-11 * vals[0]
+    with pytest.raises(gb().GapitCudaError):
+        gb().eigh_dev_range(V_t.data_ptr(), n, n - 3, 4, V_t.data_ptr(), ctx=gpu_ctx)      # past the end of the spectrum

@@ -44,28 +44,31 @@ try:
     import ctypes
     import time
     import torch.distributed._symmetric_memory as symm_mem
-    G_sym = symm_mem.empty((ldg, ldg), dtype=torch.int32, device=dev)
-    hdl = symm_mem.rendezvous(G_sym, dist.group.WORLD)
+    flat = symm_mem.empty(ldg * ldg + 8, dtype=torch.int32, device=dev)   # Gram buffer + 3 int64 mailbox for the scalar sums
+    hdl = symm_mem.rendezvous(flat, dist.group.WORLD)
+    G_sym = flat[:ldg * ldg].view(ldg, ldg)
+    box = flat[ldg * ldg:].view(torch.int64)
     peers = (ctypes.c_void_p * world)(*[int(p) for p in hdl.buffer_ptrs])
+    boxes = (ctypes.c_void_p * world)(*[int(p) + ldg * ldg * 4 for p in hdl.buffer_ptrs])
     s_f = torch.empty(3, dtype=torch.int64, device=dev)
     ref_t = torch.tril(G_t[:n, :n])
     # root = -1: reduce-scatter by block-row owner, then the finishing rank (every rank in turn here) gathers the rows
     # the others own; root = 0: reduce to one rank
     for root in (-1, 0):
-        G_sym.zero_()
+        flat.zero_()
         torch.cuda.synchronize()
         hdl.barrier()
         t0 = time.perf_counter()
-        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, root, s_f.data_ptr()))
+        _lib.check(lib.gapit_vanraden_gram_fused(ctx.h, geno.h, peers, world, rank, root, s_f.data_ptr(), boxes))
         torch.cuda.synchronize()
         hdl.barrier()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        same = True
+        same = bool(torch.equal(box[:3], s_t))          # every rank's mailbox holds the all-reduced scalar sums
         if root >= 0:
-            full = hdl.get_buffer(root, (ldg, ldg), torch.int32).clone()
+            full = hdl.get_buffer(root, (ldg * ldg + 8,), torch.int32)[:ldg * ldg].view(ldg, ldg).clone()
             torch.cuda.synchronize()
-            same = bool(torch.equal(ref_t, torch.tril(full[:n, :n])))
+            same = same and bool(torch.equal(ref_t, torch.tril(full[:n, :n])))
             hdl.barrier()
         else:
             for gatherer in range(world):     # one rank at a time pulls the others' block-rows into its own buffer
