@@ -402,11 +402,24 @@ __global__ void zhang_adjust_kernel(double* __restrict__ K, int64_t n, const Zha
   }
 }
 
-static int choose_ksplit(int ntri, int kblocks, int sms) {
-  // enough jobs for >= ~6 waves, each job keeping >= 32 k-blocks of work
-  int ks = 1;
-  while (ntri * ks < 6 * sms && kblocks / (ks + 1) >= 32) ++ks;
-  return ks;
+// Splits of the marker axis.  Every job of a launch is equally long (one tile pair x kblocks / ks k-blocks), the units
+// take them round by round, so the launch lasts ceil(jobs * ks / units) rounds of (kblocks / ks + a fixed cost per job:
+// pipeline refill and the last accumulator drain).  Pick the ks with the shortest launch, each job keeping >= 32
+// k-blocks; ties go to the smaller ks (fewer reduce-adds per tile, locally and over NVLink).  C2 (110 jobs, 74 units):
+// 2 splits = 2.97 -> 3 rounds (99 % of the units busy), where "at least six waves" gave 5 splits = 7.4 -> 8 rounds (93 %).
+static int choose_ksplit(int jobs, int kblocks, int units) {
+  const double fixed = 4.0;
+  int best = 1;
+  double best_t = 0.0;
+  for (int ks = 1; ks <= 128 && (ks == 1 || kblocks / ks >= 32); ++ks) {
+    const double rounds = double((int64_t(jobs) * ks + units - 1) / units);
+    const double t = rounds * (double(kblocks) / ks + fixed);
+    if (ks == 1 || t < best_t * 0.97) {   // a finer split must pay for its extra reduce-adds
+      best = ks;
+      best_t = t;
+    }
+  }
+  return best;
 }
 
 struct GramExchange {   // where the tiles of this launch are reduced into (world 1: the local buffer)
@@ -429,7 +442,7 @@ static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int64_t ldg, const GramExc
   sp.ntri = 0;
   for (int R = 0; R < TR; ++R) sp.ntri += std::min(cl * (R + 1), sp.tiles_side);
   sp.kblocks = static_cast<int>(round_up(g->m, 128) / kBlockK);
-  sp.ksplit = choose_ksplit(sp.ntri * cl, sp.kblocks, ctx->sm_count);
+  sp.ksplit = choose_ksplit(sp.ntri, sp.kblocks, std::max(1, ctx->sm_count / cl));
   const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
   sp.round_ctr = nullptr;
   sp.round_wait = 100000;
