@@ -91,6 +91,7 @@ SIGNATURES = {
                                  C.POINTER(ScanOut), C.POINTER(ScanBase)]),
     "gapit_eigsys_upload": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),
     "gapit_eigsys_from_device": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),
+    "gapit_eigsys_from_kinship": (C.c_int, [_P, _P, _I64, _P, C.POINTER(_P)]),
     "gapit_eigsys_project": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "gapit_eigsys_free": (None, [_P]),
     "gapit_p3d_scan_dev": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
@@ -115,6 +116,12 @@ SIGNATURES = {
     "gapit_mgeno_m": (_I64, [_P]),
     "gapit_multi_vanraden": (C.c_int, [_P, _P, _P, _P]),
     "gapit_multi_eigh": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "gapit_meigsys_from_kinship": (C.c_int, [_P, _P, _I64, _P, C.POINTER(_P)]),
+    "gapit_meigsys_upload": (C.c_int, [_P, _P, _P, _I64, C.POINTER(_P)]),
+    "gapit_meigsys_part": (_P, [_P, C.c_int]),
+    "gapit_meigsys_free": (None, [_P]),
+    "gapit_multi_p3d_scan_es": (C.c_int, [_P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
+                                          C.POINTER(ScanOut), C.POINTER(ScanBase)]),
     "gapit_multi_p3d_scan": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P, C.c_int,
                                        C.POINTER(ScanOut), C.POINTER(ScanBase)]),
 }

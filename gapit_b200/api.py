@@ -249,6 +249,21 @@ class EigenSystem:
         self.h, self.n = h, n
         return self
 
+    @classmethod
+    def from_kinship(cls, K, ctx=None):
+        """eigen(K) of a host kinship decomposed and sliced on the device in one call (gapit_eigsys_from_kinship): the
+        eigenvectors never visit the host; ``values`` holds the eigenvalues (descending)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or default_context()
+        K = np.asfortranarray(K, dtype=np.float64)
+        n = K.shape[0]
+        assert K.shape == (n, n)
+        self.values = np.empty(n)
+        h = C.c_void_p()
+        check(self.ctx.lib.gapit_eigsys_from_kinship(self.ctx.h, _ptr(K), n, _ptr(self.values), C.byref(h)))
+        self.h, self.n = h, n
+        return self
+
     def project(self, R):
         """V'R for an n x nc host matrix (the rotated phenotypes / covariates REML starts from)."""
         R = np.asfortranarray(np.asarray(R, dtype=np.float64).reshape(self.n, -1))
@@ -840,15 +855,19 @@ def GAPIT_EMMAxP3D(ys, xs, K=None, Z=None, X0=None, CVI=None, CV_Inheritance=Non
     glm = K is None
     y_last = np.ascontiguousarray(Y[:, g - 1])
     if not glm:
-        if eig_L is None:
-            eig_L = emma_eigen_L_wo_Z(K, ctx=ctx)                         # :48
-        Timmer = _timmer(Timmer, "eig.L")
-        es = EigenSystem(eig_L["values"], eig_L["vectors"], ctx=ctx)      # :224 folded into the kernel weights
+        if eig_L is None and reml_route == "eigL":
+            es = EigenSystem.from_kinship(K, ctx=ctx)                     # :48, and :224 folded into the kernel weights;
+            Timmer = _timmer(Timmer, "eig.L")                             # the eigenvectors stay on the device
+        else:
+            if eig_L is None:
+                eig_L = emma_eigen_L_wo_Z(K, ctx=ctx)                     # :48
+            Timmer = _timmer(Timmer, "eig.L")
+            es = EigenSystem(eig_L["values"], eig_L["vectors"], ctx=ctx)  # :224 folded into the kernel weights
         if reml is not None:
             remls = [reml] if isinstance(reml, dict) else list(reml)
         elif reml_route == "eigL":                                        # :202 for every trait, from eig.L alone
             proj = es.project(np.column_stack([X0, Y]))
-            remls = reml_from_projections_multi(eig_L["values"], proj[:, q0:], proj[:, :q0], ngrids, llim, ulim, esp)
+            remls = reml_from_projections_multi(es.values, proj[:, q0:], proj[:, :q0], ngrids, llim, ulim, esp)
         else:
             try:
                 eig_R = emma_eigen_R_wo_Z(K, X0, ctx=ctx)                 # :58
@@ -1048,6 +1067,46 @@ def multi_vanraden(mgeno, return_gram=False):
     return (K, G) if return_gram else K
 
 
+class MultiEigenSystem:
+    """gapit_meigsys: the eigen-system of K resident (and sliced) on every GPU of a multi-context.  Built from the host
+    kinship (decomposed on the GPUs, spectrum sliced over them, slices exchanged over NVLink) or from host eigenvectors."""
+
+    def __init__(self, mctx, K=None, values=None, vectors=None):
+        self.mctx = mctx
+        h = C.c_void_p()
+        if K is not None:
+            K = np.asfortranarray(K, dtype=np.float64)
+            n = K.shape[0]
+            self.values = np.empty(n)
+            check(mctx.lib.gapit_meigsys_from_kinship(mctx.h, _ptr(K), n, _ptr(self.values), C.byref(h)))
+        else:
+            self.values = np.ascontiguousarray(values, dtype=np.float64)
+            v = np.asfortranarray(vectors, dtype=np.float64)
+            n = self.values.shape[0]
+            assert v.shape == (n, n)
+            check(mctx.lib.gapit_meigsys_upload(mctx.h, _ptr(v), _ptr(self.values), n, C.byref(h)))
+        self.h, self.n = h, int(n)
+
+    def part(self, gpu=0):
+        """The one-GPU EigenSystem on device ``gpu`` (borrowed: projections, BLUP/PEV)."""
+        e = EigenSystem.__new__(EigenSystem)
+        e.ctx, e.values, e.n = self.mctx.context(gpu), self.values, self.n
+        e.h = C.c_void_p(self.mctx.lib.gapit_meigsys_part(self.h, int(gpu)))
+        e.close = lambda: None
+        return e
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.mctx.lib.gapit_meigsys_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def multi_eigh(K, mctx):
     """emma.eigen.L.wo.Z (emma.txt:58-61) with the spectrum sliced over the GPUs of the multi-context (gapit_multi_eigh)."""
     K = np.asfortranarray(K, dtype=np.float64)
@@ -1058,8 +1117,9 @@ def multi_eigh(K, mctx):
     return {"values": values, "vectors": vectors}
 
 
-def multi_p3d_scan(mgeno, X0, Y, values=None, vectors=None, delta=None, vg=None, glm=False, pinned=False):
-    """The P3D scan of every marker block on its GPU (gapit_multi_p3d_scan); same returns as :func:`p3d_scan`."""
+def multi_p3d_scan(mgeno, X0, Y, values=None, vectors=None, delta=None, vg=None, glm=False, pinned=False, eigsys=None):
+    """The P3D scan of every marker block on its GPU (gapit_multi_p3d_scan, or gapit_multi_p3d_scan_es against a
+    resident :class:`MultiEigenSystem`); same returns as :func:`p3d_scan`."""
     n, m = mgeno.n, mgeno.m
     X0 = np.asfortranarray(X0, dtype=np.float64)
     Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(n, -1))
@@ -1074,8 +1134,12 @@ def multi_p3d_scan(mgeno, X0, Y, values=None, vectors=None, delta=None, vg=None,
     v = np.ascontiguousarray(vg, dtype=np.float64).reshape(-1) if vg is not None else None
     vec = np.asfortranarray(vectors, dtype=np.float64) if vectors is not None else None
     val = np.ascontiguousarray(values, dtype=np.float64) if values is not None else None
-    check(mgeno.mctx.lib.gapit_multi_p3d_scan(mgeno.mctx.h, mgeno.h, _ptr(vec), _ptr(val), _ptr(X0), q0, _ptr(Y), T, _ptr(d),
-                                              _ptr(v), 1 if glm else 0, C.byref(so), base))
+    if eigsys is not None or glm:
+        check(mgeno.mctx.lib.gapit_multi_p3d_scan_es(mgeno.mctx.h, mgeno.h, eigsys.h if eigsys is not None else None, _ptr(X0),
+                                                     q0, _ptr(Y), T, _ptr(d), _ptr(v), 1 if glm else 0, C.byref(so), base))
+    else:
+        check(mgeno.mctx.lib.gapit_multi_p3d_scan(mgeno.mctx.h, mgeno.h, _ptr(vec), _ptr(val), _ptr(X0), q0, _ptr(Y), T,
+                                                  _ptr(d), _ptr(v), 0, C.byref(so), base))
     bases = [{"logL0": b.logL0, "logLM_base": b.logLM_base, "rsquare_base": b.rsquare_base, "ves": b.ves,
               "reml": b.reml, "df": b.df, "beta0": np.array(b.beta0[:q0]), "singular_x0": bool(b.singular_x0)}
              for b in base]

@@ -34,6 +34,13 @@ struct gapit_mgeno {
   std::vector<int64_t> lo;         // first marker of each block; lo[world] = m
 };
 
+// eigen-system of K resident on every GPU of the context (one sliced copy per GPU)
+struct gapit_meigsys {
+  gapit_mctx* mc = nullptr;
+  int64_t n = 0;
+  std::vector<gapit_eigsys*> es;
+};
+
 namespace gapit {
 
 // run fn(rank) on one host thread per GPU; the first failure (status, message) is returned on the calling thread
@@ -184,19 +191,23 @@ extern "C" int gapit_multi_vanraden(gapit_mctx* mc, gapit_mgeno* g, double* K_ou
   return release(rc);
 }
 
-// eigen(K) with the spectrum sliced over the GPUs: one upload, NVLink copies of K, every GPU runs the index-range
-// solver for its own n/world eigenpairs and returns them over its own PCIe link.  The tridiagonalisation (87 % of syevd
-// at n = 20,000, profiles/r2_syevd_breakdown.log) is repeated on every GPU -- what is shared out is the rest.
-extern "C" int gapit_multi_eigh(gapit_mctx* mc, const double* A, int64_t n, double* values_out, double* vectors_out) {
-  if (!mc || !A || !values_out || !vectors_out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_multi_eigh: bad argument");
-  const int world = static_cast<int>(std::min<int64_t>(int64_t(mc->ctx.size()), n / 1024));
-  if (world < 2) return gapit_eigh(mc->ctx[0], A, n, values_out, vectors_out);
-  std::vector<double*> Ad(world, nullptr), Vd(world, nullptr);
+// eigen(K) on the GPUs of the context, left ON the devices.  world_eff GPUs (those with >= 1,024 eigenpairs each) solve
+// for one slice of the spectrum each (cuSOLVER syevdx by index range; the tridiagonalisation -- 87 % of syevd at
+// n = 20,000, profiles/r2_syevd_breakdown.log -- is repeated on every GPU, the rest is shared out), the slices are
+// exchanged GPU to GPU over NVLink, every GPU ends with the complete V (n x n column-major, descending) in Vd[r].
+static int decompose_on_gpus(gapit_mctx* mc, const double* A, int64_t n, double* values_out, std::vector<double*>& Vd) {
+  const int world = static_cast<int>(mc->ctx.size());
+  const int solvers = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(world, n / 1024)));
+  std::vector<double*> Ad(world, nullptr);
+  Vd.assign(world, nullptr);
   auto release = [&](int rc) {
     for (int r = 0; r < world; ++r) {
       cudaSetDevice(mc->ctx[r]->device);
       cudaFree(Ad[r]);
-      cudaFree(Vd[r]);
+      if (rc != GAPIT_OK) {
+        cudaFree(Vd[r]);
+        Vd[r] = nullptr;
+      }
     }
     return rc;
   };
@@ -205,11 +216,12 @@ extern "C" int gapit_multi_eigh(gapit_mctx* mc, const double* A, int64_t n, doub
   GAPIT_CUDA(cudaMalloc(&Ad[0], size_t(n) * n * 8));
   cudaError_t e0 = cudaMemcpyAsync(Ad[0], A, size_t(n) * n * 8, cudaMemcpyHostToDevice, c0->stream);
   if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(c0->stream);
-  if (e0 != cudaSuccess) return release(fail(GAPIT_ERR_CUDA, std::string("gapit_multi_eigh: ") + cudaGetErrorString(e0)));
+  if (e0 != cudaSuccess) return release(fail(GAPIT_ERR_CUDA, std::string("eigen(K) upload: ") + cudaGetErrorString(e0)));
   int rc = for_each_gpu(world, [&](int r) {
     gapit_ctx* c = mc->ctx[r];
     GAPIT_CUDA(cudaSetDevice(c->device));
-    if (r > 0) {
+    GAPIT_CUDA(cudaMalloc(&Vd[r], size_t(n) * n * 8));
+    if (r > 0 && r < solvers) {
       GAPIT_CUDA(cudaMalloc(&Ad[r], size_t(n) * n * 8));
       GAPIT_CUDA(cudaMemcpyPeerAsync(Ad[r], c->device, Ad[0], c0->device, size_t(n) * n * 8, c->stream));
       GAPIT_CUDA(cudaStreamSynchronize(c->stream));
@@ -217,55 +229,148 @@ extern "C" int gapit_multi_eigh(gapit_mctx* mc, const double* A, int64_t n, doub
     return GAPIT_OK;
   });
   if (rc != GAPIT_OK) return release(rc);                       // (the join: nobody overwrites Ad[0] before it is copied)
+  auto first_of = [&](int r) { return n * r / solvers; };
+  rc = for_each_gpu(solvers, [&](int r) {
+    gapit_ctx* c = mc->ctx[r];
+    GAPIT_CUDA(cudaSetDevice(c->device));
+    if (solvers == 1) {   // one solver: plain syevd in place, then into Vd[0]
+      GAPIT_CHECK(gapit_eigh_dev(c, Ad[0], n, values_out));
+      GAPIT_CUDA(cudaMemcpyAsync(Vd[0], Ad[0], size_t(n) * n * 8, cudaMemcpyDeviceToDevice, c->stream));
+      GAPIT_CUDA(cudaStreamSynchronize(c->stream));
+      return GAPIT_OK;
+    }
+    const int64_t first = first_of(r), count = first_of(r + 1) - first;
+    return gapit_eigh_dev_range(c, Ad[r], n, first, count, values_out + first, Vd[r] + first * n);
+  });
+  if (rc != GAPIT_OK) return release(rc);
+  // every GPU pulls the slices it does not hold from the GPUs that solved them
   rc = for_each_gpu(world, [&](int r) {
     gapit_ctx* c = mc->ctx[r];
     GAPIT_CUDA(cudaSetDevice(c->device));
-    const int64_t first = n * r / world, count = n * (r + 1) / world - first;
-    GAPIT_CUDA(cudaMalloc(&Vd[r], size_t(n) * count * 8));
-    GAPIT_CHECK(gapit_eigh_dev_range(c, Ad[r], n, first, count, values_out + first, Vd[r]));
-    GAPIT_CUDA(cudaMemcpyAsync(vectors_out + first * n, Vd[r], size_t(n) * count * 8, cudaMemcpyDeviceToHost, c->stream));
+    for (int k = 1; k <= solvers; ++k) {
+      const int s = (r + k) % solvers;                           // staggered sources
+      if (s == r) continue;
+      const int64_t first = first_of(s), count = first_of(s + 1) - first;
+      GAPIT_CUDA(cudaMemcpyPeerAsync(Vd[r] + first * n, c->device, Vd[s] + first * n, mc->ctx[s]->device,
+                                     size_t(n) * count * 8, c->stream));
+    }
     GAPIT_CUDA(cudaStreamSynchronize(c->stream));
     return GAPIT_OK;
   });
   return release(rc);
 }
 
-extern "C" int gapit_multi_p3d_scan(gapit_mctx* mc, gapit_mgeno* g, const double* vectors, const double* values,
-                                    const double* X0, int q0, const double* Y, int T, const double* delta, const double* vg,
-                                    int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
-  if (!mc || !g || g->mc != mc || !out) return fail(GAPIT_ERR_ARG, "gapit_multi_p3d_scan: bad argument");
-  if (!glm && (!vectors || !values)) return fail(GAPIT_ERR_ARG, "gapit_multi_p3d_scan: MLM needs the eigen-system of K");
+extern "C" void gapit_meigsys_free(gapit_meigsys* me) {
+  if (!me) return;
+  for (gapit_eigsys* e : me->es) gapit_eigsys_free(e);
+  delete me;
+}
+
+static int meigsys_from_device_copies(gapit_mctx* mc, std::vector<double*>& Vd, const double* values, int64_t n,
+                                      gapit_meigsys** out) {
   const int world = static_cast<int>(mc->ctx.size());
-  const int64_t n = g->n;
-  std::vector<gapit_eigsys*> es(world, nullptr);
-  auto release = [&](int rc) {
-    for (gapit_eigsys* e : es) gapit_eigsys_free(e);
+  gapit_meigsys* me = new gapit_meigsys();
+  me->mc = mc;
+  me->n = n;
+  me->es.assign(world, nullptr);
+  const int rc = for_each_gpu(world, [&](int r) {
+    gapit_ctx* c = mc->ctx[r];
+    GAPIT_CUDA(cudaSetDevice(c->device));
+    const int rc2 = gapit_eigsys_from_device(c, Vd[r], values, n, &me->es[r]);
+    cudaFree(Vd[r]);
+    Vd[r] = nullptr;
+    return rc2;
+  });
+  if (rc != GAPIT_OK) {
+    for (int r = 0; r < world; ++r)
+      if (Vd[r]) {
+        cudaSetDevice(mc->ctx[r]->device);
+        cudaFree(Vd[r]);
+      }
+    gapit_meigsys_free(me);
     return rc;
-  };
-  if (!glm) {
-    // one PCIe upload, then GPU-to-GPU copies over NVLink; every GPU slices its own digit planes
-    int rc = gapit_eigsys_upload(mc->ctx[0], vectors, values, n, &es[0]);
-    if (rc != GAPIT_OK) return release(rc);
-    const double* v0 = gapit_eigsys_vectors_dev(es[0]);
+  }
+  *out = me;
+  return GAPIT_OK;
+}
+
+extern "C" int gapit_meigsys_from_kinship(gapit_mctx* mc, const double* K, int64_t n, double* values_out, gapit_meigsys** out) {
+  if (!mc || !K || !values_out || !out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_meigsys_from_kinship: bad argument");
+  std::vector<double*> Vd;
+  GAPIT_CHECK(decompose_on_gpus(mc, K, n, values_out, Vd));
+  return meigsys_from_device_copies(mc, Vd, values_out, n, out);
+}
+
+// the same handle from an eigen-system the host already holds: one PCIe upload, then GPU-to-GPU copies over NVLink
+extern "C" int gapit_meigsys_upload(gapit_mctx* mc, const double* vectors, const double* values, int64_t n, gapit_meigsys** out) {
+  if (!mc || !vectors || !values || !out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_meigsys_upload: bad argument");
+  const int world = static_cast<int>(mc->ctx.size());
+  std::vector<double*> Vd(world, nullptr);
+  gapit_ctx* c0 = mc->ctx[0];
+  GAPIT_CUDA(cudaSetDevice(c0->device));
+  GAPIT_CUDA(cudaMalloc(&Vd[0], size_t(n) * n * 8));
+  cudaError_t e0 = cudaMemcpyAsync(Vd[0], vectors, size_t(n) * n * 8, cudaMemcpyHostToDevice, c0->stream);
+  if (e0 == cudaSuccess) e0 = cudaStreamSynchronize(c0->stream);
+  int rc = e0 == cudaSuccess ? GAPIT_OK : fail(GAPIT_ERR_CUDA, std::string("eigenvector upload: ") + cudaGetErrorString(e0));
+  if (rc == GAPIT_OK)
     rc = for_each_gpu(world, [&](int r) {
-      if (r == 0 || !g->part[r]) return GAPIT_OK;
+      if (r == 0) return GAPIT_OK;
       gapit_ctx* c = mc->ctx[r];
       GAPIT_CUDA(cudaSetDevice(c->device));
-      double* v = nullptr;
-      GAPIT_CUDA(cudaMalloc(&v, size_t(n) * n * 8));
-      cudaError_t e = cudaMemcpyPeerAsync(v, c->device, v0, mc->ctx[0]->device, size_t(n) * n * 8, c->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-      int rc2 = e == cudaSuccess ? gapit_eigsys_from_device(c, v, values, n, &es[r])
-                                 : fail(GAPIT_ERR_CUDA, std::string("eigenvector peer copy: ") + cudaGetErrorString(e));
-      cudaFree(v);
-      return rc2;
+      GAPIT_CUDA(cudaMalloc(&Vd[r], size_t(n) * n * 8));
+      GAPIT_CUDA(cudaMemcpyPeerAsync(Vd[r], c->device, Vd[0], c0->device, size_t(n) * n * 8, c->stream));
+      GAPIT_CUDA(cudaStreamSynchronize(c->stream));
+      return GAPIT_OK;
     });
-    if (rc != GAPIT_OK) return release(rc);
+  if (rc != GAPIT_OK) {
+    for (int r = 0; r < world; ++r) {
+      cudaSetDevice(mc->ctx[r]->device);
+      cudaFree(Vd[r]);
+    }
+    return rc;
   }
+  return meigsys_from_device_copies(mc, Vd, values, n, out);
+}
+
+extern "C" gapit_eigsys* gapit_meigsys_part(gapit_meigsys* me, int gpu) {
+  return (me && gpu >= 0 && gpu < static_cast<int>(me->es.size())) ? me->es[gpu] : nullptr;
+}
+
+// eigen(K) back on the host (values descending, vectors n x n column-major): GPU r returns its share of the columns over
+// its own PCIe link
+extern "C" int gapit_multi_eigh(gapit_mctx* mc, const double* A, int64_t n, double* values_out, double* vectors_out) {
+  if (!mc || !A || !values_out || !vectors_out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_multi_eigh: bad argument");
+  const int world = static_cast<int>(mc->ctx.size());
+  if (world < 2 || n < 2048) return gapit_eigh(mc->ctx[0], A, n, values_out, vectors_out);
+  std::vector<double*> Vd;
+  GAPIT_CHECK(decompose_on_gpus(mc, A, n, values_out, Vd));
+  const int rc = for_each_gpu(world, [&](int r) {
+    gapit_ctx* c = mc->ctx[r];
+    GAPIT_CUDA(cudaSetDevice(c->device));
+    const int64_t first = n * r / world, count = n * (r + 1) / world - first;
+    GAPIT_CUDA(cudaMemcpyAsync(vectors_out + first * n, Vd[r] + first * n, size_t(n) * count * 8, cudaMemcpyDeviceToHost, c->stream));
+    GAPIT_CUDA(cudaStreamSynchronize(c->stream));
+    return GAPIT_OK;
+  });
+  for (int r = 0; r < world; ++r) {
+    cudaSetDevice(mc->ctx[r]->device);
+    cudaFree(Vd[r]);
+  }
+  return rc;
+}
+
+// the scan of every marker block on its GPU against the resident eigen-system (NULL: the GLM branch)
+extern "C" int gapit_multi_p3d_scan_es(gapit_mctx* mc, gapit_mgeno* g, gapit_meigsys* me, const double* X0, int q0,
+                                       const double* Y, int T, const double* delta, const double* vg, int glm,
+                                       gapit_scan_out* out, gapit_scan_base* base_out) {
+  if (!mc || !g || g->mc != mc || !out) return fail(GAPIT_ERR_ARG, "gapit_multi_p3d_scan_es: bad argument");
+  if (!glm && (!me || me->mc != mc || me->n != g->n))
+    return fail(GAPIT_ERR_ARG, "gapit_multi_p3d_scan_es: MLM needs the eigen-system of K on this multi-context");
+  const int world = static_cast<int>(mc->ctx.size());
   std::vector<std::vector<gapit_scan_base>> bases(world, std::vector<gapit_scan_base>(T));
   const int rc = for_each_gpu(world, [&](int r) {
     if (!g->part[r]) return GAPIT_OK;
-    return scan_impl(mc->ctx[r], g->part[r], glm ? nullptr : es[r], X0, q0, Y, T, delta, vg, glm, out, bases[r].data(), g->m,
+    return scan_impl(mc->ctx[r], g->part[r], glm ? nullptr : me->es[r], X0, q0, Y, T, delta, vg, glm, out, bases[r].data(), g->m,
                      g->lo[r]);
   });
   if (rc == GAPIT_OK && base_out)
@@ -274,5 +379,17 @@ extern "C" int gapit_multi_p3d_scan(gapit_mctx* mc, gapit_mgeno* g, const double
         std::copy(bases[r].begin(), bases[r].end(), base_out);
         break;
       }
-  return release(rc);
+  return rc;
+}
+
+extern "C" int gapit_multi_p3d_scan(gapit_mctx* mc, gapit_mgeno* g, const double* vectors, const double* values,
+                                    const double* X0, int q0, const double* Y, int T, const double* delta, const double* vg,
+                                    int glm, gapit_scan_out* out, gapit_scan_base* base_out) {
+  if (!mc || !g || g->mc != mc || !out) return fail(GAPIT_ERR_ARG, "gapit_multi_p3d_scan: bad argument");
+  if (!glm && (!vectors || !values)) return fail(GAPIT_ERR_ARG, "gapit_multi_p3d_scan: MLM needs the eigen-system of K");
+  gapit_meigsys* me = nullptr;
+  if (!glm) GAPIT_CHECK(gapit_meigsys_upload(mc, vectors, values, g->n, &me));
+  const int rc = gapit_multi_p3d_scan_es(mc, g, me, X0, q0, Y, T, delta, vg, glm, out, base_out);
+  gapit_meigsys_free(me);
+  return rc;
 }

@@ -238,6 +238,22 @@ extern "C" int gapit_eigh_dev_range(gapit_ctx* ctx, double* A_dev, int64_t n, in
   return GAPIT_OK;
 }
 
+// eigen(K) straight into a resident, sliced eigen-system: the eigenvectors never visit the host (at n = 20,000 they
+// are 3.2 GB each way).  values_out: host, n, descending.
+extern "C" int gapit_eigsys_from_kinship(gapit_ctx* ctx, const double* K, int64_t n, double* values_out, gapit_eigsys** out) {
+  if (!ctx || !K || !values_out || !out || n <= 0) return fail(GAPIT_ERR_ARG, "gapit_eigsys_from_kinship: bad argument");
+  GAPIT_CUDA(cudaSetDevice(ctx->device));
+  double* A_dev = nullptr;
+  GAPIT_CUDA(cudaMalloc(&A_dev, size_t(n) * n * 8));
+  cudaError_t e = cudaMemcpyAsync(A_dev, K, size_t(n) * n * 8, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  int rc = e == cudaSuccess ? GAPIT_OK : fail(GAPIT_ERR_CUDA, std::string("gapit_eigsys_from_kinship: ") + cudaGetErrorString(e));
+  if (rc == GAPIT_OK) rc = gapit_eigh_dev(ctx, A_dev, n, values_out);
+  if (rc == GAPIT_OK) rc = gapit_eigsys_from_device(ctx, A_dev, values_out, n, out);
+  cudaFree(A_dev);
+  return rc;
+}
+
 // Multi-GPU eigensolver: cusolverMgSyevd lives in libgapitcuda_mg.so next to this library and is loaded on first use.
 // (libcusolverMg binds the CUDA toolkit's own libcublas; a host process that already carries another libcublas -- a
 // PyTorch wheel's -- cannot load it, and then this call reports that and the caller keeps the one-GPU solver.)

@@ -274,6 +274,9 @@ int gapit_eigsys_upload(gapit_ctx* ctx, const double* vectors, const double* val
 /* the same from eigenvectors already on the device (gapit_eigh_dev), and the projections V'R (R: n x nc column-major
  * host, out: n x nc host) that gapit_reml_eigL takes (V'y, V'X) */
 int gapit_eigsys_from_device(gapit_ctx* ctx, const double* vectors_dev, const double* values, int64_t n, gapit_eigsys** out);
+/* eigen(K) (host K, n x n) decomposed and sliced on the device in one call: the eigenvectors never visit the host.
+ * values_out: host, n, descending. */
+int gapit_eigsys_from_kinship(gapit_ctx* ctx, const double* K, int64_t n, double* values_out, gapit_eigsys** out);
 int gapit_eigsys_project(gapit_ctx* ctx, gapit_eigsys* e, const double* R, int nc, double* out);
 void gapit_eigsys_free(gapit_eigsys* e);
 /* device address of the n x n column-major eigenvectors held by the handle (valid until gapit_eigsys_free) */
@@ -322,6 +325,20 @@ int gapit_multi_vanraden(gapit_mctx* mc, gapit_mgeno* g, double* K_out, int32_t*
 /* eigen(A) as gapit_eigh (values descending, vectors n x n column-major, both host), the spectrum sliced over the
  * GPUs of the context: each one runs gapit_eigh_dev_range for n/ngpus eigenpairs.  One GPU (or n < 2048): gapit_eigh. */
 int gapit_multi_eigh(gapit_mctx* mc, const double* A, int64_t n, double* values_out, double* vectors_out);
+/* The eigen-system of K resident on EVERY GPU of the context (one sliced copy per GPU), so that eigen(K), the REML
+ * projections, BLUP/PEV and the scan of one GAPIT.EMMAxP3D call share it without the eigenvectors crossing PCIe:
+ * gapit_meigsys_from_kinship decomposes K with the spectrum sliced over the GPUs (as gapit_multi_eigh) and exchanges the
+ * slices GPU to GPU; gapit_meigsys_upload starts from host eigenvectors instead (one upload, NVLink copies);
+ * gapit_meigsys_part(me, gpu) is the one-GPU handle on device `gpu` (use it with gapit_mctx_ctx(mc, gpu) for
+ * gapit_eigsys_project / gapit_blup_pev); gapit_multi_p3d_scan_es scans against it (me NULL with glm != 0). */
+typedef struct gapit_meigsys gapit_meigsys;
+int gapit_meigsys_from_kinship(gapit_mctx* mc, const double* K, int64_t n, double* values_out, gapit_meigsys** out);
+int gapit_meigsys_upload(gapit_mctx* mc, const double* vectors, const double* values, int64_t n, gapit_meigsys** out);
+gapit_eigsys* gapit_meigsys_part(gapit_meigsys* me, int gpu);
+void gapit_meigsys_free(gapit_meigsys* me);
+int gapit_multi_p3d_scan_es(gapit_mctx* mc, gapit_mgeno* g, gapit_meigsys* me, const double* X0, int q0, const double* Y,
+                            int T, const double* delta, const double* vg, int glm, gapit_scan_out* out,
+                            gapit_scan_base* base_out /* T entries */);
 int gapit_multi_p3d_scan(gapit_mctx* mc, gapit_mgeno* g, const double* vectors, const double* values, const double* X0,
                          int q0, const double* Y, int T, const double* delta, const double* vg, int glm,
                          gapit_scan_out* out, gapit_scan_base* base_out /* T entries */);

@@ -35,24 +35,36 @@ y <- as.numeric(ys[g,])                                                       # 
 xs.arg <- if(is.raw(xs)) xs else as.matrix(xs)        # a raw vector is the content of a PLINK .bed (r/GAPIT.Bed.R)
 impute <- switch(SNP.impute, Minor=0L, Middle=1L, Major=2L, -1L)
 glm <- is.null(K)
-if(!glm){
-  eig.L <- .Call("gapit_R_eigen_L", K)                                        # :48
+if(!glm && !identical(getOption("gapit.reml.route"), "eigR")){
+  # :48, :224  eigen(K) is decomposed ON the GPUs (spectrum sliced over them) and stays there, sliced for the rotation,
+  # behind an external pointer: eig.L$vectors (3.2 GB at n = 20,000) never comes back to R -- the REML projections,
+  # BLUP/PEV and the scan all read the resident copy.  R keeps the eigenvalues.
+  es <- .Call("gapit_R_eigsys", K)
+  on.exit(.Call("gapit_R_eigsys_free", es$handle), add=TRUE)
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="eig.L"); Memory=GAPIT.Memory(Memory=Memory,Infor="eig.L")
   # :58, :202  the REML likelihood is evaluated from eig.L alone (gapit_reml_eigL: the same function of delta as
   # emma.delta.REML.{LL,dLL}.wo.Z on eig.R, delta agrees to 1e-13), so the second eigendecomposition is skipped.
-  # options(gapit.reml.route="eigR") runs the reference's route (gapit_R_eigen_R + gapit_R_reml) instead.
-  if(identical(getOption("gapit.reml.route"), "eigR")){
-    eig.R <- try(.Call("gapit_R_eigen_R", K, X0), silent=TRUE)                # :58
-    if(inherits(eig.R, "try-error"))                                          # :70-74
-      return(list(ps = NULL, REMLs = NA, stats = NULL, effect.est = NULL, dfs = NULL,maf=NULL,nobs = NULL,Timmer=Timmer,Memory=Memory,
-          vgs = NA, ves = NA, BLUP = NULL, BLUP_Plus_Mean = NULL, PEV = NULL, BLUE=NULL))
-    etas <- crossprod(eig.R$vectors, Y)                                       # GAPIT.emma.REMLE.R:25
-    r <- sapply(1:g, function(j) .Call("gapit_R_reml", eig.R$values, as.numeric(etas[,j]), as.integer(ngrids), llim, ulim, esp))   # :202
-    rm(eig.R)
-  } else {
-    Vt <- crossprod(eig.L$vectors, cbind(X0, Y))
-    r <- .Call("gapit_R_reml_eigL_multi", eig.L$values, Vt[,-(1:q0),drop=FALSE], Vt[,1:q0,drop=FALSE], as.integer(ngrids), llim, ulim, esp)
-  }
+  Vt <- .Call("gapit_R_eigsys_project", es$handle, cbind(X0, Y))               # crossprod(eig.L$vectors, cbind(X0, Y))
+  r <- .Call("gapit_R_reml_eigL_multi", es$values, Vt[,-(1:q0),drop=FALSE], Vt[,1:q0,drop=FALSE], as.integer(ngrids), llim, ulim, esp)
+  Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="eig.R"); Memory=GAPIT.Memory(Memory=Memory,Infor="eig.R")
+  REMLs <- r[1,g]; REMLE_delta <- r[2,g]; ves <- r[3,g]; vgs <- r[4,g]
+  Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="REML"); Memory=GAPIT.Memory(Memory=Memory,Infor="REML")
+  bp <- .Call("gapit_R_eigsys_blup_pev", es$handle, X0, y, REMLE_delta, vgs)                   # :779-839
+  BLUP <- bp[[1]]; PEV <- bp[[2]]; BLUP_Plus_Mean <- bp[[3]][1] + BLUP                        # :818-819
+  Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="PEV"); Memory=GAPIT.Memory(Memory=Memory,Infor="PEV")
+  res <- .Call("gapit_R_eigsys_scan", xs.arg, es$handle, X0, Y, as.numeric(r[2,]), as.numeric(r[4,]), impute)
+} else if(!glm){
+  # options(gapit.reml.route="eigR"): the reference's own route -- eig.L and eig.R as R objects (gapit_R_eigen_L,
+  # gapit_R_eigen_R, gapit_R_reml), the eigenvectors uploaded again for BLUP/PEV and for the scan
+  eig.L <- .Call("gapit_R_eigen_L", K)                                        # :48
+  Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="eig.L"); Memory=GAPIT.Memory(Memory=Memory,Infor="eig.L")
+  eig.R <- try(.Call("gapit_R_eigen_R", K, X0), silent=TRUE)                  # :58
+  if(inherits(eig.R, "try-error"))                                            # :70-74
+    return(list(ps = NULL, REMLs = NA, stats = NULL, effect.est = NULL, dfs = NULL,maf=NULL,nobs = NULL,Timmer=Timmer,Memory=Memory,
+        vgs = NA, ves = NA, BLUP = NULL, BLUP_Plus_Mean = NULL, PEV = NULL, BLUE=NULL))
+  etas <- crossprod(eig.R$vectors, Y)                                         # GAPIT.emma.REMLE.R:25
+  r <- sapply(1:g, function(j) .Call("gapit_R_reml", eig.R$values, as.numeric(etas[,j]), as.integer(ngrids), llim, ulim, esp))   # :202
+  rm(eig.R)
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="eig.R"); Memory=GAPIT.Memory(Memory=Memory,Infor="eig.R")
   REMLs <- r[1,g]; REMLE_delta <- r[2,g]; ves <- r[3,g]; vgs <- r[4,g]
   Timmer=GAPIT.Timmer(Timmer=Timmer,Infor="REML"); Memory=GAPIT.Memory(Memory=Memory,Infor="REML")

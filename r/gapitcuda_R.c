@@ -162,15 +162,77 @@ SEXP gapit_R_reml(SEXP lambda, SEXP etas, SEXP ngrids, SEXP llim, SEXP ulim, SEX
   return out;
 }
 
+/* ---- the eigen-system of K as an R-visible handle -----------------------------------------------------------------
+ * One GAPIT.EMMAxP3D call needs eig.L four times: for the REML projections, for BLUP/PEV, for the scan, and (in the
+ * reference) as an R object in between.  At n = 20,000 the vectors are 3.2 GB: returning them to R and uploading them
+ * again for every step costs more than the scan.  gapit_R_eigsys decomposes K on the GPUs (spectrum sliced over them)
+ * and leaves the sliced eigen-system resident on every GPU behind an external pointer; R sees only the eigenvalues. */
+static void eigsys_finalizer(SEXP p) {
+  gapit_meigsys* me = (gapit_meigsys*)R_ExternalPtrAddr(p);
+  if (me) {
+    gapit_meigsys_free(me);
+    R_ClearExternalPtr(p);
+  }
+}
+
+static gapit_meigsys* eigsys_handle(SEXP h) {
+  gapit_meigsys* me = TYPEOF(h) == EXTPTRSXP ? (gapit_meigsys*)R_ExternalPtrAddr(h) : NULL;
+  if (!me) Rf_error("gapitcuda: not a live eigen-system handle (gapit_R_eigsys)");
+  return me;
+}
+
+/* .Call("gapit_R_eigsys", K): list(values = eigen(K)$values, handle = <external pointer>) */
+SEXP gapit_R_eigsys(SEXP K) {
+  const int64_t n = INTEGER(Rf_getAttrib(K, R_DimSymbol))[0];
+  gapit_mctx* mc = mctx();
+  SEXP values = PROTECT(Rf_allocVector(REALSXP, n));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 2));
+  SEXP nm = PROTECT(Rf_allocVector(STRSXP, 2));
+  SET_STRING_ELT(nm, 0, Rf_mkChar("values"));
+  SET_STRING_ELT(nm, 1, Rf_mkChar("handle"));
+  Rf_setAttrib(out, R_NamesSymbol, nm);
+  SEXP h = PROTECT(R_MakeExternalPtr(NULL, R_NilValue, R_NilValue));
+  R_RegisterCFinalizerEx(h, eigsys_finalizer, TRUE);
+  gapit_meigsys* me = NULL;   /* from here on nothing can longjmp until the handle is owned by the external pointer */
+  if (gapit_meigsys_from_kinship(mc, REAL(K), n, REAL(values), &me) != GAPIT_OK) {
+    UNPROTECT(4);
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  }
+  R_SetExternalPtrAddr(h, me);
+  SET_VECTOR_ELT(out, 0, values);
+  SET_VECTOR_ELT(out, 1, h);
+  UNPROTECT(4);
+  return out;
+}
+
+/* .Call("gapit_R_eigsys_free", handle): release the device copies now instead of at garbage collection */
+SEXP gapit_R_eigsys_free(SEXP h) {
+  if (TYPEOF(h) == EXTPTRSXP) eigsys_finalizer(h);
+  return R_NilValue;
+}
+
+/* crossprod(eig.L$vectors, R) for an n x nc matrix R, on GPU 0 */
+SEXP gapit_R_eigsys_project(SEXP h, SEXP R) {
+  gapit_meigsys* me = eigsys_handle(h);
+  SEXP dim = Rf_getAttrib(R, R_DimSymbol);
+  const int n = INTEGER(dim)[0], nc = INTEGER(dim)[1];
+  SEXP out = PROTECT(Rf_allocMatrix(REALSXP, n, nc));
+  const int rc = gapit_eigsys_project(ctx(), gapit_meigsys_part(me, 0), REAL(R), nc, REAL(out));
+  UNPROTECT(1);
+  if (rc != GAPIT_OK) Rf_error("gapitcuda: %s", gapit_last_error());
+  return out;
+}
+
 /* The marker loop of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:397-979) for T traits that share X0 and the eigen-system: the
  * reference loops the rows of ys (:81) and repeats the rotation for each; here one rotation serves them all.
- * xs n x m (numeric/integer) or the raw bytes of a .bed (see geno_source), vectors/values = eig.L (ignored when glm),
- * X0 n x q0, Y n x T (a vector is one trait), delta / vg length T.  impute: -1 none, 0 Minor, 1 Middle, 2 Major.
+ * xs n x m (numeric/integer) or the raw bytes of a .bed (see geno_source); the eigen-system is either a resident handle
+ * (me) or eig.L on the host (vectors/values; uploaded for this call); neither for the GLM branch.  X0 n x q0, Y n x T
+ * (a vector is one trait), delta / vg length T.  impute: -1 none, 0 Minor, 1 Middle, 2 Major.
  * Returns list(effect, tvalue, se, pvalue, rsquare, loglm) of m x T matrices, maf (length m) and base, a
  * (7 + q0) x T matrix with rows logL0, logLM_base, rsquare_base, ves, reml, df, singular_x0, beta0[1..q0]. */
-SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP Y, SEXP delta, SEXP vg, SEXP glm, SEXP impute) {
+static SEXP scan_core(SEXP xs, gapit_meigsys* me, SEXP vectors, SEXP values, SEXP X0, SEXP Y, SEXP delta, SEXP vg, int is_glm,
+                      SEXP impute) {
   const int q0 = INTEGER(Rf_getAttrib(X0, R_DimSymbol))[1];
-  const int is_glm = Rf_asLogical(glm);
   /* everything that can longjmp happens before a device handle exists */
   gapit_mctx* mc = mctx();
   const geno_src src = geno_source(xs);
@@ -193,23 +255,24 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP Y, SEXP 
   const double* d = is_glm ? NULL : REAL(delta);
   const double* v = is_glm ? NULL : REAL(vg);
   const gapit_impute imp = (gapit_impute)Rf_asInteger(impute);
-  int rc;
-  if (gapit_mctx_ngpus(mc) == 1) {
+  gapit_meigsys* own = NULL;   /* an eigen-system uploaded for this call only */
+  int rc = GAPIT_OK;
+  if (!is_glm && !me) {
+    rc = gapit_meigsys_upload(mc, REAL(vectors), REAL(values), n, &own);
+    me = own;
+  }
+  if (rc == GAPIT_OK && gapit_mctx_ngpus(mc) == 1) {
     /* one GPU: stream the packed rows (upload overlapped with the scan) */
-    gapit_eigsys* e = NULL;
-    rc = is_glm ? GAPIT_OK : gapit_eigsys_upload(ctx(), REAL(vectors), REAL(values), n, &e);
-    if (rc == GAPIT_OK)
-      rc = gapit_p3d_scan_host(ctx(), packed, src.dtype, n, m, nb, imp, e, REAL(X0), q0, REAL(Y), T, d, v, is_glm, &out, base);
-    gapit_eigsys_free(e);
-  } else {
+    rc = gapit_p3d_scan_host(ctx(), packed, src.dtype, n, m, nb, imp, is_glm ? NULL : gapit_meigsys_part(me, 0), REAL(X0), q0,
+                             REAL(Y), T, d, v, is_glm, &out, base);
+  } else if (rc == GAPIT_OK) {
     /* several GPUs: one marker block per GPU, results in marker order */
     gapit_mgeno* g = NULL;
     rc = gapit_mgeno_pack(mc, packed, src.dtype, n, m, nb, imp, &g);
-    if (rc == GAPIT_OK)
-      rc = gapit_multi_p3d_scan(mc, g, is_glm ? NULL : REAL(vectors), is_glm ? NULL : REAL(values), REAL(X0), q0, REAL(Y), T, d, v,
-                                is_glm, &out, base);
+    if (rc == GAPIT_OK) rc = gapit_multi_p3d_scan_es(mc, g, is_glm ? NULL : me, REAL(X0), q0, REAL(Y), T, d, v, is_glm, &out, base);
     gapit_mgeno_free(g);
   }
+  gapit_meigsys_free(own);
   if (rc != GAPIT_OK) {
     UNPROTECT(2);
     Rf_error("gapitcuda: %s", gapit_last_error());
@@ -227,6 +290,40 @@ SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP Y, SEXP 
   }
   UNPROTECT(2);
   return res;
+}
+
+/* eig.L as R objects (the reference's eig.R route of r/GAPIT.EMMAxP3D.R, and the GLM branch with glm = TRUE) */
+SEXP gapit_R_p3d_scan(SEXP xs, SEXP vectors, SEXP values, SEXP X0, SEXP Y, SEXP delta, SEXP vg, SEXP glm, SEXP impute) {
+  return scan_core(xs, NULL, vectors, values, X0, Y, delta, vg, Rf_asLogical(glm), impute);
+}
+
+/* the same against the resident handle of gapit_R_eigsys */
+SEXP gapit_R_eigsys_scan(SEXP xs, SEXP h, SEXP X0, SEXP Y, SEXP delta, SEXP vg, SEXP impute) {
+  return scan_core(xs, eigsys_handle(h), R_NilValue, R_NilValue, X0, Y, delta, vg, 0, impute);
+}
+
+/* i = 0 block of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:779-839) against the resident handle: list(BLUP, PEV, beta) */
+SEXP gapit_R_eigsys_blup_pev(SEXP h, SEXP X0, SEXP y, SEXP delta, SEXP vg) {
+  gapit_meigsys* me = eigsys_handle(h);
+  SEXP dim = Rf_getAttrib(X0, R_DimSymbol);
+  const int64_t n = INTEGER(dim)[0];
+  const int q0 = INTEGER(dim)[1];
+  gapit_ctx* c = ctx();
+  SEXP blup = PROTECT(Rf_allocMatrix(REALSXP, (int)n, 1));
+  SEXP pev = PROTECT(Rf_allocMatrix(REALSXP, (int)n, 1));
+  SEXP beta = PROTECT(Rf_allocVector(REALSXP, q0));
+  SEXP out = PROTECT(Rf_allocVector(VECSXP, 3));
+  const int rc = gapit_blup_pev(c, gapit_meigsys_part(me, 0), REAL(X0), q0, REAL(y), Rf_asReal(delta), Rf_asReal(vg), REAL(blup),
+                                REAL(pev), REAL(beta));
+  if (rc != GAPIT_OK) {
+    UNPROTECT(4);
+    Rf_error("gapitcuda: %s", gapit_last_error());
+  }
+  SET_VECTOR_ELT(out, 0, blup);
+  SET_VECTOR_ELT(out, 1, pev);
+  SET_VECTOR_ELT(out, 2, beta);
+  UNPROTECT(4);
+  return out;
 }
 
 /* i = 0 block of GAPIT.EMMAxP3D (GAPIT.EMMAxP3D.R:779-839): list(BLUP, PEV, beta) */

@@ -98,3 +98,54 @@ def test_eigen_decomposition_sliced_over_the_gpus(ngpus):
     assert np.abs(K @ V - V * vals).max() < 1e-11 * vals[0]
     mctx.close()
 
+
+@pytest.mark.parametrize("ngpus", [2, 4])
+def test_resident_eigen_system_on_every_gpu(ngpus):
+    """gapit_meigsys (what one GAPIT.EMMAxP3D call of the R shim holds): K decomposed with the spectrum sliced over the
+    GPUs, slices exchanged over NVLink, a sliced copy on every GPU; REML projections, BLUP/PEV and the scan read it.
+    Against the one-GPU pipeline: same eigenvalues, same delta, same p-values (the eigenvectors may differ by sign)."""
+    import numpy as np
+    import torch
+    import gapit_b200 as gb
+    from gapit_b200 import synth
+    if torch.cuda.device_count() < ngpus:
+        pytest.skip(f"needs {ngpus} GPUs")
+    n, m = 1024 * ngpus + 50, 4001
+    G = synth.make_genotypes(n, m, seed=31, threads=4)
+    Y = synth.make_phenotypes(G, ntraits=2, seed=31)
+    X0 = synth.make_covariates(G, npc=1)
+    ctx = gb.Context(0)
+    one = gb.Genotypes(G, ctx=ctx, marker_major=True)
+    K = gb.GAPIT_kinship_VanRaden(one, ctx=ctx, verbose=False)
+    es1 = gb.EigenSystem.from_kinship(K, ctx=ctx)
+    p1 = es1.project(np.column_stack([X0, Y]))
+    rs1 = gb.reml_from_projections_multi(es1.values, p1[:, 2:], p1[:, :2])
+    d1, v1 = [r["delta"] for r in rs1], [r["vg"] for r in rs1]
+    ref, _ = gb.p3d_scan(one, X0, Y, eigsys=es1, delta=d1, vg=v1, ctx=ctx)
+    b1 = gb.blup_pev(es1, X0, Y[:, 1], d1[1], v1[1], ctx=ctx)
+
+    mctx = gb.MultiContext(ngpus)
+    me = gb.MultiEigenSystem(mctx, K=K)
+    assert np.allclose(me.values, es1.values, rtol=0, atol=1e-12 * es1.values[0])
+    pm = me.part(0).project(np.column_stack([X0, Y]))
+    rsm = gb.reml_from_projections_multi(me.values, pm[:, 2:], pm[:, :2])
+    dm, vm = [r["delta"] for r in rsm], [r["vg"] for r in rsm]
+    assert np.allclose(dm, d1, rtol=1e-9) and np.allclose(vm, v1, rtol=1e-9)
+    mg = gb.MultiGenotypes(G, mctx, marker_major=True)
+    got, _ = gb.multi_p3d_scan(mg, X0, Y, delta=d1, vg=v1, eigsys=me)
+    for key in ("effect", "se", "rsquare", "maf"):
+        assert np.allclose(got[key], ref[key], rtol=1e-8, atol=1e-12, equal_nan=True), key
+    with np.errstate(divide="ignore"):
+        assert np.nanmax(np.abs(np.log10(got["pvalue"]) - np.log10(ref["pvalue"]))) < 1e-7
+    bm = gb.blup_pev(me.part(0), X0, Y[:, 1], d1[1], v1[1], ctx=mctx.context(0))
+    for x, y in zip(bm, b1):
+        assert np.allclose(x, y, rtol=1e-7, atol=1e-9)
+    # the upload form is the host-eigenvector call, bit for bit
+    eL = gb.emma_eigen_L_wo_Z(K, ctx=ctx)
+    mu = gb.MultiEigenSystem(mctx, values=eL["values"], vectors=eL["vectors"])
+    a, _ = gb.multi_p3d_scan(mg, X0, Y, delta=d1, vg=v1, eigsys=mu)
+    b, _ = gb.multi_p3d_scan(mg, X0, Y, values=eL["values"], vectors=eL["vectors"], delta=d1, vg=v1)
+    assert all(np.array_equal(a[k], b[k], equal_nan=True) for k in a)
+    for h in (mu, me, mg, mctx):
+        h.close()
+

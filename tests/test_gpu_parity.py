@@ -1124,3 +1124,31 @@ def test_eigh_by_index_range_assembles_the_full_decomposition(gpu_ctx):
     assert np.abs(K @ V - V * vals).max() < 1e-11 * vals[0]
     with pytest.raises(gb().GapitCudaError):
         gb().eigh_dev_range(V_t.data_ptr(), n, n - 3, 4, V_t.data_ptr(), ctx=gpu_ctx)      # past the end of the spectrum
+
+
+def test_resident_eigen_system_from_kinship(gpu_ctx):
+    """gapit_eigsys_from_kinship: eigen(K) decomposed and sliced on the device without the eigenvectors visiting the
+    host -- the same eigen-system as gapit_eigh + gapit_eigsys_upload, so projections, BLUP/PEV and scan agree."""
+    G, Y, X0 = case(260, 700, npc=2)
+    K = gb().GAPIT_kinship_VanRaden(gb().Genotypes(G, ctx=gpu_ctx, marker_major=True), ctx=gpu_ctx, verbose=False)
+    eL = gb().emma_eigen_L_wo_Z(K, ctx=gpu_ctx)
+    a = gb().EigenSystem(eL["values"], eL["vectors"], ctx=gpu_ctx)
+    b = gb().EigenSystem.from_kinship(K, ctx=gpu_ctx)
+    assert np.allclose(a.values, b.values, rtol=0, atol=1e-13 * a.values[0])
+    R = np.column_stack([X0, Y])
+    pa, pb = a.project(R), b.project(R)
+    reml_a = gb().reml_from_projections(a.values, pa[:, -1], pa[:, :-1])
+    reml_b = gb().reml_from_projections(b.values, pb[:, -1], pb[:, :-1])
+    assert reml_b["delta"] == pytest.approx(reml_a["delta"], rel=1e-10)
+    geno = gb().Genotypes(G, ctx=gpu_ctx, marker_major=True)
+    ra, _ = gb().p3d_scan(geno, X0, Y, eigsys=a, delta=[reml_a["delta"]], vg=[reml_a["vg"]], ctx=gpu_ctx)
+    rb, _ = gb().p3d_scan(geno, X0, Y, eigsys=b, delta=[reml_a["delta"]], vg=[reml_a["vg"]], ctx=gpu_ctx)
+    for k in ("effect", "se", "pvalue", "rsquare"):
+        assert np.allclose(ra[k], rb[k], rtol=1e-9, atol=1e-300, equal_nan=True), k
+    ba, bb = gb().blup_pev(a, X0, Y, reml_a["delta"], reml_a["vg"], ctx=gpu_ctx), gb().blup_pev(b, X0, Y, reml_a["delta"], reml_a["vg"], ctx=gpu_ctx)
+    for x, y in zip(ba, bb):
+        assert np.allclose(x, y, rtol=1e-8, atol=1e-10)
+    # and through the reference-facing call: no eig_L injected -> the resident route; injected -> the host route
+    r1 = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0, ctx=gpu_ctx)
+    r2 = gb().GAPIT_EMMAxP3D(Y, G.T, K, X0=X0, ctx=gpu_ctx, eig_L=eL)
+    assert np.allclose(r1["ps"], r2["ps"], rtol=1e-8, atol=1e-300, equal_nan=True) and r1["vgs"] == pytest.approx(r2["vgs"], rel=1e-9)
