@@ -1326,10 +1326,15 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
   const ScanPlan& plan = *planp;
   const size_t esz = dtype == GAPIT_F64 ? 8 : (dtype == GAPIT_I32 ? 4 : 1);
   const size_t row_bytes = is_packed2(dtype) ? size_t(nb2) : size_t(n) * esz;   // dense bytes of one marker on the host
-  // marker block: ~320 MB of int8 (multiple of 256 markers), at most 65535 for the convert grid
-  int64_t chunk = std::max<int64_t>(256, (int64_t(320) << 20) / ldn / 256 * 256);
-  if (const char* ev = getenv("GAPIT_STREAM_CHUNK")) chunk = std::max<int64_t>(256, atoll(ev) / 256 * 256);  // tests
+  // marker block: ~320 MB of int8, at most 65535 markers for the convert grid -- and WHOLE ROUNDS of the persistent
+  // grid: every launch of the tensor kernels costs ceil(jobs / units) rounds of equal jobs, a block of sm_count / 2 pair
+  // tiles (x 512 markers) fills every round whatever the eigen split, so only one block per call (the first, which takes
+  // the remainder) pays a partly filled round.  C2 in 65,280-marker blocks was 70 rounds against 67 resident.
+  const int64_t quantum = int64_t(std::max(1, ctx->sm_count / 2)) * 512;
+  int64_t chunk = (int64_t(320) << 20) / ldn;
   if (dtype != GAPIT_I8) chunk = std::min<int64_t>(chunk, 65280);
+  chunk = chunk >= quantum ? chunk / quantum * quantum : std::max<int64_t>(256, chunk / 256 * 256);
+  if (const char* ev = getenv("GAPIT_STREAM_CHUNK")) chunk = std::max<int64_t>(256, atoll(ev) / 256 * 256);  // tests
   chunk = std::min(chunk, round_up(m, 256));
   int8_t* mk[2];
   int32_t *cs[2], *cq[2];
@@ -1350,9 +1355,9 @@ static int scan_host_impl(gapit_ctx* ctx, const void* snps, gapit_dtype dtype, i
   cudaEventRecord(ctx->ev0, ctx->stream);
   // the copy stream must not start before the workspaces are initialised
   GAPIT_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev0, 0));
-  // the first block's upload cannot overlap anything, so it is a quarter-size one
-  const int64_t first = std::min<int64_t>(m, std::max<int64_t>(256, chunk / 4 / 256 * 256));
-  const int64_t nchunks = 1 + (m - first + chunk - 1) / chunk;
+  // the first block takes the remainder (its upload cannot overlap anything; every later block is a full one)
+  const int64_t first = m <= chunk ? m : ((m % chunk) ? (m % chunk) : chunk);
+  const int64_t nchunks = 1 + (m - first) / chunk;
   for (int64_t c = 0; c < nchunks; ++c) {
     const int b = static_cast<int>(c & 1);
     const int64_t k0 = (c == 0) ? 0 : first + (c - 1) * chunk;
