@@ -218,51 +218,98 @@ __global__ void gram_rowsum_kernel(const int32_t* __restrict__ G, int64_t ldg, i
   if (lane == 0) s[row] = acc;
 }
 
-// ---- K (column-major n x n) from the LOWER triangle of G alone (no mirror pass): 32 x 32 tiles with bi >= bj --------
-// s_i = sum_j G_ij over the full symmetric row = row sums of the lower 32 x 32 tiles (bj <= bi; a diagonal tile holds
-// both triangles) + column sums of the strictly lower ones (bi > bj).  One CTA owns a block of 32 rows (pass 0) or of 32
-// columns (pass 1) and walks its tiles, so every s_i has a single writer per pass: no atomics, fixed order.
-__global__ void gram_sums_lower_kernel(const int32_t* __restrict__ G, int64_t ldg, int tiles32, int pass,
-                                       long long* __restrict__ s) {
-  const int b = blockIdx.x;
-  const int x = threadIdx.x, y0 = threadIdx.y;
+// ---- K (column-major n x n) from the LOWER triangle of G alone (no mirror pass) --------------------------------------
+// s_i = sum_j G_ij over the full symmetric row = the part of row i the lower triangle holds (columns up to the end of its
+// diagonal 32 x 32 tile, which carries both triangles) + the part of column i below that tile.  ONE pass over the
+// triangle: a CTA owns a strip of 32 rows and streams it in 128-column chunks (a warp per chunk, 32 independent 16-byte
+// loads per lane: the strip is read at HBM rate); a lane keeps the 32 row partials in registers for the whole strip and the
+// column sums of its 4 columns per chunk, which go to colpart[strip][column] -- complete for that strip, single writer.
+// A second small kernel adds the column parts below each diagonal tile.  No atomics, fixed order.
+// (Two strided passes with 157 CTAs took 0.24 ms of the 3.5 ms kinship step at n = 5,000 and 11 ms of 95 ms at n = 50,000.)
+__global__ void __launch_bounds__(256) gram_strip_sums_kernel(const int32_t* __restrict__ G, int64_t ldg, int tiles32,
+                                                              long long* __restrict__ rowsum, long long* __restrict__ colpart) {
+  const int b = tiles32 - 1 - static_cast<int>(blockIdx.x);   // longest strips first
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row0 = int64_t(b) * 32;
+  const int64_t col_end = row0 + 32;   // through the diagonal tile
+  long long racc[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) racc[r] = 0;
+  const int nchunks = static_cast<int>((col_end + 127) / 128);
+  for (int c = warp; c < nchunks; c += 8) {
+    const int64_t j0 = int64_t(c) * 128 + 4 * lane;
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const int32_t* src = G + row0 * ldg + j0;
+#pragma unroll
+    for (int r8 = 0; r8 < 32; r8 += 8) {
+      int4 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = __ldg(reinterpret_cast<const int4*>(src + int64_t(r8 + r) * ldg));
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (j0 + 3 >= col_end) {   // the chunk that holds the diagonal tile: columns past it are not part of the triangle
+          if (j0 + 0 >= col_end) v[r].x = 0;
+          if (j0 + 1 >= col_end) v[r].y = 0;
+          if (j0 + 2 >= col_end) v[r].z = 0;
+          if (j0 + 3 >= col_end) v[r].w = 0;
+        }
+        racc[r8 + r] += static_cast<long long>(v[r].x) + v[r].y + v[r].z + v[r].w;
+        c0 += v[r].x;
+        c1 += v[r].y;
+        c2 += v[r].z;
+        c3 += v[r].w;
+      }
+    }
+    if (j0 < row0) {   // strictly below the diagonal tile (row0 is a multiple of 32, j0 of 4: all four columns or none)
+      long long* dst = colpart + int64_t(b) * ldg + j0;
+      reinterpret_cast<longlong2*>(dst)[0] = make_longlong2(c0, c1);
+      reinterpret_cast<longlong2*>(dst)[1] = make_longlong2(c2, c3);
+    }
+  }
   __shared__ long long red[8][32];
-  if (pass == 0) {
-    long long r[4] = {0, 0, 0, 0};
-    for (int bj = 0; bj <= b; ++bj)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) r[q] += G[(int64_t(b) * 32 + y0 + 8 * q) * ldg + int64_t(bj) * 32 + x];
+  for (int r = 0; r < 32; ++r) {
+    long long v = racc[r];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      long long v = r[q];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == r) red[warp][r] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    long long t = 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (x == 0) s[int64_t(b) * 32 + y0 + 8 * q] = v;
-    }
-  } else {
-    long long c = 0;
-    for (int bi = b + 1; bi < tiles32; ++bi)
-#pragma unroll
-      for (int q = 0; q < 4; ++q) c += G[(int64_t(bi) * 32 + y0 + 8 * q) * ldg + int64_t(b) * 32 + x];
-    red[y0][x] = c;
-    __syncthreads();
-    if (y0 == 0) {
-      long long t = 0;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) t += red[q][x];
-      s[int64_t(b) * 32 + x] += t;   // after pass 0 on the same stream
-    }
+    for (int w = 0; w < 8; ++w) t += red[w][lane];
+    rowsum[row0 + lane] = t;
   }
 }
 
-// K_ij and K_ji from the lower tile (i in block-row bi, j in block-column bj): exact int64 numerator, one fp64 division;
-// the (j, i) entry is written as read (contiguous along j), the (i, j) entry through a shared-memory transpose.
-__global__ void vanraden_epilogue_lower_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n,
-                                               const long long* __restrict__ s, const unsigned long long* __restrict__ sums,
-                                               double* __restrict__ K) {
-  const int bi = blockIdx.y, bj = blockIdx.x;
-  if (bj > bi) return;
-  __shared__ double tile[32][33];
+// s_j = rowsum_j + the column parts of the strips below j's diagonal tile
+__global__ void gram_strip_combine_kernel(const long long* __restrict__ colpart, int64_t ldg, int tiles32, int64_t n32,
+                                          long long* __restrict__ s) {
+  const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (j >= n32) return;
+  long long t = s[j];
+  for (int b = static_cast<int>(j / 32) + 1; b < tiles32; ++b) t += colpart[int64_t(b) * ldg + j];
+  s[j] = t;
+}
+
+// K_ij and K_ji from the lower 64 x 64 tile (i in block-row bi, j in block-column bj <= bi; CTAs are numbered along the
+// triangle, so none is launched for the upper half; a 512 x 512 super-tile order was measured slower: 11.9 vs 9.5 ms
+// at n = 50,000): exact int64 numerator, one fp64 division; the (j, i) entry is
+// written as read (contiguous along j), the (i, j) entry through a shared-memory transpose.  16 independent loads per
+// thread; 20 GB of fp64 written at n = 50,000 -- the kernel is bound by the HBM write rate.
+__global__ void __launch_bounds__(256) vanraden_epilogue_lower_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n,
+                                                                      const long long* __restrict__ s,
+                                                                      const unsigned long long* __restrict__ sums,
+                                                                      double* __restrict__ K) {
+  // triangular index -> (bi, bj), bj <= bi
+  const long long t = blockIdx.x;
+  int bi = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
+  while (static_cast<long long>(bi) * (bi + 1) / 2 > t) --bi;
+  while (static_cast<long long>(bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  const int bj = static_cast<int>(t - static_cast<long long>(bi) * (bi + 1) / 2);
+  __shared__ double tile[64][65];
+  __shared__ long long si_sh[64];
   const long long sum_c = static_cast<long long>(sums[0]);
   const long long sum_c2 = static_cast<long long>(sums[1]);
   const long long n2 = static_cast<long long>(sums[2]);
@@ -271,26 +318,38 @@ __global__ void vanraden_epilogue_lower_kernel(const int32_t* __restrict__ G, in
   const long long c2 = sum_c2 - n2 * 4 * nn * nn;
   const long long c1 = sum_c - n2 * 2 * nn;
   const double D = static_cast<double>(2 * nn * c1 - c2);
-  const int x = threadIdx.x, y0 = threadIdx.y;
-  const int64_t j = int64_t(bj) * 32 + x;
+  const int x = threadIdx.x & 63, y0 = threadIdx.x >> 6;
+  const int64_t i0 = int64_t(bi) * 64, j0 = int64_t(bj) * 64;
+  if (threadIdx.x < 64) si_sh[threadIdx.x] = (i0 + threadIdx.x < n) ? s[i0 + threadIdx.x] - 4 * n2 * nn : 0;
+  const int64_t j = j0 + x;
   const long long sj = (j < n) ? s[j] - 4 * n2 * nn : 0;
-  for (int y = y0; y < 32; y += 8) {
-    const int64_t i = int64_t(bi) * 32 + y;
+  int32_t g[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int64_t i = i0 + y0 + 4 * q;
+    g[q] = (i < n && j < n) ? __ldg(G + i * ldg + j) : 0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int y = y0 + 4 * q;
+    const int64_t i = i0 + y;
     double v = 0.0;
     if (i < n && j < n) {
-      const long long g = static_cast<long long>(G[i * ldg + j]) - 4 * n2;
-      const long long si = s[i] - 4 * n2 * nn;
-      const long long num = nn * nn * g - nn * (si + sj) + c2;
+      const long long gg = static_cast<long long>(g[q]) - 4 * n2;
+      const long long num = nn * nn * gg - nn * (si_sh[y] + sj) + c2;
       v = 2.0 * static_cast<double>(num) / D;
       K[j + i * n] = v;                                  // element (j, i): contiguous along j
     }
     tile[y][x] = v;
   }
-  if (bi == bj) return;                                  // the diagonal tile wrote both orientations already
+  if (bi == bj) return;                                  // the diagonal tile holds both triangles: written above
   __syncthreads();
-  const int64_t i2 = int64_t(bi) * 32 + x;               // now x runs along i
-  for (int y = y0; y < 32; y += 8) {
-    const int64_t j2 = int64_t(bj) * 32 + y;
+  const int64_t i2 = i0 + x;                             // now x runs along i
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int y = y0 + 4 * q;
+    const int64_t j2 = j0 + y;
     if (i2 < n && j2 < n) K[i2 + j2 * n] = tile[x][y];   // element (i, j): contiguous along i
   }
 }
@@ -606,16 +665,19 @@ extern "C" int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, 
   const int64_t ldg = gapit_gram_ld(n);
   long long* s = nullptr;
   double* K_dev = K_dev_out;
+  long long* colpart = nullptr;
   GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n) + 32, &s));                  // arena: no leak on the error paths below
+  GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t((n + 31) / 32) * size_t(ldg), &colpart));   // column sums per 32-row strip
   if (!K_dev) GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(n) * n, &K_dev));
   {
     // everything from the lower triangle the Gram kernel (and the row gather of the sharded form) left: the row sums,
     // then both orientations of every K entry; the int32 matrix itself is mirrored only when the caller asks for it
     const unsigned t32 = static_cast<unsigned>((n + 31) / 32);
-    dim3 grid(t32, t32);
-    gram_sums_lower_kernel<<<t32, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg, static_cast<int>(t32), 0, s);
-    gram_sums_lower_kernel<<<t32, dim3(32, 8), 0, ctx->stream>>>(G_dev, ldg, static_cast<int>(t32), 1, s);
-    vanraden_epilogue_lower_kernel<<<grid, dim3(32, 8), 0, ctx->stream>>>(
+    gram_strip_sums_kernel<<<t32, 256, 0, ctx->stream>>>(G_dev, ldg, static_cast<int>(t32), s, colpart);
+    gram_strip_combine_kernel<<<(t32 * 32 + 255) / 256, 256, 0, ctx->stream>>>(colpart, ldg, static_cast<int>(t32),
+                                                                               int64_t(t32) * 32, s);
+    const long long t64 = (n + 63) / 64;
+    vanraden_epilogue_lower_kernel<<<static_cast<unsigned>(t64 * (t64 + 1) / 2), 256, 0, ctx->stream>>>(
         G_dev, ldg, n, s, reinterpret_cast<const unsigned long long*>(sums_dev), K_dev);
     if (G_host_out) {
       dim3 gm(static_cast<unsigned>(ldg / 32), static_cast<unsigned>(ldg / 32));
