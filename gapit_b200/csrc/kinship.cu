@@ -283,14 +283,23 @@ __global__ void __launch_bounds__(256) gram_strip_sums_kernel(const int32_t* __r
   }
 }
 
-// s_j = rowsum_j + the column parts of the strips below j's diagonal tile
-__global__ void gram_strip_combine_kernel(const long long* __restrict__ colpart, int64_t ldg, int tiles32, int64_t n32,
+// s_j = rowsum_j + the column parts of the strips below j's diagonal tile; one CTA per 32 columns, 8 strips in flight
+__global__ void gram_strip_combine_kernel(const long long* __restrict__ colpart, int64_t ldg, int tiles32,
                                           long long* __restrict__ s) {
-  const int64_t j = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (j >= n32) return;
-  long long t = s[j];
-  for (int b = static_cast<int>(j / 32) + 1; b < tiles32; ++b) t += colpart[int64_t(b) * ldg + j];
-  s[j] = t;
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const int bj = blockIdx.x;
+  const int64_t j = int64_t(bj) * 32 + x;
+  long long t = 0;
+  for (int b = bj + 1 + y; b < tiles32; b += 8) t += colpart[int64_t(b) * ldg + j];
+  __shared__ long long red[8][32];
+  red[y][x] = t;
+  __syncthreads();
+  if (y == 0) {
+    long long v = s[j];
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += red[w][x];
+    s[j] = v;
+  }
 }
 
 // K_ij and K_ji from the lower 64 x 64 tile (i in block-row bi, j in block-column bj <= bi; CTAs are numbered along the
@@ -298,10 +307,10 @@ __global__ void gram_strip_combine_kernel(const long long* __restrict__ colpart,
 // at n = 50,000): exact int64 numerator, one fp64 division; the (j, i) entry is
 // written as read (contiguous along j), the (i, j) entry through a shared-memory transpose.  16 independent loads per
 // thread; 20 GB of fp64 written at n = 50,000 -- the kernel is bound by the HBM write rate.
-__global__ void __launch_bounds__(256) vanraden_epilogue_lower_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n,
-                                                                      const long long* __restrict__ s,
-                                                                      const unsigned long long* __restrict__ sums,
-                                                                      double* __restrict__ K) {
+__global__ void __launch_bounds__(256, 3) vanraden_epilogue_lower_kernel(const int32_t* __restrict__ G, int64_t ldg, int64_t n,
+                                                                         const long long* __restrict__ s,
+                                                                         const unsigned long long* __restrict__ sums,
+                                                                         double* __restrict__ K) {
   // triangular index -> (bi, bj), bj <= bi
   const long long t = blockIdx.x;
   int bi = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(256) vanraden_epilogue_lower_kernel(const int3
   while (static_cast<long long>(bi + 1) * (bi + 2) / 2 <= t) ++bi;
   const int bj = static_cast<int>(t - static_cast<long long>(bi) * (bi + 1) / 2);
   __shared__ double tile[64][65];
-  __shared__ long long si_sh[64];
+  __shared__ long long ai_sh[64];
   const long long sum_c = static_cast<long long>(sums[0]);
   const long long sum_c2 = static_cast<long long>(sums[1]);
   const long long n2 = static_cast<long long>(sums[2]);
@@ -318,11 +327,14 @@ __global__ void __launch_bounds__(256) vanraden_epilogue_lower_kernel(const int3
   const long long c2 = sum_c2 - n2 * 4 * nn * nn;
   const long long c1 = sum_c - n2 * 2 * nn;
   const double D = static_cast<double>(2 * nn * c1 - c2);
+  // num_ij = n^2 (G_ij - 4 n2) - n (s_i + s_j) + c2 = n^2 G_ij + a_i + b_j  (exact in int64)
+  const long long nn2 = nn * nn;
   const int x = threadIdx.x & 63, y0 = threadIdx.x >> 6;
   const int64_t i0 = int64_t(bi) * 64, j0 = int64_t(bj) * 64;
-  if (threadIdx.x < 64) si_sh[threadIdx.x] = (i0 + threadIdx.x < n) ? s[i0 + threadIdx.x] - 4 * n2 * nn : 0;
+  if (threadIdx.x < 64)
+    ai_sh[threadIdx.x] = (i0 + threadIdx.x < n) ? c2 - nn2 * 4 * n2 - nn * (s[i0 + threadIdx.x] - 4 * n2 * nn) : 0;
   const int64_t j = j0 + x;
-  const long long sj = (j < n) ? s[j] - 4 * n2 * nn : 0;
+  const long long b_j = (j < n) ? -nn * (s[j] - 4 * n2 * nn) : 0;
   int32_t g[16];
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
@@ -330,15 +342,18 @@ __global__ void __launch_bounds__(256) vanraden_epilogue_lower_kernel(const int3
     g[q] = (i < n && j < n) ? __ldg(G + i * ldg + j) : 0;
   }
   __syncthreads();
+  // v = 2 num / D, correctly rounded: one multiplication by the rounded reciprocal and one residual correction (the
+  // refinement step an fp64 division ends with) instead of the ~20-instruction division sequence per element
+  const double Dh = 0.5 * D, r = 1.0 / Dh;
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     const int y = y0 + 4 * q;
     const int64_t i = i0 + y;
     double v = 0.0;
     if (i < n && j < n) {
-      const long long gg = static_cast<long long>(g[q]) - 4 * n2;
-      const long long num = nn * nn * gg - nn * (si_sh[y] + sj) + c2;
-      v = 2.0 * static_cast<double>(num) / D;
+      const double numd = static_cast<double>(nn2 * static_cast<long long>(g[q]) + ai_sh[y] + b_j);
+      v = numd * r;
+      v = fma(fma(-v, Dh, numd), r, v);
       K[j + i * n] = v;                                  // element (j, i): contiguous along j
     }
     tile[y][x] = v;
@@ -674,8 +689,7 @@ extern "C" int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, 
     // then both orientations of every K entry; the int32 matrix itself is mirrored only when the caller asks for it
     const unsigned t32 = static_cast<unsigned>((n + 31) / 32);
     gram_strip_sums_kernel<<<t32, 256, 0, ctx->stream>>>(G_dev, ldg, static_cast<int>(t32), s, colpart);
-    gram_strip_combine_kernel<<<(t32 * 32 + 255) / 256, 256, 0, ctx->stream>>>(colpart, ldg, static_cast<int>(t32),
-                                                                               int64_t(t32) * 32, s);
+    gram_strip_combine_kernel<<<t32, 256, 0, ctx->stream>>>(colpart, ldg, static_cast<int>(t32), s);
     const long long t64 = (n + 63) / 64;
     vanraden_epilogue_lower_kernel<<<static_cast<unsigned>(t64 * (t64 + 1) / 2), 256, 0, ctx->stream>>>(
         G_dev, ldg, n, s, reinterpret_cast<const unsigned long long*>(sums_dev), K_dev);
