@@ -185,8 +185,13 @@ def run_config(name, ctx, dev, rank=0, world=1, n=None, m=None, T=None, blocks=8
         lam = gb.eigh_dev_range(K_dev.data_ptr(), n, lo_r[rank], lo_r[rank + 1] - lo_r[rank],
                                 V_t[lo_r[rank]:lo_r[rank + 1]].data_ptr(), ctx=ctx)
         val_t[lo_r[rank]:lo_r[rank + 1]].copy_(torch.from_numpy(lam))
+        torch.cuda.synchronize()
+        mine_s = torch.tensor([time.perf_counter() - t1], device=dev, dtype=torch.float64)
+        all_s = [torch.empty_like(mine_s) for _ in range(world)]
+        dist.all_gather(all_s, mine_s)
         sync()
         T_["eigh_s"] = time.perf_counter() - t1
+        T_["eigh_s_per_rank"] = [round(float(x[0]), 3) for x in all_s]    # the slowest rank sets eigh_s
         T_["eigh_route"] = f"spectrum sliced over {world} GPUs (K broadcast + syevdx per rank)"
         t1 = time.perf_counter()
         for r in range(world):
