@@ -682,8 +682,12 @@ extern "C" int gapit_vanraden_finish(gapit_ctx* ctx, int64_t n, int32_t* G_dev, 
   double* K_dev = K_dev_out;
   long long* colpart = nullptr;
   GAPIT_CHECK(ctx_ws_t(ctx, WS_R, size_t(n) + 32, &s));                  // arena: no leak on the error paths below
-  GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t((n + 31) / 32) * size_t(ldg), &colpart));   // column sums per 32-row strip
+  // the column sums per 32-row strip are consumed before the first K entry is written, so they live in the output
+  // buffer itself (627 MB at n = 50,000; a separate allocation cost 1-12 ms inside the call); tiny n: the arena
+  if (size_t((n + 31) / 32) * size_t(ldg) > size_t(n) * size_t(n) || (reinterpret_cast<uintptr_t>(K_dev_out) & 15))
+    GAPIT_CHECK(ctx_ws_t(ctx, WS_PART, size_t((n + 31) / 32) * size_t(ldg), &colpart));
   if (!K_dev) GAPIT_CHECK(ctx_ws_t(ctx, WS_OUT, size_t(n) * n, &K_dev));
+  if (!colpart) colpart = reinterpret_cast<long long*>(K_dev);
   {
     // everything from the lower triangle the Gram kernel (and the row gather of the sharded form) left: the row sums,
     // then both orientations of every K entry; the int32 matrix itself is mirrored only when the caller asks for it
