@@ -358,3 +358,29 @@ def test_oracle_file_format_readers():
     assert go.read_bed(bed, n, "A2").T.tolist() == [[0, -1, 1, 2, 2, 0]]
     GD, GT, names = go.read_numeric_text(b"taxa\tm1\tm2\nA 0 1.0\nB,NA,2\n")
     assert GT == ["A", "B"] and names == ["m1", "m2"] and GD[0].tolist() == [0.0, 1.0] and np.isnan(GD[1, 0]) and GD[1, 1] == 2.0
+
+
+def test_bench_workloads_are_the_named_baseline_configs():
+    """bench.py's headline shape and the full-size legs are BASELINE.json's configs[1..4], not smaller stand-ins."""
+    import json
+    import sys
+    import importlib.util
+    from gapit_b200 import fullsize
+    with open(os.path.join(ROOT, "BASELINE.json")) as f:
+        cfgs = json.load(f)["configs"]
+    nums = [[int(x.replace(",", "")) for x in re.findall(r"\d[\d,]*\d", str(c)) if int(x.replace(",", "")) >= 100] for c in cfgs]
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    old = sys.argv
+    sys.argv = ["bench.py"]
+    try:
+        args = bench.parse()
+    finally:
+        sys.argv = old
+    assert [args.n, args.m] == nums[1][:2] and args.gpus == 1 and args.warmup >= 3          # configs[1]: 5,000 x 500,000
+    c3, c4, c5 = fullsize.CONFIGS["c3"], fullsize.CONFIGS["c4"], fullsize.CONFIGS["c5"]
+    assert [c3["n"], c3["m"]] == nums[2][:2] and c3["T"] == 1 and c3["scan"]                 # 20,000 x 1,000,000
+    assert [c4["n"], c4["m"]] == nums[3][:2] and not c4["scan"]                               # 50,000 x 1,000,000, kinship only
+    assert [c5["n"], c5["m"], c5["T"]] == nums[4][:3] and c5["scan"]                          # 10,000 x 2,000,000 x 100
+    assert bench.METRIC.startswith("SNPs tested/sec") and bench.UNIT == "SNPs/s"
