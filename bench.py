@@ -539,17 +539,21 @@ def main():
             # the whole reference-facing call, nothing resident: K on the host -> eigendecomposition (cuSOLVER syevd) +
             # REML + BLUP/PEV + the scan from packed host genotypes -> the reference's result list.  The eigen phase is
             # outside the hot-path roofline (north_star) but it IS what one GAPIT.EMMAxP3D call costs.
-            whole = []
-            for _ in range(2):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                res = gb.GAPIT_EMMAxP3D(Y[:, 0], P2, K_host, X0=X0, ctx=ctx)
-                whole.append(time.perf_counter() - t0)
-            assert np.isclose(float(np.nanmin(res["ps"])), last["e2e_min_p"], rtol=1e-6, atol=0.0)
-            e2e["whole_call"] = {"value": m / whole[-1], "unit": UNIT, "ms": whole[-1] * 1e3, "first_call_ms": whole[0] * 1e3,
-                                 "note": "one GAPIT_EMMAxP3D(ys, xs, K, X0) call: host K -> syevd + REML + BLUP/PEV + scan "
-                                         "from packed host genotypes -> result list (second of two calls)"}
-            del res
+            try:
+                whole = []
+                for _ in range(2):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    res = gb.GAPIT_EMMAxP3D(Y[:, 0], P2, K_host, X0=X0, ctx=ctx)
+                    whole.append(time.perf_counter() - t0)
+                same = bool(np.isclose(float(np.nanmin(res["ps"])), last["e2e_min_p"], rtol=1e-6, atol=0.0))
+                e2e["whole_call"] = {"value": m / whole[-1], "unit": UNIT, "ms": whole[-1] * 1e3, "first_call_ms": whole[0] * 1e3,
+                                     "min_p_matches_the_resident_scan": same,
+                                     "note": "one GAPIT_EMMAxP3D(ys, xs, K, X0) call: host K -> syevd + REML + BLUP/PEV + scan "
+                                             "from packed host genotypes -> result list (second of two calls)"}
+                del res
+            except Exception as exc:   # an extra: it must not take the headline down with it
+                e2e["whole_call"] = {"error": repr(exc)[:300]}
         del P2
 
     # ---------------- CPU baseline beside it (rank 0, N=1) ----------------
