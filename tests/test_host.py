@@ -384,3 +384,24 @@ def test_bench_workloads_are_the_named_baseline_configs():
     assert [c4["n"], c4["m"]] == nums[3][:2] and not c4["scan"]                               # 50,000 x 1,000,000, kinship only
     assert [c5["n"], c5["m"], c5["T"]] == nums[4][:3] and c5["scan"]                          # 10,000 x 2,000,000 x 100
     assert bench.METRIC.startswith("SNPs tested/sec") and bench.UNIT == "SNPs/s"
+
+
+def test_kinship_quotient_by_reciprocal_and_residual_is_the_rounded_division():
+    """The kinship epilogue (csrc/kinship.cu, vanraden_epilogue_lower_kernel) forms K_ij = num / (D/2) as
+    q = num * r, r = fl(1 / (D/2)), then q + fma(-q, D/2, num) * r -- the refinement step an fp64 division ends with.
+    Restated in exact rational arithmetic (an fma is one rounding of the exact value): the result is the correctly
+    rounded quotient, so the cheaper sequence changes nothing in K."""
+    from fractions import Fraction
+    import random
+    rnd = random.Random(20160301)
+    for _ in range(20000):
+        n = rnd.choice([281, 5000, 20000, 50000])
+        m = rnd.randint(1000, 2_000_000)
+        D = float(rnd.randint(n * m // 10, n * m))
+        numd = float(rnd.randint(-int(2 * D), int(2 * D)))
+        Dh = 0.5 * D
+        r = 1.0 / Dh
+        q = numd * r
+        e = float(Fraction(numd) - Fraction(q) * Fraction(Dh))
+        v = float(Fraction(q) + Fraction(e) * Fraction(r))
+        assert v == float(Fraction(numd) / Fraction(Dh))
