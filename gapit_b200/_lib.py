@@ -70,6 +70,7 @@ SIGNATURES = {
     "gapit_vanraden": (C.c_int, [_P, _P, _P, _P]),
     "gapit_gram_ld": (_I64, [_I64]),
     "gapit_vanraden_gram": (C.c_int, [_P, _P, _P, _P]),
+    "gapit_gram_plan": (C.c_int, [_I64, _I64, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gapit_vanraden_gram_fused": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "gapit_vanraden_gram_gather": (C.c_int, [_P, C.c_int64, _P, C.c_int, C.c_int]),
     "gapit_gram_owned_rows": (C.c_int, [_I64, C.c_int, C.c_int, C.POINTER(_I64), C.POINTER(_I64)]),

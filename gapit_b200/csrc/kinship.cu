@@ -496,6 +496,24 @@ static int choose_ksplit(int jobs, int kblocks, int units) {
   return best;
 }
 
+// the cut of one cross-product launch: pair jobs of the lower triangle (a cluster of 2 CTAs takes two block-rows against
+// one block-column), k-blocks of the marker axis, marker splits per job
+struct GramPlan {
+  int tiles_side, ntri, kblocks, ksplit, units;
+};
+static GramPlan plan_gram(int64_t n, int64_t m, int sm_count) {
+  constexpr int cl = 2;
+  GramPlan p;
+  p.tiles_side = static_cast<int>((n + 255) / 256);
+  const int TR = (p.tiles_side + cl - 1) / cl;
+  p.ntri = 0;
+  for (int R = 0; R < TR; ++R) p.ntri += std::min(cl * (R + 1), p.tiles_side);
+  p.kblocks = static_cast<int>(round_up(m, 128) / kBlockK);
+  p.units = std::max(1, sm_count / cl);
+  p.ksplit = choose_ksplit(p.ntri, p.kblocks, p.units);
+  return p;
+}
+
 struct GramExchange {   // where the tiles of this launch are reduced into (world 1: the local buffer)
   int world = 1;
   int root = 0;           // >= 0: every tile goes to this rank's buffer; < 0: to the owner of its block-row
@@ -508,15 +526,14 @@ struct GramExchange {   // where the tiles of this launch are reduced into (worl
 // A pair covers two block-rows; with a single block-row (n <= 256) the second CTA multiplies zero padding.
 static int launch_gram(gapit_ctx* ctx, gapit_geno* g, int64_t ldg, const GramExchange& ex) {
   GramSched::Params sp;
-  sp.tiles_side = static_cast<int>((g->n + 255) / 256);
   constexpr int cl = 2;
+  const GramPlan gp = plan_gram(g->n, g->m, ctx->sm_count);
+  sp.tiles_side = gp.tiles_side;
   if (int64_t(round_up(sp.tiles_side, cl)) * 256 > ldg) return fail(GAPIT_ERR_ARG, "launch_gram: Gram buffer too small");
-  const int TR = (sp.tiles_side + cl - 1) / cl;
   sp.cl = cl;
-  sp.ntri = 0;
-  for (int R = 0; R < TR; ++R) sp.ntri += std::min(cl * (R + 1), sp.tiles_side);
-  sp.kblocks = static_cast<int>(round_up(g->m, 128) / kBlockK);
-  sp.ksplit = choose_ksplit(sp.ntri, sp.kblocks, std::max(1, ctx->sm_count / cl));
+  sp.ntri = gp.ntri;
+  sp.kblocks = gp.kblocks;
+  sp.ksplit = gp.ksplit;
   const int nunits = std::min(ctx->sm_count / cl, sp.ntri * sp.ksplit);
   sp.round_ctr = nullptr;
   sp.round_wait = 100000;
@@ -652,6 +669,16 @@ extern "C" int gapit_vanraden_gram_gather(gapit_ctx* ctx, int64_t n, int32_t* co
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
   ctx->stats.post_ms = ms;
+  return GAPIT_OK;
+}
+
+// how a Gram launch of n taxa x m markers is cut on a GPU with `sm_count` SMs (host arithmetic only; what launch_gram uses)
+extern "C" int gapit_gram_plan(int64_t n, int64_t m, int sm_count, int* jobs_out, int* splits_out, int* rounds_out) {
+  if (n <= 0 || m <= 0 || sm_count < 2) return fail(GAPIT_ERR_ARG, "gapit_gram_plan: bad argument");
+  const GramPlan p = plan_gram(n, m, sm_count);
+  if (jobs_out) *jobs_out = p.ntri;
+  if (splits_out) *splits_out = p.ksplit;
+  if (rounds_out) *rounds_out = static_cast<int>((int64_t(p.ntri) * p.ksplit + p.units - 1) / p.units);
   return GAPIT_OK;
 }
 

@@ -178,6 +178,10 @@ int gapit_vanraden_gram_fused(gapit_ctx* ctx, gapit_geno* g, int32_t* const* pee
                               int64_t* sums_dev, int64_t* const* sum_peers);
 int gapit_vanraden_gram_gather(gapit_ctx* ctx, int64_t n, int32_t* const* peers, int world, int rank);
 int gapit_gram_owned_rows(int64_t n, int world, int rank, int64_t* row_lo, int64_t* row_hi);
+/* How the cross-product launch of n taxa x m markers is cut on a GPU with sm_count SMs (host arithmetic, no device
+ * needed): pair jobs of the lower triangle, marker splits per job (chosen so that the equal-length jobs fill whole
+ * rounds of the sm_count / 2 CTA pairs), rounds = ceil(jobs * splits / pairs).  Any out pointer may be NULL. */
+int gapit_gram_plan(int64_t n, int64_t m, int sm_count, int* jobs_out, int* splits_out, int* rounds_out);
 
 /* ---- ZHANG kinship and PCA covariates from the same integer cross-product ----------------------------
  * gapit_zhang: GAPIT.kinship.ZHANG(snps) (GAPIT.kinship.ZHANG.R:1-66): centred cross-product (:21-26), range

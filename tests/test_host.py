@@ -405,3 +405,30 @@ def test_kinship_quotient_by_reciprocal_and_residual_is_the_rounded_division():
         e = float(Fraction(numd) - Fraction(q) * Fraction(Dh))
         v = float(Fraction(q) + Fraction(e) * Fraction(r))
         assert v == float(Fraction(numd) / Fraction(Dh))
+
+
+def test_gram_launch_is_cut_into_whole_rounds():
+    """gapit_gram_plan (host arithmetic, the plan launch_gram uses): every job of a cross-product launch is equally long,
+    so the launch lasts ceil(jobs * splits / CTA pairs) rounds.  BASELINE configs[1] on a 148-SM part: 110 pair jobs, 2
+    marker splits, 3 rounds with 99 % of the pairs busy (the earlier "at least six waves" rule took 5 splits: 7.4 -> 8
+    rounds, 93 %); and no shape is ever cut worse than with a single split."""
+    lib = _lib.load()
+
+    def plan(n, m, sms=148):
+        j, s, r = C.c_int(), C.c_int(), C.c_int()
+        assert lib.gapit_gram_plan(n, m, sms, C.byref(j), C.byref(s), C.byref(r)) == 0
+        return j.value, s.value, r.value
+
+    jobs, splits, rounds = plan(5000, 500000)
+    assert (jobs, splits, rounds) == (110, 2, 3) and jobs * splits / (74 * rounds) > 0.98
+    jobs, splits, rounds = plan(50000, 125000)                      # configs[3], one of 8 marker shards
+    assert splits == 1 and jobs * splits / (74 * rounds) > 0.99
+    for n in (281, 600, 1000, 3000, 5000, 10000, 20000):
+        for m in (1536, 3093, 40000, 200000, 1000000, 2000000):
+            jobs, splits, rounds = plan(n, m)
+            kblocks = (m + 127) // 128
+            assert splits >= 1 and (splits == 1 or kblocks // splits >= 32)
+            assert rounds == -(-jobs * splits // 74)
+            one = -(-jobs // 74) * (kblocks + 4.0)
+            assert rounds * (kblocks / splits + 4.0) <= one * 1.0001, (n, m, splits)
+    assert lib.gapit_gram_plan(0, 10, 148, None, None, None) != 0
