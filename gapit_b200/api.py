@@ -478,7 +478,8 @@ def p3d_scan_file(genotypes, X0, Y, eigsys=None, delta=None, vg=None, glm=False,
             return arrs, bases, GT, GI
         Y = np.asfortranarray(np.asarray(Y, dtype=np.float64).reshape(len(GTindex), -1))
         arrs, bases = alloc_scan_out(Y.shape[1], rows.m, pinned=False), None
-        frag = 65536                                              # marker blocks, as GAPIT.Fragment reads them
+        frag = 2 * 37888                                          # marker blocks, as GAPIT.Fragment reads them; whole rounds
+                                                                  # of the 74 CTA pairs x 512 markers of a 148-SM part
         for k0 in range(0, rows.m, frag):
             k1 = min(rows.m, k0 + frag)
             full = Genotypes(Packed2(rows.data[k0:k1], rows.n, dtype=rows.dtype), ctx=ctx, impute=SNP_impute)
